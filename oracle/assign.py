@@ -1,0 +1,89 @@
+"""numpy restatement of the reference's IoU + label assignment -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Follows (paths relative to /root/reference/):
+  pairwise_iou ...... detectron2/detectron2/structures/boxes.py:316-348 (area :173-182)
+  Matcher ........... detectron2/detectron2/modeling/matcher.py:61-126
+  TopKMatcher ....... slender_det/modeling/matchers/topk_matcher.py:38-86
+
+Parity pin: checked in tests/test_oracle_assign.py against the reference's known-answer tests
+(detectron2/tests/modeling/test_matcher.py:19-27, detectron2/tests/structures/test_boxes.py:151-173)
+and against golden vectors produced by importing the reference's own Python files
+(tests/golden/gen_golden.py).
+
+All arithmetic is IEEE float32, one rounding per operation, in the reference's operation order,
+so results are bit-comparable with the CUDA kernels (which use the non-fused _rn intrinsics).
+
+Tie rule (TopKMatcher): the reference calls torch.topk, whose order among equal values is an
+implementation detail of the backend.  The canonical rule used here and by the CUDA kernel is
+"descending value, then ascending index" (== torch.sort(stable=True, descending=True)[:k]).
+On inputs whose k-th and (k+1)-th largest values per GT row differ this equals the reference exactly.
+"""
+import numpy as np
+
+
+def pairwise_iou(boxes1, boxes2):
+    """boxes1 [N,4], boxes2 [M,4] (x1,y1,x2,y2) float32 -> IoU [N,M] float32."""
+    b1 = np.asarray(boxes1, np.float32).reshape(-1, 4)
+    b2 = np.asarray(boxes2, np.float32).reshape(-1, 4)
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    wh = np.minimum(b1[:, None, 2:], b2[None, :, 2:]) - np.maximum(b1[:, None, :2], b2[None, :, :2])
+    wh = np.maximum(wh, np.float32(0))
+    inter = wh[..., 0] * wh[..., 1]
+    union = (area1[:, None] + area2[None, :]) - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = np.where(inter > 0, inter / union, np.float32(0))
+    return iou.astype(np.float32)
+
+
+def _threshold_labels(vals, thresholds, labels):
+    th = [-np.inf] + [float(t) for t in thresholds] + [np.inf]
+    assert len(labels) == len(th) - 1
+    out = np.ones(vals.shape, np.int8)
+    for l, lo, hi in zip(labels, th[:-1], th[1:]):
+        out[(vals >= np.float32(lo)) & (vals < np.float32(hi))] = l
+    return out
+
+
+def matcher(q, thresholds, labels, allow_low_quality_matches=False):
+    """q [M,N] float32 -> (matches int64 [N], labels int8 [N]).  d2 Matcher.__call__."""
+    q = np.asarray(q, np.float32)
+    assert q.ndim == 2
+    M, N = q.shape
+    if q.size == 0:
+        return np.zeros(N, np.int64), np.full(N, labels[0], np.int8)
+    assert (q >= 0).all()
+    matches = q.argmax(axis=0).astype(np.int64)  # first (lowest GT index) on ties
+    vals = q.max(axis=0)
+    lab = _threshold_labels(vals, thresholds, labels)
+    if allow_low_quality_matches:
+        best = q.max(axis=1)
+        lab[(q == best[:, None]).any(axis=0)] = 1
+    return matches, lab
+
+
+def topk_matcher(q, thresholds, labels, topk=9):
+    """q [M,N] float32 -> (matches int64 [N], labels int8 [N]).  TopKMatcher.__call__."""
+    q = np.asarray(q, np.float32)
+    assert q.ndim == 2
+    M, N = q.shape
+    if q.size == 0:
+        return np.zeros(N, np.int64), np.full(N, labels[0], np.int8)
+    assert (q >= 0).all()
+    if topk > N:
+        raise RuntimeError("selected index k out of range")  # torch.topk's error
+    matches = q.argmax(axis=0).astype(np.int64)
+    vals = q.max(axis=0)
+    lab = _threshold_labels(vals, thresholds, labels)
+    idx = np.argsort(-q, axis=1, kind="stable")[:, :topk]
+    lab[idx.reshape(-1)] = 1
+    return matches, lab
+
+
+def topk_is_tie_free(q, topk):
+    """True when every GT row's k-th and (k+1)-th largest values differ (reference == canonical)."""
+    q = np.asarray(q, np.float32)
+    if q.size == 0 or q.shape[1] <= topk:
+        return True
+    s = -np.sort(-q, axis=1)
+    return bool((s[:, topk - 1] != s[:, topk]).all())
