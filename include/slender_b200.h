@@ -1,0 +1,160 @@
+/*
+ * slender_b200.h -- C ABI of libslender_b200.so (NVIDIA B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the dense-head hot path of wanzysky/SlenderObjDet.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference checkout;
+ * "d2/" = detectron2/detectron2/, "sd/" = slender_det/).  The reference binds its native code with
+ * pybind11 (d2/layers/csrc/vision.cpp:76-92); this library is bound with ctypes from
+ * slenderobjdet_b200/_lib.py -- plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current device, tensors are contiguous, NCHW
+ *     (the reference's layout, d2/layers/csrc/deformable/deform_conv_cuda.cu:312-314, :824-825);
+ *   - the caller allocates every output (d2/layers/deform_conv.py:42-46, :89-90, :113, :242-246);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, negative sdb_status on error; sdb_last_error() gives the
+ *     thread-local message (the Python shim turns it into RuntimeError, mirroring TORCH_CHECK in
+ *     deform_conv_cuda.cu:140-270);
+ *   - `offset` and `mask` are always float32 (sampling coordinates stay fp32 even in bf16 mode);
+ *     `io_dtype` is the type of x / weight / bias / out / grad tensors.
+ */
+#ifndef SLENDER_B200_H_
+#define SLENDER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1
+
+typedef enum {
+  SDB_OK = 0,
+  SDB_ERR_INVALID = -1,      /* bad shape / argument (shape_check, deform_conv_cuda.cu:140-270) */
+  SDB_ERR_UNSUPPORTED = -2,  /* valid, but not implemented for this dtype / math mode / shape */
+  SDB_ERR_WORKSPACE = -3,    /* workspace NULL or too small */
+  SDB_ERR_CUDA = -4          /* a CUDA runtime call or launch failed */
+} sdb_status;
+
+typedef enum { SDB_F32 = 0, SDB_BF16 = 1 } sdb_dtype;
+
+/* Arithmetic of the contraction.  FP32: SIMT kernels, fp32 multiply-accumulate, any shape.
+ * BF16: tcgen05 tensor-core kernels; sampled values and weights rounded to bf16, fp32
+ * accumulate in TMEM.  Requires groups == 1, deformable_groups == 1, C_in % 64 == 0,
+ * C_out % 16 == 0, C_out <= 256 (sdb_dcn_supported tells). */
+typedef enum { SDB_MATH_FP32 = 0, SDB_MATH_BF16 = 1 } sdb_math;
+
+/* Geometry of one deformable convolution (same meaning as the integer arguments of
+ * deform_conv_forward / modulated_deform_conv_forward, d2/layers/csrc/deformable/deform_conv.h:8-112).
+ * With has_mask == 0 this is DCN v1 (DeformConv), with has_mask == 1 modulated DCN v2. */
+typedef struct {
+  int32_t N, C_in, H, W;        /* input  [N, C_in, H, W]                                   */
+  int32_t C_out, kH, kW;        /* weight [C_out, C_in/groups, kH, kW]                      */
+  int32_t sH, sW, pH, pW, dH, dW;
+  int32_t groups, deformable_groups;
+  /* offset [N, deformable_groups*2*kH*kW, Ho, Wo]: channel 2*(i*kW+j) = dy, +1 = dx
+   * (deform_conv_cuda_kernel.cu:257-269); mask [N, deformable_groups*kH*kW, Ho, Wo] (:843-847). */
+} sdb_dcn_geom;
+
+const char* sdb_last_error(void);
+int sdb_abi_version(void);
+
+/* Output spatial size; returns SDB_ERR_INVALID if it would be <= 0 (deform_conv.py:147-152). */
+int sdb_dcn_output_size(const sdb_dcn_geom* g, int32_t* Ho, int32_t* Wo);
+
+/* 1 if (geom, io_dtype, math) can run, 0 otherwise (message in sdb_last_error). */
+int sdb_dcn_supported(const sdb_dcn_geom* g, int io_dtype, int math);
+
+typedef enum { SDB_OP_FORWARD = 0, SDB_OP_BACKWARD_DATA = 1, SDB_OP_BACKWARD_WEIGHT = 2 } sdb_dcn_op;
+
+/* Scratch bytes the op needs (0 for SDB_MATH_FP32).  The caller passes a device buffer of at
+ * least this size; it replaces the `columns` / `ones` scratch tensors of the reference
+ * (deform_conv_cuda.cu:345-352), which are no longer materialised. */
+size_t sdb_dcn_workspace_bytes(int op, const sdb_dcn_geom* g, int io_dtype, int math);
+
+/* Bytes of the packed (NHWC bf16) copy of x that BF16 math uses; forward can export it
+ * (`x_packed_out`) so the backward calls need not rebuild it (`x_packed`).  0 for FP32 math. */
+size_t sdb_dcn_packed_input_bytes(const sdb_dcn_geom* g, int math);
+
+/* Replaces deform_conv_forward (deform_conv.h:116-161 -> deform_conv_cuda.cu:272-438) and
+ * modulated_deform_conv_forward (deform_conv.h:263-312 -> deform_conv_cuda.cu:804-927).
+ *   out[n,o,h,w] = bias[o] + sum_{c,i,j} W[o,c,i,j] * mask * bilinear(x[n,c], p(h,w,i,j))
+ * mask == NULL: v1.  bias == NULL: no bias.  out is overwritten.  x_packed_out may be NULL. */
+int sdb_dcn_forward(const void* x, const float* offset, const float* mask, const void* weight,
+                    const void* bias, void* out, const sdb_dcn_geom* g, int io_dtype, int math,
+                    void* workspace, size_t workspace_bytes, void* x_packed_out, void* stream);
+
+/* Replaces deform_conv_backward_input (deform_conv.h:163-211 -> deform_conv_cuda.cu:440-628) and the
+ * grad_input / grad_offset / grad_mask part of modulated_deform_conv_backward (:929-1129).
+ *   grad_x      : ACCUMULATED into (caller pre-zeroes, deform_conv.py:89)  -- may be NULL
+ *   grad_offset : overwritten (float32)                                     -- may be NULL
+ *   grad_mask   : overwritten (float32), v2 only                            -- may be NULL
+ * x_packed: optional NHWC-bf16 copy exported by sdb_dcn_forward (BF16 math), else NULL. */
+int sdb_dcn_backward_data(const void* x, const float* offset, const float* mask, const void* weight,
+                          const void* grad_out, void* grad_x, float* grad_offset, float* grad_mask,
+                          const sdb_dcn_geom* g, int io_dtype, int math, void* workspace,
+                          size_t workspace_bytes, const void* x_packed, void* stream);
+
+/* Replaces deform_conv_backward_filter (deform_conv.h:213-260 -> deform_conv_cuda.cu:630-802) and the
+ * grad_weight / grad_bias part of modulated_deform_conv_backward.
+ *   grad_weight += scale * dY . col^T  (ACCUMULATED, as addmm_ beta=1 :770-777; float32 always)
+ *   grad_bias   += scale * sum dY      (ACCUMULATED; float32 always; may be NULL) */
+int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mask,
+                            const void* grad_out, float* grad_weight, float* grad_bias, float scale,
+                            const sdb_dcn_geom* g, int io_dtype, int math, void* workspace,
+                            size_t workspace_bytes, const void* x_packed, void* stream);
+
+/* ---- label assignment (HBM/latency-bound; no tensor cores) ------------------------------------
+ * Fuses pairwise_iou (d2/structures/boxes.py:316-348) with Matcher.__call__
+ * (d2/modeling/matcher.py:61-126) or TopKMatcher.__call__ (sd/modeling/matchers/topk_matcher.py:38-86).
+ * gt [M,4], anchors [X,4] float32 xyxy.  thresholds[n_thresholds] ascending, labels[n_thresholds+1]
+ * in {-1,0,1}.  topk > 0: TopKMatcher (every GT's k best anchors get label 1; ties -> lowest anchor
+ * index); topk == 0: Matcher, with allow_low_quality != 0 enabling set_low_quality_matches_.
+ * Outputs: matches int64 [X], match_labels int8 [X]; M == 0 gives zeros / labels[0].
+ * iou_out (optional, [M,X] float32) receives the IoU matrix, bit-identical to pairwise_iou.
+ * workspace: sdb_assign_workspace_bytes(M, X, topk). */
+size_t sdb_assign_workspace_bytes(int32_t M, int32_t X, int32_t topk);
+int sdb_iou_assign(const float* gt, const float* anchors, int32_t M, int32_t X,
+                   const float* thresholds, const int8_t* labels, int32_t n_thresholds, int32_t topk,
+                   int32_t allow_low_quality, int64_t* matches, int8_t* match_labels, float* iou_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Same, on a caller-provided match-quality matrix q [M,X] float32 (the matchers' own signature). */
+int sdb_match_quality_assign(const float* q, int32_t M, int32_t X, const float* thresholds,
+                             const int8_t* labels, int32_t n_thresholds, int32_t topk,
+                             int32_t allow_low_quality, int64_t* matches, int8_t* match_labels,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* pairwise_iou alone: iou [N1,N2] float32. */
+int sdb_pairwise_iou(const float* boxes1, const float* boxes2, int32_t N1, int32_t N2, float* iou,
+                     void* stream);
+
+/* ---- head losses (HBM-bound; fused forward + gradient, sum reduction) --------------------------
+ * sigmoid focal loss on logits [R,K] with a class index per row instead of the dense one-hot
+ * target the reference builds (sd/modeling/meta_arch/reppoints/reppointsv2.py:294-312,
+ * fcos/fcos.py:289-297; formula = fvcore sigmoid_focal_loss_jit, reduction "sum").
+ * class_idx[r] in [0,K) marks the foreground class, any other value is background.
+ * loss_sum (float32 scalar) is ACCUMULATED into; grad_logits (may be NULL) = grad_scale * dLoss/dx. */
+int sdb_sigmoid_focal_loss(const float* logits, const int64_t* class_idx, int64_t R, int32_t K,
+                           float alpha, float gamma, float grad_scale, float* loss_sum,
+                           float* grad_logits, void* stream);
+
+typedef enum {
+  SDB_LOSS_IOU = 0,        /* -log(iou)      sd/layers/iou_loss.py:24-25 */
+  SDB_LOSS_LINEAR_IOU = 1, /* 1 - iou        :26-27 */
+  SDB_LOSS_GIOU = 2,       /* 1 - giou       :28-29 */
+  SDB_LOSS_SMOOTH_L1 = 3,  /* sd/layers/smooth_l1_loss_with_weight.py:3-17 (beta) */
+  SDB_LOSS_GIOU_FVCORE = 4 /* fvcore giou_loss, xyxy, eps 1e-7 (meta/heads/anchor_head.py:369-376) */
+} sdb_box_loss_kind;
+typedef enum { SDB_BOX_LTRB = 0 /* iou_loss */, SDB_BOX_XYXY = 1 /* box_iou_loss */ } sdb_box_form;
+
+/* pred, target [R,4] float32; weight [R] float32 or NULL.  loss_sum ACCUMULATED; grad_pred
+ * (may be NULL, [R,4]) = grad_scale * dLoss/dpred. */
+int sdb_box_reg_loss(const float* pred, const float* target, const float* weight, int64_t R,
+                     int kind, int form, float beta, float grad_scale, float* loss_sum,
+                     float* grad_pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLENDER_B200_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libslender_b200.so (the C ABI declared in include/slender_b200.h).
+
+The library is the product: there is NO Python / CPU fallback.  If the shared object is missing
+(not built) every op raises ``RuntimeError`` telling the user how to build it.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libslender_b200.so")
+
+SDB_F32, SDB_BF16 = 0, 1
+SDB_MATH_FP32, SDB_MATH_BF16 = 0, 1
+SDB_OP_FORWARD, SDB_OP_BACKWARD_DATA, SDB_OP_BACKWARD_WEIGHT = 0, 1, 2
+SDB_LOSS_IOU, SDB_LOSS_LINEAR_IOU, SDB_LOSS_GIOU, SDB_LOSS_SMOOTH_L1, SDB_LOSS_GIOU_FVCORE = range(5)
+SDB_BOX_LTRB, SDB_BOX_XYXY = 0, 1
+
+# every symbol include/slender_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "sdb_last_error", "sdb_abi_version", "sdb_dcn_output_size", "sdb_dcn_supported",
+    "sdb_dcn_workspace_bytes", "sdb_dcn_packed_input_bytes", "sdb_dcn_forward",
+    "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_assign_workspace_bytes",
+    "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
+    "sdb_box_reg_loss",
+]
+
+
+class Geom(ctypes.Structure):
+    """sdb_dcn_geom"""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "N", "C_in", "H", "W", "C_out", "kH", "kW", "sH", "sW", "pH", "pW", "dH", "dW", "groups",
+        "deformable_groups")]
+
+
+_lib = None
+_vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_gp = ctypes.POINTER(Geom)
+
+
+def _declare(lib):
+    lib.sdb_last_error.restype = ctypes.c_char_p
+    lib.sdb_last_error.argtypes = []
+    lib.sdb_abi_version.restype = ctypes.c_int
+    lib.sdb_dcn_output_size.argtypes = [_gp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]
+    lib.sdb_dcn_supported.argtypes = [_gp, ctypes.c_int, ctypes.c_int]
+    lib.sdb_dcn_workspace_bytes.restype = _sz
+    lib.sdb_dcn_workspace_bytes.argtypes = [ctypes.c_int, _gp, ctypes.c_int, ctypes.c_int]
+    lib.sdb_dcn_packed_input_bytes.restype = _sz
+    lib.sdb_dcn_packed_input_bytes.argtypes = [_gp, ctypes.c_int]
+    lib.sdb_dcn_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _gp, ctypes.c_int, ctypes.c_int, _vp, _sz, _vp, _vp]
+    lib.sdb_dcn_backward_data.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _gp, ctypes.c_int,
+                                          ctypes.c_int, _vp, _sz, _vp, _vp]
+    lib.sdb_dcn_backward_weight.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _gp, ctypes.c_int,
+                                            ctypes.c_int, _vp, _sz, _vp, _vp]
+    lib.sdb_assign_workspace_bytes.restype = _sz
+    lib.sdb_assign_workspace_bytes.argtypes = [_i32, _i32, _i32]
+    lib.sdb_iou_assign.argtypes = [_vp, _vp, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int8),
+                                   _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]
+    lib.sdb_match_quality_assign.argtypes = [_vp, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int8),
+                                             _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]
+    lib.sdb_pairwise_iou.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp]
+    lib.sdb_sigmoid_focal_loss.argtypes = [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _vp, _vp]
+    lib.sdb_box_reg_loss.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _f32, _f32, _vp, _vp, _vp]
+    if hasattr(lib, "sdb_debug_umma_gemm"):
+        lib.sdb_debug_umma_gemm.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, _vp]
+    return lib
+
+
+def lib():
+    """Load (once) and return the C-ABI library; loud failure when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libslender_b200.so is not built (%s missing). Build it with "
+                "`python -m slenderobjdet_b200.csrc.build` (needs nvcc, targets sm_100a). "
+                "There is no CPU or PyTorch fallback for these ops." % LIB_PATH)
+        _lib = _declare(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("slender_b200: " + lib().sdb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)"""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def io_dtype(t):
+    if t.dtype == torch.float32:
+        return SDB_F32
+    if t.dtype == torch.bfloat16:
+        return SDB_BF16
+    raise RuntimeError("slender_b200: unsupported tensor dtype %s (float32 / bfloat16 only)" % t.dtype)

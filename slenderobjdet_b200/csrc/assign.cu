@@ -1,0 +1,284 @@
+// assign.cu -- fused pairwise IoU + label assignment (Matcher / TopKMatcher), bit-exact ints.
+//
+// Replaces ~20 eager kernels and the [M,X,2] / [M,X] temporaries of the reference
+// (d2/structures/boxes.py:316-348, d2/modeling/matcher.py:61-126,
+// sd/modeling/matchers/topk_matcher.py:38-86) with two launches:
+//   1. per-anchor kernel: IoU against all GT (GT boxes staged in shared memory), running
+//      max / argmax (first max = lowest GT index, as torch.max on ties), threshold -> label;
+//   2. per-GT kernel: k rounds of a block-wide arg-max over the anchors (value desc, index asc)
+//      for TopKMatcher, or max + equality sweep for Matcher's low-quality matches.
+// The IoU arithmetic uses the *_rn intrinsics in the reference's operation order so every IoU is
+// bit-identical to the float32 CPU result; HBM-bound by design (no tensor cores).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace sdb {
+namespace {
+
+__device__ __forceinline__ float box_area(const float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// boxes.py:333-347, one rounding per operation, no fma contraction
+__device__ __forceinline__ float iou_exact(const float4 a, float area_a, const float4 b, float area_b) {
+  float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  w = fmaxf(w, 0.f);
+  h = fmaxf(h, 0.f);
+  const float inter = __fmul_rn(w, h);
+  return inter > 0.f ? __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) : 0.f;
+}
+
+struct Thresh {
+  float t[8];
+  int8_t l[9];
+  int n;
+};
+
+__device__ __forceinline__ int8_t label_of(const Thresh& th, float v) {
+  // labels[i] for v in [t[i-1], t[i]) with t[-1] = -inf, t[n] = +inf (matcher.py:96-98)
+  int8_t lab = 1;
+  float lo = -INFINITY;
+  for (int i = 0; i <= th.n; ++i) {
+    const float hi = (i < th.n) ? th.t[i] : INFINITY;
+    if (v >= lo && v < hi) lab = th.l[i];
+    lo = hi;
+  }
+  return lab;
+}
+
+// ---- kernel 1: one thread per anchor ------------------------------------------------------------
+template <bool FROM_BOXES>
+__global__ void __launch_bounds__(256) per_anchor_kernel(const float4* __restrict__ gt,
+                                                         const float4* __restrict__ anchors,
+                                                         const float* __restrict__ q, int M, int X,
+                                                         Thresh th, int64_t* __restrict__ matches,
+                                                         int8_t* __restrict__ labels,
+                                                         float* __restrict__ iou_out) {
+  extern __shared__ float4 s_gt[];  // [M] boxes then [M] areas (as float)
+  float* s_area = reinterpret_cast<float*>(s_gt + M);
+  if (FROM_BOXES) {
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      const float4 b = gt[m];
+      s_gt[m] = b;
+      s_area[m] = box_area(b);
+    }
+    __syncthreads();
+  }
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= X) return;
+  float4 a = make_float4(0, 0, 0, 0);
+  float area_a = 0.f;
+  if (FROM_BOXES) {
+    a = anchors[x];
+    area_a = box_area(a);
+  }
+  float best = -1.f;
+  int arg = 0;
+  for (int m = 0; m < M; ++m) {
+    float v;
+    if (FROM_BOXES) {
+      v = iou_exact(s_gt[m], s_area[m], a, area_a);
+      if (iou_out) iou_out[(size_t)m * X + x] = v;
+    } else {
+      v = q[(size_t)m * X + x];
+    }
+    if (v > best) {
+      best = v;
+      arg = m;
+    }
+  }
+  matches[x] = arg;
+  labels[x] = label_of(th, best);
+}
+
+// ---- kernel 2: one CTA per GT -------------------------------------------------------------------
+struct Key {
+  float v;
+  int i;
+};
+// "a ranks before b": larger value first, then smaller index
+__device__ __forceinline__ bool before(const Key a, const Key b) {
+  return a.v > b.v || (a.v == b.v && a.i < b.i);
+}
+
+__device__ __forceinline__ Key block_best(Key k, Key* s_red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    Key o;
+    o.v = __shfl_xor_sync(0xffffffffu, k.v, d);
+    o.i = __shfl_xor_sync(0xffffffffu, k.i, d);
+    if (before(o, k)) k = o;
+  }
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // s_red reuse across rounds
+  if ((threadIdx.x & 31) == 0) s_red[warp] = k;
+  __syncthreads();
+  Key r = s_red[0];
+  for (int w = 1; w < nw; ++w)
+    if (before(s_red[w], r)) r = s_red[w];
+  return r;
+}
+
+template <bool FROM_BOXES>
+__global__ void __launch_bounds__(1024) per_gt_kernel(const float4* __restrict__ gt,
+                                                      const float4* __restrict__ anchors,
+                                                      const float* __restrict__ q, int M, int X,
+                                                      int topk, int8_t* __restrict__ labels) {
+  __shared__ Key s_red[32];
+  const int m = blockIdx.x;
+  float4 g = make_float4(0, 0, 0, 0);
+  float area_g = 0.f;
+  if (FROM_BOXES) {
+    g = gt[m];
+    area_g = box_area(g);
+  }
+  auto value = [&](int x) -> float {
+    if (FROM_BOXES) {
+      const float4 a = anchors[x];
+      return iou_exact(g, area_g, a, box_area(a));
+    }
+    return q[(size_t)m * X + x];
+  };
+  const Key none = {-INFINITY, 0x7fffffff};
+  if (topk > 0) {
+    // k rounds: best key that ranks strictly after the previously selected one
+    Key prev = {INFINITY, -1};
+    for (int r = 0; r < topk; ++r) {
+      Key best = none;
+      for (int x = threadIdx.x; x < X; x += blockDim.x) {
+        const Key k = {value(x), x};
+        if (before(prev, k) && before(k, best)) best = k;
+      }
+      best = block_best(best, s_red);
+      if (best.i >= X) break;  // fewer than k anchors (host rejects this case)
+      if (threadIdx.x == 0) labels[best.i] = 1;
+      prev = best;
+    }
+  } else {
+    // low-quality matches (matcher.py:105-126): all anchors equal to this GT's best quality
+    Key best = none;
+    for (int x = threadIdx.x; x < X; x += blockDim.x) {
+      const Key k = {value(x), x};
+      if (before(k, best)) best = k;
+    }
+    best = block_best(best, s_red);
+    for (int x = threadIdx.x; x < X; x += blockDim.x)
+      if (value(x) == best.v) labels[x] = 1;
+  }
+}
+
+__global__ void fill_default_kernel(int X, int8_t lab0, int64_t* matches, int8_t* labels) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < X) {
+    matches[x] = 0;
+    labels[x] = lab0;
+  }
+}
+
+__global__ void __launch_bounds__(256) pairwise_iou_kernel(const float4* __restrict__ b1,
+                                                           const float4* __restrict__ b2, int N1,
+                                                           int N2, float* __restrict__ iou) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N2) return;
+  const float4 b = b2[j];
+  const float ab = box_area(b);
+  for (int i = blockIdx.y; i < N1; i += gridDim.y) {
+    const float4 a = b1[i];
+    iou[(size_t)i * N2 + j] = iou_exact(a, box_area(a), b, ab);
+  }
+}
+
+int assign_impl(const float* gt, const float* anchors, const float* q, int M, int X,
+                const float* thresholds, const int8_t* labels, int nth, int topk, int alq,
+                int64_t* matches, int8_t* match_labels, float* iou_out, cudaStream_t st) {
+  SDB_REQUIRE(M >= 0 && X >= 0, SDB_ERR_INVALID, "negative sizes M=%d X=%d", M, X);
+  SDB_REQUIRE(nth >= 1 && nth <= 8, SDB_ERR_INVALID, "n_thresholds must be in [1,8], got %d", nth);
+  SDB_REQUIRE(thresholds && labels && matches && match_labels, SDB_ERR_INVALID, "NULL argument");
+  Thresh th;
+  th.n = nth;
+  for (int i = 0; i < nth; ++i) {
+    th.t[i] = thresholds[i];
+    SDB_REQUIRE(i == 0 ? thresholds[0] > 0 : thresholds[i] >= thresholds[i - 1], SDB_ERR_INVALID,
+                "thresholds must be positive and ascending");
+  }
+  for (int i = 0; i <= nth; ++i) {
+    SDB_REQUIRE(labels[i] >= -1 && labels[i] <= 1, SDB_ERR_INVALID, "labels must be in {-1,0,1}");
+    th.l[i] = labels[i];
+  }
+  if (X == 0) return SDB_OK;
+  if (M == 0) {  // topk_matcher.py:53-63
+    fill_default_kernel<<<cdiv(X, 256), 256, 0, st>>>(X, labels[0], matches, match_labels);
+    SDB_CHECK_CUDA(cudaGetLastError());
+    return SDB_OK;
+  }
+  SDB_REQUIRE(topk <= X, SDB_ERR_INVALID, "selected index k out of range (topk=%d > %d anchors)", topk, X);
+  const bool from_boxes = q == nullptr;
+  const size_t smem = from_boxes ? (size_t)M * (sizeof(float4) + sizeof(float)) : 0;
+  SDB_REQUIRE(smem <= 200 * 1024, SDB_ERR_UNSUPPORTED, "too many GT boxes (%d) for one shared-memory stage", M);
+  if (from_boxes) {
+    if (smem > 48 * 1024)
+      SDB_CHECK_CUDA(cudaFuncSetAttribute(per_anchor_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    per_anchor_kernel<true><<<cdiv(X, 256), 256, smem, st>>>(
+        (const float4*)gt, (const float4*)anchors, nullptr, M, X, th, matches, match_labels, iou_out);
+  } else {
+    per_anchor_kernel<false><<<cdiv(X, 256), 256, 0, st>>>(nullptr, nullptr, q, M, X, th, matches,
+                                                           match_labels, nullptr);
+  }
+  SDB_CHECK_CUDA(cudaGetLastError());
+  if (topk > 0 || alq) {
+    const int threads = X >= 8192 ? 1024 : 256;
+    if (from_boxes)
+      per_gt_kernel<true><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr,
+                                                 M, X, topk, match_labels);
+    else
+      per_gt_kernel<false><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels);
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SDB_OK;
+}
+
+}  // namespace
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" {
+
+size_t sdb_assign_workspace_bytes(int32_t, int32_t, int32_t) { return 0; }
+
+int sdb_iou_assign(const float* gt, const float* anchors, int32_t M, int32_t X,
+                   const float* thresholds, const int8_t* labels, int32_t n_thresholds, int32_t topk,
+                   int32_t allow_low_quality, int64_t* matches, int8_t* match_labels, float* iou_out,
+                   void*, size_t, void* stream) {
+  SDB_REQUIRE((gt || M == 0) && (anchors || X == 0), SDB_ERR_INVALID, "NULL boxes");
+  // thresholds / labels are HOST arrays (a handful of config scalars)
+  return assign_impl(gt, anchors, nullptr, M, X, thresholds, labels, n_thresholds, topk,
+                     allow_low_quality, matches, match_labels, iou_out, (cudaStream_t)stream);
+}
+
+int sdb_match_quality_assign(const float* q, int32_t M, int32_t X, const float* thresholds,
+                             const int8_t* labels, int32_t n_thresholds, int32_t topk,
+                             int32_t allow_low_quality, int64_t* matches, int8_t* match_labels,
+                             void*, size_t, void* stream) {
+  SDB_REQUIRE(q || M == 0 || X == 0, SDB_ERR_INVALID, "NULL quality matrix");
+  static const float dummy = 0.f;
+  return assign_impl(nullptr, nullptr, q ? q : &dummy, M, X, thresholds, labels, n_thresholds, topk,
+                     allow_low_quality, matches, match_labels, nullptr, (cudaStream_t)stream);
+}
+
+int sdb_pairwise_iou(const float* boxes1, const float* boxes2, int32_t N1, int32_t N2, float* iou,
+                     void* stream) {
+  SDB_REQUIRE(N1 >= 0 && N2 >= 0, SDB_ERR_INVALID, "negative sizes");
+  if (N1 == 0 || N2 == 0) return SDB_OK;
+  SDB_REQUIRE(boxes1 && boxes2 && iou, SDB_ERR_INVALID, "NULL argument");
+  dim3 grid(cdiv(N2, 256), N1 < 64 ? N1 : 64);
+  pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes1,
+                                                              (const float4*)boxes2, N1, N2, iou);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// common.cuh -- shared host/device helpers for libslender_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/slender_b200.h"
+
+namespace sdb {
+
+// thread-local error text behind sdb_last_error()
+void set_error(const char* fmt, ...);
+
+#define SDB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      sdb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                     __LINE__);                                                           \
+      return SDB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define SDB_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      sdb::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// Geometry with derived output size, passed by value to kernels.
+struct Geo {
+  int N, C, H, W, O, KH, KW, sh, sw, ph, pw, dh, dw, groups, dgroups, Ho, Wo;
+  __host__ __device__ int taps() const { return KH * KW; }
+  __host__ __device__ int HWo() const { return Ho * Wo; }
+  __host__ __device__ long long P() const { return (long long)N * Ho * Wo; }
+};
+
+inline Geo make_geo(const sdb_dcn_geom& g) {
+  Geo d{g.N, g.C_in, g.H, g.W, g.C_out, g.kH, g.kW, g.sH, g.sW, g.pH, g.pW, g.dH, g.dW,
+        g.groups, g.deformable_groups, 0, 0};
+  d.Ho = (g.H + 2 * g.pH - (g.dH * (g.kH - 1) + 1)) / (g.sH > 0 ? g.sH : 1) + 1;
+  d.Wo = (g.W + 2 * g.pW - (g.dW * (g.kW - 1) + 1)) / (g.sW > 0 ? g.sW : 1) + 1;
+  return d;
+}
+
+int check_geom(const sdb_dcn_geom* g);  // shape_check restated; sets error text
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- launchers implemented per translation unit ------------------------------------------------
+// SIMT fp32 path (dcn_simt.cu)
+int simt_forward(const float* x, const float* off, const float* mask, const float* w,
+                 const float* bias, float* out, const Geo& g, cudaStream_t st);
+int simt_backward_data(const float* x, const float* off, const float* mask, const float* w,
+                       const float* gy, float* gx, float* goff, float* gmask, const Geo& g,
+                       cudaStream_t st);
+int simt_backward_weight(const float* x, const float* off, const float* mask, const float* gy,
+                         float* gw, float* gb, float scale, const Geo& g, cudaStream_t st);
+
+// tcgen05 bf16 path (dcn_tc_*.cu)
+bool tc_supported(const Geo& g, const char** why);
+size_t tc_workspace_bytes(int op, const Geo& g, int io_dtype);
+size_t tc_packed_input_bytes(const Geo& g);
+int tc_forward(const void* x, const float* off, const float* mask, const void* w, const void* bias,
+               void* out, const Geo& g, int io_dtype, void* ws, size_t ws_bytes, void* x_packed_out,
+               cudaStream_t st);
+int tc_backward_data(const void* x, const float* off, const float* mask, const void* w,
+                     const void* gy, void* gx, float* goff, float* gmask, const Geo& g,
+                     int io_dtype, void* ws, size_t ws_bytes, const void* x_packed, cudaStream_t st);
+int tc_backward_weight(const void* x, const float* off, const float* mask, const void* gy,
+                       float* gw, float* gb, float scale, const Geo& g, int io_dtype, void* ws,
+                       size_t ws_bytes, const void* x_packed, cudaStream_t st);
+
+}  // namespace sdb

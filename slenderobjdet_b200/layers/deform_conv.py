@@ -1,0 +1,422 @@
+"""Drop-in replacement for ``detectron2.layers.deform_conv`` backed by libslender_b200.so.
+
+Mirrors /root/reference/detectron2/detectron2/layers/deform_conv.py: same names
+(``DeformConv``, ``ModulatedDeformConv``, ``deform_conv``, ``modulated_deform_conv``,
+``_DeformConv``, ``_ModulatedDeformConv``), same argument order and meaning, same state-dict keys
+(``weight`` [C_out, C_in/groups, kH, kW], ``bias``), same offset / mask layouts, same errors
+(``ValueError`` for non-4D input :29-32 and too-small output :147-152, ``NotImplementedError`` on
+CPU tensors :48-49, ``AssertionError`` when im2col_step does not divide N :52, ``RuntimeError`` for
+shape violations, deform_conv_cuda.cu:140-270).
+
+Differences, all internal: no ``columns`` / ``ones`` scratch tensors (the gather feeds the GEMM
+directly), ``im2col_step`` is accepted and validated but not used, and the contraction runs on
+tcgen05 tensor cores with bf16 operands / fp32 accumulation whenever the geometry allows
+(``set_dcn_math`` selects ``"fp32"`` for the exact SIMT path).
+"""
+import contextlib
+import ctypes
+import math
+import os
+from functools import lru_cache
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from .. import _lib
+
+_MATH = os.environ.get("SDB_DCN_MATH", "auto")  # "auto" | "bf16" | "fp32"
+
+
+def set_dcn_math(mode):
+    """'auto': tensor cores (bf16 operands, fp32 accumulate) when supported, else fp32 SIMT;
+    'bf16': require the tensor-core path; 'fp32': always the exact SIMT path."""
+    global _MATH
+    assert mode in ("auto", "bf16", "fp32")
+    _MATH = mode
+
+
+def get_dcn_math():
+    return _MATH
+
+
+@contextlib.contextmanager
+def dcn_math(mode):
+    old = _MATH
+    set_dcn_math(mode)
+    try:
+        yield
+    finally:
+        set_dcn_math(old)
+
+
+class _NewEmptyTensorOp(Function):
+    """detectron2/layers/wrappers.py:29-38"""
+
+    @staticmethod
+    def forward(ctx, x, new_shape):
+        ctx.shape = x.shape
+        return x.new_empty(new_shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _NewEmptyTensorOp.apply(grad, ctx.shape), None
+
+
+def _geom(input, weight, stride, padding, dilation, groups, deformable_groups):
+    return _lib.Geom(input.shape[0], input.shape[1], input.shape[2], input.shape[3], weight.shape[0],
+                     weight.shape[2], weight.shape[3], stride[0], stride[1], padding[0], padding[1],
+                     dilation[0], dilation[1], groups, deformable_groups)
+
+
+def _check_shapes(input, offset, mask, weight, bias, g, out_hw):
+    """shape_check (deform_conv_cuda.cu:140-270, :824-860) on the tensors the C ABI cannot see."""
+    if weight.dim() != 4:
+        raise RuntimeError("4D weight tensor (nOutputPlane,nInputPlane,kH,kW) expected, but got: %s" % weight.dim())
+    if weight.shape[1] * g.groups != input.shape[1]:
+        raise RuntimeError("invalid number of input planes, expected: %d, but got: %d"
+                           % (weight.shape[1] * g.groups, input.shape[1]))
+    n_off = g.deformable_groups * 2 * g.kH * g.kW
+    if offset.dim() != 4 or offset.shape[0] != input.shape[0]:
+        raise RuntimeError("invalid batch size of offset")
+    if offset.shape[1] != n_off:
+        raise RuntimeError("invalid number of channels of offset")
+    if tuple(offset.shape[2:]) != tuple(out_hw):
+        raise RuntimeError("invalid spatial size of offset, expected height: %d width: %d, but got height: %d width: %d"
+                           % (out_hw[0], out_hw[1], offset.shape[2], offset.shape[3]))
+    if mask is not None:
+        if tuple(mask.shape) != (input.shape[0], g.deformable_groups * g.kH * g.kW, out_hw[0], out_hw[1]):
+            raise RuntimeError("invalid shape of mask: expected %s, got %s"
+                               % ((input.shape[0], g.deformable_groups * g.kH * g.kW) + tuple(out_hw), tuple(mask.shape)))
+    if bias is not None and tuple(bias.shape) != (weight.shape[0],):
+        raise RuntimeError("invalid shape of bias")
+    for t in (weight, bias):
+        if t is not None and t.dtype != input.dtype:
+            raise RuntimeError("expected weight/bias dtype %s to match input dtype %s" % (t.dtype, input.dtype))
+    for t in (offset, mask, weight, bias):
+        if t is not None and t.device != input.device:
+            raise RuntimeError("all tensors must be on the same CUDA device")
+
+
+def _pick_math(g, iod):
+    lib = _lib.lib()
+    if _MATH == "fp32":
+        return _lib.SDB_MATH_FP32
+    ok = bool(lib.sdb_dcn_supported(ctypes.byref(g), iod, _lib.SDB_MATH_BF16))
+    if ok:
+        return _lib.SDB_MATH_BF16
+    if _MATH == "bf16":
+        raise RuntimeError("slender_b200: " + lib.sdb_last_error().decode())
+    return _lib.SDB_MATH_FP32
+
+
+def _compute_dtype(t):
+    """float32 / bfloat16 run natively; float16 (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF)
+    is computed in float32."""
+    return t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.float32
+
+
+def _plan(input, weight, g):
+    """-> (compute dtype, io_dtype enum, math enum).  bf16 tensors whose geometry the tensor-core
+    path does not cover are computed in float32 on the SIMT path."""
+    cdt = _compute_dtype(input)
+    iod = _lib.SDB_F32 if cdt == torch.float32 else _lib.SDB_BF16
+    mth = _pick_math(g, iod)
+    if mth == _lib.SDB_MATH_FP32 and iod != _lib.SDB_F32:
+        cdt, iod = torch.float32, _lib.SDB_F32
+    return cdt, iod, mth
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def _forward_impl(input, offset, mask, weight, bias, g):
+    lib = _lib.lib()
+    cdt, iod, mth = _plan(input, weight, g)
+    ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.check(lib.sdb_dcn_output_size(ctypes.byref(g), ho, wo))
+    x = input.to(cdt).contiguous()
+    w = weight.to(cdt).contiguous()
+    b = None if bias is None else bias.to(cdt).contiguous()
+    off = offset.float().contiguous()
+    m = None if mask is None else mask.float().contiguous()
+    out = torch.empty((g.N, g.C_out, ho.value, wo.value), dtype=cdt, device=input.device)
+    wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_FORWARD, ctypes.byref(g), iod, mth)
+    pkb = lib.sdb_dcn_packed_input_bytes(ctypes.byref(g), mth)
+    ws = _ws(wsb, input.device)
+    packed = _ws(pkb, input.device) if pkb else None
+    with torch.cuda.device(input.device):
+        _lib.check(lib.sdb_dcn_forward(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w), _lib.ptr(b),
+                                       _lib.ptr(out), ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb,
+                                       _lib.ptr(packed), _lib.stream_ptr(input.device)))
+    return out.to(input.dtype), packed
+
+
+def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias):
+    """-> grad_input, grad_offset, grad_mask, grad_weight, grad_bias (None where not requested)."""
+    lib = _lib.lib()
+    cdt, iod, mth = _plan(input, weight, g)
+    x = input.to(cdt).contiguous()
+    w = weight.to(cdt).contiguous()
+    gy = grad_output.to(cdt).contiguous()
+    off = offset.float().contiguous()
+    m = None if mask is None else mask.float().contiguous()
+    dev = input.device
+    gi = go = gm = gw = gb = None
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        if need_data:
+            gi = torch.zeros_like(x)  # accumulated into (deform_conv.py:89)
+            go = torch.empty_like(off)
+            gm = torch.empty_like(m) if m is not None else None
+            wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_DATA, ctypes.byref(g), iod, mth)
+            ws = _ws(wsb, dev)
+            _lib.check(lib.sdb_dcn_backward_data(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w),
+                                                 _lib.ptr(gy), _lib.ptr(gi), _lib.ptr(go), _lib.ptr(gm),
+                                                 ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb,
+                                                 _lib.ptr(packed), st))
+            gi = gi.to(input.dtype)
+            go = go.to(offset.dtype)
+            gm = gm.to(mask.dtype) if gm is not None else None
+        if need_weight:
+            gw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)  # deform_conv.py:113
+            gb = torch.zeros((g.C_out,), dtype=torch.float32, device=dev) if with_bias else None
+            wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_WEIGHT, ctypes.byref(g), iod, mth)
+            ws = _ws(wsb, dev)
+            _lib.check(lib.sdb_dcn_backward_weight(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(gy),
+                                                   _lib.ptr(gw), _lib.ptr(gb), 1.0, ctypes.byref(g), iod, mth,
+                                                   _lib.ptr(ws), wsb, _lib.ptr(packed), st))
+            gw = gw.to(weight.dtype)
+            gb = gb.to(weight.dtype) if gb is not None else None
+    return gi, go, gm, gw, gb
+
+
+class _DeformConv(Function):
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1, im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        ctx.stride = _pair(stride)
+        ctx.padding = _pair(padding)
+        ctx.dilation = _pair(dilation)
+        ctx.groups = groups
+        ctx.deformable_groups = deformable_groups
+        ctx.im2col_step = im2col_step
+
+        out_size = _DeformConv._output_size(input, weight, ctx.padding, ctx.dilation, ctx.stride)
+        if not input.is_cuda:
+            raise NotImplementedError("Deformable Conv is not supported on CPUs!")
+        cur_im2col_step = _DeformConv._cal_im2col_step(input.shape[0], ctx.im2col_step)
+        assert (input.shape[0] % cur_im2col_step) == 0, "im2col step must divide batchsize"
+
+        g = _geom(input, weight, ctx.stride, ctx.padding, ctx.dilation, groups, deformable_groups)
+        _check_shapes(input, offset, None, weight, None, g, out_size[2:])
+        output, packed = _forward_impl(input, offset, None, weight, None, g)
+        ctx.save_for_backward(input, offset, weight)
+        ctx.packed_ = packed  # NHWC-bf16 copy of the input, reused by backward (tensor-core path)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight = ctx.saved_tensors
+        if not grad_output.is_cuda:
+            raise NotImplementedError("Deformable Conv is not supported on CPUs!")
+        g = _geom(input, weight, ctx.stride, ctx.padding, ctx.dilation, ctx.groups, ctx.deformable_groups)
+        need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gi, go, _, gw, _ = _backward_impl(input, offset, None, weight, grad_output, g, ctx.packed_,
+                                          need_data, ctx.needs_input_grad[2], False)
+        return gi, go, gw, None, None, None, None, None, None
+
+    @staticmethod
+    def _output_size(input, weight, padding, dilation, stride):
+        channels = weight.size(0)
+        output_size = (input.size(0), channels)
+        for d in range(input.dim() - 2):
+            in_size = input.size(d + 2)
+            kernel = dilation[d] * (weight.size(d + 2) - 1) + 1
+            output_size += ((in_size + (2 * padding[d]) - kernel) // stride[d] + 1,)
+        if not all(map(lambda s: s > 0, output_size)):
+            raise ValueError("convolution input is too small (output would be {})".format(
+                "x".join(map(str, output_size))))
+        return output_size
+
+    @staticmethod
+    @lru_cache(maxsize=128)
+    def _cal_im2col_step(input_size, default_size):
+        """Largest divisor of input_size that is <= default_size (deform_conv.py:155-176).  Kept for
+        API compatibility; the fused kernels have no column buffer to chunk."""
+        if input_size <= default_size:
+            return input_size
+        best_step = 1
+        for step in range(2, min(int(math.sqrt(input_size)) + 1, default_size)):
+            if input_size % step == 0:
+                if input_size // step <= default_size:
+                    return input_size // step
+                best_step = step
+        return best_step
+
+
+class _ModulatedDeformConv(Function):
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
+                groups=1, deformable_groups=1):
+        ctx.stride = stride
+        ctx.padding = padding
+        ctx.dilation = dilation
+        ctx.groups = groups
+        ctx.deformable_groups = deformable_groups
+        ctx.with_bias = bias is not None
+        if not input.is_cuda:
+            raise NotImplementedError("Deformable Conv is not supported on CPUs!")
+        if not input.is_contiguous() or not weight.is_contiguous():  # deform_conv_cuda.cu:824-825
+            raise RuntimeError("input tensor has to be contiguous" if not input.is_contiguous()
+                               else "weight tensor has to be contiguous")
+        g = _geom(input, weight, _pair(stride), _pair(padding), _pair(dilation), groups, deformable_groups)
+        out_shape = _ModulatedDeformConv._infer_shape(ctx, input, weight)
+        if min(out_shape[2:]) <= 0:
+            raise RuntimeError("convolution input is too small (output would be %s)" % (out_shape,))
+        _check_shapes(input, offset, mask, weight, bias, g, out_shape[2:])
+        output, packed = _forward_impl(input, offset, mask, weight, bias, g)
+        if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
+            ctx.save_for_backward(input, offset, mask, weight)
+            ctx.packed_ = packed
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError("Deformable Conv is not supported on CPUs!")
+        input, offset, mask, weight = ctx.saved_tensors
+        g = _geom(input, weight, _pair(ctx.stride), _pair(ctx.padding), _pair(ctx.dilation), ctx.groups,
+                  ctx.deformable_groups)
+        gi, go, gm, gw, gb = _backward_impl(input, offset, mask, weight, grad_output, g, ctx.packed_,
+                                            True, True, ctx.with_bias)
+        return gi, go, gm, gw, gb, None, None, None, None, None
+
+    @staticmethod
+    def _infer_shape(ctx, input, weight):
+        n = input.size(0)
+        channels_out = weight.size(0)
+        height, width = input.shape[2:4]
+        kernel_h, kernel_w = weight.shape[2:4]
+        height_out = (height + 2 * ctx.padding - (ctx.dilation * (kernel_h - 1) + 1)) // ctx.stride + 1
+        width_out = (width + 2 * ctx.padding - (ctx.dilation * (kernel_w - 1) + 1)) // ctx.stride + 1
+        return n, channels_out, height_out, width_out
+
+
+deform_conv = _DeformConv.apply
+modulated_deform_conv = _ModulatedDeformConv.apply
+
+
+def _empty_output(x, weight, padding, dilation, kernel_size, stride):
+    output_shape = [(i + 2 * p - (di * (k - 1) + 1)) // s + 1
+                    for i, p, di, k, s in zip(x.shape[-2:], padding, dilation, kernel_size, stride)]
+    return _NewEmptyTensorOp.apply(x, [x.shape[0], weight.shape[0]] + output_shape)
+
+
+class DeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, deformable_groups=1, bias=False, norm=None, activation=None):
+        """Deformable convolution (DCN v1).  Arguments as detectron2.layers.DeformConv
+        (deform_conv.py:309-359): ``deformable_groups``, optional ``norm`` module and
+        ``activation`` callable applied after the convolution."""
+        super(DeformConv, self).__init__()
+        assert not bias
+        assert in_channels % groups == 0, "in_channels {} cannot be divisible by groups {}".format(
+            in_channels, groups)
+        assert out_channels % groups == 0, "out_channels {} cannot be divisible by groups {}".format(
+            out_channels, groups)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.norm = norm
+        self.activation = activation
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // self.groups, *self.kernel_size))
+        self.bias = None
+        nn.init.kaiming_uniform_(self.weight, nonlinearity="relu")
+
+    def forward(self, x, offset):
+        if x.numel() == 0:
+            return _empty_output(x, self.weight, self.padding, self.dilation, self.kernel_size, self.stride)
+        x = deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                        self.deformable_groups)
+        if self.norm is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.activation(x)
+        return x
+
+    def extra_repr(self):
+        tmpstr = "in_channels=" + str(self.in_channels)
+        tmpstr += ", out_channels=" + str(self.out_channels)
+        tmpstr += ", kernel_size=" + str(self.kernel_size)
+        tmpstr += ", stride=" + str(self.stride)
+        tmpstr += ", padding=" + str(self.padding)
+        tmpstr += ", dilation=" + str(self.dilation)
+        tmpstr += ", groups=" + str(self.groups)
+        tmpstr += ", deformable_groups=" + str(self.deformable_groups)
+        tmpstr += ", bias=False"
+        return tmpstr
+
+
+class ModulatedDeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, deformable_groups=1, bias=True, norm=None, activation=None):
+        """Modulated deformable convolution (DCN v2).  Arguments as
+        detectron2.layers.ModulatedDeformConv (deform_conv.py:406-452); scalar stride / padding /
+        dilation as in the reference."""
+        super(ModulatedDeformConv, self).__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.with_bias = bias
+        self.norm = norm
+        self.activation = activation
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.bias = None
+        nn.init.kaiming_uniform_(self.weight, nonlinearity="relu")
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    def forward(self, x, offset, mask):
+        if x.numel() == 0:
+            return _empty_output(x, self.weight, _pair(self.padding), _pair(self.dilation), self.kernel_size,
+                                 _pair(self.stride))
+        x = modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                  self.dilation, self.groups, self.deformable_groups)
+        if self.norm is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.activation(x)
+        return x
+
+    def extra_repr(self):
+        tmpstr = "in_channels=" + str(self.in_channels)
+        tmpstr += ", out_channels=" + str(self.out_channels)
+        tmpstr += ", kernel_size=" + str(self.kernel_size)
+        tmpstr += ", stride=" + str(self.stride)
+        tmpstr += ", padding=" + str(self.padding)
+        tmpstr += ", dilation=" + str(self.dilation)
+        tmpstr += ", groups=" + str(self.groups)
+        tmpstr += ", deformable_groups=" + str(self.deformable_groups)
+        tmpstr += ", bias=" + str(self.with_bias)
+        return tmpstr

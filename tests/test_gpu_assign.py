@@ -1,0 +1,85 @@
+"""GPU parity: fused IoU + label assignment, bit-exact against goldens from the reference's Python."""
+import numpy as np
+import pytest
+import torch
+
+import slenderobjdet_b200 as sdb
+from oracle import assign as oa
+
+pytestmark = pytest.mark.gpu
+
+
+def _d(a):
+    return torch.as_tensor(a).cuda()
+
+
+def test_known_answers(assign_cases):
+    c = assign_cases["ka_iou"]
+    assert np.allclose(sdb.pairwise_iou(_d(c["boxes1"]), _d(c["boxes2"])).cpu().numpy(), c["expected"])
+    c = assign_cases["ka_matcher"]
+    m, l = sdb.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True)(_d(c["q"]))
+    assert m.dtype == torch.int64 and l.dtype == torch.int8
+    assert np.array_equal(m.cpu().numpy(), c["matches"]) and np.array_equal(l.cpu().numpy(), c["labels"])
+
+
+@pytest.mark.parametrize("name", ["small", "mid", "slender"])
+def test_iou_bit_exact(assign_cases, name):
+    c = assign_cases[name]
+    iou = sdb.pairwise_iou(_d(c["gt"]), _d(c["anchors"])).cpu().numpy()
+    assert np.array_equal(iou.view(np.uint32), c["iou"].view(np.uint32))
+    iou_t = sdb.pairwise_iou(_d(c["anchors"]), _d(c["gt"])).cpu().numpy()  # [X,M] as bbox_targets calls it
+    assert np.array_equal(iou_t.view(np.uint32), c["iou"].T.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["small", "mid", "slender"])
+@pytest.mark.parametrize("k", [1, 9, 10])
+def test_topk_matcher_bit_exact(assign_cases, name, k):
+    c = assign_cases[name]
+    assert bool(c[f"topk{k}_tiefree"])
+    tm = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=k)
+    m, l = tm(_d(c["iou"]))
+    assert np.array_equal(m.cpu().numpy(), c[f"topk{k}_matches"])
+    assert np.array_equal(l.cpu().numpy(), c[f"topk{k}_labels"])
+    m2, l2, iou = tm.from_boxes(_d(c["gt"]), _d(c["anchors"]), return_iou=True)  # fused, no IoU matrix needed
+    assert np.array_equal(m2.cpu().numpy(), c[f"topk{k}_matches"])
+    assert np.array_equal(l2.cpu().numpy(), c[f"topk{k}_labels"])
+    assert np.array_equal(iou.cpu().numpy().view(np.uint32), c["iou"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["small", "mid", "slender"])
+@pytest.mark.parametrize("alq", [0, 1])
+def test_matcher_bit_exact(assign_cases, name, alq):
+    c = assign_cases[name]
+    mt = sdb.Matcher([0.4, 0.5], [0, -1, 1], allow_low_quality_matches=bool(alq))
+    for m, l in (mt(_d(c["iou"])), mt.from_boxes(_d(c["gt"]), _d(c["anchors"]))):
+        assert np.array_equal(m.cpu().numpy(), c[f"matcher{alq}_matches"])
+        assert np.array_equal(l.cpu().numpy(), c[f"matcher{alq}_labels"])
+
+
+def test_empty_gt_and_k_too_large(assign_cases):
+    c = assign_cases["empty"]
+    m, l = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=9)(torch.zeros(0, 11, device="cuda"))
+    assert np.array_equal(m.cpu().numpy(), c["matches"]) and np.array_equal(l.cpu().numpy(), c["labels"])
+    with pytest.raises(RuntimeError):  # torch.topk: k out of range
+        sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=9)(torch.rand(2, 5, device="cuda"))
+
+
+def test_ties_follow_canonical_rule_and_full_size():
+    """BASELINE config 4: ~22 400 points x 100 GT, k in {9,10}; ties -> lowest anchor index."""
+    g = torch.Generator().manual_seed(11)
+    X, M = 22400, 100
+    ctr = torch.rand(X, 2, generator=g) * torch.tensor([1333.0, 800.0])
+    an = torch.cat([ctr - 16, ctr + 16], 1)
+    c2 = torch.rand(M, 2, generator=g) * torch.tensor([1333.0, 800.0])
+    wh = torch.exp(torch.rand(M, 2, generator=g) * 4 + 2)
+    gt = torch.cat([c2 - wh / 2, c2 + wh / 2], 1)
+    gt[0] = torch.tensor([-500.0, -500.0, -400.0, -400.0])  # overlaps nothing: an all-zero (all-tie) row
+    q = oa.pairwise_iou(gt.numpy(), an.numpy())
+    for k in (9, 10):
+        mo, lo = oa.topk_matcher(q, [0.3, 0.7], [0, -1, 1], topk=k)
+        m, l = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=k).from_boxes(gt.cuda(), an.cuda())
+        assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)
+        assert (lo[:k] == 1).all()  # the all-tie row picks anchors 0..k-1
+    mo, lo = oa.matcher(q, [0.4, 0.5], [0, -1, 1], True)
+    m, l = sdb.Matcher([0.4, 0.5], [0, -1, 1], True).from_boxes(gt.cuda(), an.cuda())
+    assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)

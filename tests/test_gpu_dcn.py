@@ -1,0 +1,179 @@
+"""GPU parity: CUDA deformable convolution (through the Python operator API -> ctypes -> C ABI)
+against the CPU oracle / committed goldens.  Tolerances from BASELINE.json north_star:
+rel <= 1e-4 for the fp32 path, rel <= 1e-2 for bf16 tensor-core math."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+import slenderobjdet_b200 as sdb
+from oracle import dcn as odcn
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def _dev(a, dtype=torch.float32):
+    return None if a is None else torch.as_tensor(a).to("cuda", dtype)
+
+
+def _cfg(c):
+    sh, sw, ph, pw, dh, dw, g, dg = [int(v) for v in c["cfg"]]
+    return (sh, sw), (ph, pw), (dh, dw), g, dg
+
+
+def _run(c, math, need_grads=True):
+    st, pd, dl, g, dg = _cfg(c)
+    x, off, w = _dev(c["x"]).requires_grad_(), _dev(c["offset"]).requires_grad_(), _dev(c["weight"]).requires_grad_()
+    m = _dev(c.get("mask"))
+    b = _dev(c.get("bias"))
+    with sdb.dcn_math(math):
+        if m is None:
+            y = sdb.deform_conv(x, off, w, st, pd, dl, g, dg)
+        else:
+            assert st[0] == st[1] and pd[0] == pd[1] and dl[0] == dl[1]
+            m.requires_grad_()
+            if b is not None:
+                b.requires_grad_()
+            y = sdb.modulated_deform_conv(x, off, m, w, b, st[0], pd[0], dl[0], g, dg)
+        if need_grads:
+            y.backward(_dev(c["grad_out"]))
+    torch.cuda.synchronize()
+    return y, x, off, w, m, b
+
+
+def test_known_answer_reference_test():
+    """/root/reference/tests/test_deformable_conv.py:85-87 on the CUDA kernels (fp32 math)."""
+    z = np.load(f"{GOLDEN}/dcn_known_answer.npz")
+    conv = sdb.DeformConv(2, 1, 3, 1, 1, bias=False).cuda()
+    conv.weight.data = _dev(z["weight"])
+    with sdb.dcn_math("fp32"):
+        y1 = conv(_dev(z["x"]), _dev(z["offsets_1"])).cpu().numpy()
+        y2 = conv(_dev(z["x"]), _dev(z["offsets_2"])).cpu().numpy()
+    assert np.all(np.abs(y2 - z["expected_conv"]) < 1e-5)
+    assert np.all(np.abs(y2 - z["expected_dconv_zero"]) < 1e-5)
+    assert np.all(np.abs(y1 - z["expected_dconv_grid"]) < 1e-5)
+
+
+CASES = ["v1_basic", "v1_big_offsets", "v1_groups_dg", "v1_stride2_dil2", "v1_k1", "v1_k5x3", "v1_c64",
+         "v2_basic", "v2_nobias_dg2", "v2_c64"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_path_vs_golden(dcn_cases, name):
+    c = dcn_cases[name]
+    y, x, off, w, m, b = _run(c, "fp32")
+    tol = TOL["fp32"]
+    assert rel_err(y.detach().cpu().numpy(), c["out"]) < tol
+    assert rel_err(x.grad.cpu().numpy(), c["grad_x"]) < tol
+    assert rel_err(off.grad.cpu().numpy(), c["grad_offset"]) < tol
+    assert rel_err(w.grad.cpu().numpy(), c["grad_weight"]) < tol
+    if m is not None:
+        assert rel_err(m.grad.cpu().numpy(), c["grad_mask"]) < tol
+    if b is not None:
+        assert rel_err(b.grad.cpu().numpy(), c["grad_bias"]) < tol
+
+
+def _random_case(seed, N, C, H, W, O, modulated, sigma, k=3, pad=1):
+    g = torch.Generator().manual_seed(seed)
+    c = dict(x=torch.randn(N, C, H, W, generator=g).numpy(),
+             weight=(torch.randn(O, C, k, k, generator=g) * 0.05).numpy(),
+             offset=(torch.randn(N, 2 * k * k, H, W, generator=g) * sigma).numpy(),
+             grad_out=torch.randn(N, O, H, W, generator=g).numpy(),
+             cfg=np.array([1, 1, pad, pad, 1, 1, 1, 1]))
+    if modulated:
+        c["mask"] = torch.sigmoid(torch.randn(N, k * k, H, W, generator=g)).numpy()
+        c["bias"] = torch.randn(O, generator=g).numpy()
+    return c
+
+
+def _oracle(c):
+    st, pd, dl, g, dg = _cfg(c)
+    kw = dict(stride=st, padding=pd, dilation=dl, groups=g, deformable_groups=dg)
+    y = odcn.forward(c["x"], c["offset"], c["weight"], mask=c.get("mask"), bias=c.get("bias"), **kw)
+    gr = odcn.backward(c["x"], c["offset"], c["weight"], c["grad_out"], mask=c.get("mask"),
+                       with_bias="bias" in c, **kw)
+    return y, gr
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+@pytest.mark.parametrize("modulated", [False, True])
+@pytest.mark.parametrize("shape", [(2, 64, 13, 21, 64, 2.0), (1, 128, 25, 42, 256, 0.5), (2, 256, 7, 11, 256, 8.0),
+                                   (3, 256, 20, 19, 128, 30.0)])
+def test_vs_oracle_random(math, modulated, shape):
+    N, C, H, W, O, sigma = shape
+    c = _random_case(77 + N + C, N, C, H, W, O, modulated, sigma)
+    y, x, off, w, m, b = _run(c, math)
+    yo, go = _oracle(c)
+    tol = TOL[math]
+    assert rel_err(y.detach().cpu().numpy(), yo) < tol
+    assert rel_err(x.grad.cpu().numpy(), go["grad_x"]) < tol
+    assert rel_err(off.grad.cpu().numpy(), go["grad_offset"]) < tol
+    assert rel_err(w.grad.cpu().numpy(), go["grad_weight"]) < tol
+    if modulated:
+        assert rel_err(m.grad.cpu().numpy(), go["grad_mask"]) < tol
+        assert rel_err(b.grad.cpu().numpy(), go["grad_bias"]) < tol
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+def test_zero_offset_equals_conv2d(math):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 17, 23, generator=g).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).cuda()
+    with sdb.dcn_math(math):
+        y = sdb.deform_conv(x, torch.zeros(2, 18, 17, 23, device="cuda"), w, 1, 1, 1, 1, 1)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=1)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL[math]
+
+
+def test_bf16_tensors_io():
+    c = _random_case(9, 2, 64, 12, 14, 64, False, 1.0)
+    yo, go = _oracle(c)
+    x = _dev(c["x"], torch.bfloat16).requires_grad_()
+    off = _dev(c["offset"]).requires_grad_()
+    w = _dev(c["weight"], torch.bfloat16).requires_grad_()
+    y = sdb.deform_conv(x, off, w, 1, 1, 1, 1, 1)
+    assert y.dtype == torch.bfloat16
+    y.backward(_dev(c["grad_out"], torch.bfloat16))
+    assert x.grad.dtype == torch.bfloat16 and w.grad.dtype == torch.bfloat16 and off.grad.dtype == torch.float32
+    assert rel_err(y.float().detach().cpu().numpy(), yo) < 2e-2
+    assert rel_err(x.grad.float().cpu().numpy(), go["grad_x"]) < 2e-2
+    assert rel_err(w.grad.float().cpu().numpy(), go["grad_weight"]) < 2e-2
+    assert rel_err(off.grad.cpu().numpy(), go["grad_offset"]) < 2e-2
+
+
+def test_all_taps_outside():
+    x = torch.randn(1, 64, 9, 9, device="cuda", requires_grad=True)
+    w = torch.randn(64, 64, 3, 3, device="cuda", requires_grad=True)
+    off = torch.full((1, 18, 9, 9), 1000.0, device="cuda", requires_grad=True)
+    for math in ("fp32", "bf16"):
+        with sdb.dcn_math(math):
+            y = sdb.deform_conv(x, off, w, 1, 1, 1, 1, 1)
+            y.sum().backward()
+        assert float(y.abs().max()) == 0.0
+        assert float(x.grad.abs().max()) == 0.0 and float(off.grad.abs().max()) == 0.0
+        x.grad = None; off.grad = None; w.grad = None
+
+
+def test_shape_errors_are_runtime_errors():
+    x = torch.randn(1, 8, 6, 6, device="cuda")
+    w = torch.randn(4, 8, 3, 3, device="cuda")
+    with pytest.raises(RuntimeError):  # wrong offset channels (deform_conv_cuda.cu:242-244)
+        sdb.deform_conv(x, torch.zeros(1, 16, 6, 6, device="cuda"), w, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):  # wrong offset spatial size (:236-240)
+        sdb.deform_conv(x, torch.zeros(1, 18, 5, 6, device="cuda"), w, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):  # weight planes (:206-210)
+        sdb.deform_conv(x, torch.zeros(1, 18, 6, 6, device="cuda"), torch.randn(4, 6, 3, 3, device="cuda"), 1, 1, 1, 1, 1)
+
+
+def test_dfconv2d_and_grad_flow():
+    torch.manual_seed(0)
+    for mod in (False, True):
+        m = sdb.DFConv2d(64, 64, with_modulated_dcn=mod, bias=mod).cuda()
+        x = torch.randn(2, 64, 10, 12, device="cuda", requires_grad=True)
+        y = m(x)
+        y.square().mean().backward()
+        assert tuple(y.shape) == (2, 64, 10, 12)
+        for p in m.parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all()
+        assert m.offset.weight.grad.abs().sum() > 0

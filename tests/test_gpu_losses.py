@@ -1,0 +1,85 @@
+"""GPU parity: fused losses vs goldens from the reference's Python / torchvision and the float64 oracle.
+Floating-point kernels: rel <= 1e-4 (fp32 path tolerance of BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from slenderobjdet_b200 import layers as L
+from oracle import losses as ol
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _d(a):
+    return torch.as_tensor(a).cuda()
+
+
+def test_focal_vs_golden_and_onehot_signature(loss_cases):
+    c = loss_cases["focal"]
+    x = _d(c["logits"]).requires_grad_()
+    loss = L.sigmoid_focal_loss_from_class_idx(x, _d(c["cls"]), alpha=0.25, gamma=2.0)
+    (loss * 0.5).backward()
+    assert abs(float(loss) - float(c["loss"])) / float(c["loss"]) < TOL
+    assert rel_err(x.grad.cpu().numpy(), 0.5 * c["grad"]) < TOL
+    K = x.shape[1]
+    t = torch.zeros_like(x)
+    idx = _d(c["cls"])
+    fg = idx < K
+    t[fg.nonzero(as_tuple=True)[0], idx[fg]] = 1
+    x2 = _d(c["logits"]).requires_grad_()
+    l2 = L.sigmoid_focal_loss_jit(x2, t, alpha=0.25, gamma=2.0, reduction="sum")  # reference call signature
+    assert abs(float(l2) - float(c["loss"])) / float(c["loss"]) < TOL
+
+
+@pytest.mark.parametrize("gamma,alpha", [(2.0, 0.25), (1.5, -1.0), (0.0, 0.5)])
+def test_focal_vs_oracle_full_size(gamma, alpha):
+    """BASELINE config 4 shape: 2 images x 22 400 points x 80 classes."""
+    g = torch.Generator().manual_seed(1)
+    R, K = 44800, 80
+    x = torch.randn(R, K, generator=g) * 2 - 4.6
+    cls = torch.full((R,), K, dtype=torch.int64)
+    pos = torch.randperm(R, generator=g)[:450]
+    cls[pos] = torch.randint(0, K, (450,), generator=g)
+    so, go = ol.sigmoid_focal_loss(x, cls, alpha, gamma)
+    xd = x.cuda().requires_grad_()
+    loss = L.sigmoid_focal_loss_from_class_idx(xd, cls.cuda(), alpha, gamma)
+    loss.backward()
+    assert abs(float(loss) - float(so)) / float(so) < TOL
+    assert rel_err(xd.grad.cpu().numpy(), go.numpy()) < TOL
+
+
+@pytest.mark.parametrize("form", ["ltrb", "xyxy"])
+@pytest.mark.parametrize("lt", ["iou", "linear_iou", "giou"])
+@pytest.mark.parametrize("use_w", [0, 1])
+def test_iou_losses_vs_golden(loss_cases, form, lt, use_w):
+    d, c = loss_cases[form], loss_cases[f"{form}_{lt}_{use_w}"]
+    fn = L.iou_loss if form == "ltrb" else L.box_iou_loss
+    p = _d(d["pred"]).requires_grad_()
+    loss = fn(p, _d(d["target"]), _d(d["weight"]) if use_w else None, loss_type=lt)
+    loss.backward()
+    so, go = ol.iou_loss(d["pred"], d["target"], d["weight"] if use_w else None, lt, form)
+    assert abs(float(loss) - float(c["loss"])) / abs(float(c["loss"])) < TOL
+    assert rel_err(p.grad.cpu().numpy(), go.numpy()) < TOL
+
+
+@pytest.mark.parametrize("beta", [0.11, 0.0])
+@pytest.mark.parametrize("use_w", [0, 1])
+def test_smooth_l1_vs_golden(loss_cases, beta, use_w):
+    d, c = loss_cases["sl1"], loss_cases[f"sl1_{beta}_{use_w}"]
+    p = _d(d["pred"]).requires_grad_()
+    loss = L.smooth_l1_loss_with_weight(p, _d(d["target"]), _d(d["weight"]) if use_w else None, beta, reduction="sum")
+    loss.backward()
+    assert abs(float(loss) - float(c["loss"])) / abs(float(c["loss"])) < TOL
+    assert rel_err(p.grad.cpu().numpy(), c["grad"]) < TOL
+
+
+def test_fvcore_giou_vs_golden(loss_cases):
+    c = loss_cases["giou"]
+    p = _d(c["pred"]).requires_grad_()
+    loss = L.giou_loss(p, _d(c["target"]), reduction="sum")
+    loss.backward()
+    assert abs(float(loss) - float(c["loss"])) / abs(float(c["loss"])) < TOL
+    so, go = ol.giou_loss(c["pred"], c["target"])
+    assert rel_err(p.grad.cpu().numpy(), go.numpy()) < TOL
