@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SO = os.path.join(PKG, "libslender_b200.so")
-SOURCES = ["api.cu", "dcn_simt.cu", "dcn_tc.cu", "assign.cu", "losses.cu", "debug_umma.cu"]
-HEADERS = ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "slender_b200.h")]
+SOURCES = ["api.cu", "dcn_simt.cu", "dcn_tc.cu", "dcn_tc_bwd.cu", "assign.cu", "losses.cu", "debug_umma.cu"]
+HEADERS = ["common.cuh", "tc_common.cuh", "dcn_tc_shared.cuh", os.path.join("..", "..", "include", "slender_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         elif verbose or "warning" in out:
             sys.stderr.write(out)
     if failed:
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("nvcc failed (see stderr above)")
     if procs or force or not os.path.exists(SO):
         cmd = [_nvcc(), "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC"]
         subprocess.run(cmd, check=True)

@@ -1,10 +1,396 @@
-// placeholder until the tcgen05 kernels land
+// dcn_tc.cu -- deformable convolution on tcgen05 tensor cores (SDB_MATH_BF16), sm_100a only.
+//
+// Forward = implicit GEMM  out[p, o] = sum_{tap, c} col[p, (tap,c)] * W[o, (tap,c)]
+//   M = 128 output pixels per CTA tile, N = C_out (<= 256), K = taps * C_in, tap-major K order.
+//   * A operand (col) is never materialised in HBM: producer warps sample the input (NHWC bf16,
+//     one 16-byte vector load per corner per lane = 8 channels) with fp32 bilinear arithmetic and
+//     store bf16 rows straight into 128B-swizzled shared memory, the layout tcgen05.mma reads;
+//   * B operand (weights) is pre-permuted once per call into that same swizzled tile format in
+//     global memory, so one warp streams it with cp.async.bulk (TMA engine) + mbarrier tx counts;
+//   * one thread issues tcgen05.mma (128 x C_out x 16, bf16 -> fp32) into a TMEM accumulator,
+//     double-buffered so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * 4 epilogue warps drain TMEM with tcgen05.ld, add the bias and store NCHW (coalesced along
+//     the pixel dimension, which is the TMEM lane dimension).
+// The grid is persistent: one CTA per SM walking tiles round-robin.
+//
+// Reference semantics being reproduced: d2/layers/csrc/deformable/deform_conv_cuda_kernel.cu
+// :96-130 (bilinear), :216-288 (im2col + validity), :785-868 (mask), deform_conv_cuda.cu:397-409 (GEMM).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "dcn_tc_shared.cuh"
+
 namespace sdb {
-bool tc_supported(const Geo&, const char** why) { *why = "tensor-core path not built yet"; return false; }
-size_t tc_workspace_bytes(int, const Geo&, int) { return 0; }
-size_t tc_packed_input_bytes(const Geo&) { return 0; }
-int tc_forward(const void*, const float*, const float*, const void*, const void*, void*, const Geo&, int, void*, size_t, void*, cudaStream_t) { return SDB_ERR_UNSUPPORTED; }
-int tc_backward_data(const void*, const float*, const float*, const void*, const void*, void*, float*, float*, const Geo&, int, void*, size_t, const void*, cudaStream_t) { return SDB_ERR_UNSUPPORTED; }
-int tc_backward_weight(const void*, const float*, const float*, const void*, float*, float*, float, const Geo&, int, void*, size_t, const void*, cudaStream_t) { return SDB_ERR_UNSUPPORTED; }
+namespace {
+using namespace tc;
+using namespace tcshared;
+
+constexpr int NPW = 8;                       // gather producer warps
+constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
+constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
+constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+
+// W [O][C][taps] -> per (tap, 64-channel block) a K-major 128B-swizzled tile [O rows][64 c] bf16,
+// tiles ordered (tap, cblock); also bias -> fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) prep_weight_fwd_kernel(const T* __restrict__ w, const T* __restrict__ bias,
+                                                              uint8_t* __restrict__ wimg,
+                                                              float* __restrict__ bias_f32, int O, int C, int taps) {
+  const int nkb = C / 64;
+  const long long total = (long long)O * taps * (C / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (C / 8));
+    const int tap = (int)((i / (C / 8)) % taps);
+    const int o = (int)(i / ((long long)(C / 8) * taps));
+    const int c = c8 * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = to_f32(w[((size_t)o * C + c + j) * taps + tap]);
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]);
+    pk.w = pack_bf16x2(v[6], v[7]);
+    const size_t tile = (size_t)tap * nkb + (c >> 6);
+    *reinterpret_cast<uint4*>(wimg + tile * ((size_t)O * 128) + sw128_offset(o, (c & 63) >> 3)) = pk;
+  }
+  if (bias_f32 && blockIdx.x == 0)
+    for (int o = threadIdx.x; o < O; o += blockDim.x) bias_f32[o] = bias ? to_f32(bias[o]) : 0.f;
 }
+
+// ------------------------------------------------------------------------------------------------
+// sampling descriptor of one (output pixel, tap): 4 corner pixel indices + 4 weights (x mask)
+// ------------------------------------------------------------------------------------------------
+struct Sample {
+  int idx[4];   // (n*H + y)*W + x of each corner (0 when the corner does not contribute)
+  float w[4];   // bilinear weight * mask (0 when the corner does not contribute)
+};
+
+__device__ __forceinline__ Sample make_sample(const Geo& g, const float* __restrict__ off,
+                                              const float* __restrict__ mask, bool valid, int n, int ho,
+                                              int wo, int tap) {
+  Sample s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s.idx[k] = 0;
+    s.w[k] = 0.f;
+  }
+  if (!valid) return s;
+  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
+  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
+  const int i = tap / g.KW, j = tap - i * g.KW;
+  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + __ldg(o);
+  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + __ldg(o + hw);
+  if (!(h > -1.f && w > -1.f && h < (float)g.H && w < (float)g.W)) return s;
+  const float m = mask ? __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo) : 1.f;
+  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
+  const int h_high = h_low + 1, w_high = w_low + 1;
+  const float lh = h - h_low, lw = w - w_low, hh = 1.f - lh, hw_ = 1.f - lw;
+  const bool t = h_low >= 0, b = h_high <= g.H - 1, l = w_low >= 0, r = w_high <= g.W - 1;
+  const int base = n * g.H;
+  if (t && l) { s.idx[0] = (base + h_low) * g.W + w_low;   s.w[0] = hh * hw_ * m; }
+  if (t && r) { s.idx[1] = (base + h_low) * g.W + w_high;  s.w[1] = hh * lw * m; }
+  if (b && l) { s.idx[2] = (base + h_high) * g.W + w_low;  s.w[2] = lh * hw_ * m; }
+  if (b && r) { s.idx[3] = (base + h_high) * g.W + w_high; s.w[3] = lh * lw * m; }
+  return s;
+}
+
+struct FwdParams {
+  const __nv_bfloat16* xp;  // NHWC bf16
+  const float* off;
+  const float* mask;
+  const uint8_t* wimg;
+  const float* bias;        // fp32 [O] or nullptr
+  void* out;                // NCHW, f32 or bf16
+  Geo g;
+  int num_tiles, nsa, nsb;
+};
+
+// LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
+template <int LPP, bool OUT_BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams p) {
+  constexpr int CPS = LPP * 8;           // channels per A stage
+  constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
+  constexpr int A_BYTES = TILE_M * CPS * 2;
+  constexpr int PPI = 32 / LPP;          // pixels per warp instruction
+  constexpr int PIX_PER_WARP = TILE_M / NPW;
+  static_assert(CPS % 64 == 0 && PIX_PER_WARP % PPI == 0 && PIX_PER_WARP <= 32, "bad gather split");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const Geo& g = p.g;
+  const int O = g.O, C = g.C, taps = g.KH * g.KW, nchunks = C / CPS;
+  const uint32_t B_BYTES = (uint32_t)O * 128u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sA = sm;
+  uint8_t* sB = sm + (size_t)p.nsa * A_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t acc_stride = 32;
+  while ((int)acc_stride < O) acc_stride <<= 1;
+  const uint32_t ncols = 2 * acc_stride;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nsa; ++s) {
+      mbar_init(&a_full[s], NPW * 32);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.nsb; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== weight producer: bulk async copies of pre-swizzled [O x 64] tiles =====
+    if (lane == 0) {
+      uint32_t bs = 0, bp = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nkb_total = taps * (C / 64);
+        for (int kb = 0; kb < nkb_total; ++kb) {
+          mbar_wait(&b_empty[bs], bp ^ 1);
+          mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, p.wimg + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_bf16(TILE_M, O, 0, 0);
+    uint32_t as = 0, ap = 0, bs = 0, bp = 0, acc = 0, accp = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], accp ^ 1);
+      tc_fence_after_sync();
+      const uint32_t tmem_d = tmem_base + acc * acc_stride;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < taps * nchunks; ++it) {
+        mbar_wait(&a_full[as], ap);
+        for (int kb = 0; kb < KBPS; ++kb) {
+          mbar_wait(&b_full[bs], bp);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_base + as * A_BYTES + kb * (TILE_M * 128);
+            const uint32_t b_addr = smem_base + p.nsa * A_BYTES + bs * B_BYTES;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                        make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&b_empty[bs]);
+          }
+          __syncwarp();
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+        if (lane == 0) umma_commit(&a_empty[as]);
+        __syncwarp();
+        if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+      }
+      if (lane == 0) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; accp ^= 1; }
+    }
+  } else if (warp < FIRST_PW) {
+    // ===== epilogue: TMEM -> registers -> NCHW global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int hw = g.Ho * g.Wo;
+    uint32_t acc = 0, accp = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_full[acc], accp);
+      tc_fence_after_sync();
+      const long long pix = (long long)tile * TILE_M + q * 32 + lane;
+      const bool valid = pix < g.P();
+      const int n = valid ? (int)(pix / hw) : 0;
+      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
+      for (int c0 = 0; c0 < O; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int o = c0 + j;
+            if (o < O) {
+              const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + o) : 0.f);
+              const size_t di = ((size_t)n * O + o) * hw + rem;
+              if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[di] = __float2bfloat16_rn(v);
+              else          reinterpret_cast<float*>(p.out)[di] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; accp ^= 1; }
+    }
+  } else {
+    // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
+    const int pw = warp - FIRST_PW;
+    const int grp = lane / LPP, lig = lane % LPP;
+    const int hw = g.Ho * g.Wo;
+    uint32_t as = 0, ap = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // the pixel whose sampling descriptors this lane computes (lanes >= PIX_PER_WARP idle there)
+      const long long pix = (long long)tile * TILE_M + pw * PIX_PER_WARP + lane;
+      const bool valid = lane < PIX_PER_WARP && pix < g.P();
+      const int n = valid ? (int)(pix / hw) : 0;
+      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
+      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+      for (int tap = 0; tap < taps; ++tap) {
+        const Sample mine = make_sample(g, p.off, p.mask, valid, n, ho, wo, tap);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          mbar_wait(&a_empty[as], ap ^ 1);
+          uint8_t* stage = sA + (size_t)as * A_BYTES;
+          const __nv_bfloat16* xc = p.xp + ch * CPS + lig * 8;
+#pragma unroll 4
+          for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
+            const int src = it * PPI + grp;
+            int idx[4];
+            float w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              idx[k] = __shfl_sync(0xffffffffu, mine.idx[k], src);
+              w[k] = __shfl_sync(0xffffffffu, mine.w[k], src);
+            }
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              v[k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)idx[k] * C));
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fma8(acc, v[k], w[k]);
+            uint4 pk;
+            pk.x = pack_bf16x2(acc[0], acc[1]);
+            pk.y = pack_bf16x2(acc[2], acc[3]);
+            pk.z = pack_bf16x2(acc[4], acc[5]);
+            pk.w = pack_bf16x2(acc[6], acc[7]);
+            const int row = pw * PIX_PER_WARP + src;
+            *reinterpret_cast<uint4*>(stage + (lig >> 3) * (TILE_M * 128) + sw128_offset(row, lig & 7)) = pk;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&a_full[as]);
+          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+int lanes_per_pixel(const Geo& g) {
+  const char* e = getenv("SDB_TC_LPP");
+  if (e) {
+    const int v = atoi(e);
+    if ((v == 8 || v == 16 || v == 32) && g.C % (v * 8) == 0) return v;
+  }
+  if (g.C % 128 == 0) return 16;
+  return 8;
+}
+
+struct FwdWs {
+  size_t xp_off, wimg_off, bias_off, total;
+};
+FwdWs fwd_ws(const Geo& g) {
+  FwdWs w;
+  size_t o = 0;
+  w.xp_off = o;   o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 2, 1024);
+  w.wimg_off = o; o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
+  w.bias_off = o; o = align_up(o + (size_t)g.O * 4, 1024);
+  w.total = o;
+  return w;
+}
+
+template <int LPP, bool OUT_BF16>
+int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
+  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // namespace
+
+bool tc_supported(const Geo& g, const char** why) {
+  *why = "";
+  if (g.groups != 1) { *why = "groups != 1"; return false; }
+  if (g.dgroups != 1) { *why = "deformable_groups != 1"; return false; }
+  if (g.C % 64 != 0) { *why = "C_in not a multiple of 64"; return false; }
+  if (g.O % 16 != 0 || g.O < 16 || g.O > 256) { *why = "C_out must be a multiple of 16 in [16,256]"; return false; }
+  if ((long long)g.N * g.H * g.W * 1LL >= (1LL << 31) / 1 || g.P() * g.O >= (1LL << 40)) { *why = "tensor too large"; return false; }
+  return true;
+}
+
+size_t tc_packed_input_bytes(const Geo& g) { return align_up((size_t)g.N * g.H * g.W * g.C * 2, 1024); }
+
+size_t tc_workspace_bytes(int op, const Geo& g, int io_dtype) {
+  (void)io_dtype;
+  if (op == SDB_OP_FORWARD) return fwd_ws(g).total;
+  return tc_bwd_workspace_bytes(op, g);
+}
+
+int tc_forward(const void* x, const float* off, const float* mask, const void* w, const void* bias,
+               void* out, const Geo& g, int io_dtype, void* ws, size_t ws_bytes, void* x_packed_out,
+               cudaStream_t st) {
+  const FwdWs L = fwd_ws(g);
+  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "forward workspace too small: %zu < %zu", ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  __nv_bfloat16* xp = (__nv_bfloat16*)(x_packed_out ? x_packed_out : base + L.xp_off);
+  uint8_t* wimg = base + L.wimg_off;
+  float* bias32 = bias ? (float*)(base + L.bias_off) : nullptr;
+  int rc = io_dtype == SDB_F32 ? pack_input<float>(x, xp, g, st) : pack_input<__nv_bfloat16>(x, xp, g, st);
+  if (rc) return rc;
+  const long long wtotal = (long long)g.O * g.taps() * (g.C / 8);
+  const int wblocks = (int)((wtotal + 255) / 256 < 1184 ? (wtotal + 255) / 256 : 1184);
+  if (io_dtype == SDB_F32)
+    prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps());
+  else
+    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps());
+  SDB_CHECK_CUDA(cudaGetLastError());
+
+  FwdParams p;
+  p.xp = xp; p.off = off; p.mask = mask; p.wimg = wimg; p.bias = bias32; p.out = out; p.g = g;
+  p.num_tiles = cdiv(g.P(), TILE_M);
+  const int lpp = lanes_per_pixel(g);
+  const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
+  size_t budget = 200 * 1024;
+  if (const char* e = getenv("SDB_TC_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+  if (budget > 226 * 1024) budget = 226 * 1024;
+  p.nsa = 2;
+  if (const char* e = getenv("SDB_TC_NSA")) p.nsa = atoi(e);
+  if (p.nsa < 2) p.nsa = 2;
+  if (p.nsa > MAX_A_STAGES) p.nsa = MAX_A_STAGES;
+  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + 1024 > budget) --p.nsa;
+  long long nsb = ((long long)budget - 1024 - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
+  if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+  SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
+  p.nsb = (int)nsb;
+  const size_t smem = p.nsa * a_bytes + p.nsb * b_bytes + 1024;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const bool obf = io_dtype == SDB_BF16;
+  if (lpp == 32) return obf ? launch_fwd<32, true>(p, smem, grid, st) : launch_fwd<32, false>(p, smem, grid, st);
+  if (lpp == 16) return obf ? launch_fwd<16, true>(p, smem, grid, st) : launch_fwd<16, false>(p, smem, grid, st);
+  return obf ? launch_fwd<8, true>(p, smem, grid, st) : launch_fwd<8, false>(p, smem, grid, st);
+}
+
+
+}  // namespace sdb

@@ -1,0 +1,797 @@
+// dcn_tc_bwd.cu -- backward of the deformable convolution on tcgen05 tensor cores (SDB_MATH_BF16).
+//
+// backward_data (grad_input, grad_offset, grad_mask) -- ONE fused persistent kernel per call:
+//   dcol[p, (tap,c)] = sum_o dY[p,o] W[o,c,tap]        tcgen05 GEMM, M=128 pixels, N=128 channels,
+//                                                      K = C_out, accumulator in TMEM (never in HBM)
+//   4 drain warps move each 128x128 fp32 accumulator to a swizzled bf16 staging tile in smem;
+//   scatter warps (16 lanes x 8 channels per pixel) re-read the 4 input corners of (pixel, tap) and
+//     - reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels with warp
+//       shuffles -> grad_offset / grad_mask (one coalesced atomicAdd per channel chunk),
+//     - scatter w_k * mask * dcol into an NHWC fp32 accumulation buffer with red.global.add.v4.f32
+//       (the only place taps collide), converted to NCHW afterwards.
+//   Replaces G2 + K2/K5 + K3/K6 of the reference (deform_conv_cuda.cu:553-559,
+//   deform_conv_cuda_kernel.cu:291-452, :870-1066); `columns` is never written to HBM.
+//
+// backward_weight: dW[o, c, tap] = sum_p dY[p,o] col[p,(tap,c)]  -- tcgen05 GEMM with BOTH operands
+//   MN-major: A = dY^T tiles (bulk-copied), B = re-gathered col tile (same producer as forward),
+//   K = pixels.  One CTA per (tap, 128-channel chunk, pixel split); both 128-row halves of C_out
+//   accumulate in TMEM for the CTA's whole pixel range; split partials are reduced (and permuted to
+//   [O][C][kH][kW]) by a second tiny kernel -- deterministic, no atomics.
+//   Replaces K1' + G3 of the reference (deform_conv_cuda.cu:738-778).
+#include "dcn_tc_shared.cuh"
+
+namespace sdb {
+namespace {
+using namespace tc;
+using namespace tcshared;
+
+// NCH (template parameter, 128 or 64) = channels per dgrad accumulator / wgrad N tile;
+// LPB = NCH/8 lanes per pixel in the scatter / gather (8 channels per lane), PPI = 32/LPB pixels
+// per warp instruction.
+constexpr int NSW = 8;                   // scatter (dgrad) / gather (wgrad) warps
+constexpr int FIRST_SW = 6;              // warps: 0 bulk producer, 1 mma, 2-5 drain/epilogue, 6.. SIMT
+constexpr int BWD_THREADS = (FIRST_SW + NSW) * 32;
+constexpr int PIX_PER_WARP = TILE_M / NSW;   // 16
+constexpr int MAX_B_STAGES = 8;
+
+inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wide o blocks, even count
+inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
+inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
+
+// ------------------------------------------------------------------------------------------------
+// packing kernels
+// ------------------------------------------------------------------------------------------------
+// dY [N][O][HWo] (T) -> image of 128-pixel tiles: tile t, o-block kb -> [128 rows][64 o] bf16,
+// 128B-swizzled (K-major for dgrad's A operand, MN-major for wgrad's A operand).  Zero padded.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_gy_kernel(const T* __restrict__ gy, uint8_t* __restrict__ img,
+                                                      int O, int hw, long long P, int okb) {
+  __shared__ float s[64][129];
+  const int tile = blockIdx.x, kb = blockIdx.y;
+  const int tid = threadIdx.x;
+  {
+    const int px = tid & 127;
+    const long long p = (long long)tile * TILE_M + px;
+    const bool valid = p < P;
+    const int n = valid ? (int)(p / hw) : 0;
+    const int rem = valid ? (int)(p - (long long)n * hw) : 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int ol = (tid >> 7) + 2 * j, o = kb * 64 + ol;
+      s[ol][px] = (valid && o < O) ? to_f32(gy[((size_t)n * O + o) * hw + rem]) : 0.f;
+    }
+  }
+  __syncthreads();
+  uint8_t* dst = img + ((size_t)tile * okb + kb) * (TILE_M * 128);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = tid + 256 * j, row = c >> 3, ch = c & 7;
+    uint4 pk;
+    pk.x = pack_bf16x2(s[ch * 8 + 0][row], s[ch * 8 + 1][row]);
+    pk.y = pack_bf16x2(s[ch * 8 + 2][row], s[ch * 8 + 3][row]);
+    pk.z = pack_bf16x2(s[ch * 8 + 4][row], s[ch * 8 + 5][row]);
+    pk.w = pack_bf16x2(s[ch * 8 + 6][row], s[ch * 8 + 7][row]);
+    *reinterpret_cast<uint4*>(dst + sw128_offset(row, ch)) = pk;
+  }
+}
+
+// W [O][C][taps] -> tiles ordered (tap, cchunk, okb): [NCH rows (c)][64 o] bf16 K-major swizzled.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) prep_weight_dgrad_kernel(const T* __restrict__ w, uint8_t* __restrict__ img,
+                                                                int O, int C, int taps, int okb) {
+  const int o8n = okb * 8;  // 8-wide o chunks incl. zero padding
+  const long long total = (long long)taps * C * o8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % o8n);
+    const int c = (int)((i / o8n) % C);
+    const int tap = (int)(i / ((long long)o8n * C));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = o8 * 8 + j;
+      v[j] = o < O ? to_f32(w[((size_t)o * C + c) * taps + tap]) : 0.f;
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]);
+    pk.w = pack_bf16x2(v[6], v[7]);
+    const size_t tile = ((size_t)tap * (C / NCH) + c / NCH) * okb + (o8 >> 3);
+    *reinterpret_cast<uint4*>(img + tile * ((size_t)NCH * 128) + sw128_offset(c % NCH, o8 & 7)) = pk;
+  }
+}
+
+// gx32 [N][HW][C] fp32 -> grad_x [N][C][HW] (T), ACCUMULATING into grad_x.
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_add_nchw_kernel(const float* __restrict__ src, T* __restrict__ dst,
+                                                              int C, int HW) {
+  __shared__ float s[32][65];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  {
+    const int c = tid & 63;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int p = (tid >> 6) + 4 * j;
+      s[p][c] = (p0 + p < HW && c0 + c < C) ? src[((size_t)n * HW + p0 + p) * C + c0 + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ty + 8 * j;
+    if (p0 + tx < HW && c0 + c < C) {
+      T* d = dst + ((size_t)n * C + c0 + c) * HW + p0 + tx;
+      if (sizeof(T) == 4) *reinterpret_cast<float*>(d) += s[tx][c];
+      else *reinterpret_cast<__nv_bfloat16*>(d) = __float2bfloat16_rn(to_f32(*d) + s[tx][c]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ gy, float* __restrict__ gb,
+                                                        float scale, int N, int O, int hw) {
+  const int o = blockIdx.x;
+  float sum = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) sum += to_f32(gy[((size_t)n * O + o) * hw + i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(gb + o, scale * t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling descriptor for the backward pass
+// ------------------------------------------------------------------------------------------------
+struct BSample {
+  int idx[4];   // corner pixel index (n*H + y)*W + x, or -1 when that corner is outside the image
+  float lh, lw, m;
+};
+
+__device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __restrict__ off,
+                                                const float* __restrict__ mask, bool valid, int n, int ho,
+                                                int wo, int tap) {
+  BSample s;
+  s.idx[0] = s.idx[1] = s.idx[2] = s.idx[3] = -1;
+  s.lh = s.lw = 0.f;
+  s.m = 0.f;
+  if (!valid) return s;
+  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
+  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
+  const int i = tap / g.KW, j = tap - i * g.KW;
+  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + __ldg(o);
+  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + __ldg(o + hw);
+  // gradient-side validity test is the non-strict one (deform_conv_cuda_kernel.cu:140-144, :435-437)
+  if (h <= -1.f || w <= -1.f || h >= (float)g.H || w >= (float)g.W) return s;
+  s.m = mask ? __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo) : 1.f;
+  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
+  const int h_high = h_low + 1, w_high = w_low + 1;
+  s.lh = h - h_low;
+  s.lw = w - w_low;
+  const bool t = h_low >= 0, b = h_high <= g.H - 1, l = w_low >= 0, r = w_high <= g.W - 1;
+  const int base = n * g.H;
+  if (t && l) s.idx[0] = (base + h_low) * g.W + w_low;
+  if (t && r) s.idx[1] = (base + h_low) * g.W + w_high;
+  if (b && l) s.idx[2] = (base + h_high) * g.W + w_low;
+  if (b && r) s.idx[3] = (base + h_high) * g.W + w_high;
+  return s;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// byte offset of 16-byte chunk `chunk` of row `row` in the bf16 staging tile [128][NCH]
+template <int NCH>
+__device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
+  return row * (NCH * 2) + (((chunk & ~7u) | ((chunk & 7u) ^ (row & 7u))) << 4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward data kernel
+// ------------------------------------------------------------------------------------------------
+struct DgradParams {
+  const __nv_bfloat16* xp;   // NHWC bf16 input
+  const float* off;
+  const float* mask;
+  const uint8_t* gy_img;     // dY tiles
+  const uint8_t* wt_img;     // W^T tiles
+  float* gx32;               // NHWC fp32 accumulation buffer or nullptr
+  float* goff;               // [N][2*taps][HWo] fp32, pre-zeroed, or nullptr
+  float* gmask;              // [N][taps][HWo] fp32, pre-zeroed, or nullptr
+  Geo g;
+  int num_tiles, nsb, okb;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const DgradParams p) {
+  constexpr int LPB = NCH / 8, PPI = 32 / LPB;
+  constexpr uint32_t B_BYTES = NCH * 128;            // one [NCH c][64 o] weight tile
+  constexpr uint32_t STG_BYTES = TILE_M * NCH * 2;   // bf16 staging tile
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full, a_empty;
+  __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], stg_full[2], stg_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const Geo& g = p.g;
+  const int C = g.C, taps = g.KH * g.KW, nch = C / NCH, units = taps * nch, okb = p.okb;
+  const uint32_t A_BYTES = (uint32_t)okb * (TILE_M * 128);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sA = sm;
+  uint8_t* sB = sA + A_BYTES;
+  uint8_t* sS = sB + (size_t)p.nsb * B_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t NCOLS = 2 * NCH;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&a_full, 1);
+    mbar_init(&a_empty, 1);
+    for (int s = 0; s < p.nsb; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+      mbar_init(&stg_full[s], 128);
+      mbar_init(&stg_empty[s], NSW * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, NCOLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== bulk producer: dY tile once per tile, W^T tiles per (tap, chunk, o-block) =====
+    if (lane == 0) {
+      uint32_t bs = 0, bp = 0, ap = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&a_empty, ap ^ 1);
+        mbar_arrive_expect_tx(&a_full, A_BYTES);
+        bulk_g2s(sA, p.gy_img + (size_t)tile * A_BYTES, A_BYTES, &a_full);
+        ap ^= 1;
+        for (int i = 0; i < units * okb; ++i) {
+          mbar_wait(&b_empty[bs], bp ^ 1);
+          mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, p.wt_img + (size_t)i * B_BYTES, B_BYTES, &b_full[bs]);
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: dcol[128 x NCH] = dY_tile[128 x O] * W^T =====
+    const uint32_t idesc = make_idesc_bf16(TILE_M, NCH, 0, 0);
+    uint32_t bs = 0, bp = 0, acc = 0, accp = 0, ap = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&a_full, ap);
+      ap ^= 1;
+      for (int u = 0; u < units; ++u) {
+        mbar_wait(&acc_empty[acc], accp ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * NCH;
+        for (int kb = 0; kb < okb; ++kb) {
+          mbar_wait(&b_full[bs], bp);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_base + kb * (TILE_M * 128);
+            const uint32_t b_addr = smem_base + A_BYTES + bs * B_BYTES;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                        make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, (kb | k4) != 0);
+            umma_commit(&b_empty[bs]);
+          }
+          __syncwarp();
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+        if (lane == 0) umma_commit(&acc_full[acc]);
+        __syncwarp();
+        if (++acc == 2) { acc = 0; accp ^= 1; }
+      }
+      if (lane == 0) umma_commit(&a_empty);
+      __syncwarp();
+    }
+  } else if (warp < FIRST_SW) {
+    // ===== drain: TMEM accumulator -> bf16 staging tile (row = pixel, swizzled 16-byte chunks) =====
+    const int q = warp & 3;
+    const uint32_t row = q * 32 + lane;
+    uint32_t acc = 0, accp = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int u = 0; u < units; ++u) {
+        mbar_wait(&acc_full[acc], accp);
+        tc_fence_after_sync();
+        mbar_wait(&stg_empty[acc], accp ^ 1);
+        uint8_t* stg = sS + (size_t)acc * STG_BYTES;
+#pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + acc * NCH + ((uint32_t)(q * 32) << 16) + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            *reinterpret_cast<uint4*>(stg + stg_offset<NCH>(row, c0 / 8 + j)) = pk;
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&acc_empty[acc]);   // TMEM buffer may be overwritten
+        mbar_arrive(&stg_full[acc]);    // staging tile is ready (release)
+        if (++acc == 2) { acc = 0; accp ^= 1; }
+      }
+    }
+  } else {
+    // ===== scatter warps: grad_offset / grad_mask reductions + grad_x scatter =====
+    const int sw = warp - FIRST_SW;
+    const int grp = lane / LPB, lig = lane % LPB;
+    const int hw = g.Ho * g.Wo;
+    uint32_t sb = 0, sp = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
+      const bool valid = lane < PIX_PER_WARP && pix < g.P();
+      const int n = valid ? (int)(pix / hw) : 0;
+      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
+      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+      for (int tap = 0; tap < taps; ++tap) {
+        const BSample mine = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
+        float my_gy = 0.f, my_gx = 0.f, my_gm = 0.f;   // results for the pixel this lane owns
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(&stg_full[sb], sp);
+          const uint8_t* stg = sS + (size_t)sb * STG_BYTES;
+          const size_t coff = (size_t)ch * NCH + lig * 8;
+#pragma unroll 2
+          for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
+            const int src = it * PPI + grp;
+            int idx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) idx[k] = __shfl_sync(0xffffffffu, mine.idx[k], src);
+            const float lh = __shfl_sync(0xffffffffu, mine.lh, src);
+            const float lw = __shfl_sync(0xffffffffu, mine.lw, src);
+            const float m = __shfl_sync(0xffffffffu, mine.m, src);
+            const int row = sw * PIX_PER_WARP + src;
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4*>(stg + stg_offset<NCH>(row, lig)), d);
+            const float wk[4] = {(1.f - lh) * (1.f - lw), (1.f - lh) * lw, lh * (1.f - lw), lh * lw};
+            float S[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (idx[k] >= 0) {
+                float v[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.xp + (size_t)idx[k] * C + coff)), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) S[k] = fmaf(d[j], v[j], S[k]);
+                if (p.gx32) {
+                  const float wm = wk[k] * m;
+                  float* dst = p.gx32 + (size_t)idx[k] * C + coff;
+                  red_add_v4(dst, wm * d[0], wm * d[1], wm * d[2], wm * d[3]);
+                  red_add_v4(dst + 4, wm * d[4], wm * d[5], wm * d[6], wm * d[7]);
+                }
+              }
+            }
+            // d(bilinear)/dh, /dw (get_coordinate_weight :185-211) and the unmasked sample value
+            float gy = m * (-(1.f - lw) * S[0] - lw * S[1] + (1.f - lw) * S[2] + lw * S[3]);
+            float gx = m * (-(1.f - lh) * S[0] + (1.f - lh) * S[1] - lh * S[2] + lh * S[3]);
+            float gm = wk[0] * S[0] + wk[1] * S[1] + wk[2] * S[2] + wk[3] * S[3];
+#pragma unroll
+            for (int dlt = LPB / 2; dlt > 0; dlt >>= 1) {
+              gy += __shfl_xor_sync(0xffffffffu, gy, dlt);
+              gx += __shfl_xor_sync(0xffffffffu, gx, dlt);
+              gm += __shfl_xor_sync(0xffffffffu, gm, dlt);
+            }
+            // hand the result to the lane that owns this pixel's descriptor (lane == src)
+            const int from = (lane % PPI) * LPB;
+            const float rgy = __shfl_sync(0xffffffffu, gy, from);
+            const float rgx = __shfl_sync(0xffffffffu, gx, from);
+            const float rgm = __shfl_sync(0xffffffffu, gm, from);
+            if (lane / PPI == it && lane < PIX_PER_WARP) {
+              my_gy += rgy;
+              my_gx += rgx;
+              my_gm += rgm;
+            }
+          }
+          mbar_arrive(&stg_empty[sb]);
+          if (++sb == 2) { sb = 0; sp ^= 1; }
+        }
+        if (valid) {
+          const size_t ob = ((size_t)n * 2 * taps + 2 * tap) * hw + rem;
+          if (p.goff) {
+            p.goff[ob] = my_gy;        // one owner per (pixel, tap): plain stores, channel chunks
+            p.goff[ob + hw] = my_gx;   // were summed in registers above
+          }
+          if (p.gmask) p.gmask[((size_t)n * taps + tap) * hw + rem] = my_gm;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, NCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward weight kernel
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  const __nv_bfloat16* xp;
+  const float* off;
+  const float* mask;
+  const uint8_t* gy_img;
+  float* part;               // [splits][taps][O][C] fp32 partial sums
+  Geo g;
+  int num_tiles, tiles_per_split, splits, okb, nsg, nsy;
+};
+
+template <int NCH>
+__device__ __forceinline__ void gather_stage(const Geo& g, const __nv_bfloat16* __restrict__ xc, int C,
+                                             const int (&midx)[4], const float (&mw)[4], uint8_t* stage,
+                                             int warp_row0, int lane) {
+  constexpr int LPB = NCH / 8, PPI = 32 / LPB;
+  const int grp = lane / LPB, lig = lane % LPB;
+#pragma unroll 4
+  for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
+    const int src = it * PPI + grp;
+    int idx[4];
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      idx[k] = __shfl_sync(0xffffffffu, midx[k], src);
+      w[k] = __shfl_sync(0xffffffffu, mw[k], src);
+    }
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)idx[k] * C));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fma8(acc, v[k], w[k]);
+    uint4 pk;
+    pk.x = pack_bf16x2(acc[0], acc[1]);
+    pk.y = pack_bf16x2(acc[2], acc[3]);
+    pk.z = pack_bf16x2(acc[4], acc[5]);
+    pk.w = pack_bf16x2(acc[6], acc[7]);
+    const int row = warp_row0 + src;
+    *reinterpret_cast<uint4*>(stage + (lig >> 3) * (TILE_M * 128) + sw128_offset(row, lig & 7)) = pk;
+  }
+  (void)g;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const WgradParams p) {
+  constexpr int LPB = NCH / 8;
+  constexpr uint32_t G_BYTES = TILE_M * NCH * 2;   // gathered col tile [NCH/64 blocks][128 px][64 c]
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t g_full[4], g_empty[4], y_full[4], y_empty[4], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const Geo& g = p.g;
+  const int C = g.C, O = g.O, taps = g.KH * g.KW, nch = C / NCH, okb = p.okb, mh_n = okb / 2;
+  const uint32_t Y_BYTES = (uint32_t)okb * (TILE_M * 128);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sG = sm;
+  uint8_t* sY = sG + (size_t)p.nsg * G_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item of this CTA
+  const int split = blockIdx.x % p.splits;
+  const int ch = (blockIdx.x / p.splits) % nch;
+  const int tap = blockIdx.x / (p.splits * nch);
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(p.num_tiles, t0 + p.tiles_per_split);
+  uint32_t ncols = 32;
+  while ((int)ncols < mh_n * NCH) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nsg; ++s) {
+      mbar_init(&g_full[s], NSW * 32);
+      mbar_init(&g_empty[s], 1);
+    }
+    for (int s = 0; s < p.nsy; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ys = 0, yp = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(&y_empty[ys], yp ^ 1);
+        mbar_arrive_expect_tx(&y_full[ys], Y_BYTES);
+        bulk_g2s(sY + (size_t)ys * Y_BYTES, p.gy_img + (size_t)tile * Y_BYTES, Y_BYTES, &y_full[ys]);
+        if (++ys == (uint32_t)p.nsy) { ys = 0; yp ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // dW^T-free formulation: D[o, c] += sum_pixels dY[pix, o] * col[pix, c]; both operands MN-major
+    const uint32_t idesc = make_idesc_bf16(128, NCH, 1, 1);
+    uint32_t gs = 0, gp = 0, ys = 0, yp = 0;
+    uint32_t accumulate = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+      mbar_wait(&y_full[ys], yp);
+      mbar_wait(&g_full[gs], gp);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t y_addr = smem_base + p.nsg * G_BYTES + ys * Y_BYTES;
+        const uint32_t g_addr = smem_base + gs * G_BYTES;
+        for (int s = 0; s < TILE_M / 16; ++s) {
+          for (int mh = 0; mh < mh_n; ++mh)
+            umma_bf16(tmem_base + mh * NCH,
+                      make_smem_desc_sw128(y_addr + (2 * mh) * (TILE_M * 128) + s * 2048, TILE_M * 128, 1024),
+                      make_smem_desc_sw128(g_addr + s * 2048, TILE_M * 128, 1024), idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&y_empty[ys]);
+        umma_commit(&g_empty[gs]);
+      }
+      __syncwarp();
+      if (++ys == (uint32_t)p.nsy) { ys = 0; yp ^= 1; }
+      if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }
+    }
+    if (lane == 0) umma_commit(&acc_full);
+    __syncwarp();
+  } else if (warp < FIRST_SW) {
+    // epilogue: partial dW tile -> workspace [split][tap][O][C]
+    const int q = warp & 3;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after_sync();
+    for (int mh = 0; mh < mh_n; ++mh) {
+      const int o = mh * 128 + q * 32 + lane;
+#pragma unroll
+      for (int c0 = 0; c0 < NCH; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + mh * NCH + ((uint32_t)(q * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        if (o < O && t1 > t0) {
+          float4* dst = reinterpret_cast<float4*>(p.part + (((size_t)split * taps + tap) * O + o) * C + ch * NCH + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  } else {
+    // gather producers (same sampling as the forward pass)
+    const int sw = warp - FIRST_SW;
+    const int hw = g.Ho * g.Wo;
+    uint32_t gs = 0, gp = 0;
+    const __nv_bfloat16* xc = p.xp + ch * NCH + (lane % LPB) * 8;
+    for (int tile = t0; tile < t1; ++tile) {
+      const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
+      const bool valid = lane < PIX_PER_WARP && pix < g.P();
+      const int n = valid ? (int)(pix / hw) : 0;
+      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
+      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+      // forward-style descriptor (weights already x mask, zero outside)
+      int midx[4] = {0, 0, 0, 0};
+      float mw[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const BSample b = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
+        const float wk[4] = {(1.f - b.lh) * (1.f - b.lw), (1.f - b.lh) * b.lw, b.lh * (1.f - b.lw), b.lh * b.lw};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (b.idx[k] >= 0) {
+            midx[k] = b.idx[k];
+            mw[k] = wk[k] * b.m;
+          }
+      }
+      mbar_wait(&g_empty[gs], gp ^ 1);
+      gather_stage<NCH>(g, xc, C, midx, mw, sG + (size_t)gs * G_BYTES, sw * PIX_PER_WARP, lane);
+      fence_proxy_async_smem();
+      mbar_arrive(&g_full[gs]);
+      if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// grad_weight[o][c][tap] += scale * sum_split part[split][tap][o][c]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw,
+                                                           float scale, int splits, int taps, int O, int C) {
+  const long long total = (long long)O * C * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int o = (int)((i / C) % O);
+    const int tap = (int)(i / ((long long)C * O));
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += part[(((size_t)sp * taps + tap) * O + o) * C + c];
+    gw[((size_t)o * C + c) * taps + tap] += scale * s;
+  }
+}
+
+// ---- workspace layouts ----------------------------------------------------------------------
+struct BwdWs {
+  size_t xp_off, gy_off, wt_off, gx_off, part_off, total;
+};
+int wgrad_splits(const Geo& g, int num_tiles) {
+  int s = num_sms() / (g.taps() * nch_chunks(g));
+  if (s < 1) s = 1;
+  if (s > num_tiles) s = num_tiles;
+  if (s > 64) s = 64;
+  return s;
+}
+BwdWs bwd_ws(int op, const Geo& g) {
+  BwdWs w{};
+  const int okb = okb_of(g);
+  const size_t tiles = (size_t)cdiv(g.P(), TILE_M);
+  size_t o = 0;
+  w.xp_off = o; o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 2, 1024);
+  w.gy_off = o; o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
+  if (op == SDB_OP_BACKWARD_DATA) {
+    w.wt_off = o; o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
+    w.gx_off = o; o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 4, 1024);
+  } else {
+    w.part_off = o; o = align_up(o + (size_t)wgrad_splits(g, (int)tiles) * g.taps() * g.O * g.C * 4, 1024);
+  }
+  w.total = o;
+  return w;
+}
+
+template <typename T>
+int pack_gy(const void* gy, uint8_t* img, const Geo& g, cudaStream_t st) {
+  dim3 grid(cdiv(g.P(), TILE_M), okb_of(g));
+  pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g.O, g.HWo(), g.P(), okb_of(g));
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // namespace
+
+size_t tc_bwd_workspace_bytes(int op, const Geo& g) { return bwd_ws(op, g).total; }
+
+int tc_backward_data(const void* x, const float* off, const float* mask, const void* w, const void* gy,
+                     void* gx, float* goff, float* gmask, const Geo& g, int io_dtype, void* ws,
+                     size_t ws_bytes, const void* x_packed, cudaStream_t st) {
+  const int NCH = nch_of(g);
+  const BwdWs L = bwd_ws(SDB_OP_BACKWARD_DATA, g);
+  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "backward_data workspace too small: %zu < %zu", ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  const bool f32 = io_dtype == SDB_F32;
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
+  int rc;
+  if (!xp) {
+    rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
+             : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
+    if (rc) return rc;
+    xp = (const __nv_bfloat16*)(base + L.xp_off);
+  }
+  uint8_t* gy_img = base + L.gy_off;
+  uint8_t* wt_img = base + L.wt_off;
+  float* gx32 = gx ? (float*)(base + L.gx_off) : nullptr;
+  rc = f32 ? pack_gy<float>(gy, gy_img, g, st) : pack_gy<__nv_bfloat16>(gy, gy_img, g, st);
+  if (rc) return rc;
+  const int okb = okb_of(g);
+  {
+    const long long total = (long long)g.taps() * g.C * okb * 8;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    if (NCH == 128) {
+      if (f32) prep_weight_dgrad_kernel<float, 128><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
+      else prep_weight_dgrad_kernel<__nv_bfloat16, 128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
+    } else {
+      if (f32) prep_weight_dgrad_kernel<float, 64><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
+      else prep_weight_dgrad_kernel<__nv_bfloat16, 64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
+    }
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (gx32) SDB_CHECK_CUDA(cudaMemsetAsync(gx32, 0, (size_t)g.N * g.H * g.W * g.C * 4, st));
+
+  DgradParams p;
+  p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.wt_img = wt_img; p.gx32 = gx32;
+  p.goff = goff; p.gmask = mask ? gmask : nullptr; p.g = g;
+  p.num_tiles = cdiv(g.P(), TILE_M);
+  p.okb = okb;
+  const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
+  long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
+  if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+  SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
+  p.nsb = (int)nsb;
+  const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (NCH == 128) {
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+  } else {
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+  }
+  SDB_CHECK_CUDA(cudaGetLastError());
+
+  if (gx) {
+    const int HW = g.H * g.W;
+    dim3 ugrid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
+    if (f32) unpack_add_nchw_kernel<float><<<ugrid, 256, 0, st>>>(gx32, (float*)gx, g.C, HW);
+    else unpack_add_nchw_kernel<__nv_bfloat16><<<ugrid, 256, 0, st>>>(gx32, (__nv_bfloat16*)gx, g.C, HW);
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SDB_OK;
+}
+
+int tc_backward_weight(const void* x, const float* off, const float* mask, const void* gy, float* gw,
+                       float* gb, float scale, const Geo& g, int io_dtype, void* ws, size_t ws_bytes,
+                       const void* x_packed, cudaStream_t st) {
+  const int NCH = nch_of(g);
+  const BwdWs L = bwd_ws(SDB_OP_BACKWARD_WEIGHT, g);
+  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "backward_weight workspace too small: %zu < %zu", ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  const bool f32 = io_dtype == SDB_F32;
+  int rc;
+  if (gw) {
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
+    if (!xp) {
+      rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
+               : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
+      if (rc) return rc;
+      xp = (const __nv_bfloat16*)(base + L.xp_off);
+    }
+    uint8_t* gy_img = base + L.gy_off;
+    rc = f32 ? pack_gy<float>(gy, gy_img, g, st) : pack_gy<__nv_bfloat16>(gy, gy_img, g, st);
+    if (rc) return rc;
+    WgradParams p;
+    p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.part = (float*)(base + L.part_off); p.g = g;
+    p.num_tiles = cdiv(g.P(), TILE_M);
+    p.tiles_per_split = cdiv(p.num_tiles, wgrad_splits(g, p.num_tiles));
+    p.splits = cdiv(p.num_tiles, p.tiles_per_split);   // no empty split
+    p.okb = okb_of(g);
+    const size_t g_bytes = (size_t)TILE_M * NCH * 2, y_bytes = (size_t)p.okb * TILE_M * 128;
+    p.nsy = 2;
+    long long nsg = ((long long)(208 * 1024) - 1024 - (long long)(p.nsy * y_bytes)) / (long long)g_bytes;
+    if (nsg > 4) nsg = 4;
+    SDB_REQUIRE(nsg >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_weight");
+    p.nsg = (int)nsg;
+    const size_t smem = p.nsg * g_bytes + p.nsy * y_bytes + 1024;
+    const int grid = g.taps() * nch_chunks(g) * p.splits;
+    if (NCH == 128) {
+      SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dcn_bwd_weight_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+    } else {
+      SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dcn_bwd_weight_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+    }
+    SDB_CHECK_CUDA(cudaGetLastError());
+    const long long total = (long long)g.O * g.C * g.taps();
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.part, gw, scale, p.splits, g.taps(), g.O, g.C);
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (gb) {
+    if (f32) bias_grad_kernel<float><<<g.O, 256, 0, st>>>((const float*)gy, gb, scale, g.N, g.O, g.HWo());
+    else bias_grad_kernel<__nv_bfloat16><<<g.O, 256, 0, st>>>((const __nv_bfloat16*)gy, gb, scale, g.N, g.O, g.HWo());
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  return SDB_OK;
+}
+
+}  // namespace sdb

@@ -1,0 +1,87 @@
+// dcn_tc_shared.cuh -- helpers shared by the tensor-core DCN translation units (dcn_tc.cu: forward,
+// dcn_tc_bwd.cu: backward data / backward weight).
+#pragma once
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sdb {
+
+size_t tc_bwd_workspace_bytes(int op, const Geo& g);
+
+namespace tcshared {
+using namespace tc;
+
+constexpr int TILE_M = 128;
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// layout / dtype conversion kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// [N][C][HW] (T) -> [N][HW][C] bf16.  Tile 64 channels x 32 pixels.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const T* __restrict__ src,
+                                                        __nv_bfloat16* __restrict__ dst, int C, int HW) {
+  __shared__ float s[64][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const T* sp = src + ((size_t)n * C + c0) * HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = ty + 8 * j;
+    s[c][tx] = (c0 + c < C && p0 + tx < HW) ? to_f32(sp[(size_t)c * HW + p0 + tx]) : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dp = dst + ((size_t)n * HW + p0) * C + c0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = ty + 8 * j;
+    if (p0 + p < HW && c0 + 2 * tx < C)
+      *reinterpret_cast<__nv_bfloat162*>(dp + (size_t)p * C + 2 * tx) =
+          __floats2bfloat162_rn(s[2 * tx][p], s[2 * tx + 1][p]);
+  }
+}
+
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4 v, float w) {
+  acc[0] = fmaf(w, __uint_as_float(v.x << 16), acc[0]);
+  acc[1] = fmaf(w, __uint_as_float(v.x & 0xffff0000u), acc[1]);
+  acc[2] = fmaf(w, __uint_as_float(v.y << 16), acc[2]);
+  acc[3] = fmaf(w, __uint_as_float(v.y & 0xffff0000u), acc[3]);
+  acc[4] = fmaf(w, __uint_as_float(v.z << 16), acc[4]);
+  acc[5] = fmaf(w, __uint_as_float(v.z & 0xffff0000u), acc[5]);
+  acc[6] = fmaf(w, __uint_as_float(v.w << 16), acc[6]);
+  acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
+}
+
+template <typename T>
+inline int pack_input(const void* x, __nv_bfloat16* xp, const Geo& g, cudaStream_t st) {
+  const int HW = g.H * g.W;
+  dim3 grid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
+  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+
+}  // namespace tcshared
+}  // namespace sdb

@@ -177,3 +177,41 @@ def test_dfconv2d_and_grad_flow():
         for p in m.parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all()
         assert m.offset.weight.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("shape", [
+    # N, C, H, W, O, k, stride, pad, dil, modulated, sigma
+    (2, 64, 13, 21, 64, 3, 1, 1, 1, False, 2.0),
+    (1, 128, 25, 42, 256, 3, 1, 1, 1, True, 0.5),
+    (2, 256, 50, 84, 256, 3, 1, 1, 1, False, 2.0),
+    (1, 256, 7, 11, 256, 3, 1, 1, 1, True, 8.0),
+    (2, 192, 9, 10, 48, 3, 2, 1, 1, False, 1.0),
+    (1, 64, 12, 9, 16, 1, 1, 0, 1, False, 1.0),
+    (1, 512, 10, 13, 128, 3, 1, 2, 2, True, 3.0),
+    (3, 256, 20, 19, 240, 5, 1, 2, 1, False, 30.0),
+])
+def test_tensor_core_forward_vs_oracle(shape):
+    """tcgen05 forward (bf16 operands, fp32 accumulate) vs the CPU oracle, rel <= 1e-2."""
+    N, C, H, W, O, k, st, pd, dl, mod, sigma = shape
+    g = torch.Generator().manual_seed(C + O + H)
+    Ho = (H + 2 * pd - (dl * (k - 1) + 1)) // st + 1
+    Wo = (W + 2 * pd - (dl * (k - 1) + 1)) // st + 1
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(O, C, k, k, generator=g) * 0.05
+    off = torch.randn(N, 2 * k * k, Ho, Wo, generator=g) * sigma
+    m = torch.sigmoid(torch.randn(N, k * k, Ho, Wo, generator=g)) if mod else None
+    b = torch.randn(O, generator=g) if mod else None
+    yo = odcn.forward(x.numpy(), off.numpy(), w.numpy(), mask=None if m is None else m.numpy(),
+                      bias=None if b is None else b.numpy(), stride=st, padding=pd, dilation=dl)
+    with sdb.dcn_math("bf16"), torch.no_grad():
+        if mod:
+            y = sdb.modulated_deform_conv(x.cuda(), off.cuda(), m.cuda(), w.cuda(), b.cuda(), st, pd, dl, 1, 1)
+        else:
+            y = sdb.deform_conv(x.cuda(), off.cuda(), w.cuda(), st, pd, dl, 1, 1)
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu().numpy(), yo) < TOL["bf16"]
+    # against an oracle fed the SAME bf16-rounded operands the kernel uses, the gap is fp32-accumulation small
+    yq = odcn.forward(x.bfloat16().float().numpy(), off.numpy(), w.bfloat16().float().numpy(),
+                      mask=None if m is None else m.numpy(), bias=None if b is None else b.numpy(),
+                      stride=st, padding=pd, dilation=dl)
+    assert rel_err(y.cpu().numpy(), yq) < 4e-3
