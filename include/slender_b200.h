@@ -48,7 +48,7 @@ typedef enum { SDB_MATH_FP32 = 0, SDB_MATH_BF16 = 1 } sdb_math;
 
 /* Geometry of one deformable convolution (same meaning as the integer arguments of
  * deform_conv_forward / modulated_deform_conv_forward, d2/layers/csrc/deformable/deform_conv.h:8-112).
- * With has_mask == 0 this is DCN v1 (DeformConv), with has_mask == 1 modulated DCN v2. */
+ * The same struct serves DCN v1 (mask == NULL at the call) and modulated DCN v2 (mask != NULL). */
 typedef struct {
   int32_t N, C_in, H, W;        /* input  [N, C_in, H, W]                                   */
   int32_t C_out, kH, kW;        /* weight [C_out, C_in/groups, kH, kW]                      */
@@ -153,6 +153,18 @@ typedef enum { SDB_BOX_LTRB = 0 /* iou_loss */, SDB_BOX_XYXY = 1 /* box_iou_loss
 int sdb_box_reg_loss(const float* pred, const float* target, const float* weight, int64_t R,
                      int kind, int form, float beta, float grad_scale, float* loss_sum,
                      float* grad_pred, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
+ * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,
+ * not the packing helpers).  slot = sdb_dcn_op.  sdb_profile_read synchronises the recorded
+ * events and returns the summed milliseconds and the launch count since the last reset.
+ * Not capturable into CUDA graphs; leave disabled (the default) on the training path. */
+int sdb_profile_enable(int on);
+int sdb_profile_reset(void);
+int sdb_profile_read(int slot, float* total_ms, int* launches);
+/* Number of kernels this library has launched (or captured into a CUDA graph) since it was loaded. */
+long long sdb_launch_count(void);
 
 #ifdef __cplusplus
 }

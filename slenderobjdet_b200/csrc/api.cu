@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of libslender_b200.so (see include/slender_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +8,7 @@
 namespace sdb {
 
 static thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -66,6 +68,31 @@ static int require_device() {
   return SDB_OK;
 }
 
+// ---- profiling --------------------------------------------------------------------------------
+namespace {
+constexpr int kProfSlots = 3, kProfMax = 8192;
+struct ProfState {
+  bool on = false;
+  int n[kProfSlots] = {0, 0, 0};
+  cudaEvent_t* ev[kProfSlots] = {nullptr, nullptr, nullptr};  // 2 events per launch
+} g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int slot_, cudaStream_t st_) : slot(slot_), st(st_), id(-1) {
+  if (!g_prof.on || slot < 0 || slot >= kProfSlots || g_prof.n[slot] >= kProfMax) return;
+  if (!g_prof.ev[slot]) g_prof.ev[slot] = (cudaEvent_t*)calloc(2 * kProfMax, sizeof(cudaEvent_t));
+  id = g_prof.n[slot]++;
+  cudaEvent_t* e = g_prof.ev[slot] + 2 * id;
+  if (!e[0]) {
+    cudaEventCreate(&e[0]);
+    cudaEventCreate(&e[1]);
+  }
+  cudaEventRecord(e[0], st);
+}
+ProfScope::~ProfScope() {
+  if (id >= 0) cudaEventRecord(g_prof.ev[slot][2 * id + 1], st);
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -74,6 +101,30 @@ extern "C" {
 
 const char* sdb_last_error(void) { return g_err; }
 int sdb_abi_version(void) { return SDB_ABI_VERSION; }
+
+long long sdb_launch_count(void) { return g_launches; }
+int sdb_profile_enable(int on) {
+  g_prof.on = on != 0;
+  return SDB_OK;
+}
+int sdb_profile_reset(void) {
+  for (int s = 0; s < kProfSlots; ++s) g_prof.n[s] = 0;
+  return SDB_OK;
+}
+int sdb_profile_read(int slot, float* total_ms, int* launches) {
+  SDB_REQUIRE(slot >= 0 && slot < kProfSlots && total_ms && launches, SDB_ERR_INVALID, "bad profile slot");
+  float sum = 0.f;
+  for (int i = 0; i < g_prof.n[slot]; ++i) {
+    cudaEvent_t* e = g_prof.ev[slot] + 2 * i;
+    SDB_CHECK_CUDA(cudaEventSynchronize(e[1]));
+    float ms = 0.f;
+    SDB_CHECK_CUDA(cudaEventElapsedTime(&ms, e[0], e[1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = g_prof.n[slot];
+  return SDB_OK;
+}
 
 int sdb_dcn_output_size(const sdb_dcn_geom* g, int32_t* Ho, int32_t* Wo) {
   int rc = check_geom(g);

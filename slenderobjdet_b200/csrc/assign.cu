@@ -209,7 +209,7 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
   }
   if (X == 0) return SDB_OK;
   if (M == 0) {  // topk_matcher.py:53-63
-    fill_default_kernel<<<cdiv(X, 256), 256, 0, st>>>(X, labels[0], matches, match_labels);
+    fill_default_kernel<<<cdiv(X, 256), 256, 0, st>>>(X, labels[0], matches, match_labels); SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
     return SDB_OK;
   }
@@ -222,10 +222,10 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
       SDB_CHECK_CUDA(cudaFuncSetAttribute(per_anchor_kernel<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     per_anchor_kernel<true><<<cdiv(X, 256), 256, smem, st>>>(
-        (const float4*)gt, (const float4*)anchors, nullptr, M, X, th, matches, match_labels, iou_out);
+        (const float4*)gt, (const float4*)anchors, nullptr, M, X, th, matches, match_labels, iou_out); SDB_LAUNCHED(1);
   } else {
     per_anchor_kernel<false><<<cdiv(X, 256), 256, 0, st>>>(nullptr, nullptr, q, M, X, th, matches,
-                                                           match_labels, nullptr);
+                                                           match_labels, nullptr); SDB_LAUNCHED(1);
   }
   SDB_CHECK_CUDA(cudaGetLastError());
   if (topk > 0 || alq) {
@@ -234,7 +234,7 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
       per_gt_kernel<true><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr,
                                                  M, X, topk, match_labels);
     else
-      per_gt_kernel<false><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels);
+      per_gt_kernel<false><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels); SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   return SDB_OK;
@@ -276,7 +276,7 @@ int sdb_pairwise_iou(const float* boxes1, const float* boxes2, int32_t N1, int32
   SDB_REQUIRE(boxes1 && boxes2 && iou, SDB_ERR_INVALID, "NULL argument");
   dim3 grid(cdiv(N2, 256), N1 < 64 ? N1 : 64);
   pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes1,
-                                                              (const float4*)boxes2, N1, N2, iou);
+                                                              (const float4*)boxes2, N1, N2, iou); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }

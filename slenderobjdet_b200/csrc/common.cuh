@@ -12,6 +12,10 @@ namespace sdb {
 // thread-local error text behind sdb_last_error()
 void set_error(const char* fmt, ...);
 
+// every kernel launch goes through this counter (sdb_launch_count)
+extern long long g_launches;
+#define SDB_LAUNCHED(n) (sdb::g_launches += (n))
+
 #define SDB_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \
@@ -47,6 +51,15 @@ inline Geo make_geo(const sdb_dcn_geom& g) {
 }
 
 int check_geom(const sdb_dcn_geom* g);  // shape_check restated; sets error text
+
+// RAII event pair around a launcher's dominant kernel (no-op unless sdb_profile_enable(1))
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  int id;
+  ProfScope(int slot, cudaStream_t st);
+  ~ProfScope();
+};
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 }  // namespace
 
 int bias_grad_f32(const float* gy, float* gb, float scale, int N, int O, int hw, cudaStream_t st) {
-  bias_grad_kernel<<<O, 256, 0, st>>>(gy, gb, scale, N, O, hw);
+  bias_grad_kernel<<<O, 256, 0, st>>>(gy, gb, scale, N, O, hw); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -348,7 +348,8 @@ int simt_forward(const float* x, const float* off, const float* mask, const floa
                  const float* bias, float* out, const Geo& g, cudaStream_t st) {
   const int Og = g.O / g.groups;
   dim3 grid(cdiv(g.P(), BM), g.groups * cdiv(Og, BN));
-  simt_fwd_kernel<<<grid, NT, 0, st>>>(x, off, mask, w, bias, out, g);
+  ProfScope prof(SDB_OP_FORWARD, st);
+  simt_fwd_kernel<<<grid, NT, 0, st>>>(x, off, mask, w, bias, out, g); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -362,7 +363,8 @@ int simt_backward_data(const float* x, const float* off, const float* mask, cons
   if (gmask && mask)
     SDB_CHECK_CUDA(cudaMemsetAsync(gmask, 0, sizeof(float) * g.P() * g.dgroups * k2, st));
   dim3 grid(cdiv(g.P(), BM), g.groups * cdiv(Kg, BN));
-  simt_bwd_data_kernel<<<grid, NT, 0, st>>>(x, off, mask, w, gy, gx, goff, mask ? gmask : nullptr, g);
+  ProfScope prof(SDB_OP_BACKWARD_DATA, st);
+  simt_bwd_data_kernel<<<grid, NT, 0, st>>>(x, off, mask, w, gy, gx, goff, mask ? gmask : nullptr, g); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -383,7 +385,8 @@ int simt_backward_weight(const float* x, const float* off, const float* mask, co
     pps = (pps + BK - 1) / BK * BK;
     splits = cdiv(P, pps);
     dim3 grid(g.groups * cdiv(Og, BM), cdiv(Kg, BN), splits);
-    simt_bwd_weight_kernel<<<grid, NT, 0, st>>>(x, off, mask, gy, gw, scale, g, pps);
+    ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
+    simt_bwd_weight_kernel<<<grid, NT, 0, st>>>(x, off, mask, gy, gw, scale, g, pps); SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   if (gb) return bias_grad_f32(gy, gb, scale, g.N, g.O, g.HWo(), st);

@@ -323,7 +323,8 @@ template <int LPP, bool OUT_BF16>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
   SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p);
+  ProfScope prof(SDB_OP_FORWARD, st);
+  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -364,7 +365,7 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   if (io_dtype == SDB_F32)
     prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps());
   else
-    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps());
+    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps()); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
 
   FwdParams p;

@@ -663,7 +663,7 @@ BwdWs bwd_ws(int op, const Geo& g) {
 template <typename T>
 int pack_gy(const void* gy, uint8_t* img, const Geo& g, cudaStream_t st) {
   dim3 grid(cdiv(g.P(), TILE_M), okb_of(g));
-  pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g.O, g.HWo(), g.P(), okb_of(g));
+  pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g.O, g.HWo(), g.P(), okb_of(g)); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -700,9 +700,11 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
     if (NCH == 128) {
       if (f32) prep_weight_dgrad_kernel<float, 128><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
       else prep_weight_dgrad_kernel<__nv_bfloat16, 128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
+      SDB_LAUNCHED(1);
     } else {
       if (f32) prep_weight_dgrad_kernel<float, 64><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
       else prep_weight_dgrad_kernel<__nv_bfloat16, 64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
+      SDB_LAUNCHED(1);
     }
     SDB_CHECK_CUDA(cudaGetLastError());
   }
@@ -720,12 +722,13 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
   p.nsb = (int)nsb;
   const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (NCH == 128) {
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-  } else {
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof(SDB_OP_BACKWARD_DATA, st);
+    if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+    else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+    SDB_LAUNCHED(1);
   }
   SDB_CHECK_CUDA(cudaGetLastError());
 
@@ -734,6 +737,7 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
     dim3 ugrid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
     if (f32) unpack_add_nchw_kernel<float><<<ugrid, 256, 0, st>>>(gx32, (float*)gx, g.C, HW);
     else unpack_add_nchw_kernel<__nv_bfloat16><<<ugrid, 256, 0, st>>>(gx32, (__nv_bfloat16*)gx, g.C, HW);
+    SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   return SDB_OK;
@@ -773,22 +777,24 @@ int tc_backward_weight(const void* x, const float* off, const float* mask, const
     p.nsg = (int)nsg;
     const size_t smem = p.nsg * g_bytes + p.nsy * y_bytes + 1024;
     const int grid = g.taps() * nch_chunks(g) * p.splits;
-    if (NCH == 128) {
-      SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dcn_bwd_weight_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-    } else {
-      SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dcn_bwd_weight_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
+      if (NCH == 128) dcn_bwd_weight_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+      else dcn_bwd_weight_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+      SDB_LAUNCHED(1);
     }
     SDB_CHECK_CUDA(cudaGetLastError());
     const long long total = (long long)g.O * g.C * g.taps();
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.part, gw, scale, p.splits, g.taps(), g.O, g.C);
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.part, gw, scale, p.splits, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   if (gb) {
     if (f32) bias_grad_kernel<float><<<g.O, 256, 0, st>>>((const float*)gy, gb, scale, g.N, g.O, g.HWo());
     else bias_grad_kernel<__nv_bfloat16><<<g.O, 256, 0, st>>>((const __nv_bfloat16*)gy, gb, scale, g.N, g.O, g.HWo());
+    SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   return SDB_OK;

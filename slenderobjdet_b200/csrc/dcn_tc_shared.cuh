@@ -66,7 +66,7 @@ template <typename T>
 inline int pack_input(const void* x, __nv_bfloat16* xp, const Geo& g, cudaStream_t st) {
   const int HW = g.H * g.W;
   dim3 grid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
-  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW);
+  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }

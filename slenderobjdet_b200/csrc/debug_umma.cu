@@ -106,7 +106,7 @@ extern "C" int sdb_debug_umma_gemm(const void* A, const void* B, const void* B_i
   const size_t smem = (size_t)(128 + N) * K * 2 + 1024;
   SDB_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, (const uint8_t*)B_img, D, N, K, a_mn, b_mn, use_bulk);
+      (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, (const uint8_t*)B_img, D, N, K, a_mn, b_mn, use_bulk); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }

@@ -225,7 +225,7 @@ int sdb_sigmoid_focal_loss(const float* logits, const int64_t* class_idx, int64_
   if (vec)
     focal_kernel<4><<<(int)blocks, 256, 0, st>>>(logits, class_idx, R, K, alpha, gamma, grad_scale, loss_sum, grad_logits);
   else
-    focal_kernel<1><<<(int)blocks, 256, 0, st>>>(logits, class_idx, R, K, alpha, gamma, grad_scale, loss_sum, grad_logits);
+    focal_kernel<1><<<(int)blocks, 256, 0, st>>>(logits, class_idx, R, K, alpha, gamma, grad_scale, loss_sum, grad_logits); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -243,7 +243,7 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
   if (blocks > 148 * 8) blocks = 148 * 8;
   box_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)pred, (const float4*)target, weight, R, kind, form, beta, grad_scale, loss_sum,
-      (float4*)grad_pred);
+      (float4*)grad_pred); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
