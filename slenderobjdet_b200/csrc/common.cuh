@@ -37,6 +37,7 @@ extern long long g_launches;
 // Geometry with derived output size, passed by value to kernels.
 struct Geo {
   int N, C, H, W, O, KH, KW, sh, sw, ph, pw, dh, dw, groups, dgroups, Ho, Wo;
+  int th, tw;  // tensor-core path: output pixels are walked in th x tw blocks (see decode_q)
   __host__ __device__ int taps() const { return KH * KW; }
   __host__ __device__ int HWo() const { return Ho * Wo; }
   __host__ __device__ long long P() const { return (long long)N * Ho * Wo; }
@@ -44,7 +45,7 @@ struct Geo {
 
 inline Geo make_geo(const sdb_dcn_geom& g) {
   Geo d{g.N, g.C_in, g.H, g.W, g.C_out, g.kH, g.kW, g.sH, g.sW, g.pH, g.pW, g.dH, g.dW,
-        g.groups, g.deformable_groups, 0, 0};
+        g.groups, g.deformable_groups, 0, 0, 8, 16};
   d.Ho = (g.H + 2 * g.pH - (g.dH * (g.kH - 1) + 1)) / (g.sH > 0 ? g.sH : 1) + 1;
   d.Wo = (g.W + 2 * g.pW - (g.dW * (g.kW - 1) + 1)) / (g.sW > 0 ? g.sW : 1) + 1;
   return d;

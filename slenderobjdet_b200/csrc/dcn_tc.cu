@@ -31,13 +31,14 @@ constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epi
 constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 
-// W [O][C][taps] -> per (tap, 64-channel block) a K-major 128B-swizzled tile [O rows][64 c] bf16,
-// tiles ordered (tap, cblock); also bias -> fp32.
+// W [O][C][taps] -> per (channel chunk of `cps`, tap, 64-channel block) a K-major 128B-swizzled tile
+// [O rows][64 c] bf16, tiles ordered (chunk, tap, block-in-chunk) = the K order of the main loop;
+// also bias -> fp32.
 template <typename T>
 __global__ void __launch_bounds__(256) prep_weight_fwd_kernel(const T* __restrict__ w, const T* __restrict__ bias,
                                                               uint8_t* __restrict__ wimg,
-                                                              float* __restrict__ bias_f32, int O, int C, int taps) {
-  const int nkb = C / 64;
+                                                              float* __restrict__ bias_f32, int O, int C, int taps, int cps) {
+  const int kbps = cps / 64;
   const long long total = (long long)O * taps * (C / 8);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) prep_weight_fwd_kernel(const T* __restric
     pk.y = pack_bf16x2(v[2], v[3]);
     pk.z = pack_bf16x2(v[4], v[5]);
     pk.w = pack_bf16x2(v[6], v[7]);
-    const size_t tile = (size_t)tap * nkb + (c >> 6);
+    const size_t tile = ((size_t)(c / cps) * taps + tap) * kbps + ((c % cps) >> 6);
     *reinterpret_cast<uint4*>(wimg + tile * ((size_t)O * 128) + sw128_offset(o, (c & 63) >> 3)) = pk;
   }
   if (bias_f32 && blockIdx.x == 0)
@@ -68,8 +69,24 @@ struct Sample {
   float w[4];   // bilinear weight * mask (0 when the corner does not contribute)
 };
 
-__device__ __forceinline__ Sample make_sample(const Geo& g, const float* __restrict__ off,
-                                              const float* __restrict__ mask, bool valid, int n, int ho,
+// raw (dy, dx, mask) of one (pixel, tap): fetched one tap ahead so the loads overlap the gather
+struct RawOff {
+  float dy, dx, m;
+};
+__device__ __forceinline__ RawOff fetch_raw(const Geo& g, const float* __restrict__ off,
+                                            const float* __restrict__ mask, bool valid, int n, int ho, int wo,
+                                            int tap) {
+  RawOff r = {0.f, 0.f, 1.f};
+  if (!valid) return r;
+  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
+  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
+  r.dy = __ldg(o);
+  r.dx = __ldg(o + hw);
+  if (mask) r.m = __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo);
+  return r;
+}
+
+__device__ __forceinline__ Sample make_sample(const Geo& g, const RawOff raw, bool valid, int n, int ho,
                                               int wo, int tap) {
   Sample s;
 #pragma unroll
@@ -78,13 +95,11 @@ __device__ __forceinline__ Sample make_sample(const Geo& g, const float* __restr
     s.w[k] = 0.f;
   }
   if (!valid) return s;
-  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
-  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
   const int i = tap / g.KW, j = tap - i * g.KW;
-  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + __ldg(o);
-  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + __ldg(o + hw);
+  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + raw.dy;
+  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + raw.dx;
   if (!(h > -1.f && w > -1.f && h < (float)g.H && w < (float)g.W)) return s;
-  const float m = mask ? __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo) : 1.f;
+  const float m = raw.m;
   const int h_low = (int)floorf(h), w_low = (int)floorf(w);
   const int h_high = h_low + 1, w_high = w_low + 1;
   const float lh = h - h_low, lw = w - w_low, hh = 1.f - lh, hw_ = 1.f - lw;
@@ -217,8 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
       tc_fence_after_sync();
       const long long pix = (long long)tile * TILE_M + q * 32 + lane;
       const bool valid = pix < g.P();
-      const int n = valid ? (int)(pix / hw) : 0;
-      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
+      int n = 0, eho = 0, ewo = 0;
+      if (valid) decode_q(g, pix, n, eho, ewo);
+      const int rem = eho * g.Wo + ewo;
       for (int c0 = 0; c0 < O; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
@@ -250,15 +266,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
       // the pixel whose sampling descriptors this lane computes (lanes >= PIX_PER_WARP idle there)
       const long long pix = (long long)tile * TILE_M + pw * PIX_PER_WARP + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
-      const int n = valid ? (int)(pix / hw) : 0;
-      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
-      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
-      for (int tap = 0; tap < taps; ++tap) {
-        const Sample mine = make_sample(g, p.off, p.mask, valid, n, ho, wo, tap);
-        for (int ch = 0; ch < nchunks; ++ch) {
+      int n = 0, ho = 0, wo = 0;
+      if (valid) decode_q(g, pix, n, ho, wo);
+      // K order: channel chunk outermost, taps inside -- the chunk's 3x3 neighbourhood of the tile
+      // (~180 input pixels x CPS channels) stays L1-resident across the nine taps.
+      RawOff raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, 0);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const __nv_bfloat16* xc = p.xp + ch * CPS + lig * 8;
+        for (int tap = 0; tap < taps; ++tap) {
+          const Sample mine = make_sample(g, raw, valid, n, ho, wo, tap);
+          {  // prefetch the next tap's offsets (next chunk restarts at tap 0; next tile refetches)
+            const int nt = tap + 1 < taps ? tap + 1 : 0;
+            raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, nt);
+          }
           mbar_wait(&a_empty[as], ap ^ 1);
           uint8_t* stage = sA + (size_t)as * A_BYTES;
-          const __nv_bfloat16* xc = p.xp + ch * CPS + lig * 8;
 #pragma unroll 4
           for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
             const int src = it * PPI + grp;
@@ -363,9 +385,9 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   const long long wtotal = (long long)g.O * g.taps() * (g.C / 8);
   const int wblocks = (int)((wtotal + 255) / 256 < 1184 ? (wtotal + 255) / 256 : 1184);
   if (io_dtype == SDB_F32)
-    prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps());
+    prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8);
   else
-    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps()); SDB_LAUNCHED(1);
+    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
 
   FwdParams p;

@@ -45,16 +45,18 @@ inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 // 128B-swizzled (K-major for dgrad's A operand, MN-major for wgrad's A operand).  Zero padded.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_gy_kernel(const T* __restrict__ gy, uint8_t* __restrict__ img,
-                                                      int O, int hw, long long P, int okb) {
+                                                      const Geo g, int okb) {
+  const int O = g.O, hw = g.Ho * g.Wo;
   __shared__ float s[64][129];
   const int tile = blockIdx.x, kb = blockIdx.y;
   const int tid = threadIdx.x;
   {
     const int px = tid & 127;
     const long long p = (long long)tile * TILE_M + px;
-    const bool valid = p < P;
-    const int n = valid ? (int)(p / hw) : 0;
-    const int rem = valid ? (int)(p - (long long)n * hw) : 0;
+    const bool valid = p < g.P();
+    int n = 0, ho = 0, wo = 0;
+    if (valid) decode_q(g, p, n, ho, wo);
+    const int rem = ho * g.Wo + wo;
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
       const int ol = (tid >> 7) + 2 * j, o = kb * 64 + ol;
@@ -353,9 +355,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
-      const int n = valid ? (int)(pix / hw) : 0;
-      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
-      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+      int n = 0, ho = 0, wo = 0;
+      if (valid) decode_q(g, pix, n, ho, wo);
+      const int rem = ho * g.Wo + wo;
       for (int tap = 0; tap < taps; ++tap) {
         const BSample mine = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
         float my_gy = 0.f, my_gx = 0.f, my_gm = 0.f;   // results for the pixel this lane owns
@@ -589,9 +591,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
     for (int tile = t0; tile < t1; ++tile) {
       const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
-      const int n = valid ? (int)(pix / hw) : 0;
-      const int rem = valid ? (int)(pix - (long long)n * hw) : 0;
-      const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+      int n = 0, ho = 0, wo = 0;
+      if (valid) decode_q(g, pix, n, ho, wo);
+      const int rem = ho * g.Wo + wo;
       // forward-style descriptor (weights already x mask, zero outside)
       int midx[4] = {0, 0, 0, 0};
       float mw[4] = {0.f, 0.f, 0.f, 0.f};
@@ -663,7 +665,7 @@ BwdWs bwd_ws(int op, const Geo& g) {
 template <typename T>
 int pack_gy(const void* gy, uint8_t* img, const Geo& g, cudaStream_t st) {
   dim3 grid(cdiv(g.P(), TILE_M), okb_of(g));
-  pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g.O, g.HWo(), g.P(), okb_of(g)); SDB_LAUNCHED(1);
+  pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g, okb_of(g)); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }

@@ -18,6 +18,29 @@ constexpr int TILE_M = 128;
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
+// Pixel walk order of the tensor-core kernels.  Output pixels of one image are enumerated band by
+// band (g.th rows), inside a band column-group by column-group (g.tw columns), row-major inside a
+// group; a 128-pixel tile is 128 consecutive indices q of that order, i.e. (for th*tw == 128) a
+// compact th x tw patch.  Compact patches are what lets the bilinear gather hit in L1: the 3x3
+// neighbourhood of an 8x16 patch is ~180 input pixels instead of 3 rows x 130.  Partial bands /
+// groups at the image border are shorter, never padded, so ceil(P/128) tiles cover P pixels.
+// th = 1, tw >= Wo degenerates to plain row-major order.
+__device__ __forceinline__ void decode_q(const Geo& g, long long q, int& n, int& ho, int& wo) {
+  const int hw = g.Ho * g.Wo;
+  n = (int)(q / hw);
+  const int r = (int)(q - (long long)n * hw);
+  const int band_px = g.th * g.Wo;
+  const int band = r / band_px, rb = r - band * band_px;
+  const int rows_b = min(g.th, g.Ho - band * g.th);
+  const int grp_px = rows_b * g.tw;
+  const int cg = rb / grp_px, rg = rb - cg * grp_px;
+  const int cols_g = min(g.tw, g.Wo - cg * g.tw);
+  const int dy = rg / cols_g;
+  ho = band * g.th + dy;
+  wo = cg * g.tw + (rg - dy * cols_g);
+}
+
+// ------------------------------------------------------------------------------------------------
 // layout / dtype conversion kernels
 // ------------------------------------------------------------------------------------------------
 template <typename T>
