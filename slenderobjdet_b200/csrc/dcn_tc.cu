@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ GDesc sdesc[NPW][TILE_M / NPW];
 
   const Geo& g = p.g;
   const int O = g.O, C = g.C, taps = g.KH * g.KW, nchunks = C / CPS;
@@ -272,40 +273,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
       // (~180 input pixels x CPS channels) stays L1-resident across the nine taps.
       RawOff raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, 0);
       for (int ch = 0; ch < nchunks; ++ch) {
-        const __nv_bfloat16* xc = p.xp + ch * CPS + lig * 8;
+        const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * CPS + lig * 8);
         for (int tap = 0; tap < taps; ++tap) {
           const Sample mine = make_sample(g, raw, valid, n, ho, wo, tap);
           {  // prefetch the next tap's offsets (next chunk restarts at tap 0; next tile refetches)
             const int nt = tap + 1 < taps ? tap + 1 : 0;
             raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, nt);
           }
-          mbar_wait(&a_empty[as], ap ^ 1);
-          uint8_t* stage = sA + (size_t)as * A_BYTES;
-#pragma unroll 4
-          for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
-            const int src = it * PPI + grp;
-            int idx[4];
-            float w[4];
+          // publish this warp's descriptors for the tap (written by lanes < PIX_PER_WARP)
+          __syncwarp();
+          if (lane < PIX_PER_WARP) {
+            GDesc d;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              idx[k] = __shfl_sync(0xffffffffu, mine.idx[k], src);
-              w[k] = __shfl_sync(0xffffffffu, mine.w[k], src);
+              d.off[k] = (uint32_t)mine.idx[k] * (uint32_t)(C / 8);
+              d.w2[k] = pack_bf16x2(mine.w[k], mine.w[k]);
             }
-            uint4 v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              v[k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)idx[k] * C));
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) fma8(acc, v[k], w[k]);
-            uint4 pk;
-            pk.x = pack_bf16x2(acc[0], acc[1]);
-            pk.y = pack_bf16x2(acc[2], acc[3]);
-            pk.z = pack_bf16x2(acc[4], acc[5]);
-            pk.w = pack_bf16x2(acc[6], acc[7]);
-            const int row = pw * PIX_PER_WARP + src;
-            *reinterpret_cast<uint4*>(stage + (lig >> 3) * (TILE_M * 128) + sw128_offset(row, lig & 7)) = pk;
+            *reinterpret_cast<uint4*>(sdesc[pw][lane].off) = *reinterpret_cast<const uint4*>(d.off);
+            *reinterpret_cast<uint4*>(sdesc[pw][lane].w2) = *reinterpret_cast<const uint4*>(d.w2);
           }
+          __syncwarp();
+          mbar_wait(&a_empty[as], ap ^ 1);
+          gather_stage_bf16<LPP, PIX_PER_WARP>(x16, sdesc[pw], sA + (size_t)as * A_BYTES, pw * PIX_PER_WARP, lane);
           fence_proxy_async_smem();
           mbar_arrive(&a_full[as]);
           if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }

@@ -448,45 +448,13 @@ struct WgradParams {
 };
 
 template <int NCH>
-__device__ __forceinline__ void gather_stage(const Geo& g, const __nv_bfloat16* __restrict__ xc, int C,
-                                             const int (&midx)[4], const float (&mw)[4], uint8_t* stage,
-                                             int warp_row0, int lane) {
-  constexpr int LPB = NCH / 8, PPI = 32 / LPB;
-  const int grp = lane / LPB, lig = lane % LPB;
-#pragma unroll 4
-  for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
-    const int src = it * PPI + grp;
-    int idx[4];
-    float w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      idx[k] = __shfl_sync(0xffffffffu, midx[k], src);
-      w[k] = __shfl_sync(0xffffffffu, mw[k], src);
-    }
-    uint4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)idx[k] * C));
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) fma8(acc, v[k], w[k]);
-    uint4 pk;
-    pk.x = pack_bf16x2(acc[0], acc[1]);
-    pk.y = pack_bf16x2(acc[2], acc[3]);
-    pk.z = pack_bf16x2(acc[4], acc[5]);
-    pk.w = pack_bf16x2(acc[6], acc[7]);
-    const int row = warp_row0 + src;
-    *reinterpret_cast<uint4*>(stage + (lig >> 3) * (TILE_M * 128) + sw128_offset(row, lig & 7)) = pk;
-  }
-  (void)g;
-}
-
-template <int NCH>
 __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const WgradParams p) {
   constexpr int LPB = NCH / 8;
   constexpr uint32_t G_BYTES = TILE_M * NCH * 2;   // gathered col tile [NCH/64 blocks][128 px][64 c]
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t g_full[4], g_empty[4], y_full[4], y_empty[4], acc_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ GDesc sdesc[NSW][PIX_PER_WARP];
 
   const Geo& g = p.g;
   const int C = g.C, O = g.O, taps = g.KH * g.KW, nch = C / NCH, okb = p.okb, mh_n = okb / 2;
@@ -587,28 +555,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
     const int sw = warp - FIRST_SW;
     const int hw = g.Ho * g.Wo;
     uint32_t gs = 0, gp = 0;
-    const __nv_bfloat16* xc = p.xp + ch * NCH + (lane % LPB) * 8;
+    const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * NCH + (lane % LPB) * 8);
     for (int tile = t0; tile < t1; ++tile) {
       const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
       int n = 0, ho = 0, wo = 0;
       if (valid) decode_q(g, pix, n, ho, wo);
       const int rem = ho * g.Wo + wo;
-      // forward-style descriptor (weights already x mask, zero outside)
-      int midx[4] = {0, 0, 0, 0};
-      float mw[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        const BSample b = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
-        const float wk[4] = {(1.f - b.lh) * (1.f - b.lw), (1.f - b.lh) * b.lw, b.lh * (1.f - b.lw), b.lh * b.lw};
+      // forward-style descriptor (weights already x mask, zero outside) -> shared memory
+      __syncwarp();
+      if (lane < PIX_PER_WARP) {
+        const BSample bs = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
+        const float wk[4] = {(1.f - bs.lh) * (1.f - bs.lw), (1.f - bs.lh) * bs.lw, bs.lh * (1.f - bs.lw), bs.lh * bs.lw};
+        GDesc d;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (b.idx[k] >= 0) {
-            midx[k] = b.idx[k];
-            mw[k] = wk[k] * b.m;
-          }
+        for (int k = 0; k < 4; ++k) {
+          const bool on = bs.idx[k] >= 0;
+          d.off[k] = on ? (uint32_t)bs.idx[k] * (uint32_t)(C / 8) : 0u;
+          const float wv = on ? wk[k] * bs.m : 0.f;
+          d.w2[k] = pack_bf16x2(wv, wv);
+        }
+        *reinterpret_cast<uint4*>(sdesc[sw][lane].off) = *reinterpret_cast<const uint4*>(d.off);
+        *reinterpret_cast<uint4*>(sdesc[sw][lane].w2) = *reinterpret_cast<const uint4*>(d.w2);
       }
+      __syncwarp();
       mbar_wait(&g_empty[gs], gp ^ 1);
-      gather_stage<NCH>(g, xc, C, midx, mw, sG + (size_t)gs * G_BYTES, sw * PIX_PER_WARP, lane);
+      gather_stage_bf16<LPB, PIX_PER_WARP>(x16, sdesc[sw], sG + (size_t)gs * G_BYTES, sw * PIX_PER_WARP, lane);
       fence_proxy_async_smem();
       mbar_arrive(&g_full[gs]);
       if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }

@@ -85,6 +85,71 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const uint4 v, float w) {
   acc[7] = fmaf(w, __uint_as_float(v.w & 0xffff0000u), acc[7]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gather of one (tile, tap, channel chunk) into a 128B-swizzled operand stage, shared by the
+// forward kernel (A operand, K-major) and the weight-gradient kernel (B operand, MN-major): both
+// want rows = pixels, 64 channels (128 B) per row, k-blocks TILE_M*128 bytes apart.
+//
+// Per (pixel, tap) a 32-byte descriptor sits in shared memory: the four corner rows as offsets in
+// 16-byte units into the NHWC bf16 input, and the four bilinear weights (x mask) as packed
+// bf16x2 (w, w).  A group of LPP lanes handles one pixel, 8 channels per lane: four 16-byte loads,
+// 16 packed bf16x2 FMAs (HFMA2.BF16), one 16-byte swizzled store -- ~35 instructions per 2 pixels
+// where fp32 interpolation with unpack/pack needed ~110.  The sampled value is rounded to bf16
+// anyway (it is a tensor-core operand); interpolating in bf16 adds ~3 more roundings per sample.
+struct __align__(16) GDesc {
+  uint32_t off[4];  // corner row offset, units of 16 bytes (0 for a corner that does not contribute)
+  uint32_t w2[4];   // bf16x2 (w, w); 0 for a corner that does not contribute
+};
+
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// x16: input viewed as 16-byte vectors, already advanced to (chunk base + this lane's 8 channels).
+// sdesc: this warp's PIXW descriptors.  stage: operand stage base.  row0: first tile row of the warp.
+template <int LPP, int PIXW>
+__device__ __forceinline__ void gather_stage_bf16(const uint4* __restrict__ x16, const GDesc* __restrict__ sdesc,
+                                                  uint8_t* __restrict__ stage, int row0, int lane) {
+  constexpr int PPI = 32 / LPP;
+  constexpr int ITERS = PIXW / PPI;
+  constexpr int U = ITERS < 4 ? ITERS : 4;   // iterations whose 4 loads each are in flight together
+  const int grp = lane / LPP, lig = lane % LPP;
+  uint8_t* dst = stage + (lig >> 3) * (TILE_M * 128);
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += U) {
+    uint4 o[U], w[U], v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int src = (it0 + u) * PPI + grp;
+      o[u] = *reinterpret_cast<const uint4*>(sdesc[src].off);
+      w[u] = *reinterpret_cast<const uint4*>(sdesc[src].w2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      v[u][0] = __ldg(x16 + o[u].x);
+      v[u][1] = __ldg(x16 + o[u].y);
+      v[u][2] = __ldg(x16 + o[u].z);
+      v[u][3] = __ldg(x16 + o[u].w);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint4 a;
+      a.x = bf2_fma(w[u].w, v[u][3].x, bf2_fma(w[u].z, v[u][2].x, bf2_fma(w[u].y, v[u][1].x, bf2_mul(w[u].x, v[u][0].x))));
+      a.y = bf2_fma(w[u].w, v[u][3].y, bf2_fma(w[u].z, v[u][2].y, bf2_fma(w[u].y, v[u][1].y, bf2_mul(w[u].x, v[u][0].y))));
+      a.z = bf2_fma(w[u].w, v[u][3].z, bf2_fma(w[u].z, v[u][2].z, bf2_fma(w[u].y, v[u][1].z, bf2_mul(w[u].x, v[u][0].z))));
+      a.w = bf2_fma(w[u].w, v[u][3].w, bf2_fma(w[u].z, v[u][2].w, bf2_fma(w[u].y, v[u][1].w, bf2_mul(w[u].x, v[u][0].w))));
+      *reinterpret_cast<uint4*>(dst + sw128_offset(row0 + (it0 + u) * PPI + grp, lig & 7)) = a;
+    }
+  }
+}
+
 template <typename T>
 inline int pack_input(const void* x, __nv_bfloat16* xp, const Geo& g, cudaStream_t st) {
   const int HW = g.H * g.W;
