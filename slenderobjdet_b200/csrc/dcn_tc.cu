@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ GDesc sdesc[NPW][TILE_M / NPW];
 
   const Geo& g = p.g;
   const int O = g.O, C = g.C, taps = g.KH * g.KW, nchunks = C / CPS;
@@ -259,47 +258,86 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     }
   } else {
     // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
-    const int pw = warp - FIRST_PW;
+    // (1) per tile, the descriptors of this warp's 16 pixels for EVERY tap go to shared memory once;
+    // (2) the gather then runs as one continuous stream over (chunk, tap, pixel pair) with a 4-slot
+    //     register ring: the four 16-byte loads of iteration i+4 are issued right after iteration i
+    //     is consumed, across stage boundaries, so 16 loads per warp stay in flight instead of every
+    //     warp paying the full memory latency once per stage in lock-step.
+    constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
+    constexpr int RING = 4;
+    static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
+    const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
-    const int hw = g.Ho * g.Wo;
+    GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
+    const uint4* xbase = reinterpret_cast<const uint4*>(p.xp) + lig;
+    const int nstages = taps * nchunks;
     uint32_t as = 0, ap = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      // the pixel whose sampling descriptors this lane computes (lanes >= PIX_PER_WARP idle there)
-      const long long pix = (long long)tile * TILE_M + pw * PIX_PER_WARP + lane;
-      const bool valid = lane < PIX_PER_WARP && pix < g.P();
-      int n = 0, ho = 0, wo = 0;
-      if (valid) decode_q(g, pix, n, ho, wo);
-      // K order: channel chunk outermost, taps inside -- the chunk's 3x3 neighbourhood of the tile
-      // (~180 input pixels x CPS channels) stays L1-resident across the nine taps.
-      RawOff raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, 0);
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * CPS + lig * 8);
-        for (int tap = 0; tap < taps; ++tap) {
-          const Sample mine = make_sample(g, raw, valid, n, ho, wo, tap);
-          {  // prefetch the next tap's offsets (next chunk restarts at tap 0; next tile refetches)
-            const int nt = tap + 1 < taps ? tap + 1 : 0;
-            raw = fetch_raw(g, p.off, p.mask, valid, n, ho, wo, nt);
-          }
-          // publish this warp's descriptors for the tap (written by lanes < PIX_PER_WARP)
-          __syncwarp();
-          if (lane < PIX_PER_WARP) {
-            GDesc d;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              d.off[k] = (uint32_t)mine.idx[k] * (uint32_t)(C / 8);
-              d.w2[k] = pack_bf16x2(mine.w[k], mine.w[k]);
-            }
-            *reinterpret_cast<uint4*>(sdesc[pw][lane].off) = *reinterpret_cast<const uint4*>(d.off);
-            *reinterpret_cast<uint4*>(sdesc[pw][lane].w2) = *reinterpret_cast<const uint4*>(d.w2);
-          }
-          __syncwarp();
-          mbar_wait(&a_empty[as], ap ^ 1);
-          gather_stage_bf16<LPP, PIX_PER_WARP>(x16, sdesc[pw], sA + (size_t)as * A_BYTES, pw * PIX_PER_WARP, lane);
-          fence_proxy_async_smem();
-          mbar_arrive(&a_full[as]);
-          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+      {
+        const int px = lane % PIX_PER_WARP;
+        const long long pix = (long long)tile * TILE_M + r0 + px;
+        const bool valid = pix < g.P();
+        int n = 0, ho = 0, wo = 0;
+        if (valid) decode_q(g, pix, n, ho, wo);
+        __syncwarp();  // every lane is done reading the previous tile's descriptors
+        for (int tap = lane / PIX_PER_WARP; tap < taps; tap += 32 / PIX_PER_WARP) {
+          const Sample sm_ = make_sample(g, fetch_raw(g, p.off, p.mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
+          uint4 o, w;
+          o.x = (uint32_t)sm_.idx[0] * (uint32_t)(C / 8); o.y = (uint32_t)sm_.idx[1] * (uint32_t)(C / 8);
+          o.z = (uint32_t)sm_.idx[2] * (uint32_t)(C / 8); o.w = (uint32_t)sm_.idx[3] * (uint32_t)(C / 8);
+          w.x = pack_bf16x2(sm_.w[0], sm_.w[0]); w.y = pack_bf16x2(sm_.w[1], sm_.w[1]);
+          w.z = pack_bf16x2(sm_.w[2], sm_.w[2]); w.w = pack_bf16x2(sm_.w[3], sm_.w[3]);
+          GDesc* d = sD + tap * TILE_M + r0 + px;
+          *reinterpret_cast<uint4*>(d->off) = o;
+          *reinterpret_cast<uint4*>(d->w2) = w;
         }
+        __syncwarp();
       }
+      uint4 v[RING][4], wq[RING];
+      // issue the loads of iteration `it` of the stage (tap_, ch_) into ring slot `slot`
+#define SDB_ISSUE(tap_, ch_, it_, slot_)                                                     \
+      {                                                                                          \
+        const GDesc* d_ = sD + (tap_) * TILE_M + r0 + (it_) * PPI + grp;                         \
+        const uint4 o_ = *reinterpret_cast<const uint4*>(d_->off);                               \
+        wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                     \
+        const uint4* xb_ = xbase + (ch_) * (CPS / 8);                                            \
+        v[slot_][0] = __ldg(xb_ + o_.x);                                                         \
+        v[slot_][1] = __ldg(xb_ + o_.y);                                                         \
+        v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
+        v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
+      }
+#pragma unroll
+      for (int u = 0; u < RING; ++u) SDB_ISSUE(0, 0, u, u)
+      int tap = 0, ch = 0;
+      for (int st = 0; st < nstages; ++st) {
+        int ntap = tap + 1, nch = ch;   // K order: chunk outermost, taps inside (L1-friendly)
+        if (ntap == taps) { ntap = 0; ++nch; }
+        const bool has_next = st + 1 < nstages;
+        mbar_wait(&a_empty[as], ap ^ 1);
+        uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          constexpr int dummy = 0; (void)dummy;
+          const int slot = it % RING;
+          uint4 a;
+          a.x = bf2_fma(wq[slot].w, v[slot][3].x, bf2_fma(wq[slot].z, v[slot][2].x, bf2_fma(wq[slot].y, v[slot][1].x, bf2_mul(wq[slot].x, v[slot][0].x))));
+          a.y = bf2_fma(wq[slot].w, v[slot][3].y, bf2_fma(wq[slot].z, v[slot][2].y, bf2_fma(wq[slot].y, v[slot][1].y, bf2_mul(wq[slot].x, v[slot][0].y))));
+          a.z = bf2_fma(wq[slot].w, v[slot][3].z, bf2_fma(wq[slot].z, v[slot][2].z, bf2_fma(wq[slot].y, v[slot][1].z, bf2_mul(wq[slot].x, v[slot][0].z))));
+          a.w = bf2_fma(wq[slot].w, v[slot][3].w, bf2_fma(wq[slot].z, v[slot][2].w, bf2_fma(wq[slot].y, v[slot][1].w, bf2_mul(wq[slot].x, v[slot][0].w))));
+          *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
+          if (it + RING < ITERS) {
+            SDB_ISSUE(tap, ch, it + RING, slot)
+          } else if (has_next) {
+            SDB_ISSUE(ntap, nch, it + RING - ITERS, slot)
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[as]);
+        if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+        tap = ntap;
+        ch = nch;
+      }
+#undef SDB_ISSUE
     }
   }
   tc_fence_before_sync();
@@ -348,6 +386,7 @@ bool tc_supported(const Geo& g, const char** why) {
   if (g.dgroups != 1) { *why = "deformable_groups != 1"; return false; }
   if (g.C % 64 != 0) { *why = "C_in not a multiple of 64"; return false; }
   if (g.O % 16 != 0 || g.O < 16 || g.O > 256) { *why = "C_out must be a multiple of 16 in [16,256]"; return false; }
+  if (g.taps() > 16) { *why = "more than 16 kernel taps (per-tile descriptors would not fit in shared memory)"; return false; }
   if ((long long)g.N * g.H * g.W * 1LL >= (1LL << 31) / 1 || g.P() * g.O >= (1LL << 40)) { *why = "tensor too large"; return false; }
   return true;
 }
@@ -384,19 +423,20 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   p.num_tiles = cdiv(g.P(), TILE_M);
   const int lpp = lanes_per_pixel(g);
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
+  const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
   size_t budget = 200 * 1024;
   if (const char* e = getenv("SDB_TC_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
-  if (budget > 226 * 1024) budget = 226 * 1024;
+  if (budget > 222 * 1024) budget = 222 * 1024;
   p.nsa = 2;
   if (const char* e = getenv("SDB_TC_NSA")) p.nsa = atoi(e);
   if (p.nsa < 2) p.nsa = 2;
   if (p.nsa > MAX_A_STAGES) p.nsa = MAX_A_STAGES;
-  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + 1024 > budget) --p.nsa;
-  long long nsb = ((long long)budget - 1024 - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
+  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + d_bytes + 1024 > budget) --p.nsa;
+  long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
   if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
   SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   p.nsb = (int)nsb;
-  const size_t smem = p.nsa * a_bytes + p.nsb * b_bytes + 1024;
+  const size_t smem = p.nsa * a_bytes + p.nsb * b_bytes + d_bytes + 1024;
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   const bool obf = io_dtype == SDB_BF16;
   if (lpp == 32) return obf ? launch_fwd<32, true>(p, smem, grid, st) : launch_fwd<32, false>(p, smem, grid, st);

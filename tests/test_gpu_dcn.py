@@ -188,18 +188,20 @@ def test_dfconv2d_and_grad_flow():
     (2, 192, 9, 10, 48, 3, 2, 1, 1, False, 1.0),
     (1, 64, 12, 9, 16, 1, 1, 0, 1, False, 1.0),
     (1, 512, 10, 13, 128, 3, 1, 2, 2, True, 3.0),
-    (3, 256, 20, 19, 240, 5, 1, 2, 1, False, 30.0),
+    (3, 256, 20, 19, 240, 3, 1, 1, 1, False, 30.0),
+    (1, 64, 11, 12, 32, (2, 4), 1, 1, 1, False, 1.0),
 ])
 def test_tensor_core_forward_vs_oracle(shape):
     """tcgen05 forward (bf16 operands, fp32 accumulate) vs the CPU oracle, rel <= 1e-2."""
     N, C, H, W, O, k, st, pd, dl, mod, sigma = shape
+    kh, kw = (k, k) if isinstance(k, int) else k
     g = torch.Generator().manual_seed(C + O + H)
-    Ho = (H + 2 * pd - (dl * (k - 1) + 1)) // st + 1
-    Wo = (W + 2 * pd - (dl * (k - 1) + 1)) // st + 1
+    Ho = (H + 2 * pd - (dl * (kh - 1) + 1)) // st + 1
+    Wo = (W + 2 * pd - (dl * (kw - 1) + 1)) // st + 1
     x = torch.randn(N, C, H, W, generator=g)
-    w = torch.randn(O, C, k, k, generator=g) * 0.05
-    off = torch.randn(N, 2 * k * k, Ho, Wo, generator=g) * sigma
-    m = torch.sigmoid(torch.randn(N, k * k, Ho, Wo, generator=g)) if mod else None
+    w = torch.randn(O, C, kh, kw, generator=g) * 0.05
+    off = torch.randn(N, 2 * kh * kw, Ho, Wo, generator=g) * sigma
+    m = torch.sigmoid(torch.randn(N, kh * kw, Ho, Wo, generator=g)) if mod else None
     b = torch.randn(O, generator=g) if mod else None
     yo = odcn.forward(x.numpy(), off.numpy(), w.numpy(), mask=None if m is None else m.numpy(),
                       bias=None if b is None else b.numpy(), stride=st, padding=pd, dilation=dl)
@@ -215,3 +217,18 @@ def test_tensor_core_forward_vs_oracle(shape):
                       mask=None if m is None else m.numpy(), bias=None if b is None else b.numpy(),
                       stride=st, padding=pd, dilation=dl)
     assert rel_err(y.cpu().numpy(), yq) < 6e-3  # bf16 interpolation + bf16 operand rounding of the sample
+
+
+def test_auto_mode_falls_back_to_fp32_kernels_for_unsupported_geometry():
+    """5x5 taps / C_in=8 are outside the tensor-core path: 'auto' must run the exact fp32 kernels
+    (still CUDA, never CPU) and 'bf16' must refuse loudly."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 64, 9, 10, generator=g)
+    w = torch.randn(16, 64, 5, 5, generator=g) * 0.05
+    off = torch.randn(1, 50, 9, 10, generator=g)
+    yo = odcn.forward(x.numpy(), off.numpy(), w.numpy(), stride=1, padding=2)
+    with sdb.dcn_math("auto"), torch.no_grad():
+        y = sdb.deform_conv(x.cuda(), off.cuda(), w.cuda(), 1, 2, 1, 1, 1)
+    assert rel_err(y.cpu().numpy(), yo) < TOL["fp32"]
+    with sdb.dcn_math("bf16"), pytest.raises(RuntimeError):
+        sdb.deform_conv(x.cuda(), off.cuda(), w.cuda(), 1, 2, 1, 1, 1)
