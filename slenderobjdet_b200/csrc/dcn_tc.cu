@@ -13,6 +13,13 @@
 //     the pixel dimension, which is the TMEM lane dimension).
 // The grid is persistent: one CTA per SM walking tiles round-robin.
 //
+// The same kernel, MODE_DX, computes grad_input as a second implicit GEMM instead of a scatter:
+//   dX[q, c] = sum_{tap, o} G[q, (tap,o)] * W[o, c, tap],   G[q, (tap,o)] = sum_e w_e * dY[p_e, o]
+// where the list of (output pixel p_e, bilinear weight x mask w_e) that touch input pixel q through
+// tap `tap` comes from a CSR index built per call (dcn_tc_bwd.cu: count / scan / fill).  The gather
+// warps walk that list instead of four fixed corners; everything else (weights by bulk copy, tcgen05
+// into TMEM, NCHW epilogue) is shared with the forward pass.  No atomics touch grad_input.
+//
 // Reference semantics being reproduced: d2/layers/csrc/deformable/deform_conv_cuda_kernel.cu
 // :96-130 (bilinear), :216-288 (im2col + validity), :785-868 (mask), deform_conv_cuda.cu:397-409 (GEMM).
 #include <stdlib.h>
@@ -30,6 +37,7 @@ constexpr int NPW = 8;                       // gather producer warps
 constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
 constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+constexpr size_t DX_STATIC_SMEM = 4096;      // MODE_DX: s_range
 
 // W [O][C][taps] -> per (channel chunk of `cps`, tap, 64-channel block) a K-major 128B-swizzled tile
 // [O rows][64 c] bf16, tiles ordered (chunk, tap, block-in-chunk) = the K order of the main loop;
@@ -113,18 +121,29 @@ __device__ __forceinline__ Sample make_sample(const Geo& g, const RawOff raw, bo
 }
 
 struct FwdParams {
-  const __nv_bfloat16* xp;  // NHWC bf16
+  const __nv_bfloat16* xp;  // MODE_FWD: NHWC bf16 input
   const float* off;
   const float* mask;
+  const GDesc* desc;        // MODE_DX: first four entries of every transposed list, key = (tile*taps + tap)*128 + row
+  const int* start;         // MODE_DX: overflow CSR row starts (same key), nkeys + 1 values
+  const uint2* entries;     // MODE_DX: overflow entries {row offset of dY in 16 B units, w_bf16 << 16 | row in tile}
   const uint8_t* wimg;
-  const float* bias;        // fp32 [O] or nullptr
-  void* out;                // NCHW, f32 or bf16
+  const float* bias;        // fp32 [ncols] or nullptr
+  void* out;                // NCHW, f32 or bf16: [mN][out_ch][mH][mW]
   Geo g;
+  int mH, mW;               // pixel grid of the GEMM's M dimension (output grid fwd, input grid dx)
+  long long mP;             // mN * mH * mW
+  int ncols, nnb;           // GEMM N per column block, number of column blocks (dx with C_in > 256)
+  int kch;                  // gathered channels per tap (C_in fwd, okb*64 dx)
+  int out_ch;               // channel count of `out`
+  int okb;
   int num_tiles, nsa, nsb;
 };
 
+constexpr int MODE_FWD = 0, MODE_DX = 1;
+
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
-template <int LPP, bool OUT_BF16>
+template <int LPP, bool OUT_BF16, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams p) {
   constexpr int CPS = LPP * 8;           // channels per A stage
   constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
@@ -140,7 +159,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   __shared__ uint32_t tmem_base_s;
 
   const Geo& g = p.g;
-  const int O = g.O, C = g.C, taps = g.KH * g.KW, nchunks = C / CPS;
+  const int O = p.ncols, C = p.kch, taps = g.KH * g.KW, nchunks = C / CPS;
+  const int num_work = p.num_tiles * p.nnb;
   const uint32_t B_BYTES = (uint32_t)O * 128u;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -176,12 +196,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     // ===== weight producer: bulk async copies of pre-swizzled [O x 64] tiles =====
     if (lane == 0) {
       uint32_t bs = 0, bp = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
         const int nkb_total = taps * (C / 64);
+        const uint8_t* wsrc = p.wimg + (size_t)(work % p.nnb) * nkb_total * B_BYTES;
         for (int kb = 0; kb < nkb_total; ++kb) {
           mbar_wait(&b_empty[bs], bp ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-          bulk_g2s(sB + (size_t)bs * B_BYTES, p.wimg + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
@@ -190,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_bf16(TILE_M, O, 0, 0);
     uint32_t as = 0, ap = 0, bs = 0, bp = 0, acc = 0, accp = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       mbar_wait(&acc_empty[acc], accp ^ 1);
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + acc * acc_stride;
@@ -225,16 +246,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   } else if (warp < FIRST_PW) {
     // ===== epilogue: TMEM -> registers -> NCHW global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int hw = g.Ho * g.Wo;
+    const int hw = p.mH * p.mW;
     uint32_t acc = 0, accp = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.nnb, ob = (work % p.nnb) * O;
       mbar_wait(&acc_full[acc], accp);
       tc_fence_after_sync();
       const long long pix = (long long)tile * TILE_M + q * 32 + lane;
-      const bool valid = pix < g.P();
+      const bool valid = pix < p.mP;
       int n = 0, eho = 0, ewo = 0;
-      if (valid) decode_q(g, pix, n, eho, ewo);
-      const int rem = eho * g.Wo + ewo;
+      if (valid) decode_pos(p.mH, p.mW, g.th, g.tw, pix, n, eho, ewo);
+      const int rem = eho * p.mW + ewo;
       for (int c0 = 0; c0 < O; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
@@ -244,8 +266,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           for (int j = 0; j < 32; ++j) {
             const int o = c0 + j;
             if (o < O) {
-              const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + o) : 0.f);
-              const size_t di = ((size_t)n * O + o) * hw + rem;
+              float v = __uint_as_float(r[j]);
+              const size_t di = ((size_t)n * p.out_ch + ob + o) * hw + rem;
+              if (MODE == MODE_DX) {   // grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it)
+                if (OUT_BF16) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out)[di]);
+                else          v += reinterpret_cast<const float*>(p.out)[di];
+              } else if (p.bias) {
+                v += __ldg(p.bias + o);
+              }
               if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[di] = __float2bfloat16_rn(v);
               else          reinterpret_cast<float*>(p.out)[di] = v;
             }
@@ -258,22 +286,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     }
   } else {
     // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
-    // (1) per tile, the descriptors of this warp's 16 pixels for EVERY tap go to shared memory once;
+    // (1) per tile, the descriptors (4 source rows + 4 weights) of this warp's 16 pixels for EVERY tap
+    //     go to shared memory once: MODE_FWD computes them from the offsets, MODE_DX copies the first
+    //     four entries of each transposed list (built by csr_fill_kernel) with cp.async;
     // (2) the gather then runs as one continuous stream over (chunk, tap, pixel pair) with a 4-slot
     //     register ring: the four 16-byte loads of iteration i+4 are issued right after iteration i
     //     is consumed, across stage boundaries, so 16 loads per warp stay in flight instead of every
-    //     warp paying the full memory latency once per stage in lock-step.
+    //     warp paying the full memory latency once per stage in lock-step;
+    // (3) MODE_DX only: lists longer than four entries continue in an overflow index; those entries are
+    //     added to the rows just written (read-modify-write of the A stage) before the stage is published.
     constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
+    constexpr int RPG = PIX_PER_WARP / PPI;     // MODE_DX overflow: rows per lane group
+    __shared__ int s_range[MODE == MODE_DX ? NPW : 1][16][PPI + 1];   // overflow entry index at lane-group boundaries
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
     GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
     const uint4* xbase = reinterpret_cast<const uint4*>(p.xp) + lig;
     const int nstages = taps * nchunks;
     uint32_t as = 0, ap = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.nnb;
+      if constexpr (MODE == MODE_FWD) {
         const int px = lane % PIX_PER_WARP;
         const long long pix = (long long)tile * TILE_M + r0 + px;
         const bool valid = pix < g.P();
@@ -291,6 +326,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           *reinterpret_cast<uint4*>(d->off) = o;
           *reinterpret_cast<uint4*>(d->w2) = w;
         }
+        __syncwarp();
+      } else {
+        __syncwarp();
+        constexpr int U16 = PIX_PER_WARP * (int)sizeof(GDesc) / 16;   // 16-byte units per (warp, tap) slice
+        for (int i = lane; i < taps * U16; i += 32) {
+          const int tap = i / U16, u = i - tap * U16;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.desc + ((size_t)tile * taps + tap) * TILE_M + r0) + u * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sD + tap * TILE_M + r0) + u * 16)),
+                       "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int i = lane; i < taps * (PPI + 1); i += 32) {
+          const int tap = i / (PPI + 1), gq = i - tap * (PPI + 1);
+          s_range[pw][tap][gq] = __ldg(p.start + ((size_t)tile * taps + tap) * TILE_M + r0 + gq * RPG);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
       }
       uint4 v[RING][4], wq[RING];
@@ -317,7 +368,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-          constexpr int dummy = 0; (void)dummy;
           const int slot = it % RING;
           uint4 a;
           a.x = bf2_fma(wq[slot].w, v[slot][3].x, bf2_fma(wq[slot].z, v[slot][2].x, bf2_fma(wq[slot].y, v[slot][1].x, bf2_mul(wq[slot].x, v[slot][0].x))));
@@ -329,6 +379,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
             SDB_ISSUE(tap, ch, it + RING, slot)
           } else if (has_next) {
             SDB_ISSUE(ntap, nch, it + RING - ITERS, slot)
+          }
+        }
+        if constexpr (MODE == MODE_DX) {
+          const int beg = s_range[pw][tap][grp], cnt = s_range[pw][tap][grp + 1] - beg;
+          const int n_it = __reduce_max_sync(0xffffffffu, cnt);
+          if (n_it > 0) {
+            __syncwarp();   // rows written above by other lanes of this warp
+            const uint2* oe = p.entries + beg;
+            const uint4* xb = xbase + ch * (CPS / 8);
+            for (int j0 = 0; j0 < n_it; j0 += 2) {
+              uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
+              if (j0 < cnt) e0 = __ldg(oe + j0);
+              if (j0 + 1 < cnt) e1 = __ldg(oe + j0 + 1);
+              uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+              if (j0 < cnt) v0 = __ldg(xb + e0.x);
+              if (j0 + 1 < cnt) v1 = __ldg(xb + e1.x);
+              if (j0 < cnt) {
+                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e0.y & 0xffu, lig & 7));
+                uint4 a = *rp;
+                const uint32_t w2 = __byte_perm(e0.y, e0.y, 0x3232);
+                a.x = bf2_fma(w2, v0.x, a.x); a.y = bf2_fma(w2, v0.y, a.y);
+                a.z = bf2_fma(w2, v0.z, a.z); a.w = bf2_fma(w2, v0.w, a.w);
+                *rp = a;
+              }
+              if (j0 + 1 < cnt) {   // may hit the same row as e0: strictly after it
+                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e1.y & 0xffu, lig & 7));
+                uint4 a = *rp;
+                const uint32_t w2 = __byte_perm(e1.y, e1.y, 0x3232);
+                a.x = bf2_fma(w2, v1.x, a.x); a.y = bf2_fma(w2, v1.y, a.y);
+                a.z = bf2_fma(w2, v1.z, a.z); a.w = bf2_fma(w2, v1.w, a.w);
+                *rp = a;
+              }
+            }
           }
         }
         fence_proxy_async_smem();
@@ -368,14 +451,31 @@ FwdWs fwd_ws(const Geo& g) {
   return w;
 }
 
-template <int LPP, bool OUT_BF16>
+template <int LPP, bool OUT_BF16, int MODE>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16>,
+  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(SDB_OP_FORWARD, st);
-  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : SDB_OP_BACKWARD_DATA, st);
+  dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+
+// stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit)
+size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
+  size_t budget = 200 * 1024;
+  if (const char* e = getenv("SDB_TC_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+  if (budget > 222 * 1024) budget = 222 * 1024;
+  p.nsa = 2;
+  if (const char* e = getenv("SDB_TC_NSA")) p.nsa = atoi(e);
+  if (p.nsa < 2) p.nsa = 2;
+  if (p.nsa > MAX_A_STAGES) p.nsa = MAX_A_STAGES;
+  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + d_bytes + 1024 > budget) --p.nsa;
+  long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
+  if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+  if (nsb < 2) return 0;
+  p.nsb = (int)nsb;
+  return p.nsa * a_bytes + p.nsb * b_bytes + d_bytes + 1024;
 }
 
 }  // namespace
@@ -387,7 +487,10 @@ bool tc_supported(const Geo& g, const char** why) {
   if (g.C % 64 != 0) { *why = "C_in not a multiple of 64"; return false; }
   if (g.O % 16 != 0 || g.O < 16 || g.O > 256) { *why = "C_out must be a multiple of 16 in [16,256]"; return false; }
   if (g.taps() > 16) { *why = "more than 16 kernel taps (per-tile descriptors would not fit in shared memory)"; return false; }
-  if ((long long)g.N * g.H * g.W * 1LL >= (1LL << 31) / 1 || g.P() * g.O >= (1LL << 40)) { *why = "tensor too large"; return false; }
+  const long long pin = (long long)g.N * g.H * g.W;
+  if (pin * (g.C / 8) >= (1LL << 32) || g.P() * g.O >= (1LL << 40) ||
+      (4 * g.P() + pin + TILE_M) * g.taps() >= (1LL << 31) ||
+      g.P() * (((g.O + 127) / 128) * 16) >= (1LL << 32)) { *why = "tensor too large"; return false; }
   return true;
 }
 
@@ -415,34 +518,93 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   if (io_dtype == SDB_F32)
     prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8);
   else
-    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8); SDB_LAUNCHED(1);
+    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8);
+  SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
 
-  FwdParams p;
+  FwdParams p{};
   p.xp = xp; p.off = off; p.mask = mask; p.wimg = wimg; p.bias = bias32; p.out = out; p.g = g;
+  p.mH = g.Ho; p.mW = g.Wo; p.mP = g.P(); p.ncols = g.O; p.nnb = 1; p.kch = g.C; p.out_ch = g.O;
   p.num_tiles = cdiv(g.P(), TILE_M);
   const int lpp = lanes_per_pixel(g);
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
-  size_t budget = 200 * 1024;
-  if (const char* e = getenv("SDB_TC_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
-  if (budget > 222 * 1024) budget = 222 * 1024;
-  p.nsa = 2;
-  if (const char* e = getenv("SDB_TC_NSA")) p.nsa = atoi(e);
-  if (p.nsa < 2) p.nsa = 2;
-  if (p.nsa > MAX_A_STAGES) p.nsa = MAX_A_STAGES;
-  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + d_bytes + 1024 > budget) --p.nsa;
-  long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
-  if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
-  SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  p.nsb = (int)nsb;
-  const size_t smem = p.nsa * a_bytes + p.nsb * b_bytes + d_bytes + 1024;
+  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
+  SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   const bool obf = io_dtype == SDB_BF16;
-  if (lpp == 32) return obf ? launch_fwd<32, true>(p, smem, grid, st) : launch_fwd<32, false>(p, smem, grid, st);
-  if (lpp == 16) return obf ? launch_fwd<16, true>(p, smem, grid, st) : launch_fwd<16, false>(p, smem, grid, st);
-  return obf ? launch_fwd<8, true>(p, smem, grid, st) : launch_fwd<8, false>(p, smem, grid, st);
+  if (lpp == 32) return obf ? launch_fwd<32, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<32, false, MODE_FWD>(p, smem, grid, st);
+  if (lpp == 16) return obf ? launch_fwd<16, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<16, false, MODE_FWD>(p, smem, grid, st);
+  return obf ? launch_fwd<8, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<8, false, MODE_FWD>(p, smem, grid, st);
 }
 
+// column blocking of the grad_input GEMM: N = C_in split into nnb equal blocks of <= 256 columns
+int dx_col_blocks(const Geo& g) {
+  int nnb = (g.C + 255) / 256;
+  while (g.C % (nnb * 16) != 0) ++nnb;
+  return nnb;
+}
+size_t tc_dx_weight_bytes(const Geo& g, int okb) { return align_up((size_t)g.taps() * g.C * okb * 64 * 2, 1024); }
+
+// W [O][C][taps] -> B operand of the grad_input GEMM: per column block nb, tiles ordered
+// (o-chunk of 128, tap, 64-o block in chunk), each [ncols rows (c)][64 o] bf16 K-major 128B-swizzled;
+// o >= O zero padded.
+template <typename T>
+__global__ void __launch_bounds__(256) prep_weight_dx_kernel(const T* __restrict__ w, uint8_t* __restrict__ img,
+                                                             int O, int C, int taps, int okb, int ncols) {
+  const int o8n = okb * 8;
+  const long long total = (long long)taps * C * o8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % o8n);
+    const int c = (int)((i / o8n) % C);
+    const int tap = (int)(i / ((long long)o8n * C));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = o8 * 8 + j;
+      v[j] = o < O ? to_f32(w[((size_t)o * C + c) * taps + tap]) : 0.f;
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]);
+    pk.w = pack_bf16x2(v[6], v[7]);
+    const int kb = o8 >> 3;                       // 64-o block
+    const int nb = c / ncols, cr = c % ncols;
+    const size_t tile = (size_t)nb * taps * okb + ((size_t)(kb >> 1) * taps + tap) * 2 + (kb & 1);
+    *reinterpret_cast<uint4*>(img + tile * ((size_t)ncols * 128) + sw128_offset(cr, o8 & 7)) = pk;
+  }
+}
+
+int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start, const void* entries,
+          uint8_t* wimg, void* gx, const Geo& g, int okb, int io_dtype, cudaStream_t st) {
+  const int nnb = dx_col_blocks(g), ncols = g.C / nnb;
+  {
+    const long long total = (long long)g.taps() * g.C * okb * 8;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    if (io_dtype == SDB_F32)
+      prep_weight_dx_kernel<float><<<blocks, 256, 0, st>>>((const float*)w, wimg, g.O, g.C, g.taps(), okb, ncols);
+    else
+      prep_weight_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wimg, g.O, g.C, g.taps(), okb, ncols);
+    SDB_LAUNCHED(1);
+    SDB_CHECK_CUDA(cudaGetLastError());
+  }
+  FwdParams p{};
+  p.xp = (const __nv_bfloat16*)gy_nhwc; p.desc = (const GDesc*)desc; p.start = start;
+  p.entries = (const uint2*)entries; p.wimg = wimg; p.out = gx; p.g = g;
+  p.mH = g.H; p.mW = g.W; p.mP = (long long)g.N * g.H * g.W; p.ncols = ncols; p.nnb = nnb;
+  p.kch = okb * 64; p.out_ch = g.C; p.okb = okb;
+  p.num_tiles = cdiv(p.mP, TILE_M);
+  constexpr int lpp = 16;   // 128-channel stages: okb is even, so kch % 128 == 0
+  const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)ncols * 128;
+  const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);
+  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes + DX_STATIC_SMEM) - DX_STATIC_SMEM;  // static arrays come out of the same budget
+  SDB_REQUIRE(smem > 0 && smem < (1u << 20), SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
+  const int work = p.num_tiles * nnb;
+  const int grid = work < num_sms() ? work : num_sms();
+  return io_dtype == SDB_BF16 ? launch_fwd<lpp, true, MODE_DX>(p, smem, grid, st)
+                              : launch_fwd<lpp, false, MODE_DX>(p, smem, grid, st);
+}
 
 }  // namespace sdb

@@ -1,14 +1,20 @@
 // dcn_tc_bwd.cu -- backward of the deformable convolution on tcgen05 tensor cores (SDB_MATH_BF16).
 //
-// backward_data (grad_input, grad_offset, grad_mask) -- ONE fused persistent kernel per call:
+// backward_data has two halves, neither of which uses atomics on tensors:
+//  (1) grad_offset / grad_mask -- one fused persistent kernel:
 //   dcol[p, (tap,c)] = sum_o dY[p,o] W[o,c,tap]        tcgen05 GEMM, M=128 pixels, N=128 channels,
 //                                                      K = C_out, accumulator in TMEM (never in HBM)
 //   4 drain warps move each 128x128 fp32 accumulator to a swizzled bf16 staging tile in smem;
-//   scatter warps (16 lanes x 8 channels per pixel) re-read the 4 input corners of (pixel, tap) and
-//     - reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels with warp
-//       shuffles -> grad_offset / grad_mask (one coalesced atomicAdd per channel chunk),
-//     - scatter w_k * mask * dcol into an NHWC fp32 accumulation buffer with red.global.add.v4.f32
-//       (the only place taps collide), converted to NCHW afterwards.
+//   reduce warps (16 lanes x 8 channels per pixel) re-read the 4 input corners of (pixel, tap) and
+//   reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels with warp
+//   shuffles -> grad_offset / grad_mask, plain stores (one owner per (pixel, tap)).
+//  (2) grad_input -- the reference scatters w * dcol with fp32 atomics (K3/K6); here the scatter is
+//   inverted once per call into a CSR index "which (output pixel, tap, weight) touch input pixel q"
+//   (count -> scan -> fill, ~36 eight-byte entries per output pixel) and grad_input becomes a second
+//   gathered implicit GEMM  dX[q,c] = sum_{tap,o} (sum_e w_e dY[p_e,o]) W[o,c,tap]  run by the
+//   forward kernel in MODE_DX (dcn_tc.cu).  Tensor work goes up by one GEMM, HBM/L2 atomic traffic
+//   (36 KB per output pixel at C=256) goes to zero, and the fp32 NHWC accumulation buffer, its
+//   memset and the NHWC->NCHW conversion pass disappear.
 //   Replaces G2 + K2/K5 + K3/K6 of the reference (deform_conv_cuda.cu:553-559,
 //   deform_conv_cuda_kernel.cu:291-452, :870-1066); `columns` is never written to HBM.
 //
@@ -104,34 +110,6 @@ __global__ void __launch_bounds__(256) prep_weight_dgrad_kernel(const T* __restr
   }
 }
 
-// gx32 [N][HW][C] fp32 -> grad_x [N][C][HW] (T), ACCUMULATING into grad_x.
-template <typename T>
-__global__ void __launch_bounds__(256) unpack_add_nchw_kernel(const float* __restrict__ src, T* __restrict__ dst,
-                                                              int C, int HW) {
-  __shared__ float s[32][65];
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
-  const int tid = threadIdx.x;
-  {
-    const int c = tid & 63;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int p = (tid >> 6) + 4 * j;
-      s[p][c] = (p0 + p < HW && c0 + c < C) ? src[((size_t)n * HW + p0 + p) * C + c0 + c] : 0.f;
-    }
-  }
-  __syncthreads();
-  const int tx = tid & 31, ty = tid >> 5;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = ty + 8 * j;
-    if (p0 + tx < HW && c0 + c < C) {
-      T* d = dst + ((size_t)n * C + c0 + c) * HW + p0 + tx;
-      if (sizeof(T) == 4) *reinterpret_cast<float*>(d) += s[tx][c];
-      else *reinterpret_cast<__nv_bfloat16*>(d) = __float2bfloat16_rn(to_f32(*d) + s[tx][c]);
-    }
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ gy, float* __restrict__ gb,
                                                         float scale, int N, int O, int hw) {
@@ -159,22 +137,36 @@ struct BSample {
   float lh, lw, m;
 };
 
-__device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __restrict__ off,
-                                                const float* __restrict__ mask, bool valid, int n, int ho,
-                                                int wo, int tap) {
+// raw (dy, dx, mask) of one (pixel, tap): fetched ahead of use so the loads overlap other work
+struct RawB {
+  float dy, dx, m;
+};
+__device__ __forceinline__ RawB fetch_rawb(const Geo& g, const float* __restrict__ off,
+                                           const float* __restrict__ mask, bool valid, int n, int ho, int wo,
+                                           int tap) {
+  RawB r = {0.f, 0.f, 1.f};
+  if (!valid) return r;
+  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
+  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
+  r.dy = __ldg(o);
+  r.dx = __ldg(o + hw);
+  if (mask) r.m = __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo);
+  return r;
+}
+
+__device__ __forceinline__ BSample make_bsample_raw(const Geo& g, const RawB raw, bool valid, int n, int ho,
+                                                    int wo, int tap) {
   BSample s;
   s.idx[0] = s.idx[1] = s.idx[2] = s.idx[3] = -1;
   s.lh = s.lw = 0.f;
   s.m = 0.f;
   if (!valid) return s;
-  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
-  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
   const int i = tap / g.KW, j = tap - i * g.KW;
-  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + __ldg(o);
-  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + __ldg(o + hw);
+  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + raw.dy;
+  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + raw.dx;
   // gradient-side validity test is the non-strict one (deform_conv_cuda_kernel.cu:140-144, :435-437)
   if (h <= -1.f || w <= -1.f || h >= (float)g.H || w >= (float)g.W) return s;
-  s.m = mask ? __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo) : 1.f;
+  s.m = raw.m;
   const int h_low = (int)floorf(h), w_low = (int)floorf(w);
   const int h_high = h_low + 1, w_high = w_low + 1;
   s.lh = h - h_low;
@@ -188,6 +180,12 @@ __device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __res
   return s;
 }
 
+__device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __restrict__ off,
+                                                const float* __restrict__ mask, bool valid, int n, int ho,
+                                                int wo, int tap) {
+  return make_bsample_raw(g, fetch_rawb(g, off, mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
+}
+
 __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
   f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
   f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
@@ -195,8 +193,156 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
   f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// ------------------------------------------------------------------------------------------------
+// index of the transposed sampling pattern (grad_input as a gather, see file header)
+// ------------------------------------------------------------------------------------------------
+// key(q, tap) = (tile(q) * taps + tap) * 128 + row(q), q = band-order position of the INPUT pixel.
+// The list of (output pixel p, weight w = bilinear x mask) that reach q through `tap` is stored as
+//   desc[key]  : its first four entries in the forward gather's descriptor format (row offset of p in
+//                the NHWC bf16 dY in 16 B units + bf16x2 weight; unused slots are zero), and
+//   overflow   : entries five and up in a CSR (start[key] .. start[key+1]) of {row offset, w<<16 | row}.
+// With stride 1 a list holds four entries on average, so most of the work takes the fixed-width path.
+constexpr int DESC_W = 4;
+template <typename F>
+__device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restrict__ off,
+                                             const float* __restrict__ mask, int n, int ho, int wo, int tap,
+                                             F f) {
+  const BSample s = make_bsample(g, off, mask, true, n, ho, wo, tap);
+  const float wk[4] = {(1.f - s.lh) * (1.f - s.lw), (1.f - s.lh) * s.lw, s.lh * (1.f - s.lw), s.lh * s.lw};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (s.idx[k] < 0) continue;
+    const float wv = wk[k] * s.m;
+    const uint32_t wb = pack_bf16x2(wv, wv) >> 16;
+    if (wb == 0u || wb == 0x8000u) continue;       // rounds to zero as a bf16 operand: contributes nothing
+    const int pixel = s.idx[k] - n * g.H * g.W;    // y * W + x
+    const int y = pixel / g.W, x = pixel - y * g.W;
+    const long long q = encode_pos(g.H, g.W, g.th, g.tw, n, y, x);
+    const long long key = ((q >> 7) * g.taps() + tap) * TILE_M + (q & 127);
+    f(key, wb, (uint32_t)(q & 127));
+  }
+}
+
+__global__ void __launch_bounds__(256) csr_count_kernel(const float* __restrict__ off, const float* __restrict__ mask,
+                                                        int* __restrict__ cnt, const Geo g) {
+  const int tap = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.P()) return;
+  const int hw = g.Ho * g.Wo;
+  const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
+  for_each_hit(g, off, mask, n, r / g.Wo, r % g.Wo, tap,
+               [&](long long key, uint32_t, uint32_t) { atomicAdd(cnt + key, 1); });
+}
+
+constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block
+__device__ __forceinline__ int overflow_of(int c) { return max(c - DESC_W, 0); }
+__global__ void __launch_bounds__(256) csr_block_sums_kernel(const int* __restrict__ cnt, int* __restrict__ bsum,
+                                                             int nkeys) {
+  const int base = blockIdx.x * SCAN_PER_BLOCK;
+  int s = 0;
+  for (int i = threadIdx.x; i < SCAN_PER_BLOCK; i += 256) {
+    const int k = base + i;
+    if (k < nkeys) s += overflow_of(cnt[k]);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    bsum[blockIdx.x] = t;
+  }
+}
+// exclusive scan of the block sums in place (single block)
+__global__ void __launch_bounds__(1024) csr_scan_top_kernel(int* __restrict__ bsum, int nblocks) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nblocks ? bsum[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, d);
+        if (threadIdx.x >= d) w += t;
+      }
+      wsum[threadIdx.x] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int wbase = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+    if (i < nblocks) bsum[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
+    __syncthreads();
+  }
+}
+// start[k] = exclusive scan of the overflow counts; start[nkeys] = total
+__global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restrict__ cnt, const int* __restrict__ bsum,
+                                                             int* __restrict__ start, int nkeys) {
+  __shared__ int wsum[8];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = bsum[blockIdx.x];
+  __syncthreads();
+  const int base = blockIdx.x * SCAN_PER_BLOCK;
+  for (int i0 = 0; i0 < SCAN_PER_BLOCK; i0 += 256) {
+    const int k = base + i0 + threadIdx.x;
+    const int v = k < nkeys ? overflow_of(cnt[k]) : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
+    const int carry = carry_s;
+    const int excl = carry + wbase + incl - v;
+    if (k < nkeys) {
+      start[k] = excl;
+      if (k == nkeys - 1) start[nkeys] = excl + v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = carry + wbase + incl;
+    __syncthreads();
+  }
+}
+
+// row_units = 16-byte units per pixel row of the NHWC dY (okb * 8)
+__global__ void __launch_bounds__(256) csr_fill_kernel(const float* __restrict__ off, const float* __restrict__ mask,
+                                                       int* __restrict__ cnt, const int* __restrict__ start,
+                                                       GDesc* __restrict__ desc, uint2* __restrict__ entries,
+                                                       const Geo g, int row_units) {
+  const int tap = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.P()) return;
+  const int hw = g.Ho * g.Wo;
+  const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
+  const uint32_t poff = (uint32_t)p * (uint32_t)row_units;
+  for_each_hit(g, off, mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb, uint32_t row) {
+    const int pos = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
+    if (pos < DESC_W) {
+      desc[key].off[pos] = poff;
+      desc[key].w2[pos] = (wb << 16) | wb;
+    } else {
+      entries[start[key] + pos - DESC_W] = make_uint2(poff, (wb << 16) | row);
+    }
+  });
 }
 
 // byte offset of 16-byte chunk `chunk` of row `row` in the bf16 staging tile [128][NCH]
@@ -214,7 +360,6 @@ struct DgradParams {
   const float* mask;
   const uint8_t* gy_img;     // dY tiles
   const uint8_t* wt_img;     // W^T tiles
-  float* gx32;               // NHWC fp32 accumulation buffer or nullptr
   float* goff;               // [N][2*taps][HWo] fp32, pre-zeroed, or nullptr
   float* gmask;              // [N][taps][HWo] fp32, pre-zeroed, or nullptr
   Geo g;
@@ -347,86 +492,136 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
       }
     }
   } else {
-    // ===== scatter warps: grad_offset / grad_mask reductions + grad_x scatter =====
-    const int sw = warp - FIRST_SW;
+    // ===== reduce warps: grad_offset / grad_mask = channel reductions of dcol against the corners =====
+    // Same load pipeline as the forward gather: per (pixel, tap) a descriptor in shared memory (corner
+    // offsets + lh, lw, mask, corner-valid flags, built one tap ahead by lanes 0..15), and a 4-slot
+    // register ring that keeps 16 sixteen-byte corner loads per lane in flight across unit boundaries.
+    // Per (pixel, tap, 8 channels): four packed-bf16 dot products S_k = <dcol, corner_k> (16 HFMA2),
+    // combined in fp32 into this lane's share of d/dy, d/dx and d/dmask, then a 5-shuffle
+    // reduce-scatter over the pixel's lane group.  The sums over channel chunks stay in registers;
+    // one plain store per (pixel, tap, quantity) at the end of the tap.
+    constexpr int ITERS = PIX_PER_WARP / PPI;
+    constexpr int RING = 4;
+    static_assert(ITERS % RING == 0, "ring must divide the per-unit iteration count");
+    __shared__ uint4 s_od[NSW][2][PIX_PER_WARP][2];   // {off[4]}, {lh, lw, m, flags}
+    __shared__ int2 s_px[NSW][PIX_PER_WARP];          // (n, ho*Wo+wo) of the warp's pixels, n = -1 when padded
+    const int sw = warp - FIRST_SW, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
     const int hw = g.Ho * g.Wo;
+    const uint4* xbase = reinterpret_cast<const uint4*>(p.xp) + lig;
     uint32_t sb = 0, sp = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
+      const long long pix = (long long)tile * TILE_M + r0 + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
       int n = 0, ho = 0, wo = 0;
       if (valid) decode_q(g, pix, n, ho, wo);
-      const int rem = ho * g.Wo + wo;
+      __syncwarp();   // previous tile's descriptors / pixel table no longer read
+      if (lane < PIX_PER_WARP) s_px[sw][lane] = make_int2(valid ? n : -1, ho * g.Wo + wo);
+      // descriptor of this lane's pixel for tap `tap_` -> buffer tap_ & 1
+      auto build_desc = [&](int tap_, const RawB raw_) {
+        if (lane < PIX_PER_WARP) {
+          const BSample bs = make_bsample_raw(g, raw_, valid, n, ho, wo, tap_);
+          uint4 o, f;
+          uint32_t flags = 0;
+          o.x = bs.idx[0] >= 0 ? (flags |= 1u, (uint32_t)bs.idx[0] * (uint32_t)(C / 8)) : 0u;
+          o.y = bs.idx[1] >= 0 ? (flags |= 2u, (uint32_t)bs.idx[1] * (uint32_t)(C / 8)) : 0u;
+          o.z = bs.idx[2] >= 0 ? (flags |= 4u, (uint32_t)bs.idx[2] * (uint32_t)(C / 8)) : 0u;
+          o.w = bs.idx[3] >= 0 ? (flags |= 8u, (uint32_t)bs.idx[3] * (uint32_t)(C / 8)) : 0u;
+          f.x = __float_as_uint(bs.lh); f.y = __float_as_uint(bs.lw); f.z = __float_as_uint(bs.m); f.w = flags;
+          s_od[sw][tap_ & 1][lane][0] = o;
+          s_od[sw][tap_ & 1][lane][1] = f;
+        }
+      };
+      build_desc(0, fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, 0));
+      RawB raw_next = fetch_rawb(g, p.off, p.mask, valid && taps > 1, n, ho, wo, 1);   // raw offsets run two taps ahead
+      __syncwarp();
+      uint4 v[RING][4];
+#define SDB_ISSUE(tap_, ch_, it_, slot_)                                                         \
+      {                                                                                          \
+        const uint4 o_ = s_od[sw][(tap_) & 1][(it_) * PPI + grp][0];                             \
+        const uint4* xb_ = xbase + (ch_) * (NCH / 8);                                            \
+        v[slot_][0] = __ldg(xb_ + o_.x);                                                         \
+        v[slot_][1] = __ldg(xb_ + o_.y);                                                         \
+        v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
+        v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
+      }
+#pragma unroll
+      for (int u = 0; u < RING; ++u) SDB_ISSUE(0, 0, u, u)
       for (int tap = 0; tap < taps; ++tap) {
-        const BSample mine = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
-        float my_gy = 0.f, my_gx = 0.f, my_gm = 0.f;   // results for the pixel this lane owns
+        __syncwarp();
+        if (tap + 1 < taps) build_desc(tap + 1, raw_next);   // buffer (tap+1)&1 was last read during tap-1
+        raw_next = fetch_rawb(g, p.off, p.mask, valid && tap + 2 < taps, n, ho, wo, tap + 2);
+        __syncwarp();
+        float racc[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) racc[it] = 0.f;
         for (int ch = 0; ch < nch; ++ch) {
+          int ntap = tap, nchk = ch + 1;
+          if (nchk == nch) { nchk = 0; ++ntap; }
+          const bool has_next = ntap < taps;
           mbar_wait(&stg_full[sb], sp);
           const uint8_t* stg = sS + (size_t)sb * STG_BYTES;
-          const size_t coff = (size_t)ch * NCH + lig * 8;
-#pragma unroll 2
-          for (int it = 0; it < PIX_PER_WARP / PPI; ++it) {
-            const int src = it * PPI + grp;
-            int idx[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) idx[k] = __shfl_sync(0xffffffffu, mine.idx[k], src);
-            const float lh = __shfl_sync(0xffffffffu, mine.lh, src);
-            const float lw = __shfl_sync(0xffffffffu, mine.lw, src);
-            const float m = __shfl_sync(0xffffffffu, mine.m, src);
-            const int row = sw * PIX_PER_WARP + src;
-            float d[8];
-            unpack8(*reinterpret_cast<const uint4*>(stg + stg_offset<NCH>(row, lig)), d);
-            const float wk[4] = {(1.f - lh) * (1.f - lw), (1.f - lh) * lw, lh * (1.f - lw), lh * lw};
-            float S[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int it = 0; it < ITERS; ++it) {
+            const int slot = it % RING;
+            const int px = it * PPI + grp;
+            const uint4 f = s_od[sw][tap & 1][px][1];
+            const uint4 d = *reinterpret_cast<const uint4*>(stg + stg_offset<NCH>(r0 + px, lig));
+            float S[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (idx[k] >= 0) {
-                float v[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(p.xp + (size_t)idx[k] * C + coff)), v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) S[k] = fmaf(d[j], v[j], S[k]);
-                if (p.gx32) {
-                  const float wm = wk[k] * m;
-                  float* dst = p.gx32 + (size_t)idx[k] * C + coff;
-                  red_add_v4(dst, wm * d[0], wm * d[1], wm * d[2], wm * d[3]);
-                  red_add_v4(dst + 4, wm * d[4], wm * d[5], wm * d[6], wm * d[7]);
-                }
-              }
+              const uint32_t a2 = bf2_fma(d.w, v[slot][k].w, bf2_fma(d.z, v[slot][k].z,
+                                  bf2_fma(d.y, v[slot][k].y, bf2_mul(d.x, v[slot][k].x))));
+              const float sk = __uint_as_float(a2 << 16) + __uint_as_float(a2 & 0xffff0000u);
+              S[k] = (f.w >> k) & 1u ? sk : 0.f;
             }
+            if (it + RING < ITERS) {
+              SDB_ISSUE(tap, ch, it + RING, slot)
+            } else if (has_next) {
+              SDB_ISSUE(ntap, nchk, it + RING - ITERS, slot)
+            }
+            const float lh = __uint_as_float(f.x), lw = __uint_as_float(f.y), m = __uint_as_float(f.z);
             // d(bilinear)/dh, /dw (get_coordinate_weight :185-211) and the unmasked sample value
-            float gy = m * (-(1.f - lw) * S[0] - lw * S[1] + (1.f - lw) * S[2] + lw * S[3]);
-            float gx = m * (-(1.f - lh) * S[0] + (1.f - lh) * S[1] - lh * S[2] + lh * S[3]);
-            float gm = wk[0] * S[0] + wk[1] * S[1] + wk[2] * S[2] + wk[3] * S[3];
+            float qa = m * ((1.f - lw) * (S[2] - S[0]) + lw * (S[3] - S[1]));
+            float qb = m * ((1.f - lh) * (S[1] - S[0]) + lh * (S[3] - S[2]));
+            float qc = (1.f - lh) * ((1.f - lw) * S[0] + lw * S[1]) + lh * ((1.f - lw) * S[2] + lw * S[3]);
+            // reduce-scatter over the LPB lanes of this pixel: lanes [0,Q) end with sum(qa), [Q,2Q) sum(qb),
+            // [2Q,3Q) sum(qc)
+            constexpr int H = LPB / 2, Q = LPB / 4;
+            const bool up = (lig & H) != 0;
+            const float r0_ = __shfl_xor_sync(0xffffffffu, up ? qa : qc, H);
+            const float r1_ = __shfl_xor_sync(0xffffffffu, up ? qb : 0.f, H);
+            const float k0 = (up ? qc : qa) + r0_;
+            const float k1 = (up ? 0.f : qb) + r1_;
+            const bool uq = (lig & Q) != 0;
+            float kk = (uq ? k1 : k0) + __shfl_xor_sync(0xffffffffu, uq ? k0 : k1, Q);
 #pragma unroll
-            for (int dlt = LPB / 2; dlt > 0; dlt >>= 1) {
-              gy += __shfl_xor_sync(0xffffffffu, gy, dlt);
-              gx += __shfl_xor_sync(0xffffffffu, gx, dlt);
-              gm += __shfl_xor_sync(0xffffffffu, gm, dlt);
-            }
-            // hand the result to the lane that owns this pixel's descriptor (lane == src)
-            const int from = (lane % PPI) * LPB;
-            const float rgy = __shfl_sync(0xffffffffu, gy, from);
-            const float rgx = __shfl_sync(0xffffffffu, gx, from);
-            const float rgm = __shfl_sync(0xffffffffu, gm, from);
-            if (lane / PPI == it && lane < PIX_PER_WARP) {
-              my_gy += rgy;
-              my_gx += rgx;
-              my_gm += rgm;
-            }
+            for (int dlt = Q / 2; dlt > 0; dlt >>= 1) kk += __shfl_xor_sync(0xffffffffu, kk, dlt);
+            racc[it] += kk;
           }
           mbar_arrive(&stg_empty[sb]);
           if (++sb == 2) { sb = 0; sp ^= 1; }
         }
-        if (valid) {
-          const size_t ob = ((size_t)n * 2 * taps + 2 * tap) * hw + rem;
-          if (p.goff) {
-            p.goff[ob] = my_gy;        // one owner per (pixel, tap): plain stores, channel chunks
-            p.goff[ob + hw] = my_gx;   // were summed in registers above
+        // lanes lig == 0, Q, 2Q hold d/dy, d/dx, d/dmask of pixel it*PPI+grp
+        {
+          constexpr int Q = LPB / 4;
+          const int quant = lig / Q;
+          if ((lig % Q) == 0 && quant < 3) {
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+              const int2 pi = s_px[sw][it * PPI + grp];
+              if (pi.x >= 0) {
+                if (quant < 2) {
+                  if (p.goff) p.goff[((size_t)pi.x * 2 * taps + 2 * tap + quant) * hw + pi.y] = racc[it];
+                } else if (p.gmask) {
+                  p.gmask[((size_t)pi.x * taps + tap) * hw + pi.y] = racc[it];
+                }
+              }
+            }
           }
-          if (p.gmask) p.gmask[((size_t)n * taps + tap) * hw + rem] = my_gm;
         }
       }
+#undef SDB_ISSUE
     }
   }
   tc_fence_before_sync();
@@ -608,7 +803,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // ---- workspace layouts ----------------------------------------------------------------------
 struct BwdWs {
-  size_t xp_off, gy_off, wt_off, gx_off, part_off, total;
+  size_t xp_off, gy_off, wt_off, part_off, cnt_off, start_off, bsum_off, ent_off, wdx_off, desc_off, gyn_off, total;
+  long long nkeys, max_entries;
+  int scan_blocks;
 };
 int wgrad_splits(const Geo& g, int num_tiles) {
   int s = num_sms() / (g.taps() * nch_chunks(g));
@@ -626,7 +823,17 @@ BwdWs bwd_ws(int op, const Geo& g) {
   w.gy_off = o; o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
   if (op == SDB_OP_BACKWARD_DATA) {
     w.wt_off = o; o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
-    w.gx_off = o; o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 4, 1024);
+    const long long tiles_in = cdiv((long long)g.N * g.H * g.W, TILE_M);
+    w.nkeys = tiles_in * g.taps() * TILE_M;
+    w.max_entries = 4 * g.P() * g.taps();
+    w.scan_blocks = cdiv(w.nkeys, SCAN_PER_BLOCK);
+    w.cnt_off = o;   o = align_up(o + (size_t)w.nkeys * 4, 1024);
+    w.start_off = o; o = align_up(o + (size_t)(w.nkeys + 1) * 4, 1024);
+    w.bsum_off = o;  o = align_up(o + (size_t)w.scan_blocks * 4, 1024);
+    w.ent_off = o;   o = align_up(o + (size_t)w.max_entries * 8, 1024);
+    w.wdx_off = o;   o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
+    w.desc_off = o;  o = align_up(o + (size_t)w.nkeys * sizeof(GDesc), 1024);
+    w.gyn_off = o;   o = align_up(o + (size_t)g.P() * okb * 64 * 2, 1024);
   } else {
     w.part_off = o; o = align_up(o + (size_t)wgrad_splits(g, (int)tiles) * g.taps() * g.O * g.C * 4, 1024);
   }
@@ -654,65 +861,81 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
   SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "backward_data workspace too small: %zu < %zu", ws_bytes, L.total);
   uint8_t* base = (uint8_t*)ws;
   const bool f32 = io_dtype == SDB_F32;
-  const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
+  if (!mask) gmask = nullptr;
   int rc;
-  if (!xp) {
-    rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
-             : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
-    if (rc) return rc;
-    xp = (const __nv_bfloat16*)(base + L.xp_off);
-  }
   uint8_t* gy_img = base + L.gy_off;
-  uint8_t* wt_img = base + L.wt_off;
-  float* gx32 = gx ? (float*)(base + L.gx_off) : nullptr;
   rc = f32 ? pack_gy<float>(gy, gy_img, g, st) : pack_gy<__nv_bfloat16>(gy, gy_img, g, st);
   if (rc) return rc;
   const int okb = okb_of(g);
-  {
+
+  if (goff || gmask) {
+    // ---- (1) grad_offset / grad_mask: dcol GEMM + channel reduction ----
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
+    if (!xp) {
+      rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
+               : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
+      if (rc) return rc;
+      xp = (const __nv_bfloat16*)(base + L.xp_off);
+    }
+    uint8_t* wt_img = base + L.wt_off;
     const long long total = (long long)g.taps() * g.C * okb * 8;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     if (NCH == 128) {
       if (f32) prep_weight_dgrad_kernel<float, 128><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
       else prep_weight_dgrad_kernel<__nv_bfloat16, 128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
-      SDB_LAUNCHED(1);
     } else {
       if (f32) prep_weight_dgrad_kernel<float, 64><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
       else prep_weight_dgrad_kernel<__nv_bfloat16, 64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
+    }
+    SDB_LAUNCHED(1);
+    SDB_CHECK_CUDA(cudaGetLastError());
+
+    DgradParams p;
+    p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.wt_img = wt_img;
+    p.goff = goff; p.gmask = gmask; p.g = g;
+    p.num_tiles = cdiv(g.P(), TILE_M);
+    p.okb = okb;
+    const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
+    long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
+    if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+    SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
+    p.nsb = (int)nsb;
+    const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      ProfScope prof(SDB_OP_BACKWARD_DATA, st);
+      if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+      else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
       SDB_LAUNCHED(1);
     }
     SDB_CHECK_CUDA(cudaGetLastError());
   }
-  if (gx32) SDB_CHECK_CUDA(cudaMemsetAsync(gx32, 0, (size_t)g.N * g.H * g.W * g.C * 4, st));
-
-  DgradParams p;
-  p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.wt_img = wt_img; p.gx32 = gx32;
-  p.goff = goff; p.gmask = mask ? gmask : nullptr; p.g = g;
-  p.num_tiles = cdiv(g.P(), TILE_M);
-  p.okb = okb;
-  const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
-  long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
-  if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
-  SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
-  p.nsb = (int)nsb;
-  const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope prof(SDB_OP_BACKWARD_DATA, st);
-    if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-    else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
-    SDB_LAUNCHED(1);
-  }
-  SDB_CHECK_CUDA(cudaGetLastError());
 
   if (gx) {
-    const int HW = g.H * g.W;
-    dim3 ugrid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
-    if (f32) unpack_add_nchw_kernel<float><<<ugrid, 256, 0, st>>>(gx32, (float*)gx, g.C, HW);
-    else unpack_add_nchw_kernel<__nv_bfloat16><<<ugrid, 256, 0, st>>>(gx32, (__nv_bfloat16*)gx, g.C, HW);
-    SDB_LAUNCHED(1);
+    // ---- (2) grad_input: transposed sampling index + gathered implicit GEMM ----
+    int* cnt = (int*)(base + L.cnt_off);
+    int* start = (int*)(base + L.start_off);
+    int* bsum = (int*)(base + L.bsum_off);
+    uint2* entries = (uint2*)(base + L.ent_off);
+    GDesc* desc = (GDesc*)(base + L.desc_off);
+    __nv_bfloat16* gyn = (__nv_bfloat16*)(base + L.gyn_off);
+    const int nkeys = (int)L.nkeys;
+    rc = f32 ? pack_grad_nhwc<float>(gy, gyn, g, okb * 64, st) : pack_grad_nhwc<__nv_bfloat16>(gy, gyn, g, okb * 64, st);
+    if (rc) return rc;
+    SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nkeys * 4, st));
+    SDB_CHECK_CUDA(cudaMemsetAsync(desc, 0, (size_t)nkeys * sizeof(GDesc), st));
+    dim3 hgrid(cdiv(g.P(), 256), g.taps());
+    csr_count_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, g);
+    csr_block_sums_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
+    csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, L.scan_blocks);
+    csr_scan_final_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, start, nkeys);
+    csr_fill_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, start, desc, entries, g, okb * 8);
+    SDB_LAUNCHED(5);
     SDB_CHECK_CUDA(cudaGetLastError());
+    rc = tc_dx(w, gyn, desc, start, entries, base + L.wdx_off, gx, g, okb, io_dtype, st);
+    if (rc) return rc;
   }
   return SDB_OK;
 }

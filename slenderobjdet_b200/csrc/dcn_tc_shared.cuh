@@ -9,6 +9,9 @@
 namespace sdb {
 
 size_t tc_bwd_workspace_bytes(int op, const Geo& g);
+// grad_input as a gathered implicit GEMM over the transposed sampling index (dcn_tc.cu, MODE_DX)
+int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start, const void* entries,
+          uint8_t* wimg, void* gx, const Geo& g, int okb, int io_dtype, cudaStream_t st);
 
 namespace tcshared {
 using namespace tc;
@@ -25,19 +28,31 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // neighbourhood of an 8x16 patch is ~180 input pixels instead of 3 rows x 130.  Partial bands /
 // groups at the image border are shorter, never padded, so ceil(P/128) tiles cover P pixels.
 // th = 1, tw >= Wo degenerates to plain row-major order.
-__device__ __forceinline__ void decode_q(const Geo& g, long long q, int& n, int& ho, int& wo) {
-  const int hw = g.Ho * g.Wo;
+// generic form: grid of Hd x Wd pixels per image walked in th x tw blocks
+__host__ __device__ __forceinline__ void decode_pos(int Hd, int Wd, int th, int tw, long long q, int& n, int& y, int& x) {
+  const int hw = Hd * Wd;
   n = (int)(q / hw);
   const int r = (int)(q - (long long)n * hw);
-  const int band_px = g.th * g.Wo;
+  const int band_px = th * Wd;
   const int band = r / band_px, rb = r - band * band_px;
-  const int rows_b = min(g.th, g.Ho - band * g.th);
-  const int grp_px = rows_b * g.tw;
+  const int rows_b = min(th, Hd - band * th);
+  const int grp_px = rows_b * tw;
   const int cg = rb / grp_px, rg = rb - cg * grp_px;
-  const int cols_g = min(g.tw, g.Wo - cg * g.tw);
+  const int cols_g = min(tw, Wd - cg * tw);
   const int dy = rg / cols_g;
-  ho = band * g.th + dy;
-  wo = cg * g.tw + (rg - dy * cols_g);
+  y = band * th + dy;
+  x = cg * tw + (rg - dy * cols_g);
+}
+// inverse of decode_pos
+__host__ __device__ __forceinline__ long long encode_pos(int Hd, int Wd, int th, int tw, int n, int y, int x) {
+  const int band = y / th, dy = y - band * th;
+  const int rows_b = min(th, Hd - band * th);
+  const int cg = x / tw, dx = x - cg * tw;
+  const int cols_g = min(tw, Wd - cg * tw);
+  return (long long)n * Hd * Wd + (long long)band * th * Wd + cg * (rows_b * tw) + dy * cols_g + dx;
+}
+__device__ __forceinline__ void decode_q(const Geo& g, long long q, int& n, int& ho, int& wo) {
+  decode_pos(g.Ho, g.Wo, g.th, g.tw, q, n, ho, wo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -50,10 +65,10 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// [N][C][HW] (T) -> [N][HW][C] bf16.  Tile 64 channels x 32 pixels.
+// [N][C][HW] (T) -> [N][HW][Cd] bf16, Cd >= C (channels C..Cd-1 zero).  Tile 64 channels x 32 pixels.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_nhwc_kernel(const T* __restrict__ src,
-                                                        __nv_bfloat16* __restrict__ dst, int C, int HW) {
+                                                        __nv_bfloat16* __restrict__ dst, int C, int HW, int Cd) {
   __shared__ float s[64][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -64,12 +79,12 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const T* __restrict__ sr
     s[c][tx] = (c0 + c < C && p0 + tx < HW) ? to_f32(sp[(size_t)c * HW + p0 + tx]) : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* dp = dst + ((size_t)n * HW + p0) * C + c0;
+  __nv_bfloat16* dp = dst + ((size_t)n * HW + p0) * Cd + c0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int p = ty + 8 * j;
-    if (p0 + p < HW && c0 + 2 * tx < C)
-      *reinterpret_cast<__nv_bfloat162*>(dp + (size_t)p * C + 2 * tx) =
+    if (p0 + p < HW && c0 + 2 * tx < Cd)
+      *reinterpret_cast<__nv_bfloat162*>(dp + (size_t)p * Cd + 2 * tx) =
           __floats2bfloat162_rn(s[2 * tx][p], s[2 * tx + 1][p]);
   }
 }
@@ -154,7 +169,16 @@ template <typename T>
 inline int pack_input(const void* x, __nv_bfloat16* xp, const Geo& g, cudaStream_t st) {
   const int HW = g.H * g.W;
   dim3 grid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
-  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW); SDB_LAUNCHED(1);
+  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW, g.C); SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+// grad_out [N][O][HWo] -> [N][HWo][Od] bf16 (Od = okb*64 >= O, zero padded)
+template <typename T>
+inline int pack_grad_nhwc(const void* gy, __nv_bfloat16* gyp, const Geo& g, int Od, cudaStream_t st) {
+  const int HW = g.Ho * g.Wo;
+  dim3 grid(cdiv(HW, 32), cdiv(Od, 64), g.N);
+  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, gyp, g.O, HW, Od); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
