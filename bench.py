@@ -171,27 +171,54 @@ class Workload:
             self.levels.append(lv)
         self.head_grads = torch.zeros(HEAD_PARAMS, device=device)  # flat head gradient bucket (N > 1)
 
-    def step(self, stream_ptr):
-        """forward + backward_data + backward_weight of both DCNs on every level, via the C ABI."""
+    def step(self, main, serial=False):
+        """forward + backward_data + backward_weight of both DCNs on every level, via the C ABI.
+        The ten (level, branch) problems are independent, so each runs on its own stream, forked
+        from / joined to `main` with events (under CUDA-graph capture these become graph edges):
+        the P5-P7 maps are one to nine 128-pixel tiles and would otherwise leave 140+ SMs idle.
+        The weight gradient of a branch accumulates over levels, so its five calls stay in order on
+        one stream per branch."""
+        torch = self.torch
         L, lib, P = self._lib, self._lib.lib(), self._lib.ptr
         io, mth = L.SDB_BF16, L.SDB_MATH_BF16
-        for gw in self.gw:
-            gw.zero_()
+        if not hasattr(self, "side_streams"):
+            self.side_streams = [torch.cuda.Stream(self.device) for _ in range(2 * len(self.levels) + 2)]
+        # serial=True (per-kernel profiling pass): everything in order on `main`
+        self.side = [main] * len(self.side_streams) if serial else self.side_streams
+        sp = lambda st: ctypes.c_void_p(st.cuda_stream)
+        with torch.cuda.stream(main):
+            for gw in self.gw:
+                gw.zero_()
+        # ---- forward of every (level, branch) ----
+        k = 0
         for lv in self.levels:
             gp = ctypes.byref(lv["geom"])
             for b, br in enumerate(lv["br"]):
+                st = self.side[k]; k += 1
+                st.wait_stream(main)
                 L.check(lib.sdb_dcn_forward(P(br["x"]), P(lv["off"]), None, P(self.weights[b]), None, P(br["out"]), gp,
-                                            io, mth, P(br["ws"][0]), br["ws"][0].numel(), P(br["pk"]), stream_ptr))
+                                            io, mth, P(br["ws"][0]), br["ws"][0].numel(), P(br["pk"]), sp(st)))
+        for st in self.side[:k]:
+            main.wait_stream(st)
+        # ---- backward ----
+        for st in self.side:
+            st.wait_stream(main)
+        k = 0
+        nl = 2 * len(self.levels)
         for lv in reversed(self.levels):
             gp = ctypes.byref(lv["geom"])
             for b, br in enumerate(lv["br"]):
-                br["gx"].zero_()
+                st = self.side[k]; k += 1
+                with torch.cuda.stream(st):
+                    br["gx"].zero_()
                 L.check(lib.sdb_dcn_backward_data(P(br["x"]), P(lv["off"]), None, P(self.weights[b]), P(br["gy"]),
                                                   P(br["gx"]), P(lv["goff"][b]), None, gp, io, mth, P(br["ws"][1]),
-                                                  br["ws"][1].numel(), P(br["pk"]), stream_ptr))
+                                                  br["ws"][1].numel(), P(br["pk"]), sp(st)))
                 L.check(lib.sdb_dcn_backward_weight(P(br["x"]), P(lv["off"]), None, P(br["gy"]), P(self.gw[b]), None,
                                                     1.0, gp, io, mth, P(br["ws"][2]), br["ws"][2].numel(), P(br["pk"]),
-                                                    stream_ptr))
+                                                    sp(self.side[nl + b])))
+        for st in self.side:
+            main.wait_stream(st)
 
     def pack_head_grads(self):
         n = self.gw[0].numel()
@@ -231,7 +258,7 @@ def run_ours(args):
     # ---- launch count + CUDA graph of one step ------------------------------------------------
     with torch.cuda.stream(stream):
         n0 = lib.sdb_launch_count()
-        wl.step(L.stream_ptr(device))
+        wl.step(stream)
         launches_per_step = lib.sdb_launch_count() - n0
         # torch-side zero_() fills inside the step: 2 (gw) + 10 (gx)
         torch_fills_per_step = 2 + 2 * len(LEVELS)
@@ -241,7 +268,7 @@ def run_ours(args):
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
-                    wl.step(L.stream_ptr(device))
+                    wl.step(stream)
             except Exception as e:  # keep running eagerly, say so in config
                 graph = None
                 sys.stderr.write("bench.py: CUDA graph capture failed (%r); timing eager launches\n" % (e,))
@@ -251,7 +278,7 @@ def run_ours(args):
         if graph is not None:
             graph.replay()
         else:
-            wl.step(L.stream_ptr(device))
+            wl.step(stream)
         if world > 1:
             wl.pack_head_grads()
             dist.all_reduce(wl.head_grads)
@@ -284,16 +311,17 @@ def run_ours(args):
         lib.sdb_profile_enable(1)
         for _ in range(3):
             l2_flush.zero_()
-            wl.step(L.stream_ptr(device))
+            wl.step(stream, serial=True)   # kernels back to back on one stream: event pairs time each alone
         lib.sdb_profile_enable(0)
         stream.synchronize()
-    names = ["dcn_fwd_tc_kernel", "dcn_bwd_data_tc_kernel", "dcn_bwd_weight_tc_kernel"]
+    names = ["dcn_fwd_tc_kernel<MODE_FWD>", "dcn_bwd_data_tc_kernel (grad_offset)", "dcn_bwd_weight_tc_kernel",
+             "dcn_fwd_tc_kernel<MODE_DX> (grad_input)"]
     kern = []
-    for slot in range(3):
+    for slot in range(4):
         ms, n = ctypes.c_float(0), ctypes.c_int(0)
         L.check(lib.sdb_profile_read(slot, ctypes.byref(ms), ctypes.byref(n)))
         kern.append((ms.value / 3.0, n.value // 3))
-    dom = max(range(3), key=lambda s: kern[s][0])
+    dom = max(range(4), key=lambda s: kern[s][0])
     dom_ms, dom_launches = kern[dom]
     # algorithmic FLOPs of one pass over every (level, branch) = FLOP_PER_PIXEL_PASS * pixels
     achieved = FLOP_PER_PIXEL_PASS * px_step / (dom_ms * 1e-3) / 1e12
@@ -302,7 +330,7 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4),
                 "launches_per_step": dom_launches, "avg_launch_us": round(dom_ms * 1e3 / max(dom_launches, 1), 2),
                 "algorithmic_flops_per_step": FLOP_PER_PIXEL_PASS * px_step,
-                "per_kernel_ms_per_step": {names[s]: round(kern[s][0], 4) for s in range(3)},
+                "per_kernel_ms_per_step": {names[s]: round(kern[s][0], 4) for s in range(4)},
                 "traffic": None}
     tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp):
@@ -330,7 +358,7 @@ def run_ours(args):
                                    "(BASELINE.json configs[1])" % batch,
                        "global_batch": world * batch, "levels": LEVELS, "channels": [C_IN, C_OUT],
                        "parallelism": "dp%d" % world, "l2": "flushed between timed iterations (256 MiB memset)",
-                       "launch": "cuda_graph" if graph is not None else "eager",
+                       "launch": ("cuda_graph" if graph is not None else "eager") + ", one stream per (level, branch)",
                        "tflops_per_s": round(flops_step * world / (step_ms * 1e-3) / 1e12, 2),
                        "allreduce_bytes": HEAD_PARAMS * 4 if world > 1 else 0},
             "roofline": roofline,

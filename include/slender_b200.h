@@ -157,7 +157,9 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,
- * not the packing helpers).  slot = sdb_dcn_op.  sdb_profile_read synchronises the recorded
+ * not the packing helpers).  slot = sdb_dcn_op, where SDB_OP_BACKWARD_DATA (1) is the grad_offset /
+ * grad_mask kernel and slot 3 is the grad_input kernel of the same entry point.
+ * sdb_profile_read synchronises the recorded
  * events and returns the summed milliseconds and the launch count since the last reset.
  * Not capturable into CUDA graphs; leave disabled (the default) on the training path. */
 int sdb_profile_enable(int on);

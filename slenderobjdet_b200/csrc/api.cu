@@ -70,11 +70,11 @@ static int require_device() {
 
 // ---- profiling --------------------------------------------------------------------------------
 namespace {
-constexpr int kProfSlots = 3, kProfMax = 8192;
+constexpr int kProfSlots = 4, kProfMax = 8192;   // forward, grad_offset, grad_weight, grad_input
 struct ProfState {
   bool on = false;
-  int n[kProfSlots] = {0, 0, 0};
-  cudaEvent_t* ev[kProfSlots] = {nullptr, nullptr, nullptr};  // 2 events per launch
+  int n[kProfSlots] = {0, 0, 0, 0};
+  cudaEvent_t* ev[kProfSlots] = {nullptr, nullptr, nullptr, nullptr};  // 2 events per launch
 } g_prof;
 }  // namespace
 

@@ -388,28 +388,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
             __syncwarp();   // rows written above by other lanes of this warp
             const uint2* oe = p.entries + beg;
             const uint4* xb = xbase + ch * (CPS / 8);
-            for (int j0 = 0; j0 < n_it; j0 += 2) {
-              uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
-              if (j0 < cnt) e0 = __ldg(oe + j0);
-              if (j0 + 1 < cnt) e1 = __ldg(oe + j0 + 1);
-              uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-              if (j0 < cnt) v0 = __ldg(xb + e0.x);
-              if (j0 + 1 < cnt) v1 = __ldg(xb + e1.x);
-              if (j0 < cnt) {
-                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e0.y & 0xffu, lig & 7));
-                uint4 a = *rp;
-                const uint32_t w2 = __byte_perm(e0.y, e0.y, 0x3232);
-                a.x = bf2_fma(w2, v0.x, a.x); a.y = bf2_fma(w2, v0.y, a.y);
-                a.z = bf2_fma(w2, v0.z, a.z); a.w = bf2_fma(w2, v0.w, a.w);
-                *rp = a;
-              }
-              if (j0 + 1 < cnt) {   // may hit the same row as e0: strictly after it
-                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e1.y & 0xffu, lig & 7));
-                uint4 a = *rp;
-                const uint32_t w2 = __byte_perm(e1.y, e1.y, 0x3232);
-                a.x = bf2_fma(w2, v1.x, a.x); a.y = bf2_fma(w2, v1.y, a.y);
-                a.z = bf2_fma(w2, v1.z, a.z); a.w = bf2_fma(w2, v1.w, a.w);
-                *rp = a;
+            constexpr int OB = 4;   // overflow entries in flight per lane group
+            for (int j0 = 0; j0 < n_it; j0 += OB) {
+              uint2 e[OB];
+              uint4 vv[OB];
+#pragma unroll
+              for (int u = 0; u < OB; ++u) e[u] = (j0 + u < cnt) ? __ldg(oe + j0 + u) : make_uint2(0u, 0u);
+#pragma unroll
+              for (int u = 0; u < OB; ++u) vv[u] = (j0 + u < cnt) ? __ldg(xb + e[u].x) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int u = 0; u < OB; ++u) {   // in order: consecutive entries may hit the same row
+                if (j0 + u < cnt) {
+                  uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e[u].y & 0xffu, lig & 7));
+                  uint4 a = *rp;
+                  const uint32_t w2 = __byte_perm(e[u].y, e[u].y, 0x3232);
+                  a.x = bf2_fma(w2, vv[u].x, a.x); a.y = bf2_fma(w2, vv[u].y, a.y);
+                  a.z = bf2_fma(w2, vv[u].z, a.z); a.w = bf2_fma(w2, vv[u].w, a.w);
+                  *rp = a;
+                }
               }
             }
           }
@@ -455,7 +451,7 @@ template <int LPP, bool OUT_BF16, int MODE>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
   SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : SDB_OP_BACKWARD_DATA, st);
+  ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : 3, st);   // slot 3 = grad_input GEMM
   dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
