@@ -152,7 +152,12 @@ class Workload:
         bf = torch.bfloat16
         mk = lambda *s: torch.randn(*s, generator=g)
         self.weights = [(mk(C_OUT, C_IN, 3, 3) * 0.01).to(device, bf) for _ in range(2)]  # cls / refine DCN
-        self.gw = [torch.zeros(C_OUT, C_IN, 3, 3, device=device) for _ in range(2)]
+        # the two DCN weight gradients live inside the head's flat gradient bucket (all-reduced when N > 1);
+        # sdb_dcn_backward_weight accumulates straight into these views
+        from slenderobjdet_b200.dist import GradBucket
+        self.bucket = GradBucket({"cls_dcn.weight": (C_OUT, C_IN, 3, 3), "refine_dcn.weight": (C_OUT, C_IN, 3, 3)},
+                                 device, pad_to=HEAD_PARAMS)
+        self.gw = [self.bucket.views["cls_dcn.weight"], self.bucket.views["refine_dcn.weight"]]
         self.levels = []
         for (H, W) in LEVELS:
             geom = lib_mod.Geom(batch, C_IN, H, W, C_OUT, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
@@ -169,7 +174,6 @@ class Workload:
                     ws=[torch.empty(max(1, n), dtype=torch.uint8, device=device) for n in wsb],
                     pk=torch.empty(max(1, pkb), dtype=torch.uint8, device=device)))
             self.levels.append(lv)
-        self.head_grads = torch.zeros(HEAD_PARAMS, device=device)  # flat head gradient bucket (N > 1)
 
     def step(self, main, serial=False):
         """forward + backward_data + backward_weight of both DCNs on every level, via the C ABI.
@@ -219,11 +223,6 @@ class Workload:
                                                     sp(self.side[nl + b])))
         for st in self.side:
             main.wait_stream(st)
-
-    def pack_head_grads(self):
-        n = self.gw[0].numel()
-        self.head_grads[:n].copy_(self.gw[0].view(-1))
-        self.head_grads[n:2 * n].copy_(self.gw[1].view(-1))
 
 
 def run_ours(args):
@@ -280,8 +279,7 @@ def run_ours(args):
         else:
             wl.step(stream)
         if world > 1:
-            wl.pack_head_grads()
-            dist.all_reduce(wl.head_grads)
+            wl.bucket.all_reduce(average=True)   # one NCCL all-reduce of the 21.4 MB head-gradient bucket
 
     # ---- `value`: device-resident, timed with CUDA events on the launching stream --------------
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -389,7 +387,9 @@ def measure_e2e(torch, sdb, device, stream, batch, args, world, dist, rank):
     out_host = [torch.empty(C_OUT, C_IN, 3, 3, dtype=bf).pin_memory() for _ in range(2)]
     goff_host = [torch.empty(batch, 18, H, W).pin_memory() for (H, W) in LEVELS]
     d2h = sum(t.numel() * t.element_size() for t in out_host) + sum(t.numel() * 4 for t in goff_host)
-    flat = torch.zeros(HEAD_PARAMS, device=device) if world > 1 else None
+    from slenderobjdet_b200.dist import GradBucket
+    bucket = GradBucket({"cls_dcn.weight": (C_OUT, C_IN, 3, 3), "refine_dcn.weight": (C_OUT, C_IN, 3, 3)},
+                        device, pad_to=HEAD_PARAMS) if world > 1 else None
 
     def step():
         for c in convs:
@@ -404,10 +404,10 @@ def measure_e2e(torch, sdb, device, stream, batch, args, world, dist, rank):
                 y = convs[b](x, off)
                 y.backward(gy)
         if world > 1:
-            n = convs[0].weight.numel()
-            flat[:n].copy_(convs[0].weight.grad.view(-1))
-            flat[n:2 * n].copy_(convs[1].weight.grad.view(-1))
-            dist.all_reduce(flat)
+            params = {"cls_dcn.weight": convs[0].weight, "refine_dcn.weight": convs[1].weight}
+            bucket.pack({k: p.grad for k, p in params.items()})
+            bucket.all_reduce(average=True)
+            bucket.unpack(params)
         for b in range(2):
             out_host[b].copy_(convs[b].weight.grad, non_blocking=True)
         for i, off in enumerate(offs):
