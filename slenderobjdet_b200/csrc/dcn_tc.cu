@@ -37,7 +37,7 @@ constexpr int NPW = 8;                       // gather producer warps
 constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
 constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
-constexpr size_t DX_STATIC_SMEM = 4096;      // MODE_DX: s_range
+constexpr size_t DX_STATIC_SMEM = 8192 + 1024 + 1024;   // MODE_DX: s_od, s_range, barriers
 
 // W [O][C][taps] -> per (channel chunk of `cps`, tap, 64-channel block) a K-major 128B-swizzled tile
 // [O rows][64 c] bf16, tiles ordered (chunk, tap, block-in-chunk) = the K order of the main loop;
@@ -125,8 +125,8 @@ struct FwdParams {
   const float* off;
   const float* mask;
   const GDesc* desc;        // MODE_DX: first four entries of every transposed list, key = (tile*taps + tap)*128 + row
-  const int* start;         // MODE_DX: overflow CSR row starts (same key), nkeys + 1 values
-  const uint2* entries;     // MODE_DX: overflow entries {row offset of dY in 16 B units, w_bf16 << 16 | row in tile}
+  const int* start;         // MODE_DX: first overflow descriptor of every key, nkeys + 1 values
+  const ODesc* odesc;       // MODE_DX: overflow descriptors (entries 5.. of a list, four per descriptor)
   const uint8_t* wimg;
   const float* bias;        // fp32 [ncols] or nullptr
   void* out;                // NCHW, f32 or bf16: [mN][out_ch][mH][mW]
@@ -262,18 +262,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
         tmem_ld_wait();
         if (valid) {
+          const size_t d0 = ((size_t)n * p.out_ch + ob + c0) * hw + rem;
+          if (MODE == MODE_DX) {
+            // grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it): fetch the 32 old values
+            // first (independent loads in flight together), then add and store
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              old[j] = 0.f;
+              if (c0 + j < O) {
+                if (OUT_BF16) old[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out)[d0 + (size_t)j * hw]);
+                else          old[j] = reinterpret_cast<const float*>(p.out)[d0 + (size_t)j * hw];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + old[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int o = c0 + j;
             if (o < O) {
               float v = __uint_as_float(r[j]);
-              const size_t di = ((size_t)n * p.out_ch + ob + o) * hw + rem;
-              if (MODE == MODE_DX) {   // grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it)
-                if (OUT_BF16) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out)[di]);
-                else          v += reinterpret_cast<const float*>(p.out)[di];
-              } else if (p.bias) {
-                v += __ldg(p.bias + o);
-              }
+              if (MODE == MODE_FWD && p.bias) v += __ldg(p.bias + o);
+              const size_t di = d0 + (size_t)j * hw;
               if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[di] = __float2bfloat16_rn(v);
               else          reinterpret_cast<float*>(p.out)[di] = v;
             }
@@ -293,13 +304,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     //     register ring: the four 16-byte loads of iteration i+4 are issued right after iteration i
     //     is consumed, across stage boundaries, so 16 loads per warp stay in flight instead of every
     //     warp paying the full memory latency once per stage in lock-step;
-    // (3) MODE_DX only: lists longer than four entries continue in an overflow index; those entries are
-    //     added to the rows just written (read-modify-write of the A stage) before the stage is published.
+    // (3) MODE_DX only: lists longer than four entries continue in overflow descriptors (four more entries
+    //     + the row they belong to).  A stage's overflow descriptors of this warp are staged in smem one
+    //     stage ahead and processed as extra iterations of the SAME ring after the 8 regular ones, ending
+    //     in a read-modify-write of the row instead of a store - no load latency is exposed.
     constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
-    constexpr int RPG = PIX_PER_WARP / PPI;     // MODE_DX overflow: rows per lane group
-    __shared__ int s_range[MODE == MODE_DX ? NPW : 1][16][PPI + 1];   // overflow entry index at lane-group boundaries
+    constexpr int OD_CAP = 16;                  // MODE_DX: overflow descriptors staged per warp and stage
+    __shared__ int s_range[MODE == MODE_DX ? NPW : 1][16][2];         // per warp, tap: [first overflow descriptor, count]
+    __shared__ ODesc s_od[MODE == MODE_DX ? NPW : 1][2][OD_CAP];      // staged overflow descriptors, double buffered
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
     GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
@@ -337,13 +351,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
                        "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        for (int i = lane; i < taps * (PPI + 1); i += 32) {
-          const int tap = i / (PPI + 1), gq = i - tap * (PPI + 1);
-          s_range[pw][tap][gq] = __ldg(p.start + ((size_t)tile * taps + tap) * TILE_M + r0 + gq * RPG);
+        if (lane < taps) {   // this warp's slice of the overflow descriptor list, per tap: [begin, count]
+          const int* sp = p.start + ((size_t)tile * taps + lane) * TILE_M + r0;
+          const int b0 = __ldg(sp);
+          s_range[pw][lane][0] = b0;
+          s_range[pw][lane][1] = __ldg(sp + PIX_PER_WARP) - b0;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
       }
+      // MODE_DX: copy the warp's overflow descriptors of tap `tap_` into staging buffer `buf_` (async)
+      auto stage_overflow = [&](int tap_, int buf_) {
+        if constexpr (MODE == MODE_DX) {
+          const int ob = s_range[pw][tap_][0];
+          int n16 = s_range[pw][tap_][1];
+          n16 = (n16 < OD_CAP ? n16 : OD_CAP) * 2;   // 16-byte units
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.odesc + ob);
+          for (int i = lane; i < n16; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(&s_od[pw][buf_][0]) + i * 16)),
+                         "l"(src + i * 16) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      };
       uint4 v[RING][4], wq[RING];
       // issue the loads of iteration `it` of the stage (tap_, ch_) into ring slot `slot`
 #define SDB_ISSUE(tap_, ch_, it_, slot_)                                                     \
@@ -357,56 +386,126 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
         v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
       }
+      // MODE_DX: overflow iteration j_ of the current stage = overflow descriptors j_*PPI + grp of this
+      // warp's staged list (up to four more entries of one row); same ring slots, same loads
+#define SDB_ISSUE_OV(j_, slot_)                                                                  \
+      {                                                                                          \
+        const int d_ = (j_) * PPI + grp;                                                         \
+        wq[slot_] = make_uint4(0u, 0u, 0u, 0u);                                                  \
+        if (d_ < nod) {                                                                          \
+          const uint4 o_ = sod[d_].o;                                                            \
+          const uint4 m_ = sod[d_].m;                                                            \
+          wq[slot_].x = __byte_perm(m_.x, m_.x, 0x1010); wq[slot_].y = __byte_perm(m_.x, m_.x, 0x3232); \
+          wq[slot_].z = __byte_perm(m_.y, m_.y, 0x1010); wq[slot_].w = __byte_perm(m_.y, m_.y, 0x3232); \
+          const uint4* xb_ = xbase + ch * (CPS / 8);                                             \
+          const uint4 z_ = make_uint4(0u, 0u, 0u, 0u);                                           \
+          v[slot_][0] = wq[slot_].x ? __ldg(xb_ + o_.x) : z_;                                    \
+          v[slot_][1] = wq[slot_].y ? __ldg(xb_ + o_.y) : z_;                                    \
+          v[slot_][2] = wq[slot_].z ? __ldg(xb_ + o_.z) : z_;                                    \
+          v[slot_][3] = wq[slot_].w ? __ldg(xb_ + o_.w) : z_;                                    \
+        }                                                                                        \
+      }
+#define SDB_INTERP(a_, slot_)                                                                    \
+        a_.x = bf2_fma(wq[slot_].w, v[slot_][3].x, bf2_fma(wq[slot_].z, v[slot_][2].x, bf2_fma(wq[slot_].y, v[slot_][1].x, bf2_mul(wq[slot_].x, v[slot_][0].x)))); \
+        a_.y = bf2_fma(wq[slot_].w, v[slot_][3].y, bf2_fma(wq[slot_].z, v[slot_][2].y, bf2_fma(wq[slot_].y, v[slot_][1].y, bf2_mul(wq[slot_].x, v[slot_][0].y)))); \
+        a_.z = bf2_fma(wq[slot_].w, v[slot_][3].z, bf2_fma(wq[slot_].z, v[slot_][2].z, bf2_fma(wq[slot_].y, v[slot_][1].z, bf2_mul(wq[slot_].x, v[slot_][0].z)))); \
+        a_.w = bf2_fma(wq[slot_].w, v[slot_][3].w, bf2_fma(wq[slot_].z, v[slot_][2].w, bf2_fma(wq[slot_].y, v[slot_][1].w, bf2_mul(wq[slot_].x, v[slot_][0].w))));
 #pragma unroll
       for (int u = 0; u < RING; ++u) SDB_ISSUE(0, 0, u, u)
+      if constexpr (MODE == MODE_DX) stage_overflow(0, 0);
       int tap = 0, ch = 0;
       for (int st = 0; st < nstages; ++st) {
         int ntap = tap + 1, nch = ch;   // K order: chunk outermost, taps inside (L1-friendly)
         if (ntap == taps) { ntap = 0; ++nch; }
         const bool has_next = st + 1 < nstages;
+        // MODE_DX: overflow descriptors of this stage (staged one stage ahead), ring iterations they need
+        int nod = 0, m_ov = 0, ocount = 0;
+        const ODesc* sod = nullptr;
+        if constexpr (MODE == MODE_DX) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          if (has_next) stage_overflow(ntap, (st + 1) & 1);
+          ocount = s_range[pw][tap][1];
+          nod = ocount < OD_CAP ? ocount : OD_CAP;
+          m_ov = ((nod + PPI - 1) / PPI + RING - 1) / RING * RING;
+          sod = &s_od[pw][st & 1][0];
+        }
         mbar_wait(&a_empty[as], ap ^ 1);
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
           const int slot = it % RING;
           uint4 a;
-          a.x = bf2_fma(wq[slot].w, v[slot][3].x, bf2_fma(wq[slot].z, v[slot][2].x, bf2_fma(wq[slot].y, v[slot][1].x, bf2_mul(wq[slot].x, v[slot][0].x))));
-          a.y = bf2_fma(wq[slot].w, v[slot][3].y, bf2_fma(wq[slot].z, v[slot][2].y, bf2_fma(wq[slot].y, v[slot][1].y, bf2_mul(wq[slot].x, v[slot][0].y))));
-          a.z = bf2_fma(wq[slot].w, v[slot][3].z, bf2_fma(wq[slot].z, v[slot][2].z, bf2_fma(wq[slot].y, v[slot][1].z, bf2_mul(wq[slot].x, v[slot][0].z))));
-          a.w = bf2_fma(wq[slot].w, v[slot][3].w, bf2_fma(wq[slot].z, v[slot][2].w, bf2_fma(wq[slot].y, v[slot][1].w, bf2_mul(wq[slot].x, v[slot][0].w))));
+          SDB_INTERP(a, slot)
           *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
           if (it + RING < ITERS) {
             SDB_ISSUE(tap, ch, it + RING, slot)
+          } else if (MODE == MODE_DX && m_ov > 0) {
+            SDB_ISSUE_OV(it + RING - ITERS, slot)
           } else if (has_next) {
             SDB_ISSUE(ntap, nch, it + RING - ITERS, slot)
           }
         }
         if constexpr (MODE == MODE_DX) {
-          const int beg = s_range[pw][tap][grp], cnt = s_range[pw][tap][grp + 1] - beg;
-          const int n_it = __reduce_max_sync(0xffffffffu, cnt);
-          if (n_it > 0) {
+          if (m_ov > 0) {
             __syncwarp();   // rows written above by other lanes of this warp
-            const uint2* oe = p.entries + beg;
-            const uint4* xb = xbase + ch * (CPS / 8);
-            constexpr int OB = 4;   // overflow entries in flight per lane group
-            for (int j0 = 0; j0 < n_it; j0 += OB) {
-              uint2 e[OB];
-              uint4 vv[OB];
+            for (int j0 = 0; j0 < m_ov; j0 += RING) {
 #pragma unroll
-              for (int u = 0; u < OB; ++u) e[u] = (j0 + u < cnt) ? __ldg(oe + j0 + u) : make_uint2(0u, 0u);
+              for (int u = 0; u < RING; ++u) {
+                const int d = (j0 + u) * PPI + grp;
+                uint4 add;
+                SDB_INTERP(add, u)
 #pragma unroll
-              for (int u = 0; u < OB; ++u) vv[u] = (j0 + u < cnt) ? __ldg(xb + e[u].x) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-              for (int u = 0; u < OB; ++u) {   // in order: consecutive entries may hit the same row
-                if (j0 + u < cnt) {
-                  uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(e[u].y & 0xffu, lig & 7));
-                  uint4 a = *rp;
-                  const uint32_t w2 = __byte_perm(e[u].y, e[u].y, 0x3232);
-                  a.x = bf2_fma(w2, vv[u].x, a.x); a.y = bf2_fma(w2, vv[u].y, a.y);
-                  a.z = bf2_fma(w2, vv[u].z, a.z); a.w = bf2_fma(w2, vv[u].w, a.w);
-                  *rp = a;
+                for (int gs = 0; gs < PPI; ++gs) {   // one lane group at a time: two descriptors may share a row
+                  if (grp == gs && d < nod) {
+                    uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(sod[d].m.z, lig & 7));
+                    uint4 a = *rp;
+                    a.x = bf2_add(a.x, add.x); a.y = bf2_add(a.y, add.y);
+                    a.z = bf2_add(a.z, add.z); a.w = bf2_add(a.w, add.w);
+                    *rp = a;
+                  }
+                  __syncwarp();
+                }
+                if (j0 + u + RING < m_ov) {
+                  SDB_ISSUE_OV(j0 + u + RING, u)
+                } else if (has_next) {
+                  SDB_ISSUE(ntap, nch, u, u)
                 }
               }
+            }
+          }
+          // lists so long that the warp's descriptors did not fit the staging buffer: plain loop
+          for (int d0 = OD_CAP; d0 < ocount; d0 += PPI) {
+            const int d = d0 + grp;
+            uint4 add = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t row = 0;
+            if (d < ocount) {
+              const ODesc od = p.odesc[s_range[pw][tap][0] + d];
+              row = od.m.z;
+              const uint4* xb = xbase + ch * (CPS / 8);
+              const uint32_t w[4] = {__byte_perm(od.m.x, od.m.x, 0x1010), __byte_perm(od.m.x, od.m.x, 0x3232),
+                                     __byte_perm(od.m.y, od.m.y, 0x1010), __byte_perm(od.m.y, od.m.y, 0x3232)};
+              const uint32_t o[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (w[k]) {
+                  const uint4 vv = __ldg(xb + o[k]);
+                  add.x = bf2_fma(w[k], vv.x, add.x); add.y = bf2_fma(w[k], vv.y, add.y);
+                  add.z = bf2_fma(w[k], vv.z, add.z); add.w = bf2_fma(w[k], vv.w, add.w);
+                }
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int gs = 0; gs < PPI; ++gs) {
+              if (grp == gs && d < ocount) {
+                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(row, lig & 7));
+                uint4 a = *rp;
+                a.x = bf2_add(a.x, add.x); a.y = bf2_add(a.y, add.y);
+                a.z = bf2_add(a.z, add.z); a.w = bf2_add(a.w, add.w);
+                *rp = a;
+              }
+              __syncwarp();
             }
           }
         }
@@ -417,6 +516,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         ch = nch;
       }
 #undef SDB_ISSUE
+#undef SDB_ISSUE_OV
+#undef SDB_INTERP
     }
   }
   tc_fence_before_sync();
@@ -588,7 +689,7 @@ int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start
   }
   FwdParams p{};
   p.xp = (const __nv_bfloat16*)gy_nhwc; p.desc = (const GDesc*)desc; p.start = start;
-  p.entries = (const uint2*)entries; p.wimg = wimg; p.out = gx; p.g = g;
+  p.odesc = (const ODesc*)entries; p.wimg = wimg; p.out = gx; p.g = g;
   p.mH = g.H; p.mW = g.W; p.mP = (long long)g.N * g.H * g.W; p.ncols = ncols; p.nnb = nnb;
   p.kch = okb * 64; p.out_ch = g.C; p.okb = okb;
   p.num_tiles = cdiv(p.mP, TILE_M);

@@ -200,7 +200,9 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
 // The list of (output pixel p, weight w = bilinear x mask) that reach q through `tap` is stored as
 //   desc[key]  : its first four entries in the forward gather's descriptor format (row offset of p in
 //                the NHWC bf16 dY in 16 B units + bf16x2 weight; unused slots are zero), and
-//   overflow   : entries five and up in a CSR (start[key] .. start[key+1]) of {row offset, w<<16 | row}.
+//   overflow   : entries five and up, four per ODesc (same fields + the row), descriptors of a key
+//                contiguous (start[key] .. start[key+1]) and keys in (tile, tap, row) order, so the
+//                descriptors of one (tile, tap, 16-row warp slice) are one contiguous run.
 // With stride 1 a list holds four entries on average, so most of the work takes the fixed-width path.
 constexpr int DESC_W = 4;
 template <typename F>
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(256) csr_count_kernel(const float* __restrict_
 }
 
 constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block
-__device__ __forceinline__ int overflow_of(int c) { return max(c - DESC_W, 0); }
+__device__ __forceinline__ int overflow_of(int c) { return c > DESC_W ? (c - DESC_W + 3) >> 2 : 0; }   // descriptors
 __global__ void __launch_bounds__(256) csr_block_sums_kernel(const int* __restrict__ cnt, int* __restrict__ bsum,
                                                              int nkeys) {
   const int base = blockIdx.x * SCAN_PER_BLOCK;
@@ -290,9 +292,11 @@ __global__ void __launch_bounds__(1024) csr_scan_top_kernel(int* __restrict__ bs
     __syncthreads();
   }
 }
-// start[k] = exclusive scan of the overflow counts; start[nkeys] = total
+// start[k] = exclusive scan of the overflow descriptor counts; start[nkeys] = total; the descriptors of
+// key k are cleared and tagged with their row here
 __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restrict__ cnt, const int* __restrict__ bsum,
-                                                             int* __restrict__ start, int nkeys) {
+                                                             int* __restrict__ start, ODesc* __restrict__ odesc,
+                                                             int nkeys) {
   __shared__ int wsum[8];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = bsum[blockIdx.x];
@@ -316,6 +320,10 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
     if (k < nkeys) {
       start[k] = excl;
       if (k == nkeys - 1) start[nkeys] = excl + v;
+      for (int d = 0; d < v; ++d) {
+        odesc[excl + d].o = make_uint4(0u, 0u, 0u, 0u);
+        odesc[excl + d].m = make_uint4(0u, 0u, (uint32_t)(k & (TILE_M - 1)), 0u);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 255) carry_s = carry + wbase + incl;
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
 // row_units = 16-byte units per pixel row of the NHWC dY (okb * 8)
 __global__ void __launch_bounds__(256) csr_fill_kernel(const float* __restrict__ off, const float* __restrict__ mask,
                                                        int* __restrict__ cnt, const int* __restrict__ start,
-                                                       GDesc* __restrict__ desc, uint2* __restrict__ entries,
+                                                       GDesc* __restrict__ desc, ODesc* __restrict__ odesc,
                                                        const Geo g, int row_units) {
   const int tap = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,7 +348,10 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const float* __restrict__
       desc[key].off[pos] = poff;
       desc[key].w2[pos] = (wb << 16) | wb;
     } else {
-      entries[start[key] + pos - DESC_W] = make_uint2(poff, (wb << 16) | row);
+      ODesc* od = odesc + start[key] + ((pos - DESC_W) >> 2);
+      const int sl = (pos - DESC_W) & 3;
+      reinterpret_cast<uint32_t*>(&od->o)[sl] = poff;
+      reinterpret_cast<uint16_t*>(&od->m)[sl] = (uint16_t)wb;
     }
   });
 }
@@ -825,12 +836,12 @@ BwdWs bwd_ws(int op, const Geo& g) {
     w.wt_off = o; o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
     const long long tiles_in = cdiv((long long)g.N * g.H * g.W, TILE_M);
     w.nkeys = tiles_in * g.taps() * TILE_M;
-    w.max_entries = 4 * g.P() * g.taps();
+    w.max_entries = g.P() * g.taps() + 1;   // overflow descriptors: a key with c > 4 entries needs ceil((c-4)/4) <= c/4
     w.scan_blocks = cdiv(w.nkeys, SCAN_PER_BLOCK);
     w.cnt_off = o;   o = align_up(o + (size_t)w.nkeys * 4, 1024);
     w.start_off = o; o = align_up(o + (size_t)(w.nkeys + 1) * 4, 1024);
     w.bsum_off = o;  o = align_up(o + (size_t)w.scan_blocks * 4, 1024);
-    w.ent_off = o;   o = align_up(o + (size_t)w.max_entries * 8, 1024);
+    w.ent_off = o;   o = align_up(o + (size_t)w.max_entries * sizeof(ODesc), 1024);
     w.wdx_off = o;   o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
     w.desc_off = o;  o = align_up(o + (size_t)w.nkeys * sizeof(GDesc), 1024);
     w.gyn_off = o;   o = align_up(o + (size_t)g.P() * okb * 64 * 2, 1024);
@@ -918,7 +929,7 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
     int* cnt = (int*)(base + L.cnt_off);
     int* start = (int*)(base + L.start_off);
     int* bsum = (int*)(base + L.bsum_off);
-    uint2* entries = (uint2*)(base + L.ent_off);
+    ODesc* odesc = (ODesc*)(base + L.ent_off);
     GDesc* desc = (GDesc*)(base + L.desc_off);
     __nv_bfloat16* gyn = (__nv_bfloat16*)(base + L.gyn_off);
     const int nkeys = (int)L.nkeys;
@@ -930,11 +941,11 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
     csr_count_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, g);
     csr_block_sums_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
     csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, L.scan_blocks);
-    csr_scan_final_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, start, nkeys);
-    csr_fill_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, start, desc, entries, g, okb * 8);
+    csr_scan_final_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
+    csr_fill_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, start, desc, odesc, g, okb * 8);
     SDB_LAUNCHED(5);
     SDB_CHECK_CUDA(cudaGetLastError());
-    rc = tc_dx(w, gyn, desc, start, entries, base + L.wdx_off, gx, g, okb, io_dtype, st);
+    rc = tc_dx(w, gyn, desc, start, odesc, base + L.wdx_off, gx, g, okb, io_dtype, st);
     if (rc) return rc;
   }
   return SDB_OK;

@@ -116,6 +116,17 @@ struct __align__(16) GDesc {
   uint32_t w2[4];   // bf16x2 (w, w); 0 for a corner that does not contribute
 };
 
+// overflow descriptor of the transposed index (MODE_DX): four more entries of the list of one row
+struct __align__(16) ODesc {
+  uint4 o;   // row offsets of dY, units of 16 bytes
+  uint4 m;   // x = w0 | w1 << 16, y = w2 | w3 << 16 (bf16 weights, 0 = unused slot), z = row in tile, w = 0
+};
+
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
   uint32_t d;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));

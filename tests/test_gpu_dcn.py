@@ -155,6 +155,34 @@ def test_all_taps_outside():
         x.grad = None; off.grad = None; w.grad = None
 
 
+@pytest.mark.parametrize("spread", [0.0, 0.6, 3.0])
+def test_bf16_grad_input_with_long_transposed_lists(spread):
+    """grad_input is computed as a gather over the transposed sampling index; offsets that send every
+    tap of every pixel to (nearly) the same input location give lists of hundreds of entries per
+    (input pixel, tap) - far beyond the 4-entry descriptor and the staged overflow descriptors - while
+    most input pixels get empty lists."""
+    N, C, H, W, O = 2, 64, 11, 13, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(O, C, 3, 3, generator=g) * 0.05
+    gy = torch.randn(N, O, H, W, generator=g)
+    off = torch.zeros(N, 18, H, W)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    for i in range(3):
+        for j in range(3):
+            t = i * 3 + j
+            off[:, 2 * t] = (H / 2 + 0.3) - (ys - 1 + i)       # every tap lands at (H/2+0.3, W/2+0.6) ...
+            off[:, 2 * t + 1] = (W / 2 + 0.6) - (xs - 1 + j)
+    off += torch.randn(N, 18, H, W, generator=g) * spread        # ... plus a spread
+    c = dict(x=x.numpy(), offset=off.numpy(), weight=w.numpy(), grad_out=gy.numpy(), cfg=np.array([1, 1, 1, 1, 1, 1, 1, 1]))
+    y, xd, offd, wd, _, _ = _run(c, "bf16")
+    yo, go = _oracle(c)
+    assert rel_err(y.detach().cpu().numpy(), yo) < TOL["bf16"]
+    assert rel_err(xd.grad.cpu().numpy(), go["grad_x"]) < TOL["bf16"]
+    assert rel_err(offd.grad.cpu().numpy(), go["grad_offset"]) < TOL["bf16"]
+    assert rel_err(wd.grad.cpu().numpy(), go["grad_weight"]) < TOL["bf16"]
+
+
 def test_shape_errors_are_runtime_errors():
     x = torch.randn(1, 8, 6, 6, device="cuda")
     w = torch.randn(4, 8, 3, 3, device="cuda")
