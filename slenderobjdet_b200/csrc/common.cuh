@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/slender_b200.h"
 
@@ -46,6 +47,10 @@ struct Geo {
 inline Geo make_geo(const sdb_dcn_geom& g) {
   Geo d{g.N, g.C_in, g.H, g.W, g.C_out, g.kH, g.kW, g.sH, g.sW, g.pH, g.pW, g.dH, g.dW,
         g.groups, g.deformable_groups, 0, 0, 8, 16};
+  if (const char* e = getenv("SDB_TC_TILE")) {   // "4x32", "8x16", "2x64": pixel walk patch of the tensor-core path
+    int a = 0, b = 0;
+    if (sscanf(e, "%dx%d", &a, &b) == 2 && a > 0 && b > 0 && a * b == 128) { d.th = a; d.tw = b; }
+  }
   d.Ho = (g.H + 2 * g.pH - (g.dH * (g.kH - 1) + 1)) / (g.sH > 0 ? g.sH : 1) + 1;
   d.Wo = (g.W + 2 * g.pW - (g.dW * (g.kW - 1) + 1)) / (g.sW > 0 ? g.sW : 1) + 1;
   return d;

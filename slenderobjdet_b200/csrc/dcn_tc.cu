@@ -138,6 +138,7 @@ struct FwdParams {
   int out_ch;               // channel count of `out`
   int okb;
   int num_tiles, nsa, nsb;
+  int dbg;                  // SDB_TC_DEBUG: 1 = no weight streaming + no MMA issue, 2 = no gather loads (timing experiments)
 };
 
 constexpr int MODE_FWD = 0, MODE_DX = 1;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsa; ++s) {
-      mbar_init(&a_full[s], NPW * 32);
+      mbar_init(&a_full[s], NPW);   // one arrival per gather warp
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < p.nsb; ++s) {
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -201,8 +202,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         const uint8_t* wsrc = p.wimg + (size_t)(work % p.nnb) * nkb_total * B_BYTES;
         for (int kb = 0; kb < nkb_total; ++kb) {
           mbar_wait(&b_empty[bs], bp ^ 1);
+          if (p.dbg & 1) { mbar_arrive(&b_full[bs]); }
+          else {
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
           bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
+          }
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
@@ -224,11 +228,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           if (lane == 0) {
             const uint32_t a_addr = smem_base + as * A_BYTES + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + p.nsa * A_BYTES + bs * B_BYTES;
+            if (!(p.dbg & 1)) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
                         make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
               accumulate = 1;
+            }
             }
             umma_commit(&b_empty[bs]);
           }
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.dbg & 4)) {
           const size_t d0 = ((size_t)n * p.out_ch + ob + c0) * hw + rem;
           if (MODE == MODE_DX) {
             // grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it): fetch the 32 old values
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(&acc_empty[acc]);
+      mbar_arrive_warp(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
   } else {
@@ -329,16 +335,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         int n = 0, ho = 0, wo = 0;
         if (valid) decode_q(g, pix, n, ho, wo);
         __syncwarp();  // every lane is done reading the previous tile's descriptors
-        for (int tap = lane / PIX_PER_WARP; tap < taps; tap += 32 / PIX_PER_WARP) {
-          const Sample sm_ = make_sample(g, fetch_raw(g, p.off, p.mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
-          uint4 o, w;
-          o.x = (uint32_t)sm_.idx[0] * (uint32_t)(C / 8); o.y = (uint32_t)sm_.idx[1] * (uint32_t)(C / 8);
-          o.z = (uint32_t)sm_.idx[2] * (uint32_t)(C / 8); o.w = (uint32_t)sm_.idx[3] * (uint32_t)(C / 8);
-          w.x = pack_bf16x2(sm_.w[0], sm_.w[0]); w.y = pack_bf16x2(sm_.w[1], sm_.w[1]);
-          w.z = pack_bf16x2(sm_.w[2], sm_.w[2]); w.w = pack_bf16x2(sm_.w[3], sm_.w[3]);
-          GDesc* d = sD + tap * TILE_M + r0 + px;
-          *reinterpret_cast<uint4*>(d->off) = o;
-          *reinterpret_cast<uint4*>(d->w2) = w;
+        // all offset loads of the tile first (one exposed latency instead of one per round); the next
+        // tile's offsets are pulled into L2 now so that latency is an L2 hit
+        constexpr int TPR = 32 / PIX_PER_WARP;            // taps per round
+        constexpr int ROUNDS = (16 + TPR - 1) / TPR;      // taps <= 16
+        RawOff raw[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+          const int tap = lane / PIX_PER_WARP + r * TPR;
+          raw[r] = fetch_raw(g, p.off, p.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
+        }
+        {
+          const long long npix = (long long)(work + gridDim.x) / p.nnb * TILE_M + r0 + px;
+          if (npix < g.P()) {
+            int nn, nho, nwo;
+            decode_q(g, npix, nn, nho, nwo);
+            const int hwo = g.Ho * g.Wo;
+            for (int tap = lane / PIX_PER_WARP; tap < taps; tap += TPR) {
+              const float* o = p.off + ((size_t)nn * 2 * taps + 2 * tap) * hwo + nho * g.Wo + nwo;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(o));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(o + hwo));
+              if (p.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + ((size_t)nn * taps + tap) * hwo + nho * g.Wo + nwo));
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+          const int tap = lane / PIX_PER_WARP + r * TPR;
+          if (tap < taps) {
+            const Sample sm_ = make_sample(g, raw[r], valid, n, ho, wo, tap);
+            uint4 o, w;
+            o.x = (uint32_t)sm_.idx[0] * (uint32_t)(C / 8); o.y = (uint32_t)sm_.idx[1] * (uint32_t)(C / 8);
+            o.z = (uint32_t)sm_.idx[2] * (uint32_t)(C / 8); o.w = (uint32_t)sm_.idx[3] * (uint32_t)(C / 8);
+            w.x = pack_bf16x2(sm_.w[0], sm_.w[0]); w.y = pack_bf16x2(sm_.w[1], sm_.w[1]);
+            w.z = pack_bf16x2(sm_.w[2], sm_.w[2]); w.w = pack_bf16x2(sm_.w[3], sm_.w[3]);
+            GDesc* d = sD + tap * TILE_M + r0 + px;
+            *reinterpret_cast<uint4*>(d->off) = o;
+            *reinterpret_cast<uint4*>(d->w2) = w;
+          }
         }
         __syncwarp();
       } else {
@@ -432,6 +466,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         }
         mbar_wait(&a_empty[as], ap ^ 1);
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
+        if (p.dbg & 2) {   // timing experiment: publish the stage without gathering
+          fence_proxy_async_smem();
+          mbar_arrive_warp(&a_full[as]);
+          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+          tap = ntap; ch = nch;
+          continue;
+        }
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
           const int slot = it % RING;
@@ -510,7 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a_full[as]);
+        mbar_arrive_warp(&a_full[as]);
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
         tap = ntap;
         ch = nch;
@@ -623,6 +664,7 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   p.xp = xp; p.off = off; p.mask = mask; p.wimg = wimg; p.bias = bias32; p.out = out; p.g = g;
   p.mH = g.Ho; p.mW = g.Wo; p.mP = g.P(); p.ncols = g.O; p.nnb = 1; p.kch = g.C; p.out_ch = g.O;
   p.num_tiles = cdiv(g.P(), TILE_M);
+  if (const char* e = getenv("SDB_TC_DEBUG")) p.dbg = atoi(e);
   const int lpp = lanes_per_pixel(g);
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors

@@ -408,9 +408,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
-      mbar_init(&stg_full[s], 128);
-      mbar_init(&stg_empty[s], NSW * 32);
+      mbar_init(&acc_empty[s], 4);        // one arrival per drain warp
+      mbar_init(&stg_full[s], 4);
+      mbar_init(&stg_empty[s], NSW);      // one arrival per reduce warp
     }
     fence_barrier_init();
   }
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(&acc_empty[acc]);   // TMEM buffer may be overwritten
-        mbar_arrive(&stg_full[acc]);    // staging tile is ready (release)
+        mbar_arrive_warp(&acc_empty[acc]);   // TMEM buffer may be overwritten
+        mbar_arrive_warp(&stg_full[acc]);    // staging tile is ready (release)
         if (++acc == 2) { acc = 0; accp ^= 1; }
       }
     }
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
             for (int dlt = Q / 2; dlt > 0; dlt >>= 1) kk += __shfl_xor_sync(0xffffffffu, kk, dlt);
             racc[it] += kk;
           }
-          mbar_arrive(&stg_empty[sb]);
+          mbar_arrive_warp(&stg_empty[sb]);
           if (++sb == 2) { sb = 0; sp ^= 1; }
         }
         // lanes lig == 0, Q, 2Q hold d/dy, d/dx, d/dmask of pixel it*PPI+grp
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t g_full[4], g_empty[4], y_full[4], y_empty[4], acc_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ GDesc sdesc[NSW][PIX_PER_WARP];
+  __shared__ GDesc sdesc[NSW][2][PIX_PER_WARP];   // per gather warp, double buffered over tiles
 
   const Geo& g = p.g;
   const int C = g.C, O = g.O, taps = g.KH * g.KW, nch = C / NCH, okb = p.okb, mh_n = okb / 2;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsg; ++s) {
-      mbar_init(&g_full[s], NSW * 32);
+      mbar_init(&g_full[s], NSW);   // one arrival per gather warp
       mbar_init(&g_empty[s], 1);
     }
     for (int s = 0; s < p.nsy; ++s) {
@@ -757,40 +757,93 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
       }
     }
   } else {
-    // gather producers (same sampling as the forward pass)
-    const int sw = warp - FIRST_SW;
-    const int hw = g.Ho * g.Wo;
+    // gather producers (same sampling and the same continuous 4-slot load ring as the forward pass,
+    // running across TILE boundaries here: a CTA handles one (tap, channel chunk) for many tiles).
+    // Descriptors are double buffered per warp and built one tile ahead; the raw offsets they are built
+    // from are fetched two tiles ahead, so neither latency is exposed.
+    constexpr int PPI = 32 / LPB, ITERS = PIX_PER_WARP / PPI, RING = 4;
+    static_assert(ITERS % RING == 0, "ring must divide the per-tile iteration count");
+    const int sw = warp - FIRST_SW, r0 = sw * PIX_PER_WARP;
+    const int grp = lane / LPB, lig = lane % LPB;
     uint32_t gs = 0, gp = 0;
-    const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * NCH + (lane % LPB) * 8);
-    for (int tile = t0; tile < t1; ++tile) {
-      const long long pix = (long long)tile * TILE_M + sw * PIX_PER_WARP + lane;
-      const bool valid = lane < PIX_PER_WARP && pix < g.P();
-      int n = 0, ho = 0, wo = 0;
-      if (valid) decode_q(g, pix, n, ho, wo);
-      const int rem = ho * g.Wo + wo;
-      // forward-style descriptor (weights already x mask, zero outside) -> shared memory
-      __syncwarp();
+    const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * NCH + lig * 8);
+    auto locate = [&](int tile_, bool& valid_, int& n_, int& ho_, int& wo_) {
+      const long long pix = (long long)tile_ * TILE_M + r0 + lane;
+      valid_ = lane < PIX_PER_WARP && tile_ < t1 && pix < g.P();
+      n_ = ho_ = wo_ = 0;
+      if (valid_) decode_q(g, pix, n_, ho_, wo_);
+    };
+    // forward-style descriptor (weights already x mask, zero outside) of this lane's pixel -> sdesc[buf_]
+    auto build_desc = [&](const RawB raw_, bool valid_, int n_, int ho_, int wo_, int buf_) {
       if (lane < PIX_PER_WARP) {
-        const BSample bs = make_bsample(g, p.off, p.mask, valid, n, ho, wo, tap);
+        const BSample bs = make_bsample_raw(g, raw_, valid_, n_, ho_, wo_, tap);
         const float wk[4] = {(1.f - bs.lh) * (1.f - bs.lw), (1.f - bs.lh) * bs.lw, bs.lh * (1.f - bs.lw), bs.lh * bs.lw};
-        GDesc d;
+        uint4 o, w;
+        uint32_t* op = &o.x;
+        uint32_t* wp = &w.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool on = bs.idx[k] >= 0;
-          d.off[k] = on ? (uint32_t)bs.idx[k] * (uint32_t)(C / 8) : 0u;
+          op[k] = on ? (uint32_t)bs.idx[k] * (uint32_t)(C / 8) : 0u;
           const float wv = on ? wk[k] * bs.m : 0.f;
-          d.w2[k] = pack_bf16x2(wv, wv);
+          wp[k] = pack_bf16x2(wv, wv);
         }
-        *reinterpret_cast<uint4*>(sdesc[sw][lane].off) = *reinterpret_cast<const uint4*>(d.off);
-        *reinterpret_cast<uint4*>(sdesc[sw][lane].w2) = *reinterpret_cast<const uint4*>(d.w2);
+        *reinterpret_cast<uint4*>(sdesc[sw][buf_][lane].off) = o;
+        *reinterpret_cast<uint4*>(sdesc[sw][buf_][lane].w2) = w;
       }
+    };
+    bool valid;
+    int n, ho, wo;
+    locate(t0, valid, n, ho, wo);
+    build_desc(fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap), valid, n, ho, wo, t0 & 1);
+    locate(t0 + 1, valid, n, ho, wo);
+    RawB raw = fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap);   // of tile t0 + 1
+    __syncwarp();
+    uint4 v[RING][4], wq[RING];
+#define SDB_WISSUE(tile_, it_, slot_)                                                            \
+    {                                                                                            \
+      const GDesc* d_ = &sdesc[sw][(tile_) & 1][(it_) * PPI + grp];                              \
+      const uint4 o_ = *reinterpret_cast<const uint4*>(d_->off);                                 \
+      wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                       \
+      v[slot_][0] = __ldg(x16 + o_.x);                                                           \
+      v[slot_][1] = __ldg(x16 + o_.y);                                                           \
+      v[slot_][2] = __ldg(x16 + o_.z);                                                           \
+      v[slot_][3] = __ldg(x16 + o_.w);                                                           \
+    }
+    if (t0 < t1) {
+#pragma unroll
+      for (int u = 0; u < RING; ++u) SDB_WISSUE(t0, u, u)
+    }
+    for (int tile = t0; tile < t1; ++tile) {
+      const bool has_next = tile + 1 < t1;
+      // descriptors of tile+1 (its raw offsets arrived during the previous tile), then raw offsets of tile+2
+      __syncwarp();   // buffer (tile+1)&1 was read while tile-1 was gathered
+      build_desc(raw, valid, n, ho, wo, (tile + 1) & 1);
+      locate(tile + 2, valid, n, ho, wo);
+      raw = fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap);
       __syncwarp();
       mbar_wait(&g_empty[gs], gp ^ 1);
-      gather_stage_bf16<LPB, PIX_PER_WARP>(x16, sdesc[sw], sG + (size_t)gs * G_BYTES, sw * PIX_PER_WARP, lane);
+      uint8_t* dst = sG + (size_t)gs * G_BYTES + (lig >> 3) * (TILE_M * 128);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int slot = it % RING;
+        uint4 a;
+        a.x = bf2_fma(wq[slot].w, v[slot][3].x, bf2_fma(wq[slot].z, v[slot][2].x, bf2_fma(wq[slot].y, v[slot][1].x, bf2_mul(wq[slot].x, v[slot][0].x))));
+        a.y = bf2_fma(wq[slot].w, v[slot][3].y, bf2_fma(wq[slot].z, v[slot][2].y, bf2_fma(wq[slot].y, v[slot][1].y, bf2_mul(wq[slot].x, v[slot][0].y))));
+        a.z = bf2_fma(wq[slot].w, v[slot][3].z, bf2_fma(wq[slot].z, v[slot][2].z, bf2_fma(wq[slot].y, v[slot][1].z, bf2_mul(wq[slot].x, v[slot][0].z))));
+        a.w = bf2_fma(wq[slot].w, v[slot][3].w, bf2_fma(wq[slot].z, v[slot][2].w, bf2_fma(wq[slot].y, v[slot][1].w, bf2_mul(wq[slot].x, v[slot][0].w))));
+        *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
+        if (it + RING < ITERS) {
+          SDB_WISSUE(tile, it + RING, slot)
+        } else if (has_next) {
+          SDB_WISSUE(tile + 1, it + RING - ITERS, slot)
+        }
+      }
       fence_proxy_async_smem();
-      mbar_arrive(&g_full[gs]);
+      mbar_arrive_warp(&g_full[gs]);
       if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }
     }
+#undef SDB_WISSUE
   }
   tc_fence_before_sync();
   __syncthreads();
