@@ -10,7 +10,7 @@ def run(N, C, H, W, O, iters=20, mask=False):
     x = torch.randn(N, C, H, W, device="cuda")
     w = torch.randn(O, C, 3, 3, device="cuda") * 0.01
     base = torch.tensor([(y, x_) for y in (-1, 0, 1) for x_ in (-1, 0, 1)], dtype=torch.float32, device="cuda").view(1, 18, 1, 1)
-    off = torch.randn(N, 18, H, W, device="cuda") * 2.0 - base + base  # sigma=2 px around the regular grid
+    off = torch.randn(N, 18, H, W, device="cuda") * float(os.environ.get("SDB_SIGMA", "2.0"))  # sigma=2 px around the regular grid
     m = torch.rand(N, 9, H, W, device="cuda") if mask else None
     out = torch.empty(N, O, H, W, device="cuda")
     wsb = lib.sdb_dcn_workspace_bytes(0, ctypes.byref(g), 0, 1)

@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sA = sm;
   uint8_t* sB = sm + (size_t)p.nsa * A_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index via shfl = provably warp-uniform: role branches and loop counters stay in uniform registers,
+  // so tcgen05.mma takes its descriptors from the uniform datapath without an ELECT/R2UR waterfall per instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint32_t acc_stride = 32;
   while ((int)acc_stride < O) acc_stride <<= 1;
   const uint32_t ncols = 2 * acc_stride;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 0) {
     // ===== weight producer: bulk async copies of pre-swizzled [O x 64] tiles =====
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         for (int kb = 0; kb < KBPS; ++kb) {
           mbar_wait(&b_full[bs], bp);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_addr = smem_base + as * A_BYTES + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + p.nsa * A_BYTES + bs * B_BYTES;
             if (!(p.dbg & 1)) {
@@ -241,11 +243,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           __syncwarp();
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
-        if (lane == 0) umma_commit(&a_empty[as]);
+        if (elect_one()) umma_commit(&a_empty[as]);
         __syncwarp();
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
       }
-      if (lane == 0) umma_commit(&acc_full[acc]);
+      if (elect_one()) umma_commit(&acc_full[acc]);
       __syncwarp();
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
@@ -651,6 +653,7 @@ int tc_forward(const void* x, const float* off, const float* mask, const void* w
   float* bias32 = bias ? (float*)(base + L.bias_off) : nullptr;
   int rc = io_dtype == SDB_F32 ? pack_input<float>(x, xp, g, st) : pack_input<__nv_bfloat16>(x, xp, g, st);
   if (rc) return rc;
+  if (tc_win_supported(g)) return tc_forward_win(xp, off, mask, w, bias, wimg, bias32, out, g, io_dtype, st);
   const long long wtotal = (long long)g.O * g.taps() * (g.C / 8);
   const int wblocks = (int)((wtotal + 255) / 256 < 1184 ? (wtotal + 255) / 256 : 1184);
   if (io_dtype == SDB_F32)

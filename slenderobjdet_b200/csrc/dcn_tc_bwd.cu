@@ -396,7 +396,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
   uint8_t* sA = sm;
   uint8_t* sB = sA + A_BYTES;
   uint8_t* sS = sB + (size_t)p.nsb * B_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index via shfl = provably warp-uniform: role branches and loop counters stay in uniform registers,
+  // so tcgen05.mma takes its descriptors from the uniform datapath without an ELECT/R2UR waterfall per instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr uint32_t NCOLS = 2 * NCH;
 
   if (threadIdx.x == 0) {
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 0) {
     // ===== bulk producer: dY tile once per tile, W^T tiles per (tap, chunk, o-block) =====
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
         for (int kb = 0; kb < okb; ++kb) {
           mbar_wait(&b_full[bs], bp);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_addr = smem_base + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + A_BYTES + bs * B_BYTES;
 #pragma unroll
@@ -463,11 +465,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
           __syncwarp();
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
-        if (lane == 0) umma_commit(&acc_full[acc]);
+        if (elect_one()) umma_commit(&acc_full[acc]);
         __syncwarp();
         if (++acc == 2) { acc = 0; accp ^= 1; }
       }
-      if (lane == 0) umma_commit(&a_empty);
+      if (elect_one()) umma_commit(&a_empty);
       __syncwarp();
     }
   } else if (warp < FIRST_SW) {
@@ -669,7 +671,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sG = sm;
   uint8_t* sY = sG + (size_t)p.nsg * G_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index via shfl = provably warp-uniform: role branches and loop counters stay in uniform registers,
+  // so tcgen05.mma takes its descriptors from the uniform datapath without an ELECT/R2UR waterfall per instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // work item of this CTA
   const int split = blockIdx.x % p.splits;
   const int ch = (blockIdx.x / p.splits) % nch;
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
       mbar_wait(&y_full[ys], yp);
       mbar_wait(&g_full[gs], gp);
       tc_fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t y_addr = smem_base + p.nsg * G_BYTES + ys * Y_BYTES;
         const uint32_t g_addr = smem_base + gs * G_BYTES;
         for (int s = 0; s < TILE_M / 16; ++s) {
@@ -733,7 +737,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
       if (++ys == (uint32_t)p.nsy) { ys = 0; yp ^= 1; }
       if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }
     }
-    if (lane == 0) umma_commit(&acc_full);
+    if (elect_one()) umma_commit(&acc_full);
     __syncwarp();
   } else if (warp < FIRST_SW) {
     // epilogue: partial dW tile -> workspace [split][tap][O][C]

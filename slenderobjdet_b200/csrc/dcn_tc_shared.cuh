@@ -13,6 +13,11 @@ size_t tc_bwd_workspace_bytes(int op, const Geo& g);
 int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start, const void* entries,
           uint8_t* wimg, void* gx, const Geo& g, int okb, int io_dtype, cudaStream_t st);
 
+// forward with the sampling window of each tile staged in shared memory by TMA (dcn_tc_win.cu)
+bool tc_win_supported(const Geo& g);
+int tc_forward_win(const __nv_bfloat16* xp, const float* off, const float* mask, const void* w, const void* bias,
+                   uint8_t* wimg, float* bias32, void* out, const Geo& g, int io_dtype, cudaStream_t st);
+
 namespace tcshared {
 using namespace tc;
 
