@@ -1,21 +1,21 @@
 // dcn_tc_win.cu -- deformable convolution forward on tcgen05 with the input halo window of every
-// tile staged in shared memory by TMA (cp.async.bulk.tensor), sm_100a only.
+// tile staged in shared memory by TMA (cp.async.bulk.tensor), sm_100a only.  Opt-in: SDB_TC_WIN=1.
 //
 // Why: in the L2-gather kernel (dcn_tc.cu) every (pixel, tap, corner) is a 16-byte load per lane that
-// misses L1, so a 128-pixel tile pulls 2.4 MB of corner rows + 1.2 MB of weights through the L2->SM
-// fabric; at the chip-wide L2 cap (~6300 B/clk) that, not the tensor pipe, bounded the kernel
-// (profiles/r1_*: 930 MB per P3 launch, 87 us).  Here a tile is a compact th x tw patch of ONE
-// image; for each 64-channel chunk the producer warp issues one 4-D tensor-map copy of the patch's
-// sampling window [BH][BW][64 ch] (out-of-image rows/columns zero-filled by TMA, which is exactly
-// the reference's "corner outside the image reads 0" rule, deform_conv_cuda_kernel.cu:104-128)
-// into one of two window buffers, and the 16 gather warps read the four bilinear corners with
-// LDS.128 (128 B/clk/SM, conflict-free: 8 lanes cover one pixel's 128 bytes).  L2 traffic per tile
-// drops from 2.4 MB to 4 x 66 KB.  Samples whose corners fall outside the window (|offset| > R)
-// take a per-pixel fallback through global memory, so any offset is still exact.
+// mostly misses L1: a 128-pixel tile pulls 2.4 MB of corner rows + 1.2 MB of weights through the L2->SM
+// fabric and fills + reads every corner line in the L1 data array.  Here a tile is a compact th x tw patch
+// of ONE image; for each 64-channel chunk the window producer issues one 4-D tensor-map copy of the
+// patch's sampling window [BH][BW][64 ch] (out-of-image rows/columns zero-filled by TMA, which is exactly
+// the reference's "corner outside the image reads 0" rule, deform_conv_cuda_kernel.cu:104-128) into one
+// of two window buffers, and 16 gather warps read the four bilinear corners with LDS.128 (conflict-free:
+// 8 lanes cover one pixel's 128 bytes).  Samples whose corners fall outside the window (|offset| > R,
+// R = 3 px for C_out = 256) take a per-pixel path through global memory one stage ahead in the same
+// register ring, so any offset is still exact.  Weight stages can be fetched half each by the two CTAs of
+// a cluster and multicast.  K order: (chunk of 64 channels, tap); A stage = 128 px x 64 ch, 128B-swizzled;
+// B stage = C_out x 64; two stages of each.
 //
-// K order: (chunk of 64 channels, tap); a pipeline stage = A (128 pixels x 64 channels, 128B-swizzled)
-// + B (C_out x 64 weights), two stages, one full/empty barrier pair per stage.  Weight stages can be
-// fetched half each by the two CTAs of a cluster and multicast (halves the L2 reads of the weights).
+// Status (profiles/r1_win_trace.md): parity green; ~20 % slower than dcn_tc.cu on the RepPoints shapes
+// because the gather's per-stage wait / fence / arrive is not overlapped with shared-memory reads yet.
 //
 // Reference semantics: d2/layers/csrc/deformable/deform_conv_cuda_kernel.cu:96-130 (bilinear),
 // :216-288 (im2col + validity), :785-868 (mask), deform_conv_cuda.cu:397-409 (GEMM).
