@@ -121,8 +121,9 @@ __device__ __forceinline__ Key block_best(Key k, Key* s_red) {
   return r;
 }
 
-template <bool FROM_BOXES>
-__global__ void __launch_bounds__(1024) per_gt_kernel(const float4* __restrict__ gt,
+// TOPK: the per-thread candidate lists need 64+ registers -> 512-thread blocks; the low-quality-match scan runs 1024
+template <bool FROM_BOXES, bool TOPK>
+__global__ void __launch_bounds__(TOPK ? 512 : 1024) per_gt_kernel(const float4* __restrict__ gt,
                                                       const float4* __restrict__ anchors,
                                                       const float* __restrict__ q, int M, int X,
                                                       int topk, int8_t* __restrict__ labels) {
@@ -142,7 +143,48 @@ __global__ void __launch_bounds__(1024) per_gt_kernel(const float4* __restrict__
     return q[(size_t)m * X + x];
   };
   const Key none = {-INFINITY, 0x7fffffff};
-  if (topk > 0) {
+  constexpr int KMAX = 16;
+  if (TOPK && topk > 0 && topk <= KMAX) {
+    // one pass over the anchors: every thread keeps its own KMAX best keys sorted in registers (bubble
+    // insertion, static indexing); the block then pops the best list head `topk` times.  Same total order
+    // as q.topk(k, dim=1) with the lowest-index tie rule, without re-evaluating the IoU k times.
+    Key loc[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) loc[j] = none;
+    for (int x0 = threadIdx.x; x0 < X; x0 += 4 * blockDim.x) {
+      float vals[4];   // four independent loads / IoUs in flight before the (serial) insertions
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int x = x0 + u * blockDim.x;
+        vals[u] = x < X ? value(x) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int x = x0 + u * blockDim.x;
+        Key cur = {vals[u], x};
+        if (x < X && before(cur, loc[KMAX - 1])) {
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j) {
+            if (before(cur, loc[j])) {
+              const Key t = loc[j];
+              loc[j] = cur;
+              cur = t;
+            }
+          }
+        }
+      }
+    }
+    for (int r = 0; r < topk; ++r) {
+      const Key best = block_best(loc[0], s_red);
+      if (best.i >= X) break;  // fewer than k anchors (host rejects this case)
+      if (loc[0].i == best.i) {   // the owner records the label and pops its head
+        labels[best.i] = 1;
+#pragma unroll
+        for (int j = 0; j + 1 < KMAX; ++j) loc[j] = loc[j + 1];
+        loc[KMAX - 1] = none;
+      }
+    }
+  } else if (topk > 0) {
     // k rounds: best key that ranks strictly after the previously selected one
     Key prev = {INFINITY, -1};
     for (int r = 0; r < topk; ++r) {
@@ -229,12 +271,15 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
   }
   SDB_CHECK_CUDA(cudaGetLastError());
   if (topk > 0 || alq) {
-    const int threads = X >= 8192 ? 1024 : 256;
-    if (from_boxes)
-      per_gt_kernel<true><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr,
-                                                 M, X, topk, match_labels);
-    else
-      per_gt_kernel<false><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels); SDB_LAUNCHED(1);
+    const int threads = X >= 8192 ? (topk > 0 ? 512 : 1024) : 256;
+    if (from_boxes) {
+      if (topk > 0) per_gt_kernel<true, true><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr, M, X, topk, match_labels);
+      else          per_gt_kernel<true, false><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr, M, X, topk, match_labels);
+    } else {
+      if (topk > 0) per_gt_kernel<false, true><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels);
+      else          per_gt_kernel<false, false><<<M, threads, 0, st>>>(nullptr, nullptr, q, M, X, topk, match_labels);
+    }
+    SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   return SDB_OK;
