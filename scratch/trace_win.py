@@ -12,7 +12,7 @@ L = ctypes.CDLL(_lib.lib()._name) if hasattr(_lib.lib(), "_name") else _lib.lib(
 print("rc", L.sdb_debug_read_trace(buf.ctypes.data_as(ctypes.c_void_p), buf.size))
 t = buf.reshape(3, 2, 64, 4).astype(np.int64)
 t0 = t[0, 0, 0, 0]
-for k in range(1):
+for k in range(2):
     print("tile", k)
     for st in range(int(sys.argv[2]) if len(sys.argv) > 2 else 36):
         g, m, w = t[0, k, st] - t0, t[1, k, st] - t0, t[2, k, st] - t0

@@ -31,17 +31,17 @@ namespace {
 using namespace tc;
 using namespace tcshared;
 
-constexpr int W_NPW = 16;                      // gather warps (4 per scheduler: the gather is latency-bound per warp)
+constexpr int W_NPW = 8;                       // gather warps
 constexpr int W_FIRST_PW = 7;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6 window TMA, 7.. gather
 constexpr int W_NTHREADS = (W_FIRST_PW + W_NPW) * 32;
 constexpr int W_NS = 2;                        // pipeline stages (A 16 KB + B O x 128 B each)
 constexpr int W_A_BYTES = TILE_M * 128;        // one A stage: 128 pixels x 64 channels bf16
 constexpr int W_PIXW = TILE_M / W_NPW;         // pixels per gather warp
-constexpr int W_LPP = 8;                       // lanes per pixel (8 channels each)
+constexpr int W_LPP = 4;                       // lanes per pixel: 2 x 8 channels each (the gather is issue-bound: fewer, fatter iterations)
 constexpr int W_PPI = 32 / W_LPP;              // pixels per warp instruction
 constexpr int W_ITERS = W_PIXW / W_PPI;
-constexpr int W_RING = W_ITERS;                // register ring slots (one warp iteration = 4 pixels x 64 channels each)
-static_assert(W_PIXW % W_PPI == 0 && W_ITERS == W_RING, "the ring is exactly one stage deep");
+constexpr int W_RING = 2;                      // register ring slots (one warp iteration = 8 pixels x 64 channels)
+static_assert(W_PIXW % W_PPI == 0 && W_NPW == 8 && (32 / W_PPI) % W_RING == 0, "two groups of four gather warps, 32 px each");
 
 struct WinParams {
   CUtensorMap tmap;          // NHWC bf16 input as (c, x, y, n), box (64, BW, BH, 1)
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < W_NS; ++s) {
-      mbar_init(&full[s], W_NPW);
+      mbar_init(&full[s], W_NPW / 2);   // one gather warp group (4 warps x 32 px) fills a stage
       mbar_init(&empty[s], 1);
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], cl);     // released by the MMA warp of every CTA in the cluster
@@ -326,21 +326,28 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
     // through a 4-slot register ring: the corner loads of the NEXT stage are issued while this stage is
     // interpolated and stored, so out-of-window samples (global loads, L2 latency) are a full stage ahead
     // of their use instead of stalling all eight warps at every stage.
-    const int pw = warp - W_FIRST_PW, r0 = pw * W_PIXW;
+    // Two warp groups alternate stages: group gi fills the A buffer gi (stages of that parity), each of its
+    // four warps 32 pixels.  While one group waits / fences / arrives, the other one keeps the shared-memory
+    // pipe busy (with all warps in lock-step those ~700 clk per stage were dead time, profiles/r1_win_trace.md).
+    const int pw = warp - W_FIRST_PW, r0 = pw * W_PIXW;   // r0: rows whose descriptors this warp builds
+    const int gi = pw >> 2, rg = (pw & 3) * 32;            // gather: group and first row of this warp
     const int grp = lane / W_LPP, lig = lane % W_LPP;
+    // each lane owns two 16-byte chunks of its pixel's 128-byte row: chunks (lig, lig + 4), taken in opposite
+    // order by odd pixels so the two pixels of a quarter-warp never hit the same banks in one LDS / STS
+    const int ca = lig + 4 * (grp & 1), cb = lig + 4 * ((grp & 1) ^ 1);
     const uint32_t pitch = (uint32_t)p.BW * 128u;
-    const uint4* xg = reinterpret_cast<const uint4*>(p.xp) + lig;
+    const uint4* xg = reinterpret_cast<const uint4*>(p.xp);
     const uint32_t c16 = (uint32_t)(g.C / 8);
-    const uint32_t win0 = smem_u32(sWin) + lig * 16;
-    const uint32_t desc0 = smem_u32(sDesc) + (uint32_t)(r0 + grp) * 16u;
-    uint32_t s = 0, ph = 0, wb = 0, wph = 0;
+    const uint32_t win0 = smem_u32(sWin);
+    const uint32_t desc0 = smem_u32(sDesc) + (uint32_t)(rg + grp) * 16u;
+    int tcount = 0;   // tiles done by this CTA: stage / chunk counters below continue across tiles
     for (int k = 0; k < niter; ++k) {
       const int work = SDB_TILE_OF(k);
       if (work >= p.num_tiles) continue;
       const int n = work / tiles_per_img, trem = work - n * tiles_per_img;
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
       const int wy0 = ty * g.th * g.sh - g.ph - p.R, wx0 = tx * g.tw * g.sw - g.pw - p.R;
-      __syncwarp();   // every lane is done with the previous tile's descriptors
+      asm volatile("bar.sync 1, %0;" ::"n"(W_NPW * 32));   // all gather warps are done with the previous tile's descriptors
       // (1) sampling descriptors of this warp's pixels for every tap: window byte offset of corner
       //     (y0, x0) -- or, flagged, (y0, x0) itself when a corner is outside the window -- and the
       //     four bilinear weights (x mask) as bf16
@@ -409,10 +416,10 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
             sDesc[tap * TILE_M + r] = d;
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(W_NPW * 32));   // descriptors of all 128 pixels are in place
       }
       // (2) the gather stream
-      uint4 v[W_RING][4];
+      uint4 v[W_RING][8];   // [slot][corner * 2 + chunk]
       uint32_t wa[W_RING], wbv[W_RING];
       // issue the four corner loads of iteration it_ of stage (tap_, ch_), whose window buffer starts at wbase_
 #define SDB_WDESC(tap_, it_) lds128(desc0 + (uint32_t)((tap_) * TILE_M + (it_) * W_PPI) * 16u)
@@ -421,73 +428,97 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
         wa[slot_] = dd_.y;                                                                       \
         wbv[slot_] = dd_.z;                                                                      \
         if (!(dd_.x >> 31)) {                                                                    \
-          const uint32_t a_ = (wbase_) + dd_.x;                                                  \
-          v[slot_][0] = lds128(a_);                                                              \
-          v[slot_][1] = lds128(a_ + 128);                                                        \
-          v[slot_][2] = lds128(a_ + pitch);                                                      \
-          v[slot_][3] = lds128(a_ + pitch + 128);                                                \
+          const uint32_t a_ = (wbase_) + dd_.x + ca * 16, b_ = (wbase_) + dd_.x + cb * 16;       \
+          v[slot_][0] = lds128(a_);                 v[slot_][1] = lds128(b_);                    \
+          v[slot_][2] = lds128(a_ + 128);           v[slot_][3] = lds128(b_ + 128);              \
+          v[slot_][4] = lds128(a_ + pitch);         v[slot_][5] = lds128(b_ + pitch);            \
+          v[slot_][6] = lds128(a_ + pitch + 128);   v[slot_][7] = lds128(b_ + pitch + 128);      \
         } else {   /* a corner outside the staged window: the four corners come from global memory */ \
           const int y0_ = (int)((dd_.x >> 16) & 0x7fffu) - 1, x0_ = (int)(dd_.x & 0xffffu) - 1;  \
           const int ya_ = max(y0_, 0), yb_ = min(y0_ + 1, g.H - 1), xa_ = max(x0_, 0), xb_ = min(x0_ + 1, g.W - 1); \
           const uint32_t rowa_ = (uint32_t)(n * g.H + ya_) * (uint32_t)g.W, rowb_ = (uint32_t)(n * g.H + yb_) * (uint32_t)g.W; \
           const uint4* xb2_ = xg + (ch_) * 8;                                                    \
-          v[slot_][0] = __ldg(xb2_ + (size_t)(rowa_ + xa_) * c16);                               \
-          v[slot_][1] = __ldg(xb2_ + (size_t)(rowa_ + xb_) * c16);                               \
-          v[slot_][2] = __ldg(xb2_ + (size_t)(rowb_ + xa_) * c16);                               \
-          v[slot_][3] = __ldg(xb2_ + (size_t)(rowb_ + xb_) * c16);                               \
+          const uint4* p0_ = xb2_ + (size_t)(rowa_ + xa_) * c16;                                 \
+          const uint4* p1_ = xb2_ + (size_t)(rowa_ + xb_) * c16;                                 \
+          const uint4* p2_ = xb2_ + (size_t)(rowb_ + xa_) * c16;                                 \
+          const uint4* p3_ = xb2_ + (size_t)(rowb_ + xb_) * c16;                                 \
+          v[slot_][0] = __ldg(p0_ + ca); v[slot_][1] = __ldg(p0_ + cb);                          \
+          v[slot_][2] = __ldg(p1_ + ca); v[slot_][3] = __ldg(p1_ + cb);                          \
+          v[slot_][4] = __ldg(p2_ + ca); v[slot_][5] = __ldg(p2_ + cb);                          \
+          v[slot_][6] = __ldg(p3_ + ca); v[slot_][7] = __ldg(p3_ + cb);                          \
         }                                                                                        \
       }
-      mbar_wait(&w_full[wb], wph);   // window of chunk 0
-      {
-        const uint32_t wbase = win0 + wb * p.win_bytes;
+      constexpr int G_ITERS = 32 / W_PPI;   // iterations per stage per warp
+      const int gs0 = tcount * nstages, gc0 = tcount * nchunks;
+      const int st0 = ((gs0 & 1) == gi) ? 0 : 1;
+      auto wbuf = [&](int c_) { return (uint32_t)((gc0 + c_) & 1); };
+      auto wpar = [&](int c_) { return (uint32_t)(((gc0 + c_) >> 1) & 1); };
+      int rel = 0;   // next window chunk this warp has to release
+      if (st0 < nstages) {
+        const int ch0 = st0 / taps, tap0 = st0 - ch0 * taps;
+        mbar_wait(&w_full[wbuf(ch0)], wpar(ch0));
+        const uint32_t wbase = win0 + wbuf(ch0) * p.win_bytes;
 #pragma unroll
         for (int u = 0; u < W_RING; ++u) {
-          const uint4 dd = SDB_WDESC(0, u);
-          SDB_WISSUE(dd, 0, u, wbase)
+          const uint4 dd = SDB_WDESC(tap0, u);
+          SDB_WISSUE(dd, ch0, u, wbase)
         }
       }
-      int tap = 0, ch = 0;
-      for (int st = 0; st < nstages; ++st) {
-        int ntap = tap + 1, nch = ch;
-        if (ntap == taps) { ntap = 0; ++nch; }
-        const bool has_next = st + 1 < nstages;
-        uint32_t nwb = wb, nwph = wph;
-        if (ntap == 0) { nwb = wb ^ 1; nwph = wph ^ (wb == 1 ? 1u : 0u); }
-        if (has_next && ntap == 0) mbar_wait(&w_full[nwb], nwph);   // first stage of the next chunk reads the other buffer
-        const uint32_t nwbase = win0 + nwb * p.win_bytes;
-        uint4 nd[W_ITERS];   // next stage's descriptors: their latency overlaps this stage's interpolation
-#pragma unroll
-        for (int it = 0; it < W_ITERS; ++it) nd[it] = has_next ? SDB_WDESC(ntap, it) : make_uint4(0u, 0u, 0u, 0u);
+      for (int st = st0; st < nstages; st += 2) {
+        const int ch = st / taps, tap = st - ch * taps;
+        const int nst = st + 2;
+        const bool has_next = nst < nstages;
+        const int nch = has_next ? nst / taps : nchunks, ntap = has_next ? nst - nch * taps : 0;
+        if (has_next && nch != ch) mbar_wait(&w_full[wbuf(nch)], wpar(nch));
+        const uint32_t cwbase = win0 + wbuf(ch) * p.win_bytes, nwbase = win0 + wbuf(has_next ? nch : ch) * p.win_bytes;
+        const uint32_t use = (uint32_t)(gs0 + st) >> 1;   // how many times buffer gi has been filled before
         if (pw == 0) SDB_TRACE(0, k, st, 0)
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait(&empty[gi], (use & 1) ^ 1);
         if (pw == 0) SDB_TRACE(0, k, st, 1)
-        uint8_t* dst = sA + (size_t)s * W_A_BYTES;
+        uint8_t* dst = sA + (size_t)gi * W_A_BYTES;
         if (!(p.dbg & 16))
 #pragma unroll
-        for (int it = 0; it < W_ITERS; ++it) {
-          const uint32_t w00 = __byte_perm(wa[it], wa[it], 0x1010), w01 = __byte_perm(wa[it], wa[it], 0x3232);
-          const uint32_t w10 = __byte_perm(wbv[it], wbv[it], 0x1010), w11 = __byte_perm(wbv[it], wbv[it], 0x3232);
-          uint4 a;
-          a.x = bf2_fma(w11, v[it][3].x, bf2_fma(w10, v[it][2].x, bf2_fma(w01, v[it][1].x, bf2_mul(w00, v[it][0].x))));
-          a.y = bf2_fma(w11, v[it][3].y, bf2_fma(w10, v[it][2].y, bf2_fma(w01, v[it][1].y, bf2_mul(w00, v[it][0].y))));
-          a.z = bf2_fma(w11, v[it][3].z, bf2_fma(w10, v[it][2].z, bf2_fma(w01, v[it][1].z, bf2_mul(w00, v[it][0].z))));
-          a.w = bf2_fma(w11, v[it][3].w, bf2_fma(w10, v[it][2].w, bf2_fma(w01, v[it][1].w, bf2_mul(w00, v[it][0].w))));
-          if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * W_PPI + grp, lig)) = a;
-          if (has_next) SDB_WISSUE(nd[it], nch, it, nwbase)
+        for (int it = 0; it < G_ITERS; ++it) {
+          const int sl = it % W_RING;
+          const uint32_t w00 = __byte_perm(wa[sl], wa[sl], 0x1010), w01 = __byte_perm(wa[sl], wa[sl], 0x3232);
+          const uint32_t w10 = __byte_perm(wbv[sl], wbv[sl], 0x1010), w11 = __byte_perm(wbv[sl], wbv[sl], 0x3232);
+          uint4 a, b;
+          a.x = bf2_fma(w11, v[sl][6].x, bf2_fma(w10, v[sl][4].x, bf2_fma(w01, v[sl][2].x, bf2_mul(w00, v[sl][0].x))));
+          a.y = bf2_fma(w11, v[sl][6].y, bf2_fma(w10, v[sl][4].y, bf2_fma(w01, v[sl][2].y, bf2_mul(w00, v[sl][0].y))));
+          a.z = bf2_fma(w11, v[sl][6].z, bf2_fma(w10, v[sl][4].z, bf2_fma(w01, v[sl][2].z, bf2_mul(w00, v[sl][0].z))));
+          a.w = bf2_fma(w11, v[sl][6].w, bf2_fma(w10, v[sl][4].w, bf2_fma(w01, v[sl][2].w, bf2_mul(w00, v[sl][0].w))));
+          b.x = bf2_fma(w11, v[sl][7].x, bf2_fma(w10, v[sl][5].x, bf2_fma(w01, v[sl][3].x, bf2_mul(w00, v[sl][1].x))));
+          b.y = bf2_fma(w11, v[sl][7].y, bf2_fma(w10, v[sl][5].y, bf2_fma(w01, v[sl][3].y, bf2_mul(w00, v[sl][1].y))));
+          b.z = bf2_fma(w11, v[sl][7].z, bf2_fma(w10, v[sl][5].z, bf2_fma(w01, v[sl][3].z, bf2_mul(w00, v[sl][1].z))));
+          b.w = bf2_fma(w11, v[sl][7].w, bf2_fma(w10, v[sl][5].w, bf2_fma(w01, v[sl][3].w, bf2_mul(w00, v[sl][1].w))));
+          if (!(p.dbg & 2)) {
+            const uint32_t row = rg + it * W_PPI + grp;
+            *reinterpret_cast<uint4*>(dst + sw128_offset(row, ca)) = a;
+            *reinterpret_cast<uint4*>(dst + sw128_offset(row, cb)) = b;
+          }
+          if (it + W_RING < G_ITERS) {
+            const uint4 dd = SDB_WDESC(tap, it + W_RING);
+            SDB_WISSUE(dd, ch, sl, cwbase)
+          } else if (has_next) {
+            const uint4 dd = SDB_WDESC(ntap, it + W_RING - G_ITERS);
+            SDB_WISSUE(dd, nch, sl, nwbase)
+          }
         }
         if (pw == 0) SDB_TRACE(0, k, st, 2)
         fence_proxy_async_smem();
-        mbar_arrive_warp(&full[s]);
+        mbar_arrive_warp(&full[gi]);
         if (pw == 0) SDB_TRACE(0, k, st, 3)
-        if (++s == W_NS) { s = 0; ph ^= 1; }
-        if (ntap == 0) {   // last stage of this chunk: every load from its window buffer has been consumed
+        // window chunks this warp will not read again (its next stage is in chunk nch, or the tile is done)
+        for (; rel < nch; ++rel) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&w_empty[wb]);
+          if (lane == 0) mbar_arrive(&w_empty[wbuf(rel)]);
         }
-        wb = nwb; wph = nwph;
-        tap = ntap;
-        ch = nch;
       }
+      for (; rel < nchunks; ++rel) {   // (only when this warp had no stage at all in the last chunks)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_empty[wbuf(rel)]);
+      }
+      ++tcount;
 #undef SDB_WISSUE
 #undef SDB_WDESC
     }
