@@ -281,6 +281,25 @@ def test_window_forward_vs_oracle(monkeypatch, cl, modulated, shape):
     assert rel_err(y.detach().cpu().numpy(), yo) < TOL["bf16"]
 
 
+@pytest.mark.parametrize("cfg", [(2, 2, 2, 2, 2, 2), (2, 1, 1, 1, 1, 1), (1, 1, 2, 2, 2, 2), (1, 2, 0, 1, 1, 1)])
+def test_window_forward_strided_dilated(monkeypatch, cfg):
+    """Window geometry with stride / dilation / asymmetric padding (the window origin and extent depend on all
+    three): forward against the CPU oracle."""
+    monkeypatch.setenv("SDB_TC_WIN", "1")
+    sh, sw, ph, pw, dh, dw = cfg
+    g = torch.Generator().manual_seed(9)
+    N, C, H, W, O, k = 2, 64, 23, 31, 64, 3
+    Ho = (H + 2 * ph - (dh * (k - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (k - 1) + 1)) // sw + 1
+    c = dict(x=torch.randn(N, C, H, W, generator=g).numpy(), weight=(torch.randn(O, C, k, k, generator=g) * 0.05).numpy(),
+             offset=(torch.randn(N, 2 * k * k, Ho, Wo, generator=g) * 1.5).numpy(),
+             grad_out=torch.randn(N, O, Ho, Wo, generator=g).numpy(), cfg=np.array([sh, sw, ph, pw, dh, dw, 1, 1]))
+    y, *_ = _run(c, "bf16", need_grads=False)
+    yo = odcn.forward(c["x"], c["offset"], c["weight"], stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw),
+                      groups=1, deformable_groups=1)
+    assert rel_err(y.detach().cpu().numpy(), yo) < TOL["bf16"]
+
+
 def test_window_forward_matches_l2_gather_kernel(monkeypatch):
     """Both forward kernels on the RepPoints P4 shape: same bf16 operands, so they agree far inside the tolerance."""
     c = _random_case(5, 2, 256, 50, 84, 256, False, 2.0)
