@@ -126,8 +126,13 @@ def test_zero_offset_equals_conv2d(math):
     assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < TOL[math]
 
 
-def test_bf16_tensors_io():
-    c = _random_case(9, 2, 64, 12, 14, 64, False, 1.0)
+@pytest.mark.parametrize("shape", [(2, 64, 12, 14, 64), (2, 128, 13, 21, 80), (1, 64, 25, 42, 256), (3, 64, 7, 11, 48),
+                                   (2, 256, 50, 84, 256)])
+def test_bf16_tensors_io(shape):
+    """bf16 tensors in and out (the layout-pack kernels have bf16-specialised paths: even / odd plane sizes,
+    ragged 8x16 patches at the borders, C_out not a multiple of 64)."""
+    N, C, H, W, O = shape
+    c = _random_case(9 + H, N, C, H, W, O, False, 1.0)
     yo, go = _oracle(c)
     x = _dev(c["x"], torch.bfloat16).requires_grad_()
     off = _dev(c["offset"]).requires_grad_()
