@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of libslender_b200.so (see include/slender_b200.h).
 #include <stdarg.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -15,6 +16,26 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  struct Entry { const void* k; int dev; size_t bytes; };
+  static Entry tab[256];
+  static int n = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n; ++i)
+    if (tab[i].k == kernel && tab[i].dev == dev) {
+      if (bytes <= tab[i].bytes) return cudaSuccess;
+      const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e == cudaSuccess) tab[i].bytes = bytes;
+      return e;
+    }
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && n < 256) tab[n++] = Entry{kernel, dev, bytes};
+  return e;
 }
 
 // shape_check restated (d2/layers/csrc/deformable/deform_conv_cuda.cu:140-270)

@@ -69,6 +69,12 @@ struct ProfScope {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (kernel, device) and raised only when a launch
+// needs more: the attribute call is a driver round trip on every launch otherwise (the public-API step is
+// host-bound).  Implemented in api.cu.
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+#define SDB_ENSURE_SMEM(kernel, bytes) SDB_CHECK_CUDA(sdb::ensure_dynamic_smem((const void*)(kernel), (bytes)))
+
 // ---- launchers implemented per translation unit ------------------------------------------------
 // SIMT fp32 path (dcn_simt.cu)
 int simt_forward(const float* x, const float* off, const float* mask, const float* w,

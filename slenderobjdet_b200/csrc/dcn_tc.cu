@@ -593,8 +593,7 @@ FwdWs fwd_ws(const Geo& g) {
 
 template <int LPP, bool OUT_BF16, int MODE>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>), smem);
   if (const char* e = getenv("SDB_TC_CARVEOUT"))   // timing experiment: percent of the unified L1/smem array given to shared memory
     SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
   ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : 3, st);   // slot 3 = grad_input GEMM

@@ -1024,8 +1024,8 @@ int tc_backward_data(const void* x, const float* off, const float* mask, const v
     p.nsb = (int)nsb;
     const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_data_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<128>, smem);
+    else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
     {
       ProfScope prof(SDB_OP_BACKWARD_DATA, st);
       if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
@@ -1096,8 +1096,8 @@ int tc_backward_weight(const void* x, const float* off, const float* mask, const
     p.nsg = (int)nsg;
     const size_t smem = p.nsg * g_bytes + p.nsy * y_bytes + 1024;
     const int grid = g.taps() * nch_chunks(g) * p.splits;
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_bwd_weight_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<128>, smem);
+    else SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<64>, smem);
     {
       ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
       if (NCH == 128) dcn_bwd_weight_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);

@@ -631,7 +631,7 @@ int tc_forward_win(const __nv_bfloat16* xp, const float* off, const float* mask,
   if (grid > max_grid) grid = max_grid;
   const bool obf = io_dtype == SDB_BF16;
   void (*kern)(const WinParams) = obf ? dcn_fwd_win_kernel<true> : dcn_fwd_win_kernel<false>;
-  SDB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  SDB_ENSURE_SMEM(kern, pl.smem);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(W_NTHREADS);

@@ -118,79 +118,110 @@ def _compute_dtype(t):
     return t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.float32
 
 
+_PLAN_CACHE = {}
+
+
 def _plan(input, weight, g):
-    """-> (compute dtype, io_dtype enum, math enum).  bf16 tensors whose geometry the tensor-core
-    path does not cover are computed in float32 on the SIMT path."""
+    """-> (compute dtype, io_dtype enum, math enum, (Ho, Wo), workspace bytes per op, packed-input bytes).
+    bf16 tensors whose geometry the tensor-core path does not cover are computed in float32 on the SIMT
+    path.  Cached per (geometry, dtype, math mode): the public-API step is host-bound, and these are six
+    ctypes round trips per call otherwise."""
+    key = (tuple(getattr(g, f) for f, _ in g._fields_), input.dtype, _MATH)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        return hit
+    lib = _lib.lib()
     cdt = _compute_dtype(input)
     iod = _lib.SDB_F32 if cdt == torch.float32 else _lib.SDB_BF16
     mth = _pick_math(g, iod)
     if mth == _lib.SDB_MATH_FP32 and iod != _lib.SDB_F32:
         cdt, iod = torch.float32, _lib.SDB_F32
-    return cdt, iod, mth
+    ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.check(lib.sdb_dcn_output_size(ctypes.byref(g), ho, wo))
+    wsb = tuple(int(lib.sdb_dcn_workspace_bytes(op, ctypes.byref(g), iod, mth))
+                for op in (_lib.SDB_OP_FORWARD, _lib.SDB_OP_BACKWARD_DATA, _lib.SDB_OP_BACKWARD_WEIGHT))
+    pkb = int(lib.sdb_dcn_packed_input_bytes(ctypes.byref(g), mth))
+    plan = (cdt, iod, mth, (ho.value, wo.value), wsb, pkb)
+    if len(_PLAN_CACHE) < 4096:
+        _PLAN_CACHE[key] = plan
+    return plan
 
 
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
 
+def _as(t, dtype):
+    """t as a contiguous tensor of `dtype` without touching it when it already is one"""
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _on_device(object):
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs ~5 us)"""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
+        return False
+
+
 def _forward_impl(input, offset, mask, weight, bias, g):
     lib = _lib.lib()
-    cdt, iod, mth = _plan(input, weight, g)
-    ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
-    _lib.check(lib.sdb_dcn_output_size(ctypes.byref(g), ho, wo))
-    x = input.to(cdt).contiguous()
-    w = weight.to(cdt).contiguous()
-    b = None if bias is None else bias.to(cdt).contiguous()
-    off = offset.float().contiguous()
-    m = None if mask is None else mask.float().contiguous()
-    out = torch.empty((g.N, g.C_out, ho.value, wo.value), dtype=cdt, device=input.device)
-    wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_FORWARD, ctypes.byref(g), iod, mth)
-    pkb = lib.sdb_dcn_packed_input_bytes(ctypes.byref(g), mth)
-    ws = _ws(wsb, input.device)
+    cdt, iod, mth, (ho, wo), wsb, pkb = _plan(input, weight, g)
+    x, w, b = _as(input, cdt), _as(weight, cdt), _as(bias, cdt)
+    off, m = _as(offset, torch.float32), _as(mask, torch.float32)
+    out = torch.empty((g.N, g.C_out, ho, wo), dtype=cdt, device=input.device)
+    ws = _ws(wsb[0], input.device)
     packed = _ws(pkb, input.device) if pkb else None
-    with torch.cuda.device(input.device):
+    with _on_device(input.device):
         _lib.check(lib.sdb_dcn_forward(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w), _lib.ptr(b),
-                                       _lib.ptr(out), ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb,
+                                       _lib.ptr(out), ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb[0],
                                        _lib.ptr(packed), _lib.stream_ptr(input.device)))
-    return out.to(input.dtype), packed
+    return (out if out.dtype == input.dtype else out.to(input.dtype)), packed
 
 
 def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias):
     """-> grad_input, grad_offset, grad_mask, grad_weight, grad_bias (None where not requested)."""
     lib = _lib.lib()
-    cdt, iod, mth = _plan(input, weight, g)
-    x = input.to(cdt).contiguous()
-    w = weight.to(cdt).contiguous()
-    gy = grad_output.to(cdt).contiguous()
-    off = offset.float().contiguous()
-    m = None if mask is None else mask.float().contiguous()
+    cdt, iod, mth, _, wsb, _ = _plan(input, weight, g)
+    x, w, gy = _as(input, cdt), _as(weight, cdt), _as(grad_output, cdt)
+    off, m = _as(offset, torch.float32), _as(mask, torch.float32)
     dev = input.device
     gi = go = gm = gw = gb = None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         st = _lib.stream_ptr(dev)
         if need_data:
             gi = torch.zeros_like(x)  # accumulated into (deform_conv.py:89)
             go = torch.empty_like(off)
             gm = torch.empty_like(m) if m is not None else None
-            wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_DATA, ctypes.byref(g), iod, mth)
-            ws = _ws(wsb, dev)
+            ws = _ws(wsb[1], dev)
             _lib.check(lib.sdb_dcn_backward_data(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w),
                                                  _lib.ptr(gy), _lib.ptr(gi), _lib.ptr(go), _lib.ptr(gm),
-                                                 ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb,
+                                                 ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb[1],
                                                  _lib.ptr(packed), st))
-            gi = gi.to(input.dtype)
-            go = go.to(offset.dtype)
-            gm = gm.to(mask.dtype) if gm is not None else None
+            gi = _as(gi, input.dtype)
+            go = _as(go, offset.dtype)
+            gm = _as(gm, mask.dtype) if gm is not None else None
         if need_weight:
             gw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)  # deform_conv.py:113
             gb = torch.zeros((g.C_out,), dtype=torch.float32, device=dev) if with_bias else None
-            wsb = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_WEIGHT, ctypes.byref(g), iod, mth)
-            ws = _ws(wsb, dev)
+            ws = _ws(wsb[2], dev)
             _lib.check(lib.sdb_dcn_backward_weight(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(gy),
                                                    _lib.ptr(gw), _lib.ptr(gb), 1.0, ctypes.byref(g), iod, mth,
-                                                   _lib.ptr(ws), wsb, _lib.ptr(packed), st))
-            gw = gw.to(weight.dtype)
-            gb = gb.to(weight.dtype) if gb is not None else None
+                                                   _lib.ptr(ws), wsb[2], _lib.ptr(packed), st))
+            gw = _as(gw, weight.dtype)
+            gb = _as(gb, weight.dtype) if gb is not None else None
     return gi, go, gm, gw, gb
 
 
