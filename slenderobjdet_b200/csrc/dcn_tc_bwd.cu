@@ -83,38 +83,27 @@ __global__ void __launch_bounds__(256) pack_gy_kernel(const T* __restrict__ gy, 
   }
 }
 
-// bf16 source: one thread per PAIR of tile rows (one 4-byte load when the two pixels are neighbours in the
-// same image row and the address is even -- always, away from ragged borders), bf16 pairs kept packed in
-// shared memory, one 16-byte swizzled store per thread and round.
-__global__ void __launch_bounds__(256) pack_gy_bf16_kernel(const __nv_bfloat16* __restrict__ gy, uint8_t* __restrict__ img,
-                                                           const Geo g, int okb) {
+// bf16 source whose row segments are 8-byte aligned (Wo, tw, Ho*Wo multiples of 4): a lane loads FOUR pixels of
+// one channel with one 8-byte load -- a whole 128-pixel tile row per warp instruction, 8 per lane instead of 32
+// two-byte loads -- and one pixel decode per thread.
+__global__ void __launch_bounds__(256) pack_gy_bf16v_kernel(const __nv_bfloat16* __restrict__ gy, uint8_t* __restrict__ img,
+                                                            const Geo g, int okb) {
   const int O = g.O, hw = g.Ho * g.Wo;
-  __shared__ uint32_t s[64][65];   // [o][pixel pair], column swizzled by (o >> 5) << 4
+  __shared__ __align__(8) __nv_bfloat16 s[64][136];   // [o][pixel (column ^ 32 for o >= 32)], 8 spare columns
   const int tile = blockIdx.x, kb = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
-    const int q = tid & 63, oq = tid >> 6;
-    const long long p0 = (long long)tile * TILE_M + 2 * q, p1 = p0 + 1;
-    const bool v0 = p0 < g.P(), v1 = p1 < g.P();
-    int n0 = 0, h0 = 0, w0 = 0, n1 = 0, h1 = 0, w1 = 0;
-    if (v0) decode_q(g, p0, n0, h0, w0);
-    if (v1) decode_q(g, p1, n1, h1, w1);
-    const size_t r0 = (size_t)n0 * O * hw + (size_t)h0 * g.Wo + w0, r1 = (size_t)n1 * O * hw + (size_t)h1 * g.Wo + w1;
-    const bool pair = v0 && v1 && r1 == r0 + 1 && ((hw | r0) & 1) == 0;   // (o * hw + r0) even for every o
-#pragma unroll 4
-    for (int j = 0; j < 16; ++j) {
-      const int ol = oq + 4 * j, o = kb * 64 + ol;
-      uint32_t v = 0u;
-      if (o < O) {
-        if (pair) {
-          v = *reinterpret_cast<const uint32_t*>(gy + (size_t)o * hw + r0);
-        } else {
-          const uint32_t lo = v0 ? (uint32_t)__bfloat16_as_ushort(gy[(size_t)o * hw + r0]) : 0u;
-          const uint32_t hi = v1 ? (uint32_t)__bfloat16_as_ushort(gy[(size_t)o * hw + r1]) : 0u;
-          v = lo | (hi << 16);
-        }
-      }
-      s[ol][q ^ ((ol >> 5) << 4)] = v;
+    const long long p0 = (long long)tile * TILE_M + 4 * lane;
+    const bool valid = p0 < g.P();   // P % 4 == 0: all four pixels or none
+    int n = 0, ho = 0, wo = 0;
+    if (valid) decode_q(g, p0, n, ho, wo);
+    const size_t r0 = (size_t)n * O * hw + (size_t)ho * g.Wo + wo;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ol = warp + 8 * j, o = kb * 64 + ol;
+      uint2 v = make_uint2(0u, 0u);
+      if (valid && o < O) v = *reinterpret_cast<const uint2*>(gy + (size_t)o * hw + r0);
+      *reinterpret_cast<uint2*>(&s[ol][(4 * lane) ^ ((ol >> 5) << 5)]) = v;
     }
   }
   __syncthreads();
@@ -122,15 +111,15 @@ __global__ void __launch_bounds__(256) pack_gy_bf16_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = tid + 256 * j, row = c >> 3, ch = c & 7;
-    const int pp = (row >> 1) ^ ((ch >> 2) << 4), hi = row & 1;
+    const int col = row ^ ((ch >> 2) << 5);
     uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = s[ch * 8 + k][pp];
+    for (int k = 0; k < 8; ++k) v[k] = (uint32_t)__bfloat16_as_ushort(s[ch * 8 + k][col]);
     uint4 pk;
-    pk.x = hi ? __byte_perm(v[0], v[1], 0x7632) : __byte_perm(v[0], v[1], 0x5410);
-    pk.y = hi ? __byte_perm(v[2], v[3], 0x7632) : __byte_perm(v[2], v[3], 0x5410);
-    pk.z = hi ? __byte_perm(v[4], v[5], 0x7632) : __byte_perm(v[4], v[5], 0x5410);
-    pk.w = hi ? __byte_perm(v[6], v[7], 0x7632) : __byte_perm(v[6], v[7], 0x5410);
+    pk.x = v[0] | (v[1] << 16);
+    pk.y = v[2] | (v[3] << 16);
+    pk.z = v[4] | (v[5] << 16);
+    pk.w = v[6] | (v[7] << 16);
     *reinterpret_cast<uint4*>(dst + sw128_offset(row, ch)) = pk;
   }
 }
@@ -964,8 +953,11 @@ BwdWs bwd_ws(int op, const Geo& g) {
 template <typename T>
 int pack_gy(const void* gy, uint8_t* img, const Geo& g, cudaStream_t st) {
   dim3 grid(cdiv(g.P(), TILE_M), okb_of(g));
-  if (sizeof(T) == 2) pack_gy_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)gy, img, g, okb_of(g));
-  else pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g, okb_of(g));
+  const int hw = g.Ho * g.Wo;
+  if (sizeof(T) == 2 && g.Wo % 4 == 0 && g.tw % 4 == 0 && hw % 4 == 0 && ((size_t)gy & 7) == 0)
+    pack_gy_bf16v_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)gy, img, g, okb_of(g));
+  else
+    pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g, okb_of(g));
   SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;

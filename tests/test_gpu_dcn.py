@@ -127,7 +127,7 @@ def test_zero_offset_equals_conv2d(math):
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 12, 14, 64), (2, 128, 13, 21, 80), (1, 64, 25, 42, 256), (3, 64, 7, 11, 48),
-                                   (2, 256, 50, 84, 256)])
+                                   (2, 256, 50, 84, 256), (1, 64, 20, 24, 72), (2, 64, 9, 36, 64)])
 def test_bf16_tensors_io(shape):
     """bf16 tensors in and out (the layout-pack kernels have bf16-specialised paths: even / odd plane sizes,
     ragged 8x16 patches at the borders, C_out not a multiple of 64)."""
