@@ -31,17 +31,18 @@ namespace {
 using namespace tc;
 using namespace tcshared;
 
-constexpr int W_NPW = 8;                       // gather warps
+constexpr int W_NPW = 16;                      // gather warps (8 pixels x 64 channels per stage each)
 constexpr int W_FIRST_PW = 7;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6 window TMA, 7.. gather
 constexpr int W_NTHREADS = (W_FIRST_PW + W_NPW) * 32;
-constexpr int W_NS = 2;                        // pipeline stages (A 16 KB + B O x 128 B each)
+constexpr int W_NSA = 4;                       // A stages (16 KB each): the gather runs up to four stages ahead of the MMAs
+constexpr int W_NSB = 2;                       // B (weight) stages, O x 128 B each
 constexpr int W_A_BYTES = TILE_M * 128;        // one A stage: 128 pixels x 64 channels bf16
 constexpr int W_PIXW = TILE_M / W_NPW;         // pixels per gather warp
 constexpr int W_LPP = 4;                       // lanes per pixel: 2 x 8 channels each (the gather is issue-bound: fewer, fatter iterations)
 constexpr int W_PPI = 32 / W_LPP;              // pixels per warp instruction
 constexpr int W_ITERS = W_PIXW / W_PPI;
-constexpr int W_RING = 2;                      // register ring slots (one warp iteration = 8 pixels x 64 channels)
-static_assert(W_PIXW % W_PPI == 0 && W_NPW == 8 && (32 / W_PPI) % W_RING == 0, "two groups of four gather warps, 32 px each");
+constexpr int W_RING = W_ITERS;                // register ring slots = one stage (one warp iteration = 8 pixels x 64 channels)
+static_assert(W_PIXW % W_PPI == 0 && W_ITERS >= 1, "bad gather split");
 
 struct WinParams {
   CUtensorMap tmap;          // NHWC bf16 input as (c, x, y, n), box (64, BW, BH, 1)
@@ -55,6 +56,7 @@ struct WinParams {
   int tiles_x, tiles_y, num_tiles;
   int R, BH, BW;
   uint32_t win_bytes;
+  int stagger_ns;            // per-warp start offset after each window wait (x (warp & 3)), ns
   int cl;                    // CTAs per cluster (1 or 2): weight stages are loaded half each and multicast
   int dbg;
 };
@@ -131,17 +133,16 @@ namespace {
 #define SDB_TRACE(role_, k_, st_, slot_)                                                        \
   if ((p.dbg & 64) && blockIdx.x == 0 && (k_) < 2 && (threadIdx.x & 31) == 0) g_trace[role_][k_][st_][slot_] = clock64();
 
-// Pipeline: W_NS A stages (128 px x 64 ch, written by the gather warps) and W_NS B stages (O x 64
-// weights, written by the TMA engine), each ring with its own full / empty barriers so the weight
-// prefetch of stage s+2 starts the moment the MMAs of stage s retire, not when the gather gets there.
-// Per stage the MMA thread does two waits, four 128 x O x 16 MMAs and two commits.  (128-column half
-// stages cost three waits + three commits + eight MMAs per stage; one shared barrier per stage put
-// the ~1200-clock latency of the weight copy inside the stage loop: profiles/r1_win_trace.md.)
+// Pipeline: W_NSA = 4 A stages (128 px x 64 ch, written by the gather warps) and W_NSB = 2 B stages (O x 64
+// weights, written by the TMA engine), each ring with its own full / empty barriers; ONE window buffer,
+// reloaded per 64-channel chunk (a ~2 k-clock bubble per chunk, paid for a window reach of R = 5 px instead
+// of 3 and for the two extra A stages that let the gather warps run decoupled).  Per stage the MMA thread does
+// two waits, four 128 x O x 16 MMAs and two commits.  History of the alternatives: profiles/r1_win_trace.md.
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid_constant__ WinParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full[W_NS], empty[W_NS];       // A stages (gather warps <-> MMA)
-  __shared__ __align__(8) uint64_t b_full[W_NS], b_empty[W_NS];   // B stages (weight producer <-> MMA)
+  __shared__ __align__(8) uint64_t full[W_NSA], empty[W_NSA];       // A stages (gather warps <-> MMA)
+  __shared__ __align__(8) uint64_t b_full[W_NSB], b_empty[W_NSB];   // B stages (weight producer <-> MMA)
   __shared__ __align__(8) uint64_t w_full[2], w_empty[2];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -152,9 +153,9 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sA = sm;
-  uint8_t* sB = sA + W_NS * W_A_BYTES;
-  uint8_t* sWin = sB + (size_t)W_NS * B_BYTES;
-  uint4* sDesc = reinterpret_cast<uint4*>(sWin + 2 * (size_t)p.win_bytes);   // [taps][128]: off, w00|w01, w10|w11, -
+  uint8_t* sB = sA + W_NSA * W_A_BYTES;
+  uint8_t* sWin = sB + (size_t)W_NSB * B_BYTES;
+  uint4* sDesc = reinterpret_cast<uint4*>(sWin + (size_t)p.win_bytes);   // [taps][128]: off, w00|w01, w10|w11, -
   // warp index made provably warp-uniform (shfl): role branches and every loop counter below then live in
   // uniform registers, so tcgen05.mma gets its descriptors straight from the uniform datapath.  With
   // `threadIdx.x >> 5` the compiler wrapped each MMA in an ELECT / R2UR / BRA.U.ANY waterfall (~130 clk
@@ -174,9 +175,11 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
 #define SDB_TILE_OF(k_) (((k_) * ((int)gridDim.x / cl) + (int)blockIdx.x / cl) * cl + (int)crank)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < W_NS; ++s) {
-      mbar_init(&full[s], W_NPW / 2);   // one gather warp group (4 warps x 32 px) fills a stage
+    for (int s = 0; s < W_NSA; ++s) {
+      mbar_init(&full[s], W_NPW);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < W_NSB; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], cl);     // released by the MMA warp of every CTA in the cluster
     }
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
             else
               bulk_g2s(sB + (size_t)s * B_BYTES, p.wimg + (size_t)kb * B_BYTES, B_BYTES, &b_full[s]);
           }
-          if (++s == W_NS) { s = 0; ph ^= 1; }
+          if (++s == W_NSB) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_bf16(TILE_M, O, 0, 0);
     const uint64_t adesc0 = make_smem_desc_sw128(smem_base, 16, 1024);
-    const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + W_NS * W_A_BYTES, 16, 1024);
-    uint32_t s = 0, ph = 0, acc = 0, accp = 0;
+    const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + W_NSA * W_A_BYTES, 16, 1024);
+    uint32_t s = 0, ph = 0, sa = 0, pa = 0, acc = 0, accp = 0;   // s/ph: weight ring, sa/pa: A ring
     for (int k = 0; k < niter; ++k) {
       const bool real = SDB_TILE_OF(k) < p.num_tiles;
       if (real) {
@@ -234,12 +237,12 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
       for (int it = 0; it < nstages; ++it) {
         SDB_TRACE(1, k, it, 0)
         mbar_wait(&b_full[s], ph);
-        if (real) mbar_wait(&full[s], ph);
+        if (real) mbar_wait(&full[sa], pa);
         SDB_TRACE(1, k, it, 1)
         tc_fence_after_sync();
         if (elect_one()) {
           // descriptor start-address field counts 16-byte units: +2 per 16-element K step inside the swizzle atom
-          const uint64_t ad = adesc0 + (uint64_t)(s * (uint32_t)(W_A_BYTES >> 4));
+          const uint64_t ad = adesc0 + (uint64_t)(sa * (uint32_t)(W_A_BYTES >> 4));
           const uint64_t bd = bdesc0 + (uint64_t)(s * (B_BYTES >> 4));
           if (real && !(p.dbg & 1)) {
 #pragma unroll
@@ -247,11 +250,12 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
           }
           if (cl > 1) umma_commit_mc(&b_empty[s], cmask);
           else        umma_commit(&b_empty[s]);
-          if (real) umma_commit(&empty[s]);
+          if (real) umma_commit(&empty[sa]);
         }
         __syncwarp();
         SDB_TRACE(1, k, it, 2)
-        if (++s == W_NS) { s = 0; ph ^= 1; }
+        if (++s == W_NSB) { s = 0; ph ^= 1; }
+        if (real && ++sa == W_NSA) { sa = 0; pa ^= 1; }
       }
       if (real) {
         if (elect_one()) umma_commit(&acc_full[acc]);
@@ -299,24 +303,23 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
   } else if (warp == 6) {
-    // ===== window producer: one tensor-map copy per (tile, 64-channel chunk), double buffered =====
+    // ===== window producer: one tensor-map copy per (tile, 64-channel chunk) into the single window buffer =====
     if (elect_one()) {
-      uint32_t wb = 0, wph = 0;
+      uint32_t cnt = 0;
       for (int k = 0; k < niter; ++k) {
         const int work = SDB_TILE_OF(k);
         if (work >= p.num_tiles) continue;
         const int n = work / tiles_per_img, trem = work - n * tiles_per_img;
         const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
         const int wy0 = ty * g.th * g.sh - g.ph - p.R, wx0 = tx * g.tw * g.sw - g.pw - p.R;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          mbar_wait(&w_empty[wb], wph ^ 1);
+        for (int ch = 0; ch < nchunks; ++ch, ++cnt) {
+          mbar_wait(&w_empty[0], (cnt & 1) ^ 1);   // every gather warp is done with the previous chunk's window
           if (p.dbg & 8) {
-            mbar_arrive(&w_full[wb]);
+            mbar_arrive(&w_full[0]);
           } else {
-            mbar_arrive_expect_tx(&w_full[wb], p.win_bytes);
-            tma_load_4d(smem_u32(sWin) + wb * p.win_bytes, &p.tmap, ch * 64, wx0, wy0, n, &w_full[wb]);
+            mbar_arrive_expect_tx(&w_full[0], p.win_bytes);
+            tma_load_4d(smem_u32(sWin), &p.tmap, ch * 64, wx0, wy0, n, &w_full[0]);
           }
-          if (++wb == 2) { wb = 0; wph ^= 1; }
         }
       }
     }
@@ -326,11 +329,12 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
     // through a 4-slot register ring: the corner loads of the NEXT stage are issued while this stage is
     // interpolated and stored, so out-of-window samples (global loads, L2 latency) are a full stage ahead
     // of their use instead of stalling all eight warps at every stage.
-    // Two warp groups alternate stages: group gi fills the A buffer gi (stages of that parity), each of its
-    // four warps 32 pixels.  While one group waits / fences / arrives, the other one keeps the shared-memory
-    // pipe busy (with all warps in lock-step those ~700 clk per stage were dead time, profiles/r1_win_trace.md).
-    const int pw = warp - W_FIRST_PW, r0 = pw * W_PIXW;   // r0: rows whose descriptors this warp builds
-    const int gi = pw >> 2, rg = (pw & 3) * 32;            // gather: group and first row of this warp
+    // Each warp owns 16 pixels of every stage and runs at its own pace: with four A buffers the `empty` wait of
+    // a stage is for MMAs issued four stages ago, so the warps drift apart and the shared-memory pipe stays
+    // busy while individual warps wait / fence / arrive (in lock-step on two buffers those ~700 clk per stage
+    // were dead time for everybody, profiles/r1_win_trace.md).
+    const int pw = warp - W_FIRST_PW, r0 = pw * W_PIXW;
+    const int rg = r0;
     const int grp = lane / W_LPP, lig = lane % W_LPP;
     // each lane owns two 16-byte chunks of its pixel's 128-byte row: chunks (lig, lig + 4), taken in opposite
     // order by odd pixels so the two pixels of a quarter-warp never hit the same banks in one LDS / STS
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
       const int n = work / tiles_per_img, trem = work - n * tiles_per_img;
       const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
       const int wy0 = ty * g.th * g.sh - g.ph - p.R, wx0 = tx * g.tw * g.sw - g.pw - p.R;
-      asm volatile("bar.sync 1, %0;" ::"n"(W_NPW * 32));   // all gather warps are done with the previous tile's descriptors
+      __syncwarp();   // every lane is done with the previous tile's descriptors (each warp builds and reads its own rows)
       // (1) sampling descriptors of this warp's pixels for every tap: window byte offset of corner
       //     (y0, x0) -- or, flagged, (y0, x0) itself when a corner is outside the window -- and the
       //     four bilinear weights (x mask) as bf16
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
             sDesc[tap * TILE_M + r] = d;
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(W_NPW * 32));   // descriptors of all 128 pixels are in place
+        __syncwarp();
       }
       // (2) the gather stream
       uint4 v[W_RING][8];   // [slot][corner * 2 + chunk]
@@ -448,75 +452,63 @@ __global__ void __launch_bounds__(W_NTHREADS, 1) dcn_fwd_win_kernel(const __grid
           v[slot_][6] = __ldg(p3_ + ca); v[slot_][7] = __ldg(p3_ + cb);                          \
         }                                                                                        \
       }
-      constexpr int G_ITERS = 32 / W_PPI;   // iterations per stage per warp
       const int gs0 = tcount * nstages, gc0 = tcount * nchunks;
-      const int st0 = ((gs0 & 1) == gi) ? 0 : 1;
-      auto wbuf = [&](int c_) { return (uint32_t)((gc0 + c_) & 1); };
-      auto wpar = [&](int c_) { return (uint32_t)(((gc0 + c_) >> 1) & 1); };
-      int rel = 0;   // next window chunk this warp has to release
-      if (st0 < nstages) {
-        const int ch0 = st0 / taps, tap0 = st0 - ch0 * taps;
-        mbar_wait(&w_full[wbuf(ch0)], wpar(ch0));
-        const uint32_t wbase = win0 + wbuf(ch0) * p.win_bytes;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        mbar_wait(&w_full[0], (uint32_t)(gc0 + ch) & 1u);   // this chunk's window has landed
+        // all warps leave this wait together and have identical per-stage timelines, so without help they
+        // hit the shared-memory pipe in the same phase and leave it idle in the same phase: stagger them
+        if (p.stagger_ns > 0 && (pw & 3)) __nanosleep((unsigned)(p.stagger_ns * (pw & 3)));
+        {
 #pragma unroll
-        for (int u = 0; u < W_RING; ++u) {
-          const uint4 dd = SDB_WDESC(tap0, u);
-          SDB_WISSUE(dd, ch0, u, wbase)
-        }
-      }
-      for (int st = st0; st < nstages; st += 2) {
-        const int ch = st / taps, tap = st - ch * taps;
-        const int nst = st + 2;
-        const bool has_next = nst < nstages;
-        const int nch = has_next ? nst / taps : nchunks, ntap = has_next ? nst - nch * taps : 0;
-        if (has_next && nch != ch) mbar_wait(&w_full[wbuf(nch)], wpar(nch));
-        const uint32_t cwbase = win0 + wbuf(ch) * p.win_bytes, nwbase = win0 + wbuf(has_next ? nch : ch) * p.win_bytes;
-        const uint32_t use = (uint32_t)(gs0 + st) >> 1;   // how many times buffer gi has been filled before
-        if (pw == 0) SDB_TRACE(0, k, st, 0)
-        mbar_wait(&empty[gi], (use & 1) ^ 1);
-        if (pw == 0) SDB_TRACE(0, k, st, 1)
-        uint8_t* dst = sA + (size_t)gi * W_A_BYTES;
-        if (!(p.dbg & 16))
-#pragma unroll
-        for (int it = 0; it < G_ITERS; ++it) {
-          const int sl = it % W_RING;
-          const uint32_t w00 = __byte_perm(wa[sl], wa[sl], 0x1010), w01 = __byte_perm(wa[sl], wa[sl], 0x3232);
-          const uint32_t w10 = __byte_perm(wbv[sl], wbv[sl], 0x1010), w11 = __byte_perm(wbv[sl], wbv[sl], 0x3232);
-          uint4 a, b;
-          a.x = bf2_fma(w11, v[sl][6].x, bf2_fma(w10, v[sl][4].x, bf2_fma(w01, v[sl][2].x, bf2_mul(w00, v[sl][0].x))));
-          a.y = bf2_fma(w11, v[sl][6].y, bf2_fma(w10, v[sl][4].y, bf2_fma(w01, v[sl][2].y, bf2_mul(w00, v[sl][0].y))));
-          a.z = bf2_fma(w11, v[sl][6].z, bf2_fma(w10, v[sl][4].z, bf2_fma(w01, v[sl][2].z, bf2_mul(w00, v[sl][0].z))));
-          a.w = bf2_fma(w11, v[sl][6].w, bf2_fma(w10, v[sl][4].w, bf2_fma(w01, v[sl][2].w, bf2_mul(w00, v[sl][0].w))));
-          b.x = bf2_fma(w11, v[sl][7].x, bf2_fma(w10, v[sl][5].x, bf2_fma(w01, v[sl][3].x, bf2_mul(w00, v[sl][1].x))));
-          b.y = bf2_fma(w11, v[sl][7].y, bf2_fma(w10, v[sl][5].y, bf2_fma(w01, v[sl][3].y, bf2_mul(w00, v[sl][1].y))));
-          b.z = bf2_fma(w11, v[sl][7].z, bf2_fma(w10, v[sl][5].z, bf2_fma(w01, v[sl][3].z, bf2_mul(w00, v[sl][1].z))));
-          b.w = bf2_fma(w11, v[sl][7].w, bf2_fma(w10, v[sl][5].w, bf2_fma(w01, v[sl][3].w, bf2_mul(w00, v[sl][1].w))));
-          if (!(p.dbg & 2)) {
-            const uint32_t row = rg + it * W_PPI + grp;
-            *reinterpret_cast<uint4*>(dst + sw128_offset(row, ca)) = a;
-            *reinterpret_cast<uint4*>(dst + sw128_offset(row, cb)) = b;
-          }
-          if (it + W_RING < G_ITERS) {
-            const uint4 dd = SDB_WDESC(tap, it + W_RING);
-            SDB_WISSUE(dd, ch, sl, cwbase)
-          } else if (has_next) {
-            const uint4 dd = SDB_WDESC(ntap, it + W_RING - G_ITERS);
-            SDB_WISSUE(dd, nch, sl, nwbase)
+          for (int u = 0; u < W_RING; ++u) {
+            const uint4 dd = SDB_WDESC(0, u);
+            SDB_WISSUE(dd, ch, u, win0)
           }
         }
-        if (pw == 0) SDB_TRACE(0, k, st, 2)
-        fence_proxy_async_smem();
-        mbar_arrive_warp(&full[gi]);
-        if (pw == 0) SDB_TRACE(0, k, st, 3)
-        // window chunks this warp will not read again (its next stage is in chunk nch, or the tile is done)
-        for (; rel < nch; ++rel) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&w_empty[wbuf(rel)]);
+        bool rdy = false;   // readiness of this stage's A buffer, tested (non-blocking) one stage ahead
+        for (int tap = 0; tap < taps; ++tap) {
+          const int st = ch * taps + tap;
+          const uint32_t gs = (uint32_t)(gs0 + st), sa = gs % W_NSA, use = gs / W_NSA;
+          const bool has_next = tap + 1 < taps;   // the ring does not cross a chunk: the next window is not there yet
+          if (pw == 0) SDB_TRACE(0, k, st, 0)
+          if (!rdy) mbar_wait(&empty[sa], (use & 1) ^ 1);
+          if (pw == 0) SDB_TRACE(0, k, st, 1)
+          // the gather, not the MMAs, paces the kernel, so the next buffer is almost always free already: ask
+          // now, look at the answer after this stage's work (a ready try_wait costs ~190 clk on the critical path)
+          rdy = has_next && mbar_test(&empty[(gs + 1) % W_NSA], (((gs + 1) / W_NSA) & 1) ^ 1);
+          uint8_t* dst = sA + (size_t)sa * W_A_BYTES;
+          if (!(p.dbg & 16))
+#pragma unroll
+          for (int it = 0; it < W_ITERS; ++it) {
+            const int sl = it % W_RING;
+            const uint32_t w00 = __byte_perm(wa[sl], wa[sl], 0x1010), w01 = __byte_perm(wa[sl], wa[sl], 0x3232);
+            const uint32_t w10 = __byte_perm(wbv[sl], wbv[sl], 0x1010), w11 = __byte_perm(wbv[sl], wbv[sl], 0x3232);
+            uint4 a, b;
+            a.x = bf2_fma(w11, v[sl][6].x, bf2_fma(w10, v[sl][4].x, bf2_fma(w01, v[sl][2].x, bf2_mul(w00, v[sl][0].x))));
+            a.y = bf2_fma(w11, v[sl][6].y, bf2_fma(w10, v[sl][4].y, bf2_fma(w01, v[sl][2].y, bf2_mul(w00, v[sl][0].y))));
+            a.z = bf2_fma(w11, v[sl][6].z, bf2_fma(w10, v[sl][4].z, bf2_fma(w01, v[sl][2].z, bf2_mul(w00, v[sl][0].z))));
+            a.w = bf2_fma(w11, v[sl][6].w, bf2_fma(w10, v[sl][4].w, bf2_fma(w01, v[sl][2].w, bf2_mul(w00, v[sl][0].w))));
+            b.x = bf2_fma(w11, v[sl][7].x, bf2_fma(w10, v[sl][5].x, bf2_fma(w01, v[sl][3].x, bf2_mul(w00, v[sl][1].x))));
+            b.y = bf2_fma(w11, v[sl][7].y, bf2_fma(w10, v[sl][5].y, bf2_fma(w01, v[sl][3].y, bf2_mul(w00, v[sl][1].y))));
+            b.z = bf2_fma(w11, v[sl][7].z, bf2_fma(w10, v[sl][5].z, bf2_fma(w01, v[sl][3].z, bf2_mul(w00, v[sl][1].z))));
+            b.w = bf2_fma(w11, v[sl][7].w, bf2_fma(w10, v[sl][5].w, bf2_fma(w01, v[sl][3].w, bf2_mul(w00, v[sl][1].w))));
+            if (!(p.dbg & 2)) {
+              const uint32_t row = rg + it * W_PPI + grp;
+              *reinterpret_cast<uint4*>(dst + sw128_offset(row, ca)) = a;
+              *reinterpret_cast<uint4*>(dst + sw128_offset(row, cb)) = b;
+            }
+            if (has_next) {
+              const uint4 dd = SDB_WDESC(tap + 1, it);
+              SDB_WISSUE(dd, ch, sl, win0)
+            }
+          }
+          if (pw == 0) SDB_TRACE(0, k, st, 2)
+          fence_proxy_async_smem();
+          mbar_arrive_warp(&full[sa]);
+          if (pw == 0) SDB_TRACE(0, k, st, 3)
         }
-      }
-      for (; rel < nchunks; ++rel) {   // (only when this warp had no stage at all in the last chunks)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&w_empty[wbuf(rel)]);
+        __syncwarp();   // every load from this chunk's window has been consumed
+        if (lane == 0) mbar_arrive(&w_empty[0]);
       }
       ++tcount;
 #undef SDB_WISSUE
@@ -567,7 +559,7 @@ WinPlan plan_window(const Geo& g) {
   if (g.H >= 32767 || g.W >= 65535) return w;
   if (g.th * g.tw != TILE_M) return w;
   const size_t b_bytes = (size_t)g.O * 128;
-  const size_t fixed = 1024 + (size_t)W_NS * (W_A_BYTES + b_bytes) + (size_t)g.taps() * TILE_M * 16;
+  const size_t fixed = 1024 + (size_t)W_NSA * W_A_BYTES + (size_t)W_NSB * b_bytes + (size_t)g.taps() * TILE_M * 16;
   const int span_y = (g.th - 1) * g.sh + (g.KH - 1) * g.dh + 2, span_x = (g.tw - 1) * g.sw + (g.KW - 1) * g.dw + 2;
   int rmax = 8;
   if (const char* e = getenv("SDB_TC_WIN_R")) rmax = atoi(e);
@@ -575,10 +567,10 @@ WinPlan plan_window(const Geo& g) {
     const int BH = span_y + 2 * R, BW = span_x + 2 * R;
     if (BH > 256 || BW > 256) continue;
     const size_t wbytes = (size_t)BH * BW * 128;
-    if (fixed + 2 * wbytes <= W_SMEM_LIMIT) {
+    if (fixed + wbytes <= W_SMEM_LIMIT) {
       w.ok = true;
       w.R = R; w.BH = BH; w.BW = BW; w.win_bytes = (uint32_t)wbytes;
-      w.smem = fixed + 2 * wbytes;
+      w.smem = fixed + wbytes;
       return w;
     }
   }
@@ -623,6 +615,8 @@ int tc_forward_win(const __nv_bfloat16* xp, const float* off, const float* mask,
   p.R = pl.R; p.BH = pl.BH; p.BW = pl.BW; p.win_bytes = pl.win_bytes;
   if (const char* e = getenv("SDB_TC_DEBUG")) p.dbg = atoi(e);
   if (p.num_tiles == 0) return SDB_OK;
+  p.stagger_ns = 0;   // measured: no effect (the shared-memory queue re-forms the convoy), kept as an experiment switch
+  if (const char* e = getenv("SDB_TC_WIN_STAGGER")) p.stagger_ns = atoi(e);
   p.cl = 2;
   if (const char* e = getenv("SDB_TC_WIN_CL")) p.cl = atoi(e) == 1 ? 1 : 2;
   if (p.num_tiles < 2) p.cl = 1;
