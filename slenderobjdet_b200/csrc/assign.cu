@@ -211,6 +211,80 @@ __global__ void __launch_bounds__(TOPK ? 512 : 1024) per_gt_kernel(const float4*
   }
 }
 
+// ---- per-GT top-k split over TOPK_SPLITS blocks (needs the workspace) ---------------------------------
+// One block per GT leaves 48 SMs idle and is instruction-bound (profiles/r1_secondary_kernels.md).  Part 1:
+// block (m, s) scans its 1/TOPK_SPLITS of the anchors with the same per-thread sorted lists and writes its
+// k best keys; part 2: one warp-sized block per GT merges TOPK_SPLITS x k candidates.  Same total order
+// (value desc, index asc) at both levels, so the result is identical to the single-block scan.
+constexpr int TOPK_SPLITS = 8, TOPK_KMAX = 16;
+
+template <bool FROM_BOXES>
+__global__ void __launch_bounds__(256) per_gt_topk_part_kernel(const float4* __restrict__ gt,
+                                                               const float4* __restrict__ anchors,
+                                                               const float* __restrict__ q, int M, int X, int topk,
+                                                               Key* __restrict__ cand) {
+  __shared__ Key s_red[32];
+  const int m = blockIdx.x, sp = blockIdx.y;
+  const int chunk = (X + TOPK_SPLITS - 1) / TOPK_SPLITS, x_lo = sp * chunk, x_hi = min(X, x_lo + chunk);
+  float4 g = make_float4(0, 0, 0, 0);
+  float area_g = 0.f;
+  if (FROM_BOXES) {
+    g = gt[m];
+    area_g = box_area(g);
+  }
+  const Key none = {-INFINITY, 0x7fffffff};
+  Key loc[TOPK_KMAX];
+#pragma unroll
+  for (int j = 0; j < TOPK_KMAX; ++j) loc[j] = none;
+  for (int x = x_lo + threadIdx.x; x < x_hi; x += blockDim.x) {
+    float v;
+    if (FROM_BOXES) {
+      const float4 a = anchors[x];
+      v = iou_exact(g, area_g, a, box_area(a));
+    } else {
+      v = q[(size_t)m * X + x];
+    }
+    Key cur = {v, x};
+    if (before(cur, loc[TOPK_KMAX - 1])) {
+#pragma unroll
+      for (int j = 0; j < TOPK_KMAX; ++j) {
+        if (before(cur, loc[j])) {
+          const Key t = loc[j];
+          loc[j] = cur;
+          cur = t;
+        }
+      }
+    }
+  }
+  Key* out = cand + ((size_t)m * TOPK_SPLITS + sp) * TOPK_KMAX;
+  for (int r = 0; r < topk; ++r) {
+    const Key best = block_best(loc[0], s_red);
+    if (threadIdx.x == 0) out[r] = best;
+    if (best.i < X && loc[0].i == best.i) {
+#pragma unroll
+      for (int j = 0; j + 1 < TOPK_KMAX; ++j) loc[j] = loc[j + 1];
+      loc[TOPK_KMAX - 1] = none;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) per_gt_topk_merge_kernel(const Key* __restrict__ cand, int X, int topk,
+                                                                int8_t* __restrict__ labels) {
+  __shared__ Key s_red[32];
+  const int m = blockIdx.x, t = threadIdx.x;
+  const Key none = {-INFINITY, 0x7fffffff};
+  Key mine = none;   // thread t holds candidate (split t / KMAX, rank t % KMAX)
+  if ((t % TOPK_KMAX) < topk) mine = cand[(size_t)m * TOPK_SPLITS * TOPK_KMAX + t];
+  for (int r = 0; r < topk; ++r) {
+    const Key best = block_best(mine, s_red);
+    if (best.i >= X) break;
+    if (mine.i == best.i) {
+      labels[best.i] = 1;
+      mine = none;
+    }
+  }
+}
+
 __global__ void fill_default_kernel(int X, int8_t lab0, int64_t* matches, int8_t* labels) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x < X) {
@@ -234,7 +308,7 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(const float4* __restr
 
 int assign_impl(const float* gt, const float* anchors, const float* q, int M, int X,
                 const float* thresholds, const int8_t* labels, int nth, int topk, int alq,
-                int64_t* matches, int8_t* match_labels, float* iou_out, cudaStream_t st) {
+                int64_t* matches, int8_t* match_labels, float* iou_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   SDB_REQUIRE(M >= 0 && X >= 0, SDB_ERR_INVALID, "negative sizes M=%d X=%d", M, X);
   SDB_REQUIRE(nth >= 1 && nth <= 8, SDB_ERR_INVALID, "n_thresholds must be in [1,8], got %d", nth);
   SDB_REQUIRE(thresholds && labels && matches && match_labels, SDB_ERR_INVALID, "NULL argument");
@@ -270,7 +344,16 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
                                                            match_labels, nullptr); SDB_LAUNCHED(1);
   }
   SDB_CHECK_CUDA(cudaGetLastError());
-  if (topk > 0 || alq) {
+  if (topk > 0 && topk <= TOPK_KMAX && ws && ws_bytes >= sdb_assign_workspace_bytes(M, X, topk) &&
+      sdb_assign_workspace_bytes(M, X, topk) > 0) {
+    Key* cand = (Key*)ws;
+    dim3 grid(M, TOPK_SPLITS);
+    if (from_boxes) per_gt_topk_part_kernel<true><<<grid, 256, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr, M, X, topk, cand);
+    else            per_gt_topk_part_kernel<false><<<grid, 256, 0, st>>>(nullptr, nullptr, q, M, X, topk, cand);
+    per_gt_topk_merge_kernel<<<M, TOPK_SPLITS * TOPK_KMAX, 0, st>>>(cand, X, topk, match_labels);
+    SDB_LAUNCHED(2);
+    SDB_CHECK_CUDA(cudaGetLastError());
+  } else if (topk > 0 || alq) {
     const int threads = X >= 8192 ? (topk > 0 ? 512 : 1024) : 256;
     if (from_boxes) {
       if (topk > 0) per_gt_kernel<true, true><<<M, threads, 0, st>>>((const float4*)gt, (const float4*)anchors, nullptr, M, X, topk, match_labels);
@@ -292,26 +375,30 @@ using namespace sdb;
 
 extern "C" {
 
-size_t sdb_assign_workspace_bytes(int32_t, int32_t, int32_t) { return 0; }
+size_t sdb_assign_workspace_bytes(int32_t M, int32_t X, int32_t topk) {
+  // candidate keys of the split per-GT top-k; small problems use the single-block scan and need none
+  if (topk <= 0 || topk > 16 || M <= 0 || X < 8192) return 0;
+  return (size_t)M * 8 * 16 * 8;   // M x TOPK_SPLITS x TOPK_KMAX x sizeof(Key)
+}
 
 int sdb_iou_assign(const float* gt, const float* anchors, int32_t M, int32_t X,
                    const float* thresholds, const int8_t* labels, int32_t n_thresholds, int32_t topk,
                    int32_t allow_low_quality, int64_t* matches, int8_t* match_labels, float* iou_out,
-                   void*, size_t, void* stream) {
+                   void* workspace, size_t workspace_bytes, void* stream) {
   SDB_REQUIRE((gt || M == 0) && (anchors || X == 0), SDB_ERR_INVALID, "NULL boxes");
   // thresholds / labels are HOST arrays (a handful of config scalars)
   return assign_impl(gt, anchors, nullptr, M, X, thresholds, labels, n_thresholds, topk,
-                     allow_low_quality, matches, match_labels, iou_out, (cudaStream_t)stream);
+                     allow_low_quality, matches, match_labels, iou_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int sdb_match_quality_assign(const float* q, int32_t M, int32_t X, const float* thresholds,
                              const int8_t* labels, int32_t n_thresholds, int32_t topk,
                              int32_t allow_low_quality, int64_t* matches, int8_t* match_labels,
-                             void*, size_t, void* stream) {
+                             void* workspace, size_t workspace_bytes, void* stream) {
   SDB_REQUIRE(q || M == 0 || X == 0, SDB_ERR_INVALID, "NULL quality matrix");
   static const float dummy = 0.f;
   return assign_impl(nullptr, nullptr, q ? q : &dummy, M, X, thresholds, labels, n_thresholds, topk,
-                     allow_low_quality, matches, match_labels, nullptr, (cudaStream_t)stream);
+                     allow_low_quality, matches, match_labels, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int sdb_pairwise_iou(const float* boxes1, const float* boxes2, int32_t N1, int32_t N2, float* iou,

@@ -62,10 +62,12 @@ class _MatcherBase(object):
         matches = torch.empty((X,), dtype=torch.int64, device=q.device)
         mlabels = torch.empty((X,), dtype=torch.int8, device=q.device)
         th, lb = _cfg_arrays(self._user_thresholds, self.labels)
+        wsb = int(_lib.lib().sdb_assign_workspace_bytes(M, X, topk))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=q.device) if wsb else None
         with torch.cuda.device(q.device):
             _lib.check(_lib.lib().sdb_match_quality_assign(_lib.ptr(q), M, X, th, lb, len(self._user_thresholds),
                                                            topk, int(alq), _lib.ptr(matches), _lib.ptr(mlabels),
-                                                           None, 0, _lib.stream_ptr(q.device)))
+                                                           _lib.ptr(ws), wsb, _lib.stream_ptr(q.device)))
         return matches, mlabels
 
     def _run_boxes(self, gt, anchors, topk, alq, return_iou=False):
@@ -78,10 +80,12 @@ class _MatcherBase(object):
         mlabels = torch.empty((X,), dtype=torch.int8, device=an.device)
         iou = torch.empty((M, X), dtype=torch.float32, device=an.device) if return_iou else None
         th, lb = _cfg_arrays(self._user_thresholds, self.labels)
+        wsb = int(_lib.lib().sdb_assign_workspace_bytes(M, X, topk))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=an.device) if wsb else None
         with torch.cuda.device(an.device):
             _lib.check(_lib.lib().sdb_iou_assign(_lib.ptr(gt), _lib.ptr(an), M, X, th, lb,
                                                  len(self._user_thresholds), topk, int(alq), _lib.ptr(matches),
-                                                 _lib.ptr(mlabels), _lib.ptr(iou), None, 0,
+                                                 _lib.ptr(mlabels), _lib.ptr(iou), _lib.ptr(ws), wsb,
                                                  _lib.stream_ptr(an.device)))
         return (matches, mlabels, iou) if return_iou else (matches, mlabels)
 

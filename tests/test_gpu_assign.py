@@ -80,6 +80,13 @@ def test_ties_follow_canonical_rule_and_full_size():
         m, l = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=k).from_boxes(gt.cuda(), an.cuda())
         assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)
         assert (lo[:k] == 1).all()  # the all-tie row picks anchors 0..k-1
+        # same through the matcher's own signature (quality matrix), and on a size the 8 scan splits do not divide
+        m2, l2 = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=k)(torch.from_numpy(q).cuda())
+        assert np.array_equal(m2.cpu().numpy(), mo) and np.array_equal(l2.cpu().numpy(), lo)
+        q3 = q[:, :22397]
+        mo3, lo3 = oa.topk_matcher(q3, [0.3, 0.7], [0, -1, 1], topk=k)
+        m3, l3 = sdb.TopKMatcher([0.3, 0.7], [0, -1, 1], topk=k)(torch.from_numpy(np.ascontiguousarray(q3)).cuda())
+        assert np.array_equal(m3.cpu().numpy(), mo3) and np.array_equal(l3.cpu().numpy(), lo3)
     mo, lo = oa.matcher(q, [0.4, 0.5], [0, -1, 1], True)
     m, l = sdb.Matcher([0.4, 0.5], [0, -1, 1], True).from_boxes(gt.cuda(), an.cuda())
     assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)
