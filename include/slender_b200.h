@@ -154,6 +154,11 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
                      int kind, int form, float beta, float grad_scale, float* loss_sum,
                      float* grad_pred, void* stream);
 
+/* compute_centerness_targets (sd/modeling/meta_arch/fcos/utils.py:295-300):
+ * out[r] = sqrt( min(l,r)/max(l,r) * min(t,b)/max(t,b) ) for reg_targets [R,4] float32 in (l,t,r,b) order;
+ * one rounding per operation in the reference's order, so the result is bit-identical to torch on CPU. */
+int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

@@ -206,6 +206,22 @@ __global__ void __launch_bounds__(256) box_loss_kernel(const float4* __restrict_
 
 using namespace sdb;
 
+namespace sdb {
+namespace {
+// compute_centerness_targets (fcos/utils.py:295-300): one thread per row, IEEE division / sqrt and no fma
+// contraction, in the reference's operation order -> bit-identical to torch's elementwise result.
+__global__ void __launch_bounds__(256) centerness_kernel(const float4* __restrict__ ltrb, long long R,
+                                                         float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ltrb[i];   // (l, t, r, b)
+    const float lr = __fdiv_rn(fminf(v.x, v.z), fmaxf(v.x, v.z));
+    const float tb = __fdiv_rn(fminf(v.y, v.w), fmaxf(v.y, v.w));
+    out[i] = __fsqrt_rn(__fmul_rn(lr, tb));
+  }
+}
+}  // namespace
+}  // namespace sdb
+
 extern "C" {
 
 int sdb_sigmoid_focal_loss(const float* logits, const int64_t* class_idx, int64_t R, int32_t K,
@@ -244,6 +260,17 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
   box_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)pred, (const float4*)target, weight, R, kind, form, beta, grad_scale, loss_sum,
       (float4*)grad_pred); SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream) {
+  SDB_REQUIRE(R >= 0, SDB_ERR_INVALID, "negative row count");
+  if (R == 0) return SDB_OK;
+  SDB_REQUIRE(reg_targets && out, SDB_ERR_INVALID, "NULL argument");
+  long long blocks = (R + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sdb::centerness_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)reg_targets, R, out); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }

@@ -3,6 +3,7 @@ from .deform_conv import (DeformConv, ModulatedDeformConv, deform_conv, modulate
                           set_dcn_math, get_dcn_math, dcn_math)
 from .df_conv import DFConv2d
 from .losses import (sigmoid_focal_loss, sigmoid_focal_loss_jit, sigmoid_focal_loss_from_class_idx,
-                     iou_loss, box_iou_loss, smooth_l1_loss, smooth_l1_loss_with_weight, giou_loss)
+                     iou_loss, box_iou_loss, smooth_l1_loss, smooth_l1_loss_with_weight, giou_loss,
+                     compute_centerness_targets)
 
 __all__ = [k for k in globals().keys() if not k.startswith("_")]

@@ -129,3 +129,17 @@ def giou_loss(boxes1, boxes2, reduction="none", eps=1e-7):
     _req(reduction == "sum", "only reduction='sum' is implemented")
     _req(abs(eps - 1e-7) < 1e-12, "eps is fixed at 1e-7")
     return _BoxLoss.apply(boxes1, boxes2, None, _lib.SDB_LOSS_GIOU_FVCORE, _lib.SDB_BOX_XYXY, 0.0)
+
+
+def compute_centerness_targets(reg_targets):
+    """``slender_det.modeling.meta_arch.fcos.utils.compute_centerness_targets`` (fcos/utils.py:295-300):
+    ``sqrt(min(l, r) / max(l, r) * min(t, b) / max(t, b))`` for ``reg_targets [R, 4]`` in (l, t, r, b) order.
+    No gradient (the reference uses it as a target)."""
+    _req(reg_targets.dim() == 2 and reg_targets.shape[1] == 4, "reg_targets must be [R, 4]")
+    if not reg_targets.is_cuda:
+        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
+    r = _f32c(reg_targets.detach())
+    out = torch.empty((r.shape[0],), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        _lib.check(_lib.lib().sdb_centerness_targets(_lib.ptr(r), r.shape[0], _lib.ptr(out), _lib.stream_ptr(r.device)))
+    return out.to(reg_targets.dtype)

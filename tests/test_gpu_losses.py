@@ -83,3 +83,25 @@ def test_fvcore_giou_vs_golden(loss_cases):
     assert abs(float(loss) - float(c["loss"])) / abs(float(c["loss"])) < TOL
     so, go = ol.giou_loss(c["pred"], c["target"])
     assert rel_err(p.grad.cpu().numpy(), go.numpy()) < TOL
+
+
+def test_centerness_targets_bit_exact():
+    """compute_centerness_targets (fcos/utils.py:295-300): bit-exact against the reference's lines on CUDA tensors,
+    within float32 rounding of the float64 oracle; degenerate rows (a zero side -> 0, equal sides -> 1)."""
+    g = torch.Generator().manual_seed(3)
+    r = torch.rand(5000, 4, generator=g) * 200 + 1e-3
+    r[0] = torch.tensor([5.0, 5.0, 5.0, 5.0])
+    r[1] = torch.tensor([0.0, 3.0, 7.0, 9.0])
+    out = L.compute_centerness_targets(r.cuda())
+    assert out.dtype == torch.float32 and out.shape == (5000,)
+    # the reference's own lines, executed where the reference executes them (float32 CUDA tensors): bit-exact.
+    # (torch's vectorised CPU kernels differ from the CUDA ones in the last bit on ~1 % of rows.)
+    rd = r.cuda()
+    lr, tb = rd[:, [0, 2]], rd[:, [1, 3]]
+    ref32 = torch.sqrt((lr.min(dim=-1)[0] / lr.max(dim=-1)[0]) * (tb.min(dim=-1)[0] / tb.max(dim=-1)[0]))
+    assert np.array_equal(out.cpu().numpy(), ref32.cpu().numpy())
+    # and the float64 oracle restatement within float32 rounding
+    ref = np.asarray(ol.centerness_targets(r), dtype=np.float64)
+    assert np.max(np.abs(out.cpu().numpy().astype(np.float64) - ref)) <= 1e-6
+    assert float(out[0]) == 1.0 and float(out[1]) == 0.0
+    assert L.compute_centerness_targets(torch.zeros(0, 4, device="cuda")).shape == (0,)
