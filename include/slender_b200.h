@@ -159,6 +159,18 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
  * one rounding per operation in the reference's order, so the result is bit-identical to torch on CPU. */
 int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream);
 
+/* ---- RepPoints DCN offset construction (first piece) -------------------------
+ * dcn_offset = ((1 - gm) * pts.detach() + gm * pts) - dcn_base_offset   (reppointsv2.py:638-642, 742-744;
+ * rpd.py:105-110, 624-635), fused into one pass.  pts, out: [N, 2*K, H, W] float32, K = ks*ks points;
+ * dcn_base_offset[2k] = k / ks - (ks-1)/2 (y), [2k+1] = k % ks - (ks-1)/2 (x).  flip_xy != 0 first swaps the
+ * two channels of every point ((x,y) -> (y,x), rpd.py:628-634); reppointsv2.py does not flip.  The four
+ * float32 roundings of the reference expression are kept, so the result is bit-identical to it.
+ * Backward: grad_pts = gm * grad_out (with the same channel swap). */
+int sdb_reppoints_dcn_offset(const float* pts, int32_t N, int32_t ks, int32_t H, int32_t W, float gradient_mul,
+                             int32_t flip_xy, float* out, void* stream);
+int sdb_reppoints_dcn_offset_backward(const float* grad_out, int32_t N, int32_t ks, int32_t H, int32_t W,
+                                      float gradient_mul, int32_t flip_xy, float* grad_pts, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

@@ -219,6 +219,29 @@ __global__ void __launch_bounds__(256) centerness_kernel(const float4* __restric
     out[i] = __fsqrt_rn(__fmul_rn(lr, tb));
   }
 }
+
+// dcn_offset = ((1 - gm) * p + gm * p) - base, one rounding per operation as in the reference's four torch ops;
+// BWD: grad_pts = gm * grad_out.  Channel c of the output reads channel c ^ flip of the input.
+template <bool BWD>
+__global__ void __launch_bounds__(256) reppoints_offset_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                               long long total, int hw, int ks, float a, float b,
+                                                               int flip) {
+  const int K2 = 2 * ks * ks;
+  const float pad = (float)((ks - 1) / 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long plane = i / hw;
+    const int c = (int)(plane % K2);
+    const long long j = flip ? (plane - c + (c ^ 1)) * hw + (i - plane * hw) : i;   // element of the other tensor
+    if (BWD) {
+      dst[j] = __fmul_rn(b, src[i]);   // i indexes grad_out (channel c), j the point channel it came from
+    } else {
+      const float pv = src[j];
+      const int k = c >> 1;
+      const float base = (c & 1) ? (float)(k % ks) - pad : (float)(k / ks) - pad;
+      dst[i] = __fsub_rn(__fadd_rn(__fmul_rn(a, pv), __fmul_rn(b, pv)), base);
+    }
+  }
+}
 }  // namespace
 }  // namespace sdb
 
@@ -273,6 +296,30 @@ int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void
   sdb::centerness_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)reg_targets, R, out); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+
+static int reppoints_offset_launch(bool bwd, const float* src, int32_t N, int32_t ks, int32_t H, int32_t W, float gm,
+                                   int32_t flip, float* dst, void* stream) {
+  SDB_REQUIRE(N >= 0 && ks > 0 && H > 0 && W > 0, SDB_ERR_INVALID, "bad sizes N=%d ks=%d H=%d W=%d", N, ks, H, W);
+  const long long total = (long long)N * 2 * ks * ks * H * W;
+  if (total == 0) return SDB_OK;
+  SDB_REQUIRE(src && dst, SDB_ERR_INVALID, "NULL argument");
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const float a = (float)(1.0 - (double)gm), b = gm;   // python: (1 - gm) in double, each scalar cast to float32 by the op
+  if (bwd) sdb::reppoints_offset_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, total, H * W, ks, a, b, flip != 0);
+  else     sdb::reppoints_offset_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, total, H * W, ks, a, b, flip != 0);
+  SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+int sdb_reppoints_dcn_offset(const float* pts, int32_t N, int32_t ks, int32_t H, int32_t W, float gradient_mul,
+                             int32_t flip_xy, float* out, void* stream) {
+  return reppoints_offset_launch(false, pts, N, ks, H, W, gradient_mul, flip_xy, out, stream);
+}
+int sdb_reppoints_dcn_offset_backward(const float* grad_out, int32_t N, int32_t ks, int32_t H, int32_t W,
+                                      float gradient_mul, int32_t flip_xy, float* grad_pts, void* stream) {
+  return reppoints_offset_launch(true, grad_out, N, ks, H, W, gradient_mul, flip_xy, grad_pts, stream);
 }
 
 }  // extern "C"
