@@ -87,3 +87,22 @@ def topk_is_tie_free(q, topk):
         return True
     s = -np.sort(-q, axis=1)
     return bool((s[:, topk - 1] != s[:, topk]).all())
+
+
+def bbox_targets(candidates, gt, gt_labels, num_classes, pos_iou_thr=0.5, neg_iou_thr=0.4, gt_max_matching=True):
+    """RepPointsV2.bbox_targets restated (reppointsv2.py:430-484), numpy.  `candidates` is clamped in place."""
+    np.maximum(candidates, 0, out=candidates)                                  # :452-455
+    overlaps = pairwise_iou(candidates, gt)                                    # [X, M]  :459
+    labels = np.full((overlaps.shape[0],), num_classes, dtype=np.int64)        # :460
+    max_ov, argmax_ov = overlaps.max(axis=1), overlaps.argmax(axis=1)          # :464
+    gt_max = overlaps.max(axis=0)                                              # :467
+    labels[max_ov < neg_iou_thr] = num_classes                                 # :469-470
+    fg = max_ov >= pos_iou_thr                                                 # :472-473
+    labels[fg] = gt_labels[argmax_ov[fg]]
+    if gt_max_matching:                                                        # :475-477
+        rows = np.nonzero(overlaps == gt_max[None, :])[0]
+        labels[rows] = gt_labels[argmax_ov[rows]]
+    boxes = np.zeros((overlaps.shape[0], 4), dtype=gt.dtype)                   # :479
+    sel = (labels >= 0) & (labels != num_classes)                              # :481-482
+    boxes[sel] = gt[argmax_ov[sel]]
+    return boxes, labels

@@ -1,0 +1,34 @@
+"""Target assignment built on the fused IoU / matcher kernels.
+
+``bbox_targets`` mirrors ``RepPointsV2.bbox_targets``
+(/root/reference/slender_det/modeling/meta_arch/reppoints/reppointsv2.py:430-484): MaxIoU assignment of the
+refined boxes.  The reference materialises the [X, M] IoU matrix, takes two maxima, and uses boolean-mask /
+``nonzero`` indexing (host synchronisations); here the IoU + per-candidate argmax + per-GT maximum matching
+is ONE pass of ``sdb_iou_assign`` and the gathers are ``torch.where`` - no IoU matrix, no host sync.
+"""
+import torch
+
+from .matchers import Matcher, _tensor_of
+
+
+@torch.no_grad()
+def bbox_targets(candidate_bboxes, gt_bboxes, gt_labels, num_classes, pos_iou_thr=0.5, neg_iou_thr=0.4,
+                 gt_max_matching=True):
+    """-> (assigned_bboxes [X, 4], assigned_labels int64 [X]).
+
+    * ``candidate_bboxes`` [X, 4] is clamped to >= 0 IN PLACE, as the reference does (:452-455);
+    * a candidate is foreground when its best IoU is >= ``pos_iou_thr`` or (``gt_max_matching``) when its IoU
+      with some GT equals that GT's maximum over all candidates (:471-477 - including GTs whose maximum is 0);
+    * foreground rows get the box / label of their argmax GT, the rest ``num_classes`` and a zero box.  The
+      ``neg_iou_thr`` band never changes the result (the labels start at ``num_classes``, :460, :468-469).
+    """
+    gt = _tensor_of(gt_bboxes)
+    if candidate_bboxes.size(0) == 0 or gt.size(0) == 0:
+        raise ValueError("No gt or anchors")
+    candidate_bboxes.clamp_(min=0)
+    matcher = Matcher([pos_iou_thr], [0, 1], allow_low_quality_matches=bool(gt_max_matching))
+    matches, mlabels = matcher.from_boxes(gt, candidate_bboxes)
+    fg = mlabels == 1
+    labels = torch.where(fg, gt_labels.to(torch.long)[matches], torch.full_like(matches, num_classes))
+    boxes = torch.where(fg[:, None], gt.to(candidate_bboxes.dtype)[matches], torch.zeros_like(candidate_bboxes))
+    return boxes, labels

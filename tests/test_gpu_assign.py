@@ -90,3 +90,22 @@ def test_ties_follow_canonical_rule_and_full_size():
     mo, lo = oa.matcher(q, [0.4, 0.5], [0, -1, 1], True)
     m, l = sdb.Matcher([0.4, 0.5], [0, -1, 1], True).from_boxes(gt.cuda(), an.cuda())
     assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)
+
+
+@pytest.mark.parametrize("gmm", [True, False])
+@pytest.mark.parametrize("size", [(3000, 23), (22400, 100)])
+def test_bbox_targets_bit_exact(size, gmm):
+    """RepPointsV2.bbox_targets (reppointsv2.py:430-484) on the fused IoU/matcher kernel: labels and boxes
+    bit-identical to the oracle, candidates clamped in place, no IoU matrix."""
+    from test_oracle_assign import _bbox_case
+    from slenderobjdet_b200.targets import bbox_targets
+    cand, gt, labels = _bbox_case(7, *size)
+    cd = cand.clone().cuda()
+    b, l = bbox_targets(cd, gt.cuda(), labels.cuda(), 80, gt_max_matching=gmm)
+    cn = cand.clone().numpy()
+    ob, ol_ = oa.bbox_targets(cn, gt.numpy(), labels.numpy(), 80, gt_max_matching=gmm)
+    assert np.array_equal(cd.cpu().numpy(), cn)
+    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), ol_)
+    assert np.array_equal(b.cpu().numpy(), ob)
+    with pytest.raises(ValueError):
+        bbox_targets(torch.zeros(0, 4, device="cuda"), gt.cuda(), labels.cuda(), 80)

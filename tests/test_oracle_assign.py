@@ -64,3 +64,55 @@ def test_tie_rule_is_lowest_index():
     # GT0: anchor 5 then lowest-index zeros {0,1}; GT1: anchor 3 then {0,1}
     assert sorted(np.nonzero(l == 1)[0].tolist()) == [0, 1, 3, 5]
     assert m[5] == 0 and m[3] == 1 and m[0] == 0
+
+
+def _bbox_targets_reference_lines(candidate_bboxes, gt, gt_labels, num_classes, pos_iou_thr=0.5, neg_iou_thr=0.4,
+                                  gt_max_matching=True):
+    """reppointsv2.py:452-484 in torch (CPU), with the IoU of boxes.py:333-347."""
+    import torch
+    candidate_bboxes[:, 0].clamp_(min=0); candidate_bboxes[:, 1].clamp_(min=0)
+    candidate_bboxes[:, 2].clamp_(min=0); candidate_bboxes[:, 3].clamp_(min=0)
+    b1, b2 = candidate_bboxes, gt
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    wh = torch.min(b1[:, None, 2:], b2[:, 2:]) - torch.max(b1[:, None, :2], b2[:, :2])
+    wh.clamp_(min=0)
+    inter = wh.prod(dim=2)
+    overlaps = torch.where(inter > 0, inter / (area1[:, None] + area2 - inter), torch.zeros(1, dtype=inter.dtype))
+    assigned_labels = overlaps.new_full((overlaps.size(0),), num_classes, dtype=torch.long)
+    max_overlaps, argmax_overlaps = overlaps.max(dim=1)
+    gt_max_overlaps, _ = overlaps.max(dim=0)
+    assigned_labels[max_overlaps < neg_iou_thr] = num_classes
+    fg_inds = max_overlaps >= pos_iou_thr
+    assigned_labels[fg_inds] = gt_labels[argmax_overlaps[fg_inds]]
+    if gt_max_matching:
+        fg_inds = torch.nonzero(overlaps == gt_max_overlaps)[:, 0]
+        assigned_labels[fg_inds] = gt_labels[argmax_overlaps[fg_inds]]
+    assigned_bboxes = overlaps.new_zeros((b1.size(0), 4))
+    fg_inds = (assigned_labels >= 0) & (assigned_labels != num_classes)
+    assigned_bboxes[fg_inds] = gt[argmax_overlaps[fg_inds]]
+    return assigned_bboxes, assigned_labels
+
+
+def _bbox_case(seed, X=3000, M=23):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ctr = torch.rand(X, 2, generator=g) * torch.tensor([640.0, 480.0])
+    wh = torch.exp(torch.rand(X, 2, generator=g) * 3.5 + 1.5)
+    cand = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)            # some coordinates negative: exercises the clamp
+    c2 = torch.rand(M, 2, generator=g) * torch.tensor([640.0, 480.0])
+    wh2 = torch.exp(torch.rand(M, 2, generator=g) * 3.5 + 2.0)
+    gt = torch.cat([c2 - wh2 / 2, c2 + wh2 / 2], 1).clamp(min=0)
+    gt[0] = torch.tensor([5000.0, 5000.0, 5100.0, 5100.0])      # a GT nothing overlaps: its maximum is 0
+    labels = torch.randint(0, 80, (M,), generator=g)
+    return cand, gt, labels
+
+
+def test_bbox_targets_oracle_matches_reference_lines():
+    for seed, gmm in ((0, True), (1, False), (2, True)):
+        cand, gt, labels = _bbox_case(seed)
+        c1, c2 = cand.clone(), cand.clone().numpy()
+        rb, rl = _bbox_targets_reference_lines(c1, gt, labels, 80, gt_max_matching=gmm)
+        ob, ol_ = oa.bbox_targets(c2, gt.numpy(), labels.numpy(), 80, gt_max_matching=gmm)
+        assert np.array_equal(c1.numpy(), c2)                     # same in-place clamp
+        assert np.array_equal(ol_, rl.numpy()) and np.array_equal(ob, rb.numpy())
