@@ -171,6 +171,20 @@ int sdb_reppoints_dcn_offset(const float* pts, int32_t N, int32_t ks, int32_t H,
 int sdb_reppoints_dcn_offset_backward(const float* grad_out, int32_t N, int32_t ks, int32_t H, int32_t W,
                                       float gradient_mul, int32_t flip_xy, float* grad_pts, void* stream);
 
+/* ---- RepPoints point assignment (reppointsv2.py:370-428) --------------------
+ * Every GT claims the point nearest to its centre (L2 of (point - centre) / (w, h)) among the points of ITS
+ * pyramid level, level = clamp(int((log2(w/scale) + log2(h/scale)) / 2), min/max level of the points); a point
+ * claimed by several GTs keeps the closest one, ties -> the lowest GT index (the reference's sequential
+ * "strictly less than recorded" rule).  The reference loops over GTs on the host (~12 launches each); here:
+ * one block per GT + one pass over the points.
+ * points [X,2], strides [X] float32; gt [M,4] xyxy float32; gt_labels [M] int64.
+ * assigned_bboxes [X,4] float32 (zeros where unassigned), assigned_labels [X] int64 (num_classes where
+ * unassigned).  workspace: sdb_point_targets_workspace_bytes(X). */
+size_t sdb_point_targets_workspace_bytes(int32_t X);
+int sdb_point_targets(const float* points, const float* strides, const float* gt, const int64_t* gt_labels,
+                      int32_t X, int32_t M, float scale, int64_t num_classes, float* assigned_bboxes,
+                      int64_t* assigned_labels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

@@ -106,3 +106,36 @@ def bbox_targets(candidates, gt, gt_labels, num_classes, pos_iou_thr=0.5, neg_io
     sel = (labels >= 0) & (labels != num_classes)                              # :481-482
     boxes[sel] = gt[argmax_ov[sel]]
     return boxes, labels
+
+
+def point_targets(points, strides, gt, gt_labels, num_classes, scale=4):
+    """RepPointsV2.point_targets restated (reppointsv2.py:370-428): the sequential loop over GTs, float32."""
+    f = np.float32
+    points = np.asarray(points, f)[:, :2]
+    strides = np.asarray(strides, f)
+    gt = np.asarray(gt, f)
+    points_lvl = np.log2(strides).astype(np.int32)                              # :385
+    lvl_min, lvl_max = points_lvl.min(), points_lvl.max()
+    ctr = ((gt[:, :2] + gt[:, 2:]) / f(2)).astype(f)                            # :390
+    wh = np.maximum(gt[:, 2:] - gt[:, :2], f(1e-6)).astype(f)                   # :391
+    lvl = (((np.log2((wh[:, 0] / f(scale)).astype(f)) + np.log2((wh[:, 1] / f(scale)).astype(f))).astype(f) / f(2))
+           .astype(f)).astype(np.int32)                                        # :395-396 (.int() truncates)
+    lvl = np.clip(lvl, lvl_min, lvl_max)
+    assigned = np.zeros((points.shape[0],), np.int64)
+    dist_rec = np.full((points.shape[0],), np.inf, f)
+    for idx in range(gt.shape[0]):                                              # :403-417
+        sel = np.nonzero(points_lvl == lvl[idx])[0]
+        if sel.size == 0:
+            continue
+        d = ((points[sel] - ctr[idx]) / wh[idx]).astype(f)
+        dist = np.sqrt((d[:, 0] * d[:, 0]).astype(f) + (d[:, 1] * d[:, 1]).astype(f)).astype(f)
+        j = int(np.argmin(dist))                                                # lowest index among equal minima
+        if dist[j] < dist_rec[sel[j]]:
+            assigned[sel[j]] = idx + 1
+            dist_rec[sel[j]] = dist[j]
+    boxes = np.zeros((points.shape[0], 4), gt.dtype)
+    labels = np.full((points.shape[0],), num_classes, dtype=np.asarray(gt_labels).dtype)
+    pos = assigned > 0
+    labels[pos] = np.asarray(gt_labels)[assigned[pos] - 1]
+    boxes[pos] = gt[assigned[pos] - 1]
+    return boxes, labels

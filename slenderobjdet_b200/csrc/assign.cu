@@ -373,7 +373,107 @@ int assign_impl(const float* gt, const float* anchors, const float* q, int M, in
 
 using namespace sdb;
 
+// ---- RepPoints point_targets (reppointsv2.py:370-428) -------------------------------------------------
+namespace sdb {
+namespace {
+struct PtWs {
+  int lvl_min, lvl_max;   // memset to 0x7f7f7f7f / 0x80808080 before the min/max pass
+};
+__device__ __forceinline__ int point_level(float stride) { return (int)log2f(stride); }   // torch.log2(s).int()
+
+__global__ void __launch_bounds__(256) pt_level_range_kernel(const float* __restrict__ strides, int X, PtWs* ws) {
+  int lo = 0x7fffffff, hi = (int)0x80000000;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < X; i += gridDim.x * blockDim.x) {
+    const int l = point_level(strides[i]);
+    lo = min(lo, l);
+    hi = max(hi, l);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&ws->lvl_min, lo);
+    atomicMax(&ws->lvl_max, hi);
+  }
+}
+
+// one block per GT: nearest point of the GT's level, then claim it with atomicMin on (distance bits, GT index)
+__global__ void __launch_bounds__(512) pt_claim_kernel(const float2* __restrict__ points, const float* __restrict__ strides,
+                                                       const float4* __restrict__ gt, int X, float scale,
+                                                       const PtWs* __restrict__ ws, unsigned long long* __restrict__ keys) {
+  __shared__ Key s_red[32];
+  const int m = blockIdx.x;
+  const float4 b = gt[m];
+  const float cx = __fdiv_rn(__fadd_rn(b.x, b.z), 2.f), cy = __fdiv_rn(__fadd_rn(b.y, b.w), 2.f);
+  const float w = fmaxf(__fsub_rn(b.z, b.x), 1e-6f), h = fmaxf(__fsub_rn(b.w, b.y), 1e-6f);
+  int lvl = (int)__fdiv_rn(__fadd_rn(log2f(__fdiv_rn(w, scale)), log2f(__fdiv_rn(h, scale))), 2.f);
+  lvl = max(ws->lvl_min, min(ws->lvl_max, lvl));
+  // "before" ranks larger values first: search the maximum of -distance, lowest point index on ties
+  Key best = {-INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < X; i += blockDim.x) {
+    if (point_level(strides[i]) != lvl) continue;
+    const float2 p = points[i];
+    const float dx = __fdiv_rn(__fsub_rn(p.x, cx), w), dy = __fdiv_rn(__fsub_rn(p.y, cy), h);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const Key k = {-dist, i};
+    if (before(k, best)) best = k;
+  }
+  best = block_best(best, s_red);
+  if (threadIdx.x == 0 && best.i < X) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(-best.v) << 32) | (unsigned)m;
+    atomicMin(keys + best.i, key);   // distances are >= 0: their bit patterns order like the values
+  }
+}
+
+__global__ void __launch_bounds__(256) pt_write_kernel(const unsigned long long* __restrict__ keys, const float4* __restrict__ gt,
+                                                       const int64_t* __restrict__ gt_labels, int X, int64_t num_classes,
+                                                       float4* __restrict__ boxes, int64_t* __restrict__ labels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= X) return;
+  const unsigned long long k = keys[i];
+  if (k == ~0ull) {
+    boxes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    labels[i] = num_classes;
+  } else {
+    const int m = (int)(k & 0xffffffffu);
+    boxes[i] = gt[m];
+    labels[i] = gt_labels[m];
+  }
+}
+}  // namespace
+}  // namespace sdb
+
 extern "C" {
+
+size_t sdb_point_targets_workspace_bytes(int32_t X) { return X > 0 ? 256 + (size_t)X * 8 : 0; }
+
+int sdb_point_targets(const float* points, const float* strides, const float* gt, const int64_t* gt_labels,
+                      int32_t X, int32_t M, float scale, int64_t num_classes, float* assigned_bboxes,
+                      int64_t* assigned_labels, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace sdb;
+  SDB_REQUIRE(X > 0 && M > 0, SDB_ERR_INVALID, "No gt or bboxes");   // reppointsv2.py:383-384
+  SDB_REQUIRE(points && strides && gt && gt_labels && assigned_bboxes && assigned_labels, SDB_ERR_INVALID, "NULL argument");
+  SDB_REQUIRE(workspace && workspace_bytes >= sdb_point_targets_workspace_bytes(X), SDB_ERR_WORKSPACE,
+              "point_targets workspace too small");
+  SDB_REQUIRE(scale > 0.f, SDB_ERR_INVALID, "point_base_scale must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  PtWs* ws = (PtWs*)workspace;
+  unsigned long long* keys = (unsigned long long*)((uint8_t*)workspace + 256);
+  SDB_CHECK_CUDA(cudaMemsetAsync(&ws->lvl_min, 0x7f, 4, st));
+  SDB_CHECK_CUDA(cudaMemsetAsync(&ws->lvl_max, 0x80, 4, st));
+  SDB_CHECK_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)X * 8, st));
+  int blocks = cdiv(X, 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  pt_level_range_kernel<<<blocks, 256, 0, st>>>(strides, X, ws);
+  pt_claim_kernel<<<M, 512, 0, st>>>((const float2*)points, strides, (const float4*)gt, X, scale, ws, keys);
+  pt_write_kernel<<<cdiv(X, 256), 256, 0, st>>>(keys, (const float4*)gt, gt_labels, X, num_classes, (float4*)assigned_bboxes,
+                                                assigned_labels);
+  SDB_LAUNCHED(3);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
 
 size_t sdb_assign_workspace_bytes(int32_t M, int32_t X, int32_t topk) {
   // candidate keys of the split per-GT top-k; small problems use the single-block scan and need none

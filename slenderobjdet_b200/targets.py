@@ -32,3 +32,34 @@ def bbox_targets(candidate_bboxes, gt_bboxes, gt_labels, num_classes, pos_iou_th
     labels = torch.where(fg, gt_labels.to(torch.long)[matches], torch.full_like(matches, num_classes))
     boxes = torch.where(fg[:, None], gt.to(candidate_bboxes.dtype)[matches], torch.zeros_like(candidate_bboxes))
     return boxes, labels
+
+
+@torch.no_grad()
+def point_targets(points, pts_strides, gt_bboxes, gt_labels, num_classes, point_base_scale=4):
+    """``RepPointsV2.point_targets`` (reppointsv2.py:370-428): every GT claims the nearest point (normalised L2)
+    of its pyramid level; contested points keep the closest GT (lowest GT index on ties).
+    ``points`` [X, 2] or [X, >=2] (only the first two columns are used, as in the reference's callers),
+    ``pts_strides`` [X], ``gt_bboxes`` [M, 4] xyxy, ``gt_labels`` [M] -> (assigned_bboxes [X, 4],
+    assigned_labels [X]).  The reference's host loop over GTs (~12 launches + index ops per GT) becomes three
+    launches."""
+    from . import _lib
+    gt = _tensor_of(gt_bboxes)
+    if points.shape[0] == 0 or gt.shape[0] == 0:
+        raise ValueError("No gt or bboxes")
+    if not points.is_cuda:
+        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
+    pts = points[:, :2].detach().float().contiguous()
+    st = pts_strides.detach().float().contiguous()
+    g = gt.detach().float().contiguous()
+    gl = gt_labels.detach().to(torch.long).contiguous()
+    X, M = pts.shape[0], g.shape[0]
+    boxes = torch.empty((X, 4), dtype=torch.float32, device=pts.device)
+    labels = torch.empty((X,), dtype=torch.long, device=pts.device)
+    lib = _lib.lib()
+    wsb = int(lib.sdb_point_targets_workspace_bytes(X))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.check(lib.sdb_point_targets(_lib.ptr(pts), _lib.ptr(st), _lib.ptr(g), _lib.ptr(gl), X, M,
+                                         float(point_base_scale), int(num_classes), _lib.ptr(boxes), _lib.ptr(labels),
+                                         _lib.ptr(ws), wsb, _lib.stream_ptr(pts.device)))
+    return boxes.to(gt.dtype), labels.to(gt_labels.dtype)

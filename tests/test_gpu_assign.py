@@ -109,3 +109,22 @@ def test_bbox_targets_bit_exact(size, gmm):
     assert np.array_equal(b.cpu().numpy(), ob)
     with pytest.raises(ValueError):
         bbox_targets(torch.zeros(0, 4, device="cuda"), gt.cuda(), labels.cuda(), 80)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_point_targets_bit_exact(seed):
+    """RepPointsV2.point_targets (reppointsv2.py:370-428): three launches instead of the host loop over GTs;
+    boxes and labels identical to the oracle, incl. two GTs at equal distance from one point (first GT keeps it)
+    and the full P3-P7 point set of an 800x1344 image."""
+    from test_oracle_assign import _points_case
+    from slenderobjdet_b200.targets import point_targets
+    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128)) if seed else None
+    pts, strides, gt, labels = _points_case(seed, 100, lv) if lv else _points_case(seed)
+    if lv:
+        gt = gt * 4.0
+    b, l = point_targets(pts.cuda(), strides.cuda(), gt.cuda(), labels.cuda(), 80)
+    ob, ol_ = oa.point_targets(pts.numpy(), strides.numpy(), gt.numpy(), labels.numpy(), 80)
+    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), ol_)
+    assert np.array_equal(b.cpu().numpy(), ob)
+    with pytest.raises(ValueError):
+        point_targets(pts[:0].cuda(), strides[:0].cuda(), gt.cuda(), labels.cuda(), 80)

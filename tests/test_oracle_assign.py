@@ -116,3 +116,66 @@ def test_bbox_targets_oracle_matches_reference_lines():
         ob, ol_ = oa.bbox_targets(c2, gt.numpy(), labels.numpy(), 80, gt_max_matching=gmm)
         assert np.array_equal(c1.numpy(), c2)                     # same in-place clamp
         assert np.array_equal(ol_, rl.numpy()) and np.array_equal(ob, rb.numpy())
+
+
+def _point_targets_reference_lines(points, pts_strides, gt_bboxes, gt_labels, num_classes, point_base_scale=4):
+    """reppointsv2.py:383-428 in torch (CPU)."""
+    import torch
+    points_lvl = torch.log2(pts_strides).int()
+    lvl_min, lvl_max = points_lvl.min(), points_lvl.max()
+    num_gts, num_points = gt_bboxes.shape[0], points.shape[0]
+    gt_bboxes_ctr_xy = (gt_bboxes[:, :2] + gt_bboxes[:, 2:]) / 2
+    gt_bboxes_wh = (gt_bboxes[:, 2:] - gt_bboxes[:, :2]).clamp(min=1e-6)
+    scale = point_base_scale
+    gt_bboxes_lvl = ((torch.log2(gt_bboxes_wh[:, 0] / scale) + torch.log2(gt_bboxes_wh[:, 1] / scale)) / 2).int()
+    gt_bboxes_lvl = torch.clamp(gt_bboxes_lvl, min=lvl_min, max=lvl_max)
+    assigned_gt_inds = points.new_zeros((num_points,), dtype=torch.long)
+    assigned_gt_dist = points.new_full((num_points,), float('inf'))
+    points_range = torch.arange(points.shape[0])
+    for idx in range(num_gts):
+        gt_lvl = gt_bboxes_lvl[idx]
+        lvl_idx = gt_lvl == points_lvl
+        points_index = points_range[lvl_idx]
+        lvl_points = points[lvl_idx, :]
+        gt_point = gt_bboxes_ctr_xy[[idx], :]
+        gt_wh = gt_bboxes_wh[[idx], :]
+        points_gt_dist = ((lvl_points - gt_point) / gt_wh).norm(dim=1)
+        min_dist, min_dist_index = torch.topk(points_gt_dist, 1, largest=False)
+        min_dist_points_index = points_index[min_dist_index]
+        less_than_recorded_index = min_dist < assigned_gt_dist[min_dist_points_index]
+        min_dist_points_index = min_dist_points_index[less_than_recorded_index]
+        assigned_gt_inds[min_dist_points_index] = idx + 1
+        assigned_gt_dist[min_dist_points_index] = min_dist[less_than_recorded_index]
+    assigned_bboxes = gt_bboxes.new_zeros((num_points, 4))
+    assigned_labels = gt_labels.new_full((num_points,), num_classes)
+    pos_inds = torch.nonzero(assigned_gt_inds > 0).squeeze().long()
+    if pos_inds.numel() > 0:
+        assigned_labels[pos_inds] = gt_labels[assigned_gt_inds[pos_inds] - 1]
+        assigned_bboxes[pos_inds] = gt_bboxes[assigned_gt_inds[pos_inds] - 1]
+    return assigned_bboxes, assigned_labels
+
+
+def _points_case(seed, M=60, levels=((25, 42, 8), (13, 21, 16), (7, 11, 32), (4, 6, 64), (2, 3, 128))):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pts, strides = [], []
+    for (h, w, s) in levels:
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        pts.append(torch.stack([xs.reshape(-1) * s, ys.reshape(-1) * s], 1))      # reference: shifts = arange * stride
+        strides.append(torch.full((h * w,), float(s)))
+    pts, strides = torch.cat(pts), torch.cat(strides)
+    c = torch.rand(M, 2, generator=g) * torch.tensor([320.0, 190.0])
+    wh = torch.exp(torch.rand(M, 2, generator=g) * 5.0 + 0.5)                     # 1.6 .. 245 px: every level + clamping
+    gt = torch.cat([c - wh / 2, c + wh / 2], 1)
+    gt[1] = gt[0]                                                                 # two GTs claim the same point at equal distance
+    labels = torch.randint(0, 80, (M,), generator=g)
+    return pts, strides, gt, labels
+
+
+def test_point_targets_oracle_matches_reference_lines():
+    for seed in (0, 1, 2):
+        pts, strides, gt, labels = _points_case(seed)
+        rb, rl = _point_targets_reference_lines(pts, strides, gt, labels, 80)
+        ob, ol_ = oa.point_targets(pts.numpy(), strides.numpy(), gt.numpy(), labels.numpy(), 80)
+        assert np.array_equal(ol_, rl.numpy()) and np.array_equal(ob, rb.numpy())
+        assert (rl != 80).sum() > 10
