@@ -185,6 +185,20 @@ int sdb_point_targets(const float* points, const float* strides, const float* gt
                       int32_t X, int32_t M, float scale, int64_t num_classes, float* assigned_bboxes,
                       int64_t* assigned_labels, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- FCOS location targets (fcos/utils.py:108-212), one image per call -----
+ * For every location: ltrb to every GT, "inside" = min(ltrb) > 0 (center_sampling_radius <= 0) or inside the
+ * GT's centre region of radius stride*radius clipped to the box (get_sample_region :108-157, including its
+ * "first GT centred at x == 0 means no GT" shortcut), "cared" = size_lo <= max(ltrb) <= size_hi; among the
+ * qualifying GTs the one of minimal area (lowest index on ties; INF = 1e8 as in the reference).
+ * out_classes[x] = class of that GT or num_classes; out_reg[x] = ltrb to that GT (GT 0 for background rows,
+ * as the reference's argmin of an all-INF row gives).  The [X, M, 4] temporaries never exist.
+ * locations, sizes_of_interest [X,2] float32; gt [M,4] xyxy float32; gt_classes [M] int64;
+ * num_points_per_level / level_strides: HOST arrays of n_levels (<= 8) entries. */
+int sdb_fcos_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
+                              const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
+                              const float* level_strides, int32_t n_levels, float center_sampling_radius,
+                              int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

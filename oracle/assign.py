@@ -139,3 +139,45 @@ def point_targets(points, strides, gt, gt_labels, num_classes, scale=4):
     labels[pos] = np.asarray(gt_labels)[assigned[pos] - 1]
     boxes[pos] = gt[assigned[pos] - 1]
     return boxes, labels
+
+
+def fcos_location_targets(locations, soi, gt, gt_classes, num_points, strides, radius, num_classes):
+    """compute_targets_for_locations for ONE image restated (fcos/utils.py:108-212), numpy float32."""
+    f = np.float32
+    INF = f(100000000)
+    loc, soi, gt = np.asarray(locations, f), np.asarray(soi, f), np.asarray(gt, f)
+    xs, ys = loc[:, 0], loc[:, 1]
+    area = ((gt[:, 2] - gt[:, 0]) * (gt[:, 3] - gt[:, 1])).astype(f)
+    l = xs[:, None] - gt[None, :, 0]; t = ys[:, None] - gt[None, :, 1]           # :176-180
+    r = gt[None, :, 2] - xs[:, None]; b = gt[None, :, 3] - ys[:, None]
+    reg = np.stack([l, t, r, b], axis=2).astype(f)
+    if radius > 0:                                                               # get_sample_region :108-157
+        cx = ((gt[:, 0] + gt[:, 2]) / f(2)).astype(f); cy = ((gt[:, 1] + gt[:, 3]) / f(2)).astype(f)
+        if (cx[0] * len(xs)) == 0:                                               # :122-123 (sum of K copies)
+            inside = np.zeros((len(xs), gt.shape[0]), bool)
+        else:
+            cg = np.zeros((len(xs), gt.shape[0], 4), f)
+            beg = 0
+            for level, n_p in enumerate(num_points):
+                end = beg + n_p
+                s = f(strides[level] * radius)
+                xmin, ymin, xmax, ymax = cx - s, cy - s, cx + s, cy + s
+                cg[beg:end, :, 0] = np.where(xmin > gt[:, 0], xmin, gt[:, 0])
+                cg[beg:end, :, 1] = np.where(ymin > gt[:, 1], ymin, gt[:, 1])
+                cg[beg:end, :, 2] = np.where(xmax > gt[:, 2], gt[:, 2], xmax)
+                cg[beg:end, :, 3] = np.where(ymax > gt[:, 3], gt[:, 3], ymax)
+                beg = end
+            cb = np.stack([xs[:, None] - cg[..., 0], ys[:, None] - cg[..., 1], cg[..., 2] - xs[:, None],
+                           cg[..., 3] - ys[:, None]], -1).astype(f)
+            inside = cb.min(-1) > 0
+    else:
+        inside = reg.min(axis=2) > 0                                             # :186
+    mx = reg.max(axis=2)
+    cared = (mx >= soi[:, [0]]) & (mx <= soi[:, [1]])                            # :190-192
+    a = np.repeat(area[None], len(xs), axis=0)
+    a[~inside] = INF
+    a[~cared] = INF
+    idx = a.argmin(axis=1)                                                       # first minimum
+    cls = np.asarray(gt_classes)[idx].copy()
+    cls[a.min(axis=1) == INF] = num_classes                                      # :203
+    return cls, reg[np.arange(len(xs)), idx]

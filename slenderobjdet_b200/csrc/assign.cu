@@ -445,7 +445,104 @@ __global__ void __launch_bounds__(256) pt_write_kernel(const unsigned long long*
 }  // namespace
 }  // namespace sdb
 
+// ---- FCOS compute_targets_for_locations (fcos/utils.py:108-212) ------------------------------------------
+namespace sdb {
+namespace {
+struct FcosLevels {
+  int end[8];        // cumulative location count per level
+  float radius[8];   // stride * center_sampling_radius
+  int n;
+};
+
+__global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restrict__ loc, const float2* __restrict__ soi,
+                                                           const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls,
+                                                           int X, int M, const FcosLevels lv, int center_sampling,
+                                                           int64_t num_classes, int64_t* __restrict__ out_cls,
+                                                           float4* __restrict__ out_reg) {
+  extern __shared__ float4 s_gt[];   // M boxes, then M areas
+  float* s_area = reinterpret_cast<float*>(s_gt + M);
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const float4 b = gt[m];
+    s_gt[m] = b;
+    s_area[m] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));   // Boxes.area()
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= X) return;
+  const float2 p = loc[i], so = soi[i];
+  float rad = 0.f;
+  if (center_sampling) {
+    int l = 0;
+    while (l + 1 < lv.n && i >= lv.end[l]) ++l;
+    rad = lv.radius[l];
+  }
+  // get_sample_region's shortcut: sum over locations of GT 0's centre x == 0 -> "no gt", nothing is inside
+  const bool no_gt = center_sampling && __fdiv_rn(__fadd_rn(s_gt[0].x, s_gt[0].z), 2.f) == 0.f;
+  const float INF = 100000000.f;
+  float best = __int_as_float(0x7f800000);
+  int best_m = 0;
+  for (int m = 0; m < M; ++m) {
+    const float4 b = s_gt[m];
+    const float l = __fsub_rn(p.x, b.x), t = __fsub_rn(p.y, b.y), r = __fsub_rn(b.z, p.x), bt = __fsub_rn(b.w, p.y);
+    bool inside;
+    if (center_sampling) {
+      const float cx = __fdiv_rn(__fadd_rn(b.x, b.z), 2.f), cy = __fdiv_rn(__fadd_rn(b.y, b.w), 2.f);
+      const float xmin = __fsub_rn(cx, rad), ymin = __fsub_rn(cy, rad), xmax = __fadd_rn(cx, rad), ymax = __fadd_rn(cy, rad);
+      const float x0 = xmin > b.x ? xmin : b.x, y0 = ymin > b.y ? ymin : b.y;
+      const float x1 = xmax > b.z ? b.z : xmax, y1 = ymax > b.w ? b.w : ymax;
+      const float cl = __fsub_rn(p.x, x0), cr = __fsub_rn(x1, p.x), ct = __fsub_rn(p.y, y0), cb = __fsub_rn(y1, p.y);
+      inside = !no_gt && fminf(fminf(cl, ct), fminf(cr, cb)) > 0.f;
+    } else {
+      inside = fminf(fminf(l, t), fminf(r, bt)) > 0.f;
+    }
+    const float mx = fmaxf(fmaxf(l, t), fmaxf(r, bt));
+    const bool cared = mx >= so.x && mx <= so.y;
+    const float v = (inside && cared) ? s_area[m] : INF;
+    if (v < best) {
+      best = v;
+      best_m = m;
+    }
+  }
+  const float4 b = s_gt[best_m];
+  out_reg[i] = make_float4(__fsub_rn(p.x, b.x), __fsub_rn(p.y, b.y), __fsub_rn(b.z, p.x), __fsub_rn(b.w, p.y));
+  out_cls[i] = best == INF ? num_classes : gt_cls[best_m];
+}
+}  // namespace
+}  // namespace sdb
+
 extern "C" {
+
+int sdb_fcos_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
+                              const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
+                              const float* level_strides, int32_t n_levels, float center_sampling_radius,
+                              int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream) {
+  using namespace sdb;
+  SDB_REQUIRE(X >= 0 && M > 0, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
+  if (X == 0) return SDB_OK;
+  SDB_REQUIRE(locations && sizes_of_interest && gt && gt_classes && out_classes && out_reg, SDB_ERR_INVALID, "NULL argument");
+  FcosLevels lv{};
+  const bool cs = center_sampling_radius > 0.f;
+  if (cs) {
+    SDB_REQUIRE(num_points_per_level && level_strides && n_levels >= 1 && n_levels <= 8, SDB_ERR_INVALID,
+                "center sampling needs 1..8 levels");
+    int acc = 0;
+    for (int l = 0; l < n_levels; ++l) {
+      acc += num_points_per_level[l];
+      lv.end[l] = acc;
+      lv.radius[l] = (float)((double)level_strides[l] * (double)center_sampling_radius);
+    }
+    SDB_REQUIRE(acc == X, SDB_ERR_INVALID, "num_points_per_level sums to %d, expected %d", acc, X);
+    lv.n = n_levels;
+  }
+  const size_t smem = (size_t)M * (sizeof(float4) + sizeof(float));
+  SDB_REQUIRE(smem <= 48 * 1024, SDB_ERR_UNSUPPORTED, "too many GT boxes (%d) for one shared-memory stage", M);
+  fcos_targets_kernel<<<cdiv(X, 256), 256, smem, (cudaStream_t)stream>>>(
+      (const float2*)locations, (const float2*)sizes_of_interest, (const float4*)gt, gt_classes, X, M, lv, cs ? 1 : 0,
+      num_classes, out_classes, (float4*)out_reg);
+  SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
 
 size_t sdb_point_targets_workspace_bytes(int32_t X) { return X > 0 ? 256 + (size_t)X * 8 : 0; }
 

@@ -63,3 +63,47 @@ def point_targets(points, pts_strides, gt_bboxes, gt_labels, num_classes, point_
                                          float(point_base_scale), int(num_classes), _lib.ptr(boxes), _lib.ptr(labels),
                                          _lib.ptr(ws), wsb, _lib.stream_ptr(pts.device)))
     return boxes.to(gt.dtype), labels.to(gt_labels.dtype)
+
+
+def _boxes_and_classes(t):
+    """Instances-like (``.gt_boxes`` / ``.gt_classes``) or a (boxes, classes) pair."""
+    if hasattr(t, "gt_boxes"):
+        return _tensor_of(t.gt_boxes), t.gt_classes
+    b, c = t
+    return _tensor_of(b), c
+
+
+@torch.no_grad()
+def compute_targets_for_locations(locations, targets, object_sizes_of_interest, strides, center_sampling_radius,
+                                  num_classes):
+    """``slender_det.modeling.meta_arch.fcos.utils.compute_targets_for_locations`` (fcos/utils.py:160-212).
+
+    ``locations``: list of per-level [X_l, 2] tensors; ``targets``: per image an Instances-like object or a
+    (boxes [M,4], classes [M]) pair; ``object_sizes_of_interest`` [X, 2]; ``strides``: per-level ints.
+    -> (gt_classes [N, X], reg_targets [N, X, 4]).  One fused kernel per image (GT boxes in shared memory, one
+    thread per location) instead of [X, M, 4] temporaries and ~25 launches; results are identical."""
+    import ctypes
+    from . import _lib
+    num_points = [len(l) for l in locations]
+    loc = torch.cat(locations, dim=0).float().contiguous()
+    if not loc.is_cuda:
+        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
+    soi = object_sizes_of_interest.float().contiguous()
+    X, L = loc.shape[0], len(num_points)
+    npl = (ctypes.c_int32 * L)(*num_points)
+    lst = (ctypes.c_float * L)(*[float(s) for s in strides])
+    lib = _lib.lib()
+    cls_out, reg_out = [], []
+    for t in targets:
+        boxes, classes = _boxes_and_classes(t)
+        b = boxes.float().contiguous()
+        c = classes.to(torch.long).contiguous()
+        oc = torch.empty((X,), dtype=torch.long, device=loc.device)
+        orr = torch.empty((X, 4), dtype=torch.float32, device=loc.device)
+        with torch.cuda.device(loc.device):
+            _lib.check(lib.sdb_fcos_location_targets(_lib.ptr(loc), _lib.ptr(soi), _lib.ptr(b), _lib.ptr(c), X, b.shape[0],
+                                                     npl, lst, L, float(center_sampling_radius), int(num_classes),
+                                                     _lib.ptr(oc), _lib.ptr(orr), _lib.stream_ptr(loc.device)))
+        cls_out.append(oc.to(classes.dtype))
+        reg_out.append(orr.to(boxes.dtype))
+    return torch.stack(cls_out), torch.stack(reg_out)

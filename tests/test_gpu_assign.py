@@ -128,3 +128,36 @@ def test_point_targets_bit_exact(seed):
     assert np.array_equal(b.cpu().numpy(), ob)
     with pytest.raises(ValueError):
         point_targets(pts[:0].cuda(), strides[:0].cuda(), gt.cuda(), labels.cuda(), 80)
+
+
+@pytest.mark.parametrize("radius", [0.0, 1.5])
+@pytest.mark.parametrize("full", [False, True])
+def test_fcos_location_targets_bit_exact(radius, full):
+    """compute_targets_for_locations (fcos/utils.py:160-212), one fused kernel per image: classes and ltrb targets
+    identical to the oracle, with and without centre sampling, two images, equal-area ties, the P3-P7 grid."""
+    from test_oracle_assign import _fcos_case
+    from slenderobjdet_b200.targets import compute_targets_for_locations
+    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
+    cases = [_fcos_case(s, 100, lv) if full else _fcos_case(s) for s in (4, 5)]
+    locs, soi, _, _, strides = cases[0]
+    targets = [(c[2].cuda(), c[3].cuda()) for c in cases]
+    cls, reg = compute_targets_for_locations([l.cuda() for l in locs], targets, soi.cuda(), strides, radius, 80)
+    assert cls.shape == (2, soi.shape[0]) and reg.shape == (2, soi.shape[0], 4) and cls.dtype == torch.int64
+    for i, c in enumerate(cases):
+        oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(),
+                                           [len(l) for l in locs], strides, radius, 80)
+        assert np.array_equal(cls[i].cpu().numpy(), oc) and np.array_equal(reg[i].cpu().numpy(), orr)
+
+
+def test_fcos_location_targets_first_gt_at_origin_shortcut():
+    """get_sample_region's `center_x[..., 0].sum() == 0` shortcut: a first GT centred at x == 0 disables centre
+    sampling for the whole image (everything background), reproduced as is."""
+    from test_oracle_assign import _fcos_case
+    from slenderobjdet_b200.targets import compute_targets_for_locations
+    locs, soi, boxes, classes, strides = _fcos_case(6)
+    boxes[0] = torch.tensor([-20.0, 10.0, 20.0, 60.0])
+    cls, reg = compute_targets_for_locations([l.cuda() for l in locs], [(boxes.cuda(), classes.cuda())], soi.cuda(),
+                                             strides, 1.5, 80)
+    oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), boxes.numpy(), classes.numpy(),
+                                       [len(l) for l in locs], strides, 1.5, 80)
+    assert (oc == 80).all() and np.array_equal(cls[0].cpu().numpy(), oc) and np.array_equal(reg[0].cpu().numpy(), orr)

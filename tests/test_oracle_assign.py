@@ -179,3 +179,80 @@ def test_point_targets_oracle_matches_reference_lines():
         ob, ol_ = oa.point_targets(pts.numpy(), strides.numpy(), gt.numpy(), labels.numpy(), 80)
         assert np.array_equal(ol_, rl.numpy()) and np.array_equal(ob, rb.numpy())
         assert (rl != 80).sum() > 10
+
+
+def _fcos_reference_lines(locations, boxes, classes, soi, strides, radius, num_classes):
+    """fcos/utils.py:108-212 for one image, in torch (CPU), with the reference's own helper restated verbatim."""
+    import torch
+    INF = 100000000
+    num_points = [len(_) for _ in locations]
+    locations = torch.cat(locations, dim=0)
+    xs, ys = locations[:, 0], locations[:, 1]
+    area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+    l = xs[:, None] - boxes[:, 0][None]; t = ys[:, None] - boxes[:, 1][None]
+    r = boxes[:, 2][None] - xs[:, None]; b = boxes[:, 3][None] - ys[:, None]
+    reg = torch.stack([l, t, r, b], dim=2)
+    if radius > 0:
+        gt = boxes; K = len(xs); num_gts = gt.shape[0]
+        gt = gt[None].expand(K, num_gts, 4)
+        center_x = (gt[..., 0] + gt[..., 2]) / 2
+        center_y = (gt[..., 1] + gt[..., 3]) / 2
+        center_gt = gt.new_zeros(gt.shape)
+        if center_x[..., 0].sum() == 0:
+            is_in = xs.new_zeros(xs.shape, dtype=torch.uint8)[:, None].expand(K, num_gts)
+        else:
+            beg = 0
+            for level, n_p in enumerate(num_points):
+                end = beg + n_p
+                stride = strides[level] * radius
+                xmin = center_x[beg:end] - stride; ymin = center_y[beg:end] - stride
+                xmax = center_x[beg:end] + stride; ymax = center_y[beg:end] + stride
+                center_gt[beg:end, :, 0] = torch.where(xmin > gt[beg:end, :, 0], xmin, gt[beg:end, :, 0])
+                center_gt[beg:end, :, 1] = torch.where(ymin > gt[beg:end, :, 1], ymin, gt[beg:end, :, 1])
+                center_gt[beg:end, :, 2] = torch.where(xmax > gt[beg:end, :, 2], gt[beg:end, :, 2], xmax)
+                center_gt[beg:end, :, 3] = torch.where(ymax > gt[beg:end, :, 3], gt[beg:end, :, 3], ymax)
+                beg = end
+            cb = torch.stack((xs[:, None] - center_gt[..., 0], ys[:, None] - center_gt[..., 1],
+                              center_gt[..., 2] - xs[:, None], center_gt[..., 3] - ys[:, None]), -1)
+            is_in = cb.min(-1)[0] > 0
+    else:
+        is_in = reg.min(dim=2)[0] > 0
+    mx = reg.max(dim=2)[0]
+    cared = (mx >= soi[:, [0]]) & (mx <= soi[:, [1]])
+    a = area[None].repeat(len(locations), 1)
+    a[is_in == 0] = INF
+    a[cared == 0] = INF
+    mn, ind = a.min(dim=1)
+    cls = classes[ind]
+    cls[mn == INF] = num_classes
+    return cls, reg[range(len(locations)), ind]
+
+
+def _fcos_case(seed, M=40, levels=((25, 42, 8), (13, 21, 16), (7, 11, 32), (4, 6, 64), (2, 3, 128))):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    locs, soi = [], []
+    ranges = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, 100000000]]
+    for (h, w, s), rg in zip(levels, ranges):
+        ys, xs = torch.meshgrid(torch.arange(0, h * s, s, dtype=torch.float32), torch.arange(0, w * s, s, dtype=torch.float32),
+                                indexing="ij")
+        locs.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), dim=1) + s // 2)     # compute_locations_per_level
+        soi.append(torch.tensor(rg, dtype=torch.float32)[None].expand(h * w, -1))
+    W, H = levels[0][1] * levels[0][2], levels[0][0] * levels[0][2]
+    c = torch.rand(M, 2, generator=g) * torch.tensor([float(W), float(H)])
+    wh = torch.exp(torch.rand(M, 2, generator=g) * 4.5 + 1.5)
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(min=0)
+    boxes[3] = boxes[2]                                                                # equal areas: first index wins
+    classes = torch.randint(0, 80, (M,), generator=g)
+    return locs, torch.cat(soi), boxes, classes, [l[2] for l in levels]
+
+
+def test_fcos_location_targets_oracle_matches_reference_lines():
+    for seed, radius in ((0, 0.0), (1, 1.5), (2, 1.0)):
+        locs, soi, boxes, classes, strides = _fcos_case(seed)
+        rc, rr = _fcos_reference_lines(locs, boxes, classes, soi, strides, radius, 80)
+        import torch
+        oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), boxes.numpy(), classes.numpy(),
+                                           [len(l) for l in locs], strides, radius, 80)
+        assert np.array_equal(oc, rc.numpy()) and np.array_equal(orr, rr.numpy())
+        assert (rc != 80).sum() > 20
