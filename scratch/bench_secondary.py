@@ -66,3 +66,37 @@ rows.append(("GIoU loss fwd+grad, 2 000 boxes", us, P * 16 * 3))
 print("peak HBM %.0f GB/s (MEASURED_PEAKS.json)" % peaks["hbm_gbs"])
 for name, us, by in rows:
     print("%-72s %8.1f us  %8.2f MB algorithmic  %7.1f GB/s  %5.1f %% of HBM peak" % (name, us, by / 1e6, by / us / 1e3, 100 * by / us / 1e3 / peaks["hbm_gbs"]))
+
+# ---- rows a7 / a11 / a12 / a13 / a18: target assignment + glue kernels ------------------------
+from slenderobjdet_b200 import targets as T
+rows = []
+lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
+pts, strides, locs, soi = [], [], [], []
+ranges = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, 100000000]]
+for (h, w, s), rg in zip(lv, ranges):
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    p = torch.stack([xs.reshape(-1) * s, ys.reshape(-1) * s], 1)
+    pts.append(p); strides.append(torch.full((h * w,), float(s))); locs.append((p + s // 2).to(dev))
+    soi.append(torch.tensor(rg, dtype=torch.float32)[None].expand(h * w, -1))
+pts, strides, soi = torch.cat(pts).to(dev), torch.cat(strides).to(dev), torch.cat(soi).to(dev)
+glab = torch.randint(0, 80, (M,), generator=g).to(dev)
+us = timeit(lambda: T.point_targets(pts, strides, gt, glab, 80))
+rows.append(("point_targets (a11), 22 400 points x 100 GT", us, X * 12 + M * 24 + X * 24))
+cand = anchors.clone()
+us = timeit(lambda: T.bbox_targets(cand, gt, glab, 80))
+rows.append(("bbox_targets (a12), 22 400 boxes x 100 GT", us, X * 16 + M * 24 + X * 24))
+for radius in (0.0, 1.5):
+    us = timeit(lambda: T.compute_targets_for_locations(locs, [(gt, glab)], soi, [8, 16, 32, 64, 128], radius, 80))
+    rows.append(("fcos compute_targets_for_locations (a13), radius %.1f, 1 image" % radius, us, X * 16 + M * 24 + X * 24))
+ltrb = torch.rand(2 * X, 4, generator=g).to(dev) * 100 + 1
+us = timeit(lambda: L.compute_centerness_targets(ltrb))
+rows.append(("compute_centerness_targets (a18), 44 800 rows", us, 2 * X * 20))
+p3 = torch.randn(2, 18, 100, 168, generator=g).to(dev).requires_grad_()
+gop = torch.randn(2, 18, 100, 168, generator=g).to(dev)
+def offs():
+    p3.grad = None
+    L.reppoints_dcn_offset(p3, 0.1).backward(gop)
+us = timeit(offs)
+rows.append(("reppoints_dcn_offset fwd+bwd (a7), P3 N=2", us, 2 * 18 * 16800 * 4 * 4))
+for name, us, by in rows:
+    print("%-72s %8.1f us  %8.2f MB algorithmic  %7.1f GB/s" % (name, us, by / 1e6, by / us / 1e3))
