@@ -199,6 +199,20 @@ int sdb_fcos_location_targets(const float* locations, const float* sizes_of_inte
                               const float* level_strides, int32_t n_levels, float center_sampling_radius,
                               int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream);
 
+/* compute_topk_targets_for_locations (fcos/utils.py:215-292; the active FCOSRepPoints model's stage 1), one
+ * image per call: the targets above plus out_topk[x] (uint8 0/1) = location x is among the `topk` foreground
+ * locations of ITS GT with the highest centerness (all of them when the GT has <= topk; ties -> lowest location
+ * index).  Regression targets are NOT stride-normalised here (the caller divides, as :284-285 does after the
+ * selection).  The reference loops over GTs on the host with a `.sum().item()` sync per GT.
+ * workspace: sdb_fcos_topk_workspace_bytes(X); topk <= 16. */
+size_t sdb_fcos_topk_workspace_bytes(int32_t X);
+int sdb_fcos_topk_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
+                                   const int64_t* gt_classes, int32_t X, int32_t M,
+                                   const int32_t* num_points_per_level, const float* level_strides, int32_t n_levels,
+                                   float center_sampling_radius, int64_t num_classes, int32_t topk,
+                                   int64_t* out_classes, float* out_reg, uint8_t* out_topk, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

@@ -141,7 +141,7 @@ def point_targets(points, strides, gt, gt_labels, num_classes, scale=4):
     return boxes, labels
 
 
-def fcos_location_targets(locations, soi, gt, gt_classes, num_points, strides, radius, num_classes):
+def fcos_location_targets(locations, soi, gt, gt_classes, num_points, strides, radius, num_classes, return_index=False):
     """compute_targets_for_locations for ONE image restated (fcos/utils.py:108-212), numpy float32."""
     f = np.float32
     INF = f(100000000)
@@ -180,4 +180,25 @@ def fcos_location_targets(locations, soi, gt, gt_classes, num_points, strides, r
     idx = a.argmin(axis=1)                                                       # first minimum
     cls = np.asarray(gt_classes)[idx].copy()
     cls[a.min(axis=1) == INF] = num_classes                                      # :203
+    if return_index:
+        return cls, reg[np.arange(len(xs)), idx], idx
     return cls, reg[np.arange(len(xs)), idx]
+
+
+def fcos_topk_locations(cls, reg, gt_index, num_classes, topk=5):
+    """The per-GT top-k-by-centerness selection of compute_topk_targets_for_locations (fcos/utils.py:264-279):
+    `cls`, `reg` from fcos_location_targets, `gt_index` = the argmin GT of every location."""
+    f = np.float32
+    fg = (cls >= 0) & (cls != num_classes)
+    out = np.zeros((len(cls),), bool)
+    for m in range(int(gt_index.max()) + 1 if len(gt_index) else 0):
+        sel = np.nonzero((gt_index == m) & fg)[0]
+        if sel.size > topk:
+            r = reg[sel]
+            c = np.sqrt(((np.minimum(r[:, 0], r[:, 2]) / np.maximum(r[:, 0], r[:, 2])).astype(f) *
+                         (np.minimum(r[:, 1], r[:, 3]) / np.maximum(r[:, 1], r[:, 3])).astype(f)).astype(f)).astype(f)
+            order = np.lexsort((sel, -c))[:topk]                              # highest centerness, lowest index on ties
+            out[sel[order]] = True
+        elif sel.size > 0:
+            out[sel] = True
+    return out

@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restr
                                                            const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls,
                                                            int X, int M, const FcosLevels lv, int center_sampling,
                                                            int64_t num_classes, int64_t* __restrict__ out_cls,
-                                                           float4* __restrict__ out_reg) {
+                                                           float4* __restrict__ out_reg, int* __restrict__ out_gt,
+                                                           float* __restrict__ out_ctr, uint8_t* __restrict__ out_topk) {
   extern __shared__ float4 s_gt[];   // M boxes, then M areas
   float* s_area = reinterpret_cast<float*>(s_gt + M);
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -504,22 +505,76 @@ __global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restr
     }
   }
   const float4 b = s_gt[best_m];
-  out_reg[i] = make_float4(__fsub_rn(p.x, b.x), __fsub_rn(p.y, b.y), __fsub_rn(b.z, p.x), __fsub_rn(b.w, p.y));
-  out_cls[i] = best == INF ? num_classes : gt_cls[best_m];
+  const float4 rg = make_float4(__fsub_rn(p.x, b.x), __fsub_rn(p.y, b.y), __fsub_rn(b.z, p.x), __fsub_rn(b.w, p.y));
+  out_reg[i] = rg;
+  const int64_t cls = best == INF ? num_classes : gt_cls[best_m];
+  out_cls[i] = cls;
+  if (out_gt) {   // top-k variant: the GT this location belongs to (foreground only) and its centerness (:270-273)
+    const bool fg = cls >= 0 && cls != num_classes;
+    out_gt[i] = fg ? best_m : -1;
+    out_ctr[i] = __fsqrt_rn(__fmul_rn(__fdiv_rn(fminf(rg.x, rg.z), fmaxf(rg.x, rg.z)), __fdiv_rn(fminf(rg.y, rg.w), fmaxf(rg.y, rg.w))));
+    out_topk[i] = 0;
+  }
+}
+
+// one block per GT: the `topk` locations assigned to it with the highest centerness (all when it has fewer)
+__global__ void __launch_bounds__(512) fcos_topk_kernel(const int* __restrict__ loc_gt, const float* __restrict__ ctr, int X,
+                                                        int topk, uint8_t* __restrict__ out_topk) {
+  __shared__ Key s_red[32];
+  constexpr int KMAX = 16;
+  const int m = blockIdx.x;
+  const Key none = {-INFINITY, 0x7fffffff};
+  Key loc[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) loc[j] = none;
+  for (int x = threadIdx.x; x < X; x += blockDim.x) {
+    if (loc_gt[x] != m) continue;
+    Key cur = {ctr[x], x};
+    if (before(cur, loc[KMAX - 1])) {
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (before(cur, loc[j])) {
+          const Key t = loc[j];
+          loc[j] = cur;
+          cur = t;
+        }
+      }
+    }
+  }
+  for (int r = 0; r < topk; ++r) {
+    const Key best = block_best(loc[0], s_red);
+    if (best.i >= X) break;   // fewer than topk locations belong to this GT: all of them are marked already
+    if (loc[0].i == best.i) {
+      out_topk[best.i] = 1;
+#pragma unroll
+      for (int j = 0; j + 1 < KMAX; ++j) loc[j] = loc[j + 1];
+      loc[KMAX - 1] = none;
+    }
+  }
 }
 }  // namespace
 }  // namespace sdb
 
 extern "C" {
 
-int sdb_fcos_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
-                              const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
-                              const float* level_strides, int32_t n_levels, float center_sampling_radius,
-                              int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream) {
+static int fcos_targets_impl(const float* locations, const float* sizes_of_interest, const float* gt,
+                             const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
+                             const float* level_strides, int32_t n_levels, float center_sampling_radius,
+                             int64_t num_classes, int32_t topk, int64_t* out_classes, float* out_reg, uint8_t* out_topk,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   using namespace sdb;
   SDB_REQUIRE(X >= 0 && M > 0, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
   if (X == 0) return SDB_OK;
   SDB_REQUIRE(locations && sizes_of_interest && gt && gt_classes && out_classes && out_reg, SDB_ERR_INVALID, "NULL argument");
+  int* loc_gt = nullptr;
+  float* ctr = nullptr;
+  if (out_topk) {
+    SDB_REQUIRE(topk > 0 && topk <= 16, SDB_ERR_UNSUPPORTED, "topk must be in [1,16], got %d", topk);
+    SDB_REQUIRE(workspace && workspace_bytes >= sdb_fcos_topk_workspace_bytes(X), SDB_ERR_WORKSPACE,
+                "fcos top-k workspace too small");
+    loc_gt = (int*)workspace;
+    ctr = (float*)workspace + X;
+  }
   FcosLevels lv{};
   const bool cs = center_sampling_radius > 0.f;
   if (cs) {
@@ -536,12 +591,40 @@ int sdb_fcos_location_targets(const float* locations, const float* sizes_of_inte
   }
   const size_t smem = (size_t)M * (sizeof(float4) + sizeof(float));
   SDB_REQUIRE(smem <= 48 * 1024, SDB_ERR_UNSUPPORTED, "too many GT boxes (%d) for one shared-memory stage", M);
-  fcos_targets_kernel<<<cdiv(X, 256), 256, smem, (cudaStream_t)stream>>>(
+  cudaStream_t st = (cudaStream_t)stream;
+  fcos_targets_kernel<<<cdiv(X, 256), 256, smem, st>>>(
       (const float2*)locations, (const float2*)sizes_of_interest, (const float4*)gt, gt_classes, X, M, lv, cs ? 1 : 0,
-      num_classes, out_classes, (float4*)out_reg);
+      num_classes, out_classes, (float4*)out_reg, loc_gt, ctr, out_topk);
   SDB_LAUNCHED(1);
+  if (out_topk) {
+    fcos_topk_kernel<<<M, X >= 8192 ? 512 : 256, 0, st>>>(loc_gt, ctr, X, topk, out_topk);
+    SDB_LAUNCHED(1);
+  }
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+
+int sdb_fcos_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
+                              const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
+                              const float* level_strides, int32_t n_levels, float center_sampling_radius,
+                              int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream) {
+  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, X, M, num_points_per_level, level_strides,
+                           n_levels, center_sampling_radius, num_classes, 0, out_classes, out_reg, nullptr, nullptr, 0,
+                           stream);
+}
+
+size_t sdb_fcos_topk_workspace_bytes(int32_t X) { return X > 0 ? (size_t)X * 8 : 0; }
+
+int sdb_fcos_topk_location_targets(const float* locations, const float* sizes_of_interest, const float* gt,
+                                   const int64_t* gt_classes, int32_t X, int32_t M,
+                                   const int32_t* num_points_per_level, const float* level_strides, int32_t n_levels,
+                                   float center_sampling_radius, int64_t num_classes, int32_t topk,
+                                   int64_t* out_classes, float* out_reg, uint8_t* out_topk, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  SDB_REQUIRE(out_topk != nullptr, SDB_ERR_INVALID, "out_topk is NULL");
+  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, X, M, num_points_per_level, level_strides,
+                           n_levels, center_sampling_radius, num_classes, topk, out_classes, out_reg, out_topk, workspace,
+                           workspace_bytes, stream);
 }
 
 size_t sdb_point_targets_workspace_bytes(int32_t X) { return X > 0 ? 256 + (size_t)X * 8 : 0; }

@@ -107,3 +107,48 @@ def compute_targets_for_locations(locations, targets, object_sizes_of_interest, 
         cls_out.append(oc.to(classes.dtype))
         reg_out.append(orr.to(boxes.dtype))
     return torch.stack(cls_out), torch.stack(reg_out)
+
+
+@torch.no_grad()
+def compute_topk_targets_for_locations(locations, targets, object_sizes_of_interest, strides, center_sampling_radius,
+                                       num_classes, norm_reg_targets=False, topk=5):
+    """``compute_topk_targets_for_locations`` (fcos/utils.py:215-292, stage 1 of the active FCOSRepPoints model):
+    ``compute_targets_for_locations`` plus, per GT, its ``topk`` foreground locations of highest centerness.
+    -> (gt_classes [N, X], reg_targets [N, X, 4], topk_locations bool [N, X]).  Two launches per image; the
+    reference's host loop over GTs with a ``.sum().item()`` sync each is gone."""
+    import ctypes
+    from . import _lib
+    num_points = [len(l) for l in locations]
+    loc = torch.cat(locations, dim=0).float().contiguous()
+    if not loc.is_cuda:
+        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
+    norm_weights = None
+    if norm_reg_targets:   # :221-223 (built on the CPU in the reference, moved to the locations' device here)
+        norm_weights = torch.cat([torch.empty(n).fill_(s) for n, s in zip(num_points, strides)]).to(loc.device)
+    soi = object_sizes_of_interest.float().contiguous()
+    X, L = loc.shape[0], len(num_points)
+    npl = (ctypes.c_int32 * L)(*num_points)
+    lst = (ctypes.c_float * L)(*[float(s) for s in strides])
+    lib = _lib.lib()
+    wsb = int(lib.sdb_fcos_topk_workspace_bytes(X))
+    cls_out, reg_out, topk_out = [], [], []
+    for t in targets:
+        boxes, classes = _boxes_and_classes(t)
+        b = boxes.float().contiguous()
+        c = classes.to(torch.long).contiguous()
+        oc = torch.empty((X,), dtype=torch.long, device=loc.device)
+        orr = torch.empty((X, 4), dtype=torch.float32, device=loc.device)
+        ot = torch.empty((X,), dtype=torch.uint8, device=loc.device)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=loc.device)
+        with torch.cuda.device(loc.device):
+            _lib.check(lib.sdb_fcos_topk_location_targets(_lib.ptr(loc), _lib.ptr(soi), _lib.ptr(b), _lib.ptr(c), X,
+                                                          b.shape[0], npl, lst, L, float(center_sampling_radius),
+                                                          int(num_classes), int(topk), _lib.ptr(oc), _lib.ptr(orr),
+                                                          _lib.ptr(ot), _lib.ptr(ws), wsb, _lib.stream_ptr(loc.device)))
+        orr = orr.to(boxes.dtype)
+        if norm_weights is not None:
+            orr /= norm_weights[:, None]                                     # :284-285
+        cls_out.append(oc.to(classes.dtype))
+        reg_out.append(orr)
+        topk_out.append(ot.bool())
+    return torch.stack(cls_out), torch.stack(reg_out), torch.stack(topk_out)

@@ -161,3 +161,26 @@ def test_fcos_location_targets_first_gt_at_origin_shortcut():
     oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), boxes.numpy(), classes.numpy(),
                                        [len(l) for l in locs], strides, 1.5, 80)
     assert (oc == 80).all() and np.array_equal(cls[0].cpu().numpy(), oc) and np.array_equal(reg[0].cpu().numpy(), orr)
+
+
+@pytest.mark.parametrize("radius,norm", [(0.0, False), (1.5, True)])
+def test_fcos_topk_location_targets_bit_exact(radius, norm):
+    """compute_topk_targets_for_locations (fcos/utils.py:215-292): classes, ltrb targets (optionally stride-
+    normalised) and the per-GT top-5-by-centerness mask identical to the oracle, on the P3-P7 grid, two images."""
+    from test_oracle_assign import _fcos_case
+    from slenderobjdet_b200.targets import compute_topk_targets_for_locations
+    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
+    cases = [_fcos_case(s, 60, lv) for s in (8, 9)]
+    locs, soi, _, _, strides = cases[0]
+    npts = [len(l) for l in locs]
+    cls, reg, tk = compute_topk_targets_for_locations([l.cuda() for l in locs], [(c[2].cuda(), c[3].cuda()) for c in cases],
+                                                      soi.cuda(), strides, radius, 80, norm_reg_targets=norm, topk=5)
+    assert tk.dtype == torch.bool and tk.shape == cls.shape
+    for i, c in enumerate(cases):
+        oc, orr, idx = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(), npts,
+                                                strides, radius, 80, return_index=True)
+        ot = oa.fcos_topk_locations(oc, orr, idx, 80, topk=5)
+        if norm:
+            orr = orr / np.concatenate([np.full(n, s, np.float32) for n, s in zip(npts, strides)])[:, None]
+        assert np.array_equal(cls[i].cpu().numpy(), oc) and np.array_equal(reg[i].cpu().numpy(), orr)
+        assert np.array_equal(tk[i].cpu().numpy(), ot) and ot.sum() > 20

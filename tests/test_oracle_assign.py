@@ -256,3 +256,27 @@ def test_fcos_location_targets_oracle_matches_reference_lines():
                                            [len(l) for l in locs], strides, radius, 80)
         assert np.array_equal(oc, rc.numpy()) and np.array_equal(orr, rr.numpy())
         assert (rc != 80).sum() > 20
+
+
+def test_fcos_topk_oracle_matches_reference_loop():
+    """fcos/utils.py:264-279 in torch on CPU against the oracle's selection (tie-free centerness)."""
+    import torch
+    locs, soi, boxes, classes, strides = _fcos_case(3, 12)
+    cls, reg, idx = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), boxes.numpy(), classes.numpy(),
+                                             [len(l) for l in locs], strides, 0.0, 80, return_index=True)
+    got = oa.fcos_topk_locations(cls, reg, idx, 80, topk=5)
+    gt_classes_per_im, reg_t, inds_t = torch.from_numpy(cls), torch.from_numpy(reg), torch.from_numpy(idx)
+    fore = (gt_classes_per_im >= 0) & (gt_classes_per_im != 80)
+    ref = torch.zeros(len(inds_t)).bool()
+    for gi in range(len(boxes)):
+        sel = (inds_t == gi) & fore
+        n = sel.sum().item()
+        if n > 5:
+            r = reg_t[sel]
+            lr, tb = r[:, [0, 2]], r[:, [1, 3]]
+            score = torch.sqrt((lr.min(dim=-1)[0] / lr.max(dim=-1)[0]) * (tb.min(dim=-1)[0] / tb.max(dim=-1)[0]))
+            _, ii = torch.topk(score, 5, sorted=False)
+            ref[sel.nonzero()[ii]] = True
+        elif n > 0:
+            ref[sel.nonzero()] = True
+    assert np.array_equal(got, ref.numpy()) and 0 < got.sum() < fore.sum().item()
