@@ -202,3 +202,20 @@ def fcos_topk_locations(cls, reg, gt_index, num_classes, topk=5):
         elif sel.size > 0:
             out[sel] = True
     return out
+
+
+def fcos_rpd_refine_targets(centers, init_boxes, gt, gt_classes, image_size, num_classes, thresholds=(0.4, 0.5),
+                            labels=(0, -1, 1)):
+    """FCOSRepPoints.get_ground_truth stage 2 restated (fcos_rpd_s1_topk.py:346-370), numpy float32."""
+    f = np.float32
+    centers, gt = np.asarray(centers, f), np.asarray(gt, f)
+    q = pairwise_iou(gt, init_boxes)                                             # :352-354  [M, X]
+    idx, matched = matcher(q, list(thresholds), list(labels), True)             # :355
+    cls = np.asarray(gt_classes)[idx].copy()
+    cls[matched == 0] = num_classes                                              # :357
+    invalid = (centers[:, 0] >= image_size[1]) | (centers[:, 1] >= image_size[0])   # :349-350
+    cls[invalid] = -1                                                            # :358
+    box = gt[idx]
+    xs, ys = centers[:, 0], centers[:, 1]
+    reg = np.stack([xs - box[:, 0], ys - box[:, 1], box[:, 2] - xs, box[:, 3] - ys], axis=1).astype(f)   # :363-368
+    return cls, reg

@@ -152,3 +152,52 @@ def compute_topk_targets_for_locations(locations, targets, object_sizes_of_inter
         reg_out.append(orr)
         topk_out.append(ot.bool())
     return torch.stack(cls_out), torch.stack(reg_out), torch.stack(topk_out)
+
+
+@torch.no_grad()
+def fcos_rpd_refine_targets(centers, init_boxes, gt_boxes, gt_classes, image_size, num_classes,
+                            iou_thresholds=(0.4, 0.5), iou_labels=(0, -1, 1), allow_low_quality_matches=True):
+    """Stage 2 of ``FCOSRepPoints.get_ground_truth`` for one image (fcos_rpd_s1_topk.py:346-370): match the
+    stage-1 boxes to the GTs by IoU (``Matcher(RETINANET.IOU_THRESHOLDS, IOU_LABELS, allow_low_quality=True)``,
+    :174-178), class labels (``num_classes`` where the match label is 0, GT class where it is 1 or -1, then -1
+    for centres outside the image) and ltrb refine targets to the matched GT.
+    ``centers`` [X,2], ``init_boxes`` [X,4], ``gt_boxes`` [M,4], ``gt_classes`` [M], ``image_size`` (h, w).
+    One fused IoU + matcher pass instead of the [M, X] matrix; no host sync."""
+    gt = _tensor_of(gt_boxes)
+    matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches=allow_low_quality_matches)
+    idx, matched = matcher.from_boxes(gt, _tensor_of(init_boxes))
+    cls = gt_classes[idx]
+    cls = torch.where(matched == 0, torch.full_like(cls, num_classes), cls)
+    invalid = (centers[:, 0] >= image_size[1]).logical_or(centers[:, 1] >= image_size[0])
+    cls = torch.where(invalid, torch.full_like(cls, -1), cls)
+    box = gt[idx]
+    xs, ys = centers[:, 0], centers[:, 1]
+    reg = torch.stack([xs - box[:, 0], ys - box[:, 1], box[:, 2] - xs, box[:, 3] - ys], dim=1)
+    return cls, reg
+
+
+@torch.no_grad()
+def fcos_rpd_get_ground_truth(points, init_boxes, gt_instances, fpn_strides, center_sampling_radius, num_classes,
+                              iou_thresholds=(0.4, 0.5), iou_labels=(0, -1, 1), topk=5):
+    """``FCOSRepPoints.get_ground_truth`` (fcos_rpd_s1_topk.py:320-376): stage-1 FCOS location targets with the
+    per-GT top-k-by-centerness mask, and stage-2 IoU-matched refine targets.  ``gt_instances``: per image an
+    Instances-like object (``gt_boxes``, ``gt_classes``, ``image_size``) or a (boxes, classes, image_size) triple.
+    -> (init_gt_classes, init_reg_targets, refine_gt_classes, refine_reg_targets, topk_locations)."""
+    INF = 100000000
+    sizes = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, INF]]
+    soi = torch.cat([p.new_tensor(sizes[l])[None].expand(len(p), -1) for l, p in enumerate(points)], dim=0)
+    trip = []
+    for t in gt_instances:
+        if hasattr(t, "gt_boxes"):
+            trip.append((_tensor_of(t.gt_boxes), t.gt_classes, t.image_size))
+        else:
+            trip.append((_tensor_of(t[0]), t[1], t[2]))
+    init_cls, init_reg, topk_loc = compute_topk_targets_for_locations(
+        points, [(b, c) for b, c, _ in trip], soi, fpn_strides, center_sampling_radius, num_classes, topk=topk)
+    centers = torch.cat(points, 0)
+    cls_labels, reg_labels = [], []
+    for i, (b, c, sz) in enumerate(trip):
+        cl, rg = fcos_rpd_refine_targets(centers, init_boxes[i], b, c, sz, num_classes, iou_thresholds, iou_labels)
+        cls_labels.append(cl)
+        reg_labels.append(rg)
+    return init_cls, init_reg, torch.stack(cls_labels), torch.stack(reg_labels), topk_loc

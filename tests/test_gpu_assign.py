@@ -184,3 +184,30 @@ def test_fcos_topk_location_targets_bit_exact(radius, norm):
             orr = orr / np.concatenate([np.full(n, s, np.float32) for n, s in zip(npts, strides)])[:, None]
         assert np.array_equal(cls[i].cpu().numpy(), oc) and np.array_equal(reg[i].cpu().numpy(), orr)
         assert np.array_equal(tk[i].cpu().numpy(), ot) and ot.sum() > 20
+
+
+def test_fcos_rpd_get_ground_truth_bit_exact():
+    """FCOSRepPoints.get_ground_truth (fcos_rpd_s1_topk.py:320-376): both stages against the oracle."""
+    from test_oracle_assign import _fcos_case
+    from slenderobjdet_b200.targets import fcos_rpd_get_ground_truth
+    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
+    g = torch.Generator().manual_seed(21)
+    cases = [_fcos_case(s, 50, lv) for s in (12, 13)]
+    locs, soi, _, _, strides = cases[0]
+    centers = torch.cat(locs)
+    sizes = [(800, 1333), (704, 1216)]
+    init = []
+    for _ in cases:   # stage-1 boxes: noisy boxes around the centres
+        wh = torch.exp(torch.rand(centers.shape[0], 2, generator=g) * 3.5 + 2.0)
+        init.append(torch.cat([centers - wh / 2, centers + wh / 2], 1))
+    gts = [(c[2].cuda(), c[3].cuda(), sz) for c, sz in zip(cases, sizes)]
+    ic, ir, rc, rr, tk = fcos_rpd_get_ground_truth([l.cuda() for l in locs], [b.cuda() for b in init], gts, strides, 0.0, 80)
+    npts = [len(l) for l in locs]
+    for i, (c, sz) in enumerate(zip(cases, sizes)):
+        oc, orr, idx = oa.fcos_location_targets(centers.numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(), npts, strides,
+                                                0.0, 80, return_index=True)
+        assert np.array_equal(ic[i].cpu().numpy(), oc) and np.array_equal(ir[i].cpu().numpy(), orr)
+        assert np.array_equal(tk[i].cpu().numpy(), oa.fcos_topk_locations(oc, orr, idx, 80, topk=5))
+        c2, r2 = oa.fcos_rpd_refine_targets(centers.numpy(), init[i].numpy(), c[2].numpy(), c[3].numpy(), sz, 80)
+        assert np.array_equal(rc[i].cpu().numpy(), c2) and np.array_equal(rr[i].cpu().numpy(), r2)
+        assert (c2 == -1).any() and (c2 == 80).any() and ((c2 >= 0) & (c2 < 80)).any()

@@ -280,3 +280,37 @@ def test_fcos_topk_oracle_matches_reference_loop():
         elif n > 0:
             ref[sel.nonzero()] = True
     assert np.array_equal(got, ref.numpy()) and 0 < got.sum() < fore.sum().item()
+
+
+def test_fcos_rpd_refine_targets_oracle_matches_reference_lines():
+    """fcos_rpd_s1_topk.py:346-370 with the reference's own Matcher / pairwise_iou (imported by path in
+    gen_golden.py; restated here with torch on CPU)."""
+    import torch
+    locs, soi, boxes, classes, strides = _fcos_case(14, 30)
+    centers = torch.cat(locs)
+    g = torch.Generator().manual_seed(2)
+    wh = torch.exp(torch.rand(centers.shape[0], 2, generator=g) * 3.0 + 2.0)
+    init = torch.cat([centers - wh / 2, centers + wh / 2], 1)
+    image_size = (160, 300)
+    # pairwise_iou (boxes.py:333-347) + Matcher with allow_low_quality_matches (matcher.py:61-126)
+    b1, b2 = boxes, init
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1]); a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    whi = (torch.min(b1[:, None, 2:], b2[:, 2:]) - torch.max(b1[:, None, :2], b2[:, :2])).clamp(min=0)
+    inter = whi.prod(dim=2)
+    q = torch.where(inter > 0, inter / (a1[:, None] + a2 - inter), torch.zeros(1))
+    matched_vals, matches = q.max(dim=0)
+    match_labels = matches.new_full(matches.size(), 1, dtype=torch.int8)
+    for l, low, high in zip([0, -1, 1], [-float("inf"), 0.4, 0.5], [0.4, 0.5, float("inf")]):
+        match_labels[(matched_vals >= low) & (matched_vals < high)] = l
+    highest, _ = q.max(dim=1)
+    _, pred_inds = torch.nonzero(q == highest[:, None], as_tuple=True)
+    match_labels[pred_inds] = 1
+    cls_label = classes[matches]
+    cls_label[match_labels == 0] = 80
+    invalid = (centers[:, 0] >= image_size[1]).logical_or(centers[:, 1] >= image_size[0])
+    cls_label[invalid] = -1
+    rb = boxes[matches]
+    xs, ys = centers[:, 0], centers[:, 1]
+    reg = torch.stack([xs - rb[:, 0], ys - rb[:, 1], rb[:, 2] - xs, rb[:, 3] - ys], dim=1)
+    oc, orr = oa.fcos_rpd_refine_targets(centers.numpy(), init.numpy(), boxes.numpy(), classes.numpy(), image_size, 80)
+    assert np.array_equal(oc, cls_label.numpy()) and np.array_equal(orr, reg.numpy())
