@@ -128,3 +128,40 @@ def centerness_targets(ltrb):
     tb = r[:, [1, 3]]
     c = (lr.min(dim=-1)[0] / lr.max(dim=-1)[0]) * (tb.min(dim=-1)[0] / tb.max(dim=-1)[0])
     return torch.sqrt(c)
+
+
+def fcos_rpd_losses(init_gt_classes, init_reg_targets, refine_gt_classes, refine_reg_targets, pred_class_logits,
+                    pred_box_reg_init, pred_box_reg, pred_center_score, strides, topk_locations, num_classes,
+                    alpha=0.25, gamma=2.0, iou_loss_type="iou"):
+    """FCOSRepPoints.losses restated for one process (fcos_rpd_s1_topk.py:249-317), float64 on the CPU, with the
+    reference's boolean-mask selections and normalisers.  -> (dict of the four losses, dict of the gradients of
+    their SUM with respect to the four prediction tensors)."""
+    K = num_classes
+    icls = torch.as_tensor(init_gt_classes).flatten().long().cpu()
+    rcls = torch.as_tensor(refine_gt_classes).flatten().long().cpu()
+    (ireg, rreg, logits, pbi, pb, pc, st) = _prep(torch.as_tensor(init_reg_targets).reshape(-1, 4),
+                                                  torch.as_tensor(refine_reg_targets).reshape(-1, 4), pred_class_logits,
+                                                  pred_box_reg_init, pred_box_reg, pred_center_score, strides)
+    topk = torch.as_tensor(topk_locations).reshape(-1).bool().cpu()
+    ifg = (icls >= 0) & (icls != K)                                                 # :261
+    rfg = (rcls >= 0) & (rcls != K)                                                 # :272
+    init_num = max(float(ifg.sum()), 1.0)                                           # :266-267 (one process)
+    ref_num = max(float(rfg.sum()), 1.0)                                            # :277-278
+    cls_idx = torch.where(rfg, rcls, torch.full_like(rcls, K))
+    cls_sum, g_logits = sigmoid_focal_loss(logits, cls_idx, alpha, gamma)           # :283-287
+    gt_center = centerness_targets(ireg[ifg])                                       # :289
+    topk_center = centerness_targets(ireg[topk])                                    # :292
+    sum_topk = float(topk_center.sum())                                             # :293-294
+    ri_sum, g_pbi_sel = iou_loss(pbi[topk], ireg[topk], topk_center, iou_loss_type, "ltrb")    # :298-301
+    norm = (st[rfg] * 4).unsqueeze(-1)                                              # :303
+    rg_sum, g_pb_sel = smooth_l1_loss(pb[rfg] / norm, rreg[rfg] / norm, 0.11)       # :304-307
+    x = pc[ifg].clone().requires_grad_(True)
+    ce = torch.nn.functional.binary_cross_entropy_with_logits(x, gt_center, reduction="sum")     # :313-315
+    (g_pc_sel,) = torch.autograd.grad(ce, x)
+    losses = dict(cls_loss=cls_sum / ref_num, reg_loss_init=ri_sum / sum_topk, reg_loss=rg_sum / max(1, ref_num),
+                  centerness_loss=ce.detach() / init_num)
+    g_pbi = torch.zeros_like(pbi); g_pbi[topk] = g_pbi_sel / sum_topk
+    g_pb = torch.zeros_like(pb); g_pb[rfg] = g_pb_sel / norm / max(1, ref_num)
+    g_pc = torch.zeros_like(pc); g_pc[ifg] = g_pc_sel / init_num
+    grads = dict(pred_class_logits=g_logits / ref_num, pred_box_reg_init=g_pbi, pred_box_reg=g_pb, pred_center_score=g_pc)
+    return losses, grads

@@ -105,3 +105,39 @@ def test_centerness_targets_bit_exact():
     assert np.max(np.abs(out.cpu().numpy().astype(np.float64) - ref)) <= 1e-6
     assert float(out[0]) == 1.0 and float(out[1]) == 0.0
     assert L.compute_centerness_targets(torch.zeros(0, 4, device="cuda")).shape == (0,)
+
+
+def test_fcos_rpd_losses_match_oracle():
+    """FCOSRepPoints.losses (fcos_rpd_s1_topk.py:249-317) composed from the fused kernels without host sync:
+    the four loss values and the gradients of their sum against the float64 restatement with the reference's
+    boolean-mask selections (rel <= 1e-4)."""
+    from slenderobjdet_b200.fcos_rpd_losses import fcos_rpd_losses
+    g = torch.Generator().manual_seed(17)
+    N, X, K = 2, 3000, 80
+    R = N * X
+    icls = torch.full((R,), K, dtype=torch.long)
+    fg = torch.randperm(R, generator=g)[:400]
+    icls[fg] = torch.randint(0, K, (400,), generator=g)
+    ireg = torch.randn(R, 4, generator=g) * 30                      # background rows: arbitrary, also negative
+    ireg[fg] = torch.rand(400, 4, generator=g) * 60 + 1
+    topk = torch.zeros(R, dtype=torch.bool); topk[fg[:150]] = True
+    rcls = torch.full((R,), K, dtype=torch.long)
+    rfg = torch.randperm(R, generator=g)[:500]
+    rcls[rfg] = torch.randint(0, K, (500,), generator=g)
+    rcls[torch.randperm(R, generator=g)[:100]] = -1                # centres outside the image
+    rreg = torch.randn(R, 4, generator=g) * 40
+    logits = torch.randn(R, K, generator=g) * 2 - 4.6
+    pbi = torch.rand(R, 4, generator=g) * 60 + 0.5
+    pb = torch.randn(R, 4, generator=g) * 40
+    pc = torch.randn(R, generator=g)
+    strides = torch.tensor([8.0, 16.0, 32.0])[torch.randint(0, 3, (R,), generator=g)]
+    d = lambda t: t.cuda()
+    preds = [d(logits).requires_grad_(), d(pbi).requires_grad_(), d(pb).requires_grad_(), d(pc).requires_grad_()]
+    out = fcos_rpd_losses(d(icls).view(N, X), d(ireg).view(N, X, 4), d(rcls).view(N, X), d(rreg).view(N, X, 4), *preds,
+                          d(strides), d(topk).view(N, X), K)
+    sum(out.values()).backward()
+    lo, go = ol.fcos_rpd_losses(icls, ireg, rcls, rreg, logits, pbi, pb, pc, strides, topk, K)
+    for k in ("cls_loss", "reg_loss_init", "reg_loss", "centerness_loss"):
+        assert abs(float(out[k]) - float(lo[k])) <= 1e-4 * abs(float(lo[k])), (k, float(out[k]), float(lo[k]))
+    for p, k in zip(preds, ("pred_class_logits", "pred_box_reg_init", "pred_box_reg", "pred_center_score")):
+        assert rel_err(p.grad.cpu().numpy(), go[k].numpy()) < 1e-4, k
