@@ -517,38 +517,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
               }
             }
           }
-          // lists so long that the warp's descriptors did not fit the staging buffer: plain loop
-          for (int d0 = OD_CAP; d0 < ocount; d0 += PPI) {
-            const int d = d0 + grp;
-            uint4 add = make_uint4(0u, 0u, 0u, 0u);
-            uint32_t row = 0;
-            if (d < ocount) {
-              const ODesc od = p.odesc[s_range[pw][tap][0] + d];
-              row = od.m.z;
-              const uint4* xb = xbase + ch * (CPS / 8);
-              const uint32_t w[4] = {__byte_perm(od.m.x, od.m.x, 0x1010), __byte_perm(od.m.x, od.m.x, 0x3232),
-                                     __byte_perm(od.m.y, od.m.y, 0x1010), __byte_perm(od.m.y, od.m.y, 0x3232)};
-              const uint32_t o[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
+          // lists so long that the warp's descriptors did not fit the staging buffer: the tail is summed in
+          // fp32 per lane group while consecutive descriptors stay on the same row, and added to the operand
+          // row once per run (a bf16 read-modify-write per descriptor lost ~1e-2 on ~140-entry lists)
+          if (ocount > OD_CAP) {
+            float acc[8];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (w[k]) {
-                  const uint4 vv = __ldg(xb + o[k]);
-                  add.x = bf2_fma(w[k], vv.x, add.x); add.y = bf2_fma(w[k], vv.y, add.y);
-                  add.z = bf2_fma(w[k], vv.z, add.z); add.w = bf2_fma(w[k], vv.w, add.w);
-                }
-              }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int gs = 0; gs < PPI; ++gs) {
-              if (grp == gs && d < ocount) {
-                uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(row, lig & 7));
-                uint4 a = *rp;
-                a.x = bf2_add(a.x, add.x); a.y = bf2_add(a.y, add.y);
-                a.z = bf2_add(a.z, add.z); a.w = bf2_add(a.w, add.w);
-                *rp = a;
-              }
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            int acc_row = -1;
+            for (int d0 = OD_CAP; d0 < ocount + PPI; d0 += PPI) {   // the extra round flushes the last rows
+              const int d = d0 + grp;
+              const bool have = d < ocount;
+              ODesc od;
+              od.o = make_uint4(0u, 0u, 0u, 0u);
+              od.m = make_uint4(0u, 0u, 0u, 0u);
+              if (have) od = p.odesc[s_range[pw][tap][0] + d];
+              const int row = (int)od.m.z;
+              const bool flush = acc_row >= 0 && (!have || row != acc_row);
               __syncwarp();
+#pragma unroll
+              for (int gs = 0; gs < PPI; ++gs) {   // one lane group at a time: two groups may hold the same row
+                if (grp == gs && flush) {
+                  uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(acc_row, lig & 7));
+                  const uint4 a = *rp;
+                  uint4 r;
+                  r.x = pack_bf16x2(__uint_as_float(a.x << 16) + acc[0], __uint_as_float(a.x & 0xffff0000u) + acc[1]);
+                  r.y = pack_bf16x2(__uint_as_float(a.y << 16) + acc[2], __uint_as_float(a.y & 0xffff0000u) + acc[3]);
+                  r.z = pack_bf16x2(__uint_as_float(a.z << 16) + acc[4], __uint_as_float(a.z & 0xffff0000u) + acc[5]);
+                  r.w = pack_bf16x2(__uint_as_float(a.w << 16) + acc[6], __uint_as_float(a.w & 0xffff0000u) + acc[7]);
+                  *rp = r;
+                }
+                __syncwarp();
+              }
+              if (flush) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                acc_row = -1;
+              }
+              if (have) {
+                const uint4* xb = xbase + ch * (CPS / 8);
+                const uint32_t wbits[4] = {od.m.x << 16, od.m.x & 0xffff0000u, od.m.y << 16, od.m.y & 0xffff0000u};
+                const uint32_t o[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (wbits[k]) fma8(acc, __ldg(xb + o[k]), __uint_as_float(wbits[k]));
+                acc_row = row;
+              }
             }
           }
         }
