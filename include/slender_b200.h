@@ -158,6 +158,10 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
  * out[r] = sqrt( min(l,r)/max(l,r) * min(t,b)/max(t,b) ) for reg_targets [R,4] float32 in (l,t,r,b) order;
  * one rounding per operation in the reference's order, so the result is bit-identical to torch on CPU. */
 int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream);
+/* The FCOSRepPoints module's OWN compute_centerness_targets (fcos/fcos_rpd_s1_topk.py:25-55), which shadows the one
+ * above inside that model (losses :288, :291; top-5 selection :117):  out[r] = pow(c, min(w/h, h/w)) with
+ * c = min(l,r)/max(l,r) * min(t,b)/max(t,b), w = l + r, h = t + b -- the slender-object exponent. */
+int sdb_slender_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream);
 
 /* ---- RepPoints DCN offset construction (first piece) -------------------------
  * dcn_offset = ((1 - gm) * pts.detach() + gm * pts) - dcn_base_offset   (reppointsv2.py:638-642, 742-744;
@@ -212,6 +216,20 @@ int sdb_fcos_topk_location_targets(const float* locations, const float* sizes_of
                                    float center_sampling_radius, int64_t num_classes, int32_t topk,
                                    int64_t* out_classes, float* out_reg, uint8_t* out_topk, void* workspace,
                                    size_t workspace_bytes, void* stream);
+
+/* Both of the above for a whole batch in ONE call (no per-image host loop): image n uses GT rows
+ * gt[n*M_pad .. n*M_pad + gt_counts[n]) of the padded gt [n_images, M_pad, 4] / gt_classes [n_images, M_pad];
+ * gt_counts is a DEVICE int32 [n_images] (0 allowed: the image is all background, regression rows measured from a
+ * zero box).  topk == 0: no top-k mask (out_topk may be NULL).  centerness_kind: 0 = sqrt form (fcos/utils.py:295-300),
+ * 1 = the FCOSRepPoints module's pow form (fcos_rpd_s1_topk.py:25-55, used by ITS top-5 loop :110-121).
+ * out_classes [n_images, X], out_reg [n_images, X, 4], out_topk [n_images, X].
+ * workspace: n_images * sdb_fcos_topk_workspace_bytes(X) when topk > 0. */
+int sdb_fcos_location_targets_batched(const float* locations, const float* sizes_of_interest, const float* gt,
+                                      const int64_t* gt_classes, const int32_t* gt_counts, int32_t n_images, int32_t X,
+                                      int32_t M_pad, const int32_t* num_points_per_level, const float* level_strides,
+                                      int32_t n_levels, float center_sampling_radius, int64_t num_classes, int32_t topk,
+                                      int32_t centerness_kind, int64_t* out_classes, float* out_reg, uint8_t* out_topk,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a

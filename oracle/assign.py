@@ -185,9 +185,11 @@ def fcos_location_targets(locations, soi, gt, gt_classes, num_points, strides, r
     return cls, reg[np.arange(len(xs)), idx]
 
 
-def fcos_topk_locations(cls, reg, gt_index, num_classes, topk=5):
+def fcos_topk_locations(cls, reg, gt_index, num_classes, topk=5, slender=False):
     """The per-GT top-k-by-centerness selection of compute_topk_targets_for_locations (fcos/utils.py:264-279):
-    `cls`, `reg` from fcos_location_targets, `gt_index` = the argmin GT of every location."""
+    `cls`, `reg` from fcos_location_targets, `gt_index` = the argmin GT of every location.
+    slender=True: the FCOSRepPoints module's own copy of the loop (fcos_rpd_s1_topk.py:110-121), which scores with
+    ITS compute_centerness_targets = pow(c, min(w/h, h/w)) (:25-55) instead of sqrt(c)."""
     f = np.float32
     fg = (cls >= 0) & (cls != num_classes)
     out = np.zeros((len(cls),), bool)
@@ -195,8 +197,13 @@ def fcos_topk_locations(cls, reg, gt_index, num_classes, topk=5):
         sel = np.nonzero((gt_index == m) & fg)[0]
         if sel.size > topk:
             r = reg[sel]
-            c = np.sqrt(((np.minimum(r[:, 0], r[:, 2]) / np.maximum(r[:, 0], r[:, 2])).astype(f) *
-                         (np.minimum(r[:, 1], r[:, 3]) / np.maximum(r[:, 1], r[:, 3])).astype(f)).astype(f)).astype(f)
+            c = ((np.minimum(r[:, 0], r[:, 2]) / np.maximum(r[:, 0], r[:, 2])).astype(f) *
+                 (np.minimum(r[:, 1], r[:, 3]) / np.maximum(r[:, 1], r[:, 3])).astype(f)).astype(f)
+            if slender:
+                r1 = ((r[:, 0] + r[:, 2]).astype(f) / (r[:, 1] + r[:, 3]).astype(f)).astype(f)
+                c = np.power(c, np.minimum(r1, (f(1) / r1).astype(f))).astype(f)
+            else:
+                c = np.sqrt(c).astype(f)
             order = np.lexsort((sel, -c))[:topk]                              # highest centerness, lowest index on ties
             out[sel[order]] = True
         elif sel.size > 0:

@@ -130,6 +130,20 @@ def centerness_targets(ltrb):
     return torch.sqrt(c)
 
 
+def slender_centerness_targets(ltrb):
+    """The FCOSRepPoints module's own compute_centerness_targets
+    (/root/reference/slender_det/modeling/meta_arch/fcos/fcos_rpd_s1_topk.py:25-55): pow(c, gt_ratio) with
+    c as above and gt_ratio = min((l+r)/(t+b), (t+b)/(l+r)) -- the slender-object exponent.  It shadows the
+    fcos/utils.py function inside that module (:288, :291 and the top-5 loop :117)."""
+    (r,) = _prep(ltrb)
+    lr = r[:, [0, 2]]
+    tb = r[:, [1, 3]]
+    ratio1 = (r[:, 0] + r[:, 2]) / (r[:, 1] + r[:, 3])
+    ratio = torch.stack((ratio1, 1 / ratio1), dim=1).min(dim=1)[0]
+    c = (lr.min(dim=-1)[0] / lr.max(dim=-1)[0]) * (tb.min(dim=-1)[0] / tb.max(dim=-1)[0])
+    return torch.pow(c, ratio)
+
+
 def fcos_rpd_losses(init_gt_classes, init_reg_targets, refine_gt_classes, refine_reg_targets, pred_class_logits,
                     pred_box_reg_init, pred_box_reg, pred_center_score, strides, topk_locations, num_classes,
                     alpha=0.25, gamma=2.0, iou_loss_type="iou"):
@@ -149,8 +163,8 @@ def fcos_rpd_losses(init_gt_classes, init_reg_targets, refine_gt_classes, refine
     ref_num = max(float(rfg.sum()), 1.0)                                            # :277-278
     cls_idx = torch.where(rfg, rcls, torch.full_like(rcls, K))
     cls_sum, g_logits = sigmoid_focal_loss(logits, cls_idx, alpha, gamma)           # :283-287
-    gt_center = centerness_targets(ireg[ifg])                                       # :289
-    topk_center = centerness_targets(ireg[topk])                                    # :292
+    gt_center = slender_centerness_targets(ireg[ifg])                               # :288 (the module's own pow form, :25-55)
+    topk_center = slender_centerness_targets(ireg[topk])                            # :291
     sum_topk = float(topk_center.sum())                                             # :293-294
     ri_sum, g_pbi_sel = iou_loss(pbi[topk], ireg[topk], topk_center, iou_loss_type, "ltrb")    # :298-301
     norm = (st[rfg] * 4).unsqueeze(-1)                                              # :303

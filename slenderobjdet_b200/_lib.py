@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "sdb_dcn_workspace_bytes", "sdb_dcn_packed_input_bytes", "sdb_dcn_forward",
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
-    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
+    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
 ]
 
 
@@ -64,6 +64,10 @@ def _declare(lib):
     lib.sdb_sigmoid_focal_loss.argtypes = [_vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _vp, _vp]
     lib.sdb_box_reg_loss.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _f32, _f32, _vp, _vp, _vp]
     lib.sdb_centerness_targets.argtypes = [_vp, _i64, _vp, _vp]
+    lib.sdb_slender_centerness_targets.argtypes = [_vp, _i64, _vp, _vp]
+    lib.sdb_fcos_location_targets_batched.argtypes = [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, ctypes.POINTER(_i32),
+                                                      ctypes.POINTER(_f32), _i32, _f32, _i64, _i32, _i32, _vp, _vp, _vp,
+                                                      _vp, _sz, _vp]
     lib.sdb_fcos_location_targets.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_f32), _i32, _f32, _i64, _vp, _vp, _vp]
     lib.sdb_fcos_topk_workspace_bytes.restype = _sz
     lib.sdb_fcos_topk_workspace_bytes.argtypes = [_i32]

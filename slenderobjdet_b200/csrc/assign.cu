@@ -454,14 +454,34 @@ struct FcosLevels {
   int n;
 };
 
+// centerness of an ltrb target: kind 0 = sqrt(c) (fcos/utils.py:295-300), kind 1 = pow(c, min(w/h, h/w)), the
+// FCOSRepPoints module's own definition (fcos_rpd_s1_topk.py:25-55); c = min(l,r)/max(l,r) * min(t,b)/max(t,b)
+__device__ __forceinline__ float centerness_of(const float4 rg, int kind) {
+  const float c = __fmul_rn(__fdiv_rn(fminf(rg.x, rg.z), fmaxf(rg.x, rg.z)), __fdiv_rn(fminf(rg.y, rg.w), fmaxf(rg.y, rg.w)));
+  if (kind == 0) return __fsqrt_rn(c);
+  const float r1 = __fdiv_rn(__fadd_rn(rg.x, rg.z), __fadd_rn(rg.y, rg.w));
+  return powf(c, fminf(r1, __fdiv_rn(1.f, r1)));
+}
+
+// grid (ceil(X / 256), images): image n reads GT rows [n*Mpad, n*Mpad + count[n]) (count == nullptr: Mpad rows)
 __global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restrict__ loc, const float2* __restrict__ soi,
-                                                           const float4* __restrict__ gt, const int64_t* __restrict__ gt_cls,
-                                                           int X, int M, const FcosLevels lv, int center_sampling,
-                                                           int64_t num_classes, int64_t* __restrict__ out_cls,
-                                                           float4* __restrict__ out_reg, int* __restrict__ out_gt,
-                                                           float* __restrict__ out_ctr, uint8_t* __restrict__ out_topk) {
+                                                           const float4* __restrict__ gt_all, const int64_t* __restrict__ gt_cls_all,
+                                                           const int32_t* __restrict__ gt_count, int X, int Mpad,
+                                                           const FcosLevels lv, int center_sampling, int ctr_kind,
+                                                           int64_t num_classes, int64_t* __restrict__ out_cls_all,
+                                                           float4* __restrict__ out_reg_all, int* __restrict__ out_gt_all,
+                                                           float* __restrict__ out_ctr_all, uint8_t* __restrict__ out_topk_all) {
   extern __shared__ float4 s_gt[];   // M boxes, then M areas
-  float* s_area = reinterpret_cast<float*>(s_gt + M);
+  const int img = blockIdx.y;
+  const int M = gt_count ? gt_count[img] : Mpad;
+  const float4* gt = gt_all + (size_t)img * Mpad;
+  const int64_t* gt_cls = gt_cls_all + (size_t)img * Mpad;
+  int64_t* out_cls = out_cls_all + (size_t)img * X;
+  float4* out_reg = out_reg_all + (size_t)img * X;
+  int* out_gt = out_gt_all ? out_gt_all + (size_t)img * X : nullptr;
+  float* out_ctr = out_ctr_all ? out_ctr_all + (size_t)img * X : nullptr;
+  uint8_t* out_topk = out_topk_all ? out_topk_all + (size_t)img * X : nullptr;
+  float* s_area = reinterpret_cast<float*>(s_gt + Mpad);
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     const float4 b = gt[m];
     s_gt[m] = b;
@@ -478,7 +498,7 @@ __global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restr
     rad = lv.radius[l];
   }
   // get_sample_region's shortcut: sum over locations of GT 0's centre x == 0 -> "no gt", nothing is inside
-  const bool no_gt = center_sampling && __fdiv_rn(__fadd_rn(s_gt[0].x, s_gt[0].z), 2.f) == 0.f;
+  const bool no_gt = center_sampling && M > 0 && __fdiv_rn(__fadd_rn(s_gt[0].x, s_gt[0].z), 2.f) == 0.f;
   const float INF = 100000000.f;
   float best = __int_as_float(0x7f800000);
   int best_m = 0;
@@ -504,25 +524,29 @@ __global__ void __launch_bounds__(256) fcos_targets_kernel(const float2* __restr
       best_m = m;
     }
   }
-  const float4 b = s_gt[best_m];
+  const float4 b = M > 0 ? s_gt[best_m] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 rg = make_float4(__fsub_rn(p.x, b.x), __fsub_rn(p.y, b.y), __fsub_rn(b.z, p.x), __fsub_rn(b.w, p.y));
   out_reg[i] = rg;
-  const int64_t cls = best == INF ? num_classes : gt_cls[best_m];
+  const int64_t cls = (best == INF || M == 0) ? num_classes : gt_cls[best_m];
   out_cls[i] = cls;
   if (out_gt) {   // top-k variant: the GT this location belongs to (foreground only) and its centerness (:270-273)
     const bool fg = cls >= 0 && cls != num_classes;
     out_gt[i] = fg ? best_m : -1;
-    out_ctr[i] = __fsqrt_rn(__fmul_rn(__fdiv_rn(fminf(rg.x, rg.z), fmaxf(rg.x, rg.z)), __fdiv_rn(fminf(rg.y, rg.w), fmaxf(rg.y, rg.w))));
+    out_ctr[i] = centerness_of(rg, ctr_kind);
     out_topk[i] = 0;
   }
 }
 
 // one block per GT: the `topk` locations assigned to it with the highest centerness (all when it has fewer)
-__global__ void __launch_bounds__(512) fcos_topk_kernel(const int* __restrict__ loc_gt, const float* __restrict__ ctr, int X,
-                                                        int topk, uint8_t* __restrict__ out_topk) {
+// grid (Mpad, images)
+__global__ void __launch_bounds__(512) fcos_topk_kernel(const int* __restrict__ loc_gt_all, const float* __restrict__ ctr_all, int X,
+                                                        int topk, uint8_t* __restrict__ out_topk_all) {
   __shared__ Key s_red[32];
   constexpr int KMAX = 16;
   const int m = blockIdx.x;
+  const int* loc_gt = loc_gt_all + (size_t)blockIdx.y * X;
+  const float* ctr = ctr_all + (size_t)blockIdx.y * X;
+  uint8_t* out_topk = out_topk_all + (size_t)blockIdx.y * X;
   const Key none = {-INFINITY, 0x7fffffff};
   Key loc[KMAX];
 #pragma unroll
@@ -558,22 +582,26 @@ __global__ void __launch_bounds__(512) fcos_topk_kernel(const int* __restrict__ 
 extern "C" {
 
 static int fcos_targets_impl(const float* locations, const float* sizes_of_interest, const float* gt,
-                             const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
-                             const float* level_strides, int32_t n_levels, float center_sampling_radius,
-                             int64_t num_classes, int32_t topk, int64_t* out_classes, float* out_reg, uint8_t* out_topk,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             const int64_t* gt_classes, const int32_t* gt_counts, int32_t n_images, int32_t X, int32_t M,
+                             const int32_t* num_points_per_level, const float* level_strides, int32_t n_levels,
+                             float center_sampling_radius, int64_t num_classes, int32_t topk, int32_t centerness_kind,
+                             int64_t* out_classes, float* out_reg, uint8_t* out_topk, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   using namespace sdb;
-  SDB_REQUIRE(X >= 0 && M > 0, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
-  if (X == 0) return SDB_OK;
-  SDB_REQUIRE(locations && sizes_of_interest && gt && gt_classes && out_classes && out_reg, SDB_ERR_INVALID, "NULL argument");
+  SDB_REQUIRE(X >= 0 && n_images >= 0, SDB_ERR_INVALID, "negative sizes");
+  SDB_REQUIRE(M > 0 || gt_counts != nullptr, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
+  if (X == 0 || n_images == 0) return SDB_OK;
+  SDB_REQUIRE(locations && sizes_of_interest && out_classes && out_reg && (M == 0 || (gt && gt_classes)), SDB_ERR_INVALID,
+              "NULL argument");
+  SDB_REQUIRE(centerness_kind == 0 || centerness_kind == 1, SDB_ERR_INVALID, "unknown centerness kind %d", centerness_kind);
   int* loc_gt = nullptr;
   float* ctr = nullptr;
   if (out_topk) {
     SDB_REQUIRE(topk > 0 && topk <= 16, SDB_ERR_UNSUPPORTED, "topk must be in [1,16], got %d", topk);
-    SDB_REQUIRE(workspace && workspace_bytes >= sdb_fcos_topk_workspace_bytes(X), SDB_ERR_WORKSPACE,
+    SDB_REQUIRE(workspace && workspace_bytes >= (size_t)n_images * sdb_fcos_topk_workspace_bytes(X), SDB_ERR_WORKSPACE,
                 "fcos top-k workspace too small");
     loc_gt = (int*)workspace;
-    ctr = (float*)workspace + X;
+    ctr = (float*)workspace + (size_t)n_images * X;
   }
   FcosLevels lv{};
   const bool cs = center_sampling_radius > 0.f;
@@ -589,15 +617,15 @@ static int fcos_targets_impl(const float* locations, const float* sizes_of_inter
     SDB_REQUIRE(acc == X, SDB_ERR_INVALID, "num_points_per_level sums to %d, expected %d", acc, X);
     lv.n = n_levels;
   }
-  const size_t smem = (size_t)M * (sizeof(float4) + sizeof(float));
+  const size_t smem = (size_t)(M > 0 ? M : 1) * (sizeof(float4) + sizeof(float));
   SDB_REQUIRE(smem <= 48 * 1024, SDB_ERR_UNSUPPORTED, "too many GT boxes (%d) for one shared-memory stage", M);
   cudaStream_t st = (cudaStream_t)stream;
-  fcos_targets_kernel<<<cdiv(X, 256), 256, smem, st>>>(
-      (const float2*)locations, (const float2*)sizes_of_interest, (const float4*)gt, gt_classes, X, M, lv, cs ? 1 : 0,
-      num_classes, out_classes, (float4*)out_reg, loc_gt, ctr, out_topk);
+  fcos_targets_kernel<<<dim3(cdiv(X, 256), n_images), 256, smem, st>>>(
+      (const float2*)locations, (const float2*)sizes_of_interest, (const float4*)gt, gt_classes, gt_counts, X, M, lv,
+      cs ? 1 : 0, centerness_kind, num_classes, out_classes, (float4*)out_reg, loc_gt, ctr, out_topk);
   SDB_LAUNCHED(1);
-  if (out_topk) {
-    fcos_topk_kernel<<<M, X >= 8192 ? 512 : 256, 0, st>>>(loc_gt, ctr, X, topk, out_topk);
+  if (out_topk && M > 0) {
+    fcos_topk_kernel<<<dim3(M, n_images), X >= 8192 ? 512 : 256, 0, st>>>(loc_gt, ctr, X, topk, out_topk);
     SDB_LAUNCHED(1);
   }
   SDB_CHECK_CUDA(cudaGetLastError());
@@ -608,9 +636,10 @@ int sdb_fcos_location_targets(const float* locations, const float* sizes_of_inte
                               const int64_t* gt_classes, int32_t X, int32_t M, const int32_t* num_points_per_level,
                               const float* level_strides, int32_t n_levels, float center_sampling_radius,
                               int64_t num_classes, int64_t* out_classes, float* out_reg, void* stream) {
-  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, X, M, num_points_per_level, level_strides,
-                           n_levels, center_sampling_radius, num_classes, 0, out_classes, out_reg, nullptr, nullptr, 0,
-                           stream);
+  SDB_REQUIRE(M > 0, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
+  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, nullptr, 1, X, M, num_points_per_level,
+                           level_strides, n_levels, center_sampling_radius, num_classes, 0, 0, out_classes, out_reg, nullptr,
+                           nullptr, 0, stream);
 }
 
 size_t sdb_fcos_topk_workspace_bytes(int32_t X) { return X > 0 ? (size_t)X * 8 : 0; }
@@ -622,9 +651,23 @@ int sdb_fcos_topk_location_targets(const float* locations, const float* sizes_of
                                    int64_t* out_classes, float* out_reg, uint8_t* out_topk, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   SDB_REQUIRE(out_topk != nullptr, SDB_ERR_INVALID, "out_topk is NULL");
-  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, X, M, num_points_per_level, level_strides,
-                           n_levels, center_sampling_radius, num_classes, topk, out_classes, out_reg, out_topk, workspace,
-                           workspace_bytes, stream);
+  SDB_REQUIRE(M > 0, SDB_ERR_INVALID, "fcos targets need at least one GT box (M=%d)", M);
+  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, nullptr, 1, X, M, num_points_per_level,
+                           level_strides, n_levels, center_sampling_radius, num_classes, topk, 0, out_classes, out_reg,
+                           out_topk, workspace, workspace_bytes, stream);
+}
+
+int sdb_fcos_location_targets_batched(const float* locations, const float* sizes_of_interest, const float* gt,
+                                      const int64_t* gt_classes, const int32_t* gt_counts, int32_t n_images, int32_t X,
+                                      int32_t M_pad, const int32_t* num_points_per_level, const float* level_strides,
+                                      int32_t n_levels, float center_sampling_radius, int64_t num_classes, int32_t topk,
+                                      int32_t centerness_kind, int64_t* out_classes, float* out_reg, uint8_t* out_topk,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  SDB_REQUIRE(gt_counts != nullptr && M_pad >= 0, SDB_ERR_INVALID, "gt_counts is NULL or M_pad < 0");
+  return fcos_targets_impl(locations, sizes_of_interest, gt, gt_classes, gt_counts, n_images, X, M_pad,
+                           num_points_per_level, level_strides, n_levels, center_sampling_radius, num_classes, topk,
+                           centerness_kind, out_classes, out_reg, topk > 0 ? out_topk : nullptr, workspace, workspace_bytes,
+                           stream);
 }
 
 size_t sdb_point_targets_workspace_bytes(int32_t X) { return X > 0 ? 256 + (size_t)X * 8 : 0; }

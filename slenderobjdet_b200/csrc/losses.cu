@@ -210,13 +210,22 @@ namespace sdb {
 namespace {
 // compute_centerness_targets (fcos/utils.py:295-300): one thread per row, IEEE division / sqrt and no fma
 // contraction, in the reference's operation order -> bit-identical to torch's elementwise result.
+// SLENDER: the FCOSRepPoints module's own definition (fcos_rpd_s1_topk.py:25-55): pow(c, min(w/h, h/w)) with
+// w = l + r, h = t + b (powf is within a few ulp of torch's CPU pow, not bit-identical).
+template <bool SLENDER>
 __global__ void __launch_bounds__(256) centerness_kernel(const float4* __restrict__ ltrb, long long R,
                                                          float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = ltrb[i];   // (l, t, r, b)
     const float lr = __fdiv_rn(fminf(v.x, v.z), fmaxf(v.x, v.z));
     const float tb = __fdiv_rn(fminf(v.y, v.w), fmaxf(v.y, v.w));
-    out[i] = __fsqrt_rn(__fmul_rn(lr, tb));
+    const float c = __fmul_rn(lr, tb);
+    if (SLENDER) {
+      const float r1 = __fdiv_rn(__fadd_rn(v.x, v.z), __fadd_rn(v.y, v.w));
+      out[i] = powf(c, fminf(r1, __fdiv_rn(1.f, r1)));
+    } else {
+      out[i] = __fsqrt_rn(c);
+    }
   }
 }
 
@@ -287,15 +296,23 @@ int sdb_box_reg_loss(const float* pred, const float* target, const float* weight
   return SDB_OK;
 }
 
-int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream) {
+static int centerness_launch(bool slender, const float* reg_targets, int64_t R, float* out, void* stream) {
   SDB_REQUIRE(R >= 0, SDB_ERR_INVALID, "negative row count");
   if (R == 0) return SDB_OK;
   SDB_REQUIRE(reg_targets && out, SDB_ERR_INVALID, "NULL argument");
   long long blocks = (R + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sdb::centerness_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)reg_targets, R, out); SDB_LAUNCHED(1);
+  if (slender) sdb::centerness_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)reg_targets, R, out);
+  else         sdb::centerness_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)reg_targets, R, out);
+  SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream) {
+  return centerness_launch(false, reg_targets, R, out, stream);
+}
+int sdb_slender_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream) {
+  return centerness_launch(true, reg_targets, R, out, stream);
 }
 
 static int reppoints_offset_launch(bool bwd, const float* src, int32_t N, int32_t ks, int32_t H, int32_t W, float gm,

@@ -47,8 +47,9 @@ def fcos_rpd_losses(init_gt_classes, init_reg_targets, refine_gt_classes, refine
     cls_idx = torch.where(ref_fg, ref_cls, torch.full_like(ref_cls, K))
     cls_loss = LL.sigmoid_focal_loss_from_class_idx(pred_class_logits, cls_idx, focal_loss_alpha, focal_loss_gamma) / ref_num_pos
 
-    # centerness targets of the stage-1 foreground / top-k rows (:289-299), as per-row weights
-    ctr = LL.compute_centerness_targets(torch.where(init_fg[:, None] | topk[:, None], init_reg, torch.ones_like(init_reg)))
+    # centerness targets of the stage-1 foreground / top-k rows (:288-299), as per-row weights.  Inside this model
+    # `compute_centerness_targets` is the module's OWN pow(c, min(w/h, h/w)) (:25-55), not fcos/utils.py's sqrt(c)
+    ctr = LL.compute_slender_centerness_targets(torch.where(init_fg[:, None] | topk[:, None], init_reg, torch.ones_like(init_reg)))
     w_fg = torch.where(init_fg, ctr, torch.zeros_like(ctr))
     w_topk = torch.where(topk, ctr, torch.zeros_like(ctr))
     sum_topk = _reduce_sum(w_topk.sum().reshape(1)) / ng                            # :293-294

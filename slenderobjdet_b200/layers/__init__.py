@@ -4,7 +4,7 @@ from .deform_conv import (DeformConv, ModulatedDeformConv, deform_conv, modulate
 from .df_conv import DFConv2d
 from .losses import (sigmoid_focal_loss, sigmoid_focal_loss_jit, sigmoid_focal_loss_from_class_idx,
                      iou_loss, box_iou_loss, smooth_l1_loss, smooth_l1_loss_with_weight, giou_loss,
-                     compute_centerness_targets)
+                     compute_centerness_targets, compute_slender_centerness_targets)
 from .reppoints_offset import reppoints_dcn_offset, dcn_base_offset
 
 __all__ = [k for k in globals().keys() if not k.startswith("_")]

@@ -131,15 +131,27 @@ def giou_loss(boxes1, boxes2, reduction="none", eps=1e-7):
     return _BoxLoss.apply(boxes1, boxes2, None, _lib.SDB_LOSS_GIOU_FVCORE, _lib.SDB_BOX_XYXY, 0.0)
 
 
-def compute_centerness_targets(reg_targets):
-    """``slender_det.modeling.meta_arch.fcos.utils.compute_centerness_targets`` (fcos/utils.py:295-300):
-    ``sqrt(min(l, r) / max(l, r) * min(t, b) / max(t, b))`` for ``reg_targets [R, 4]`` in (l, t, r, b) order.
-    No gradient (the reference uses it as a target)."""
+def _centerness(reg_targets, slender):
     _req(reg_targets.dim() == 2 and reg_targets.shape[1] == 4, "reg_targets must be [R, 4]")
     if not reg_targets.is_cuda:
         raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
     r = _f32c(reg_targets.detach())
     out = torch.empty((r.shape[0],), dtype=torch.float32, device=r.device)
+    fn = _lib.lib().sdb_slender_centerness_targets if slender else _lib.lib().sdb_centerness_targets
     with torch.cuda.device(r.device):
-        _lib.check(_lib.lib().sdb_centerness_targets(_lib.ptr(r), r.shape[0], _lib.ptr(out), _lib.stream_ptr(r.device)))
+        _lib.check(fn(_lib.ptr(r), r.shape[0], _lib.ptr(out), _lib.stream_ptr(r.device)))
     return out.to(reg_targets.dtype)
+
+
+def compute_centerness_targets(reg_targets):
+    """``slender_det.modeling.meta_arch.fcos.utils.compute_centerness_targets`` (fcos/utils.py:295-300):
+    ``sqrt(min(l, r) / max(l, r) * min(t, b) / max(t, b))`` for ``reg_targets [R, 4]`` in (l, t, r, b) order.
+    No gradient (the reference uses it as a target)."""
+    return _centerness(reg_targets, False)
+
+
+def compute_slender_centerness_targets(reg_targets):
+    """The ``compute_centerness_targets`` that the active FCOSRepPoints model defines for itself
+    (fcos/fcos_rpd_s1_topk.py:25-55) and uses in its losses (:288, :291) and top-5 selection (:117):
+    ``pow(c, min(w/h, h/w))`` with ``c`` the product above, ``w = l + r``, ``h = t + b``."""
+    return _centerness(reg_targets, True)

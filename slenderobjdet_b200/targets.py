@@ -73,6 +73,43 @@ def _boxes_and_classes(t):
     return _tensor_of(b), c
 
 
+def _fcos_targets_batched(locations, targets, object_sizes_of_interest, strides, center_sampling_radius, num_classes,
+                          topk, centerness_kind):
+    """One ``sdb_fcos_location_targets_batched`` call for the whole batch: the GT boxes / classes of all images are
+    padded to [N, M_pad] (one ``pad_sequence`` each), the per-image counts go along as a device int32 vector, and the
+    kernels take the image as a grid dimension - no per-image host loop, two launches per batch."""
+    import ctypes
+    from torch.nn.utils.rnn import pad_sequence
+    from . import _lib
+    num_points = [len(l) for l in locations]
+    loc = torch.cat(locations, dim=0).float().contiguous()
+    if not loc.is_cuda:
+        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
+    soi = object_sizes_of_interest.float().contiguous()
+    X, L, N = loc.shape[0], len(num_points), len(targets)
+    pairs = [_boxes_and_classes(t) for t in targets]
+    counts = [int(b.shape[0]) for b, _ in pairs]
+    if min(counts) == 0:
+        raise ValueError("every image needs at least one GT box (the reference indexes an empty tensor otherwise)")
+    gt = pad_sequence([b.float() for b, _ in pairs], batch_first=True).contiguous()              # [N, M_pad, 4]
+    gc = pad_sequence([c.to(torch.long) for _, c in pairs], batch_first=True).contiguous()        # [N, M_pad]
+    cnt = torch.tensor(counts, dtype=torch.int32).to(loc.device, non_blocking=True)
+    npl = (ctypes.c_int32 * L)(*num_points)
+    lst = (ctypes.c_float * L)(*[float(s) for s in strides])
+    lib = _lib.lib()
+    oc = torch.empty((N, X), dtype=torch.long, device=loc.device)
+    orr = torch.empty((N, X, 4), dtype=torch.float32, device=loc.device)
+    ot = torch.empty((N, X), dtype=torch.uint8, device=loc.device) if topk else None
+    wsb = N * int(lib.sdb_fcos_topk_workspace_bytes(X)) if topk else 0
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=loc.device)
+    with torch.cuda.device(loc.device):
+        _lib.check(lib.sdb_fcos_location_targets_batched(
+            _lib.ptr(loc), _lib.ptr(soi), _lib.ptr(gt), _lib.ptr(gc), _lib.ptr(cnt), N, X, gt.shape[1], npl, lst, L,
+            float(center_sampling_radius), int(num_classes), int(topk), int(centerness_kind), _lib.ptr(oc), _lib.ptr(orr),
+            _lib.ptr(ot), _lib.ptr(ws), wsb, _lib.stream_ptr(loc.device)))
+    return oc.to(pairs[0][1].dtype), orr.to(pairs[0][0].dtype), (ot.bool() if topk else None), num_points
+
+
 @torch.no_grad()
 def compute_targets_for_locations(locations, targets, object_sizes_of_interest, strides, center_sampling_radius,
                                   num_classes):
@@ -80,78 +117,29 @@ def compute_targets_for_locations(locations, targets, object_sizes_of_interest, 
 
     ``locations``: list of per-level [X_l, 2] tensors; ``targets``: per image an Instances-like object or a
     (boxes [M,4], classes [M]) pair; ``object_sizes_of_interest`` [X, 2]; ``strides``: per-level ints.
-    -> (gt_classes [N, X], reg_targets [N, X, 4]).  One fused kernel per image (GT boxes in shared memory, one
-    thread per location) instead of [X, M, 4] temporaries and ~25 launches; results are identical."""
-    import ctypes
-    from . import _lib
-    num_points = [len(l) for l in locations]
-    loc = torch.cat(locations, dim=0).float().contiguous()
-    if not loc.is_cuda:
-        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
-    soi = object_sizes_of_interest.float().contiguous()
-    X, L = loc.shape[0], len(num_points)
-    npl = (ctypes.c_int32 * L)(*num_points)
-    lst = (ctypes.c_float * L)(*[float(s) for s in strides])
-    lib = _lib.lib()
-    cls_out, reg_out = [], []
-    for t in targets:
-        boxes, classes = _boxes_and_classes(t)
-        b = boxes.float().contiguous()
-        c = classes.to(torch.long).contiguous()
-        oc = torch.empty((X,), dtype=torch.long, device=loc.device)
-        orr = torch.empty((X, 4), dtype=torch.float32, device=loc.device)
-        with torch.cuda.device(loc.device):
-            _lib.check(lib.sdb_fcos_location_targets(_lib.ptr(loc), _lib.ptr(soi), _lib.ptr(b), _lib.ptr(c), X, b.shape[0],
-                                                     npl, lst, L, float(center_sampling_radius), int(num_classes),
-                                                     _lib.ptr(oc), _lib.ptr(orr), _lib.stream_ptr(loc.device)))
-        cls_out.append(oc.to(classes.dtype))
-        reg_out.append(orr.to(boxes.dtype))
-    return torch.stack(cls_out), torch.stack(reg_out)
+    -> (gt_classes [N, X], reg_targets [N, X, 4]).  ONE fused kernel for the whole batch (image = grid dimension,
+    GT boxes in shared memory, one thread per location) instead of [X, M, 4] temporaries and ~25 launches per
+    image; results are identical."""
+    cls, reg, _, _ = _fcos_targets_batched(locations, targets, object_sizes_of_interest, strides,
+                                           center_sampling_radius, num_classes, 0, 0)
+    return cls, reg
 
 
 @torch.no_grad()
 def compute_topk_targets_for_locations(locations, targets, object_sizes_of_interest, strides, center_sampling_radius,
-                                       num_classes, norm_reg_targets=False, topk=5):
-    """``compute_topk_targets_for_locations`` (fcos/utils.py:215-292, stage 1 of the active FCOSRepPoints model):
-    ``compute_targets_for_locations`` plus, per GT, its ``topk`` foreground locations of highest centerness.
-    -> (gt_classes [N, X], reg_targets [N, X, 4], topk_locations bool [N, X]).  Two launches per image; the
-    reference's host loop over GTs with a ``.sum().item()`` sync each is gone."""
-    import ctypes
-    from . import _lib
-    num_points = [len(l) for l in locations]
-    loc = torch.cat(locations, dim=0).float().contiguous()
-    if not loc.is_cuda:
-        raise RuntimeError("slender_b200: CUDA tensors only (no CPU fallback)")
-    norm_weights = None
-    if norm_reg_targets:   # :221-223 (built on the CPU in the reference, moved to the locations' device here)
-        norm_weights = torch.cat([torch.empty(n).fill_(s) for n, s in zip(num_points, strides)]).to(loc.device)
-    soi = object_sizes_of_interest.float().contiguous()
-    X, L = loc.shape[0], len(num_points)
-    npl = (ctypes.c_int32 * L)(*num_points)
-    lst = (ctypes.c_float * L)(*[float(s) for s in strides])
-    lib = _lib.lib()
-    wsb = int(lib.sdb_fcos_topk_workspace_bytes(X))
-    cls_out, reg_out, topk_out = [], [], []
-    for t in targets:
-        boxes, classes = _boxes_and_classes(t)
-        b = boxes.float().contiguous()
-        c = classes.to(torch.long).contiguous()
-        oc = torch.empty((X,), dtype=torch.long, device=loc.device)
-        orr = torch.empty((X, 4), dtype=torch.float32, device=loc.device)
-        ot = torch.empty((X,), dtype=torch.uint8, device=loc.device)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=loc.device)
-        with torch.cuda.device(loc.device):
-            _lib.check(lib.sdb_fcos_topk_location_targets(_lib.ptr(loc), _lib.ptr(soi), _lib.ptr(b), _lib.ptr(c), X,
-                                                          b.shape[0], npl, lst, L, float(center_sampling_radius),
-                                                          int(num_classes), int(topk), _lib.ptr(oc), _lib.ptr(orr),
-                                                          _lib.ptr(ot), _lib.ptr(ws), wsb, _lib.stream_ptr(loc.device)))
-        orr = orr.to(boxes.dtype)
-        if norm_weights is not None:
-            orr /= norm_weights[:, None]                                     # :284-285
-        cls_out.append(oc.to(classes.dtype))
-        reg_out.append(orr)
-        topk_out.append(ot.bool())
-    return torch.stack(cls_out), torch.stack(reg_out), torch.stack(topk_out)
+                                       num_classes, norm_reg_targets=False, topk=5, slender_centerness=False):
+    """``compute_topk_targets_for_locations`` (fcos/utils.py:215-292): ``compute_targets_for_locations`` plus, per GT,
+    its ``topk`` foreground locations of highest centerness.  ``slender_centerness=True`` scores with the
+    FCOSRepPoints module's own pow-form centerness, as ITS copy of this function does (fcos_rpd_s1_topk.py:57-134).
+    -> (gt_classes [N, X], reg_targets [N, X, 4], topk_locations bool [N, X]).  Two launches per BATCH; the
+    reference's host loops over images and GTs (a ``.sum().item()`` sync per GT) are gone."""
+    cls, reg, tk, num_points = _fcos_targets_batched(locations, targets, object_sizes_of_interest, strides,
+                                                     center_sampling_radius, num_classes, topk,
+                                                     1 if slender_centerness else 0)
+    if norm_reg_targets:   # :221-223, :284-285 (built on the CPU in the reference, on the locations' device here)
+        norm_weights = torch.cat([torch.empty(n).fill_(s) for n, s in zip(num_points, strides)]).to(reg.device)
+        reg = reg / norm_weights[None, :, None]
+    return cls, reg, tk
 
 
 @torch.no_grad()
@@ -193,7 +181,8 @@ def fcos_rpd_get_ground_truth(points, init_boxes, gt_instances, fpn_strides, cen
         else:
             trip.append((_tensor_of(t[0]), t[1], t[2]))
     init_cls, init_reg, topk_loc = compute_topk_targets_for_locations(
-        points, [(b, c) for b, c, _ in trip], soi, fpn_strides, center_sampling_radius, num_classes, topk=topk)
+        points, [(b, c) for b, c, _ in trip], soi, fpn_strides, center_sampling_radius, num_classes, topk=topk,
+        slender_centerness=True)   # the module's own pow-form centerness ranks the top-5 (:25-55, :117)
     centers = torch.cat(points, 0)
     cls_labels, reg_labels = [], []
     for i, (b, c, sz) in enumerate(trip):

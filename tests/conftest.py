@@ -35,6 +35,12 @@ def assign_cases():
 
 
 @pytest.fixture(scope="session")
+def target_cases():
+    """Outputs of the reference's own target-assignment / FCOSRepPoints loss code (tests/golden/gen_target_golden.py)."""
+    return load_golden("target_cases.npz")
+
+
+@pytest.fixture(scope="session")
 def loss_cases():
     return load_golden("loss_cases.npz")
 

@@ -92,122 +92,87 @@ def test_ties_follow_canonical_rule_and_full_size():
     assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(l.cpu().numpy(), lo)
 
 
-@pytest.mark.parametrize("gmm", [True, False])
-@pytest.mark.parametrize("size", [(3000, 23), (22400, 100)])
-def test_bbox_targets_bit_exact(size, gmm):
+# ---------------------------------------------------------------------------------------------------------------------
+# Target assignment on the GPU against the REFERENCE's own outputs (tests/golden/target_cases.npz, produced by
+# tests/golden/gen_target_golden.py executing reppointsv2.py / fcos/utils.py / fcos_rpd_s1_topk.py by file path).
+# ---------------------------------------------------------------------------------------------------------------------
+from target_cases import locations_of, soi_of, strides_of  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["bb0", "bb1", "bb7"])
+def test_bbox_targets_bit_exact_vs_reference(target_cases, name):
     """RepPointsV2.bbox_targets (reppointsv2.py:430-484) on the fused IoU/matcher kernel: labels and boxes
-    bit-identical to the oracle, candidates clamped in place, no IoU matrix."""
-    from test_oracle_assign import _bbox_case
+    bit-identical to the reference's output, candidates clamped in place, no IoU matrix."""
     from slenderobjdet_b200.targets import bbox_targets
-    cand, gt, labels = _bbox_case(7, *size)
-    cd = cand.clone().cuda()
-    b, l = bbox_targets(cd, gt.cuda(), labels.cuda(), 80, gt_max_matching=gmm)
-    cn = cand.clone().numpy()
-    ob, ol_ = oa.bbox_targets(cn, gt.numpy(), labels.numpy(), 80, gt_max_matching=gmm)
-    assert np.array_equal(cd.cpu().numpy(), cn)
-    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), ol_)
-    assert np.array_equal(b.cpu().numpy(), ob)
+    c = target_cases[name]
+    cd = _d(c["cand"].copy())
+    b, l = bbox_targets(cd, _d(c["gt"]), _d(c["labels"]), 80, gt_max_matching=bool(c["gmm"]))
+    assert np.array_equal(cd.cpu().numpy(), c["cand_clamped"])
+    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), c["assigned"])
+    assert np.array_equal(b.cpu().numpy(), c["boxes"])
     with pytest.raises(ValueError):
-        bbox_targets(torch.zeros(0, 4, device="cuda"), gt.cuda(), labels.cuda(), 80)
+        bbox_targets(torch.zeros(0, 4, device="cuda"), _d(c["gt"]), _d(c["labels"]), 80)
 
 
-@pytest.mark.parametrize("seed", [0, 3])
-def test_point_targets_bit_exact(seed):
-    """RepPointsV2.point_targets (reppointsv2.py:370-428): three launches instead of the host loop over GTs;
-    boxes and labels identical to the oracle, incl. two GTs at equal distance from one point (first GT keeps it)
-    and the full P3-P7 point set of an 800x1344 image."""
-    from test_oracle_assign import _points_case
+@pytest.mark.parametrize("name", ["pt0", "pt1", "pt3"])
+def test_point_targets_bit_exact_vs_reference(target_cases, name):
+    """RepPointsV2.point_targets (reppointsv2.py:370-428): three launches instead of the host loop over GTs; boxes and
+    labels identical to the reference's, incl. two GTs at equal distance from one point (the first GT keeps it) and
+    the full P3-P7 point set of an 800x1344 image (pt3)."""
     from slenderobjdet_b200.targets import point_targets
-    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128)) if seed else None
-    pts, strides, gt, labels = _points_case(seed, 100, lv) if lv else _points_case(seed)
-    if lv:
-        gt = gt * 4.0
-    b, l = point_targets(pts.cuda(), strides.cuda(), gt.cuda(), labels.cuda(), 80)
-    ob, ol_ = oa.point_targets(pts.numpy(), strides.numpy(), gt.numpy(), labels.numpy(), 80)
-    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), ol_)
-    assert np.array_equal(b.cpu().numpy(), ob)
+    c = target_cases[name]
+    b, l = point_targets(_d(c["points"]), _d(c["strides"]), _d(c["gt"]), _d(c["labels"]), 80)
+    assert l.dtype == torch.int64 and np.array_equal(l.cpu().numpy(), c["assigned"])
+    assert np.array_equal(b.cpu().numpy(), c["boxes"])
     with pytest.raises(ValueError):
-        point_targets(pts[:0].cuda(), strides[:0].cuda(), gt.cuda(), labels.cuda(), 80)
+        point_targets(_d(c["points"][:0]), _d(c["strides"][:0]), _d(c["gt"]), _d(c["labels"]), 80)
 
 
-@pytest.mark.parametrize("radius", [0.0, 1.5])
-@pytest.mark.parametrize("full", [False, True])
-def test_fcos_location_targets_bit_exact(radius, full):
-    """compute_targets_for_locations (fcos/utils.py:160-212), one fused kernel per image: classes and ltrb targets
-    identical to the oracle, with and without centre sampling, two images, equal-area ties, the P3-P7 grid."""
-    from test_oracle_assign import _fcos_case
-    from slenderobjdet_b200.targets import compute_targets_for_locations
-    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
-    cases = [_fcos_case(s, 100, lv) if full else _fcos_case(s) for s in (4, 5)]
-    locs, soi, _, _, strides = cases[0]
-    targets = [(c[2].cuda(), c[3].cuda()) for c in cases]
-    cls, reg = compute_targets_for_locations([l.cuda() for l in locs], targets, soi.cuda(), strides, radius, 80)
-    assert cls.shape == (2, soi.shape[0]) and reg.shape == (2, soi.shape[0], 4) and cls.dtype == torch.int64
-    for i, c in enumerate(cases):
-        oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(),
-                                           [len(l) for l in locs], strides, radius, 80)
-        assert np.array_equal(cls[i].cpu().numpy(), oc) and np.array_equal(reg[i].cpu().numpy(), orr)
+def _fcos_inputs(c):
+    lv = c["levels"]
+    return [_d(l) for l in locations_of(lv)], _d(soi_of(lv)), strides_of(lv)
 
 
-def test_fcos_location_targets_first_gt_at_origin_shortcut():
-    """get_sample_region's `center_x[..., 0].sum() == 0` shortcut: a first GT centred at x == 0 disables centre
-    sampling for the whole image (everything background), reproduced as is."""
-    from test_oracle_assign import _fcos_case
-    from slenderobjdet_b200.targets import compute_targets_for_locations
-    locs, soi, boxes, classes, strides = _fcos_case(6)
-    boxes[0] = torch.tensor([-20.0, 10.0, 20.0, 60.0])
-    cls, reg = compute_targets_for_locations([l.cuda() for l in locs], [(boxes.cuda(), classes.cuda())], soi.cuda(),
-                                             strides, 1.5, 80)
-    oc, orr = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), boxes.numpy(), classes.numpy(),
-                                       [len(l) for l in locs], strides, 1.5, 80)
-    assert (oc == 80).all() and np.array_equal(cls[0].cpu().numpy(), oc) and np.array_equal(reg[0].cpu().numpy(), orr)
+@pytest.mark.parametrize("names", [("fc0",), ("fc1",), ("fc2",), ("fc5",), ("fc6",), ("fc1", "fc1")])
+def test_fcos_location_targets_bit_exact_vs_reference(target_cases, names):
+    """compute_targets_for_locations / compute_topk_targets_for_locations (fcos/utils.py:160-292), one batched call:
+    classes, ltrb targets (optionally stride-normalised) and the per-GT top-5-by-centerness mask identical to the
+    reference's output; with and without centre sampling; equal-area ties; the P3-P7 grid (fc5); get_sample_region's
+    "first GT centred at x == 0" shortcut (fc6); images with different GT counts in one batch share the padded call."""
+    from slenderobjdet_b200.targets import compute_targets_for_locations, compute_topk_targets_for_locations
+    cs = [target_cases[n] for n in names]
+    locs, soi, strides = _fcos_inputs(cs[0])
+    radius = float(cs[0]["radius"])
+    targets = [(_d(c["boxes"]), _d(c["classes"])) for c in cs]
+    if len(cs) > 1:   # ragged batch: the second image keeps only its first 17 GTs; checked against the oracle
+        targets[1] = (targets[1][0][:17].contiguous(), targets[1][1][:17].contiguous())
+    cls, reg = compute_targets_for_locations(locs, targets, soi, strides, radius, 80)
+    assert cls.shape == (len(cs), soi.shape[0]) and reg.shape == (len(cs), soi.shape[0], 4) and cls.dtype == torch.int64
+    assert np.array_equal(cls[0].cpu().numpy(), cs[0]["out_classes"]) and np.array_equal(reg[0].cpu().numpy(), cs[0]["out_reg"])
+    if len(cs) > 1:
+        lv = cs[0]["levels"]
+        oc, orr = oa.fcos_location_targets(np.concatenate(locations_of(lv)), soi_of(lv), cs[1]["boxes"][:17],
+                                           cs[1]["classes"][:17], [len(l) for l in locs], strides, radius, 80)
+        assert np.array_equal(cls[1].cpu().numpy(), oc) and np.array_equal(reg[1].cpu().numpy(), orr)
+    if "topk_mask0" in cs[0]:
+        for norm in (0, 1):
+            c2, r2, tk = compute_topk_targets_for_locations(locs, targets, soi, strides, radius, 80,
+                                                            norm_reg_targets=bool(norm), topk=5)
+            assert tk.dtype == torch.bool and np.array_equal(tk[0].cpu().numpy(), cs[0]["topk_mask%d" % norm])
+            assert np.array_equal(c2[0].cpu().numpy(), cs[0]["out_classes"])
+            assert np.array_equal(r2[0].cpu().numpy(), cs[0]["topk_reg%d" % norm])
 
 
-@pytest.mark.parametrize("radius,norm", [(0.0, False), (1.5, True)])
-def test_fcos_topk_location_targets_bit_exact(radius, norm):
-    """compute_topk_targets_for_locations (fcos/utils.py:215-292): classes, ltrb targets (optionally stride-
-    normalised) and the per-GT top-5-by-centerness mask identical to the oracle, on the P3-P7 grid, two images."""
-    from test_oracle_assign import _fcos_case
-    from slenderobjdet_b200.targets import compute_topk_targets_for_locations
-    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
-    cases = [_fcos_case(s, 60, lv) for s in (8, 9)]
-    locs, soi, _, _, strides = cases[0]
-    npts = [len(l) for l in locs]
-    cls, reg, tk = compute_topk_targets_for_locations([l.cuda() for l in locs], [(c[2].cuda(), c[3].cuda()) for c in cases],
-                                                      soi.cuda(), strides, radius, 80, norm_reg_targets=norm, topk=5)
-    assert tk.dtype == torch.bool and tk.shape == cls.shape
-    for i, c in enumerate(cases):
-        oc, orr, idx = oa.fcos_location_targets(torch.cat(locs).numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(), npts,
-                                                strides, radius, 80, return_index=True)
-        ot = oa.fcos_topk_locations(oc, orr, idx, 80, topk=5)
-        if norm:
-            orr = orr / np.concatenate([np.full(n, s, np.float32) for n, s in zip(npts, strides)])[:, None]
-        assert np.array_equal(cls[i].cpu().numpy(), oc) and np.array_equal(reg[i].cpu().numpy(), orr)
-        assert np.array_equal(tk[i].cpu().numpy(), ot) and ot.sum() > 20
-
-
-def test_fcos_rpd_get_ground_truth_bit_exact():
-    """FCOSRepPoints.get_ground_truth (fcos_rpd_s1_topk.py:320-376): both stages against the oracle."""
-    from test_oracle_assign import _fcos_case
+@pytest.mark.parametrize("name", ["rpd_small", "rpd_full", "rpd_cs"])
+def test_fcos_rpd_get_ground_truth_bit_exact_vs_reference(target_cases, name):
+    """FCOSRepPoints.get_ground_truth (fcos_rpd_s1_topk.py:320-376), both stages, against the reference's output:
+    stage-1 classes / ltrb / top-5 mask (ranked by the module's own pow-form centerness) and stage-2 IoU-matched
+    classes (incl. -1 outside the image, num_classes for unmatched) / ltrb."""
     from slenderobjdet_b200.targets import fcos_rpd_get_ground_truth
-    lv = ((100, 168, 8), (50, 84, 16), (25, 42, 32), (13, 21, 64), (7, 11, 128))
-    g = torch.Generator().manual_seed(21)
-    cases = [_fcos_case(s, 50, lv) for s in (12, 13)]
-    locs, soi, _, _, strides = cases[0]
-    centers = torch.cat(locs)
-    sizes = [(800, 1333), (704, 1216)]
-    init = []
-    for _ in cases:   # stage-1 boxes: noisy boxes around the centres
-        wh = torch.exp(torch.rand(centers.shape[0], 2, generator=g) * 3.5 + 2.0)
-        init.append(torch.cat([centers - wh / 2, centers + wh / 2], 1))
-    gts = [(c[2].cuda(), c[3].cuda(), sz) for c, sz in zip(cases, sizes)]
-    ic, ir, rc, rr, tk = fcos_rpd_get_ground_truth([l.cuda() for l in locs], [b.cuda() for b in init], gts, strides, 0.0, 80)
-    npts = [len(l) for l in locs]
-    for i, (c, sz) in enumerate(zip(cases, sizes)):
-        oc, orr, idx = oa.fcos_location_targets(centers.numpy(), soi.numpy(), c[2].numpy(), c[3].numpy(), npts, strides,
-                                                0.0, 80, return_index=True)
-        assert np.array_equal(ic[i].cpu().numpy(), oc) and np.array_equal(ir[i].cpu().numpy(), orr)
-        assert np.array_equal(tk[i].cpu().numpy(), oa.fcos_topk_locations(oc, orr, idx, 80, topk=5))
-        c2, r2 = oa.fcos_rpd_refine_targets(centers.numpy(), init[i].numpy(), c[2].numpy(), c[3].numpy(), sz, 80)
-        assert np.array_equal(rc[i].cpu().numpy(), c2) and np.array_equal(rr[i].cpu().numpy(), r2)
-        assert (c2 == -1).any() and (c2 == 80).any() and ((c2 >= 0) & (c2 < 80)).any()
+    c = target_cases[name]
+    locs, _, strides = _fcos_inputs(c)
+    gts = [(_d(c["boxes%d" % i]), _d(c["classes%d" % i]), tuple(int(v) for v in c["sizes"][i])) for i in range(2)]
+    ic, ir, rc, rr, tk = fcos_rpd_get_ground_truth(locs, [_d(c["init0"]), _d(c["init1"])], gts, strides, float(c["radius"]), 80)
+    assert np.array_equal(ic.cpu().numpy(), c["init_classes"]) and np.array_equal(ir.cpu().numpy(), c["init_reg"])
+    assert np.array_equal(tk.cpu().numpy(), c["topk"])
+    assert np.array_equal(rc.cpu().numpy(), c["refine_classes"]) and np.array_equal(rr.cpu().numpy(), c["refine_reg"])

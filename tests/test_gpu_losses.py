@@ -141,3 +141,31 @@ def test_fcos_rpd_losses_match_oracle():
         assert abs(float(out[k]) - float(lo[k])) <= 1e-4 * abs(float(lo[k])), (k, float(out[k]), float(lo[k]))
     for p, k in zip(preds, ("pred_class_logits", "pred_box_reg_init", "pred_box_reg", "pred_center_score")):
         assert rel_err(p.grad.cpu().numpy(), go[k].numpy()) < 1e-4, k
+
+
+def test_fcos_rpd_losses_vs_reference(target_cases):
+    """The same composition against FCOSRepPoints.losses EXECUTED from the reference on the targets its own
+    get_ground_truth produced (tests/golden/gen_target_golden.py; fvcore's focal / smooth-L1 stood in by the
+    published formulas): the four losses and the gradients of their sum.  The reference ran in float32 on the CPU."""
+    from slenderobjdet_b200.fcos_rpd_losses import fcos_rpd_losses
+    t, c = target_cases["rpd_small"], target_cases["rpd_small_loss"]
+    d = lambda a: torch.as_tensor(a).cuda()
+    preds = [d(c["logits"]).requires_grad_(), d(c["box_init"]).requires_grad_(), d(c["box_ref"]).requires_grad_(),
+             d(c["ctr"]).requires_grad_()]
+    out = fcos_rpd_losses(d(t["init_classes"]), d(t["init_reg"]), d(t["refine_classes"]), d(t["refine_reg"]), *preds,
+                          d(c["strides"]), d(t["topk"]), 80)
+    sum(out.values()).backward()
+    for k in ("cls_loss", "reg_loss_init", "reg_loss", "centerness_loss"):
+        assert abs(float(out[k]) - float(c[k])) <= 5e-5 * abs(float(c[k])), (k, float(out[k]), float(c[k]))
+    for p, k, tol in zip(preds, ("g_logits", "g_box_init", "g_box_ref", "g_ctr"), (1e-4, 3e-4, 1e-4, 1e-4)):
+        assert rel_err(p.grad.cpu().numpy(), c[k]) < tol, k
+
+
+def test_slender_centerness_vs_reference(target_cases):
+    """compute_centerness_targets as the FCOSRepPoints module defines it for itself (fcos_rpd_s1_topk.py:25-55):
+    pow(c, min(w/h, h/w)), against the reference's output (CUDA powf vs torch CPU pow: a few ulp)."""
+    c = target_cases["ctr"]
+    out = L.compute_slender_centerness_targets(torch.as_tensor(c["ltrb"]).cuda()).cpu().numpy()
+    assert np.allclose(out, c["slender"], rtol=2e-6, atol=0)
+    out2 = L.compute_centerness_targets(torch.as_tensor(c["ltrb"]).cuda()).cpu().numpy()
+    assert np.allclose(out2, c["fcos"], rtol=2e-7, atol=0)

@@ -37,3 +37,18 @@ def test_giou_vs_torchvision_golden(loss_cases):
     s, g = ol.giou_loss(c["pred"], c["target"])
     assert abs(float(s) - float(c["loss"])) / abs(float(c["loss"])) < 1e-5
     assert rel_err(g.numpy(), c["grad"]) < 1e-4
+
+
+def test_fcos_rpd_losses_oracle_vs_reference(target_cases):
+    """FCOSRepPoints.losses EXECUTED from the reference (fcos_rpd_s1_topk.py:249-317, gen_target_golden.py) on the
+    targets its own get_ground_truth produced: four loss values and the gradients of their sum with respect to the
+    four prediction tensors.  (The reference ran in float32; the oracle is float64.)"""
+    t, c = target_cases["rpd_small"], target_cases["rpd_small_loss"]
+    losses, grads = ol.fcos_rpd_losses(t["init_classes"], t["init_reg"], t["refine_classes"], t["refine_reg"], c["logits"],
+                                       c["box_init"], c["box_ref"], c["ctr"], c["strides"], t["topk"], 80)
+    for k in ("cls_loss", "reg_loss_init", "reg_loss", "centerness_loss"):
+        assert abs(float(losses[k]) - float(c[k])) / abs(float(c[k])) < 2e-5, k
+    assert rel_err(grads["pred_class_logits"].numpy(), c["g_logits"]) < 2e-5
+    assert rel_err(grads["pred_box_reg_init"].numpy(), c["g_box_init"]) < 2e-4
+    assert rel_err(grads["pred_box_reg"].numpy(), c["g_box_ref"]) < 2e-5
+    assert rel_err(grads["pred_center_score"].numpy(), c["g_ctr"]) < 2e-5
