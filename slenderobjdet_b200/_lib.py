@@ -81,9 +81,6 @@ def _declare(lib):
     lib.sdb_launch_count.argtypes = []
     lib.sdb_profile_enable.argtypes = [ctypes.c_int]
     lib.sdb_profile_read.argtypes = [ctypes.c_int, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int)]
-    if hasattr(lib, "sdb_debug_umma_gemm"):
-        lib.sdb_debug_umma_gemm.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_int, ctypes.c_int, _vp]
     return lib
 
 

@@ -56,15 +56,19 @@ class GradBucket:
         for name, g in grads.items():
             self.views[name].copy_(g)
 
-    def all_reduce(self, group=None, average=True, async_op=False):
-        """Sum over ranks in place (one collective for the whole head); divide by world size when
-        ``average`` (DDP semantics).  No-op without an initialised process group."""
+    def all_reduce(self, group=None, average=True, async_op=False, prescaled=False):
+        """Sum over ranks in place (one collective for the whole head) with DDP's averaging semantics.
+
+        ``average``: the result is the mean over ranks.  The division is applied BEFORE the collective (the buffer
+        is multiplied by 1/world, then summed), so it also holds for ``async_op=True``: waiting on the returned
+        handle leaves the averaged gradients in ``flat``.  ``prescaled=True`` says the producer already folded
+        1/world into what it accumulated (``sdb_dcn_backward`` takes a ``scale``), so no extra pass is made.
+        No-op (returns None) without an initialised process group or with a single rank."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        if average and not async_op:
-            self.flat.div_(dist.get_world_size(group))
-        return work
+        if average and not prescaled:
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     def unpack(self, params):
         """Write the bucket's views into ``params[name].grad`` (cast to the parameter dtype)."""

@@ -9,9 +9,14 @@ CPU tensors :48-49, ``AssertionError`` when im2col_step does not divide N :52, `
 shape violations, deform_conv_cuda.cu:140-270).
 
 Differences, all internal: no ``columns`` / ``ones`` scratch tensors (the gather feeds the GEMM
-directly), ``im2col_step`` is accepted and validated but not used, and the contraction runs on
-tcgen05 tensor cores with bf16 operands / fp32 accumulation whenever the geometry allows
-(``set_dcn_math`` selects ``"fp32"`` for the exact SIMT path).
+directly) and ``im2col_step`` is accepted and validated but not used.
+
+Arithmetic (``set_dcn_math`` / ``SDB_DCN_MATH``).  The reference computes float32 tensors in exact fp32
+(im2col + fp32 GEMM, deform_conv_cuda_kernel.cu:486), so the default ``"auto"`` does the same: float32
+tensors run the exact fp32 kernels (rel <= 1e-4 against the oracle).  The tcgen05 tensor-core kernels (bf16
+operands, fp32 accumulation in TMEM, rel <= 1e-2) are used when the TENSORS are bfloat16, under
+``torch.autocast(dtype=torch.bfloat16)``, or when ``set_dcn_math("bf16")`` asks for them explicitly.
+float16 tensors are computed in float32 (the reference dispatches half too); float64 is refused.
 """
 import contextlib
 import ctypes
@@ -31,8 +36,10 @@ _MATH = os.environ.get("SDB_DCN_MATH", "auto")  # "auto" | "bf16" | "fp32"
 
 
 def set_dcn_math(mode):
-    """'auto': tensor cores (bf16 operands, fp32 accumulate) when supported, else fp32 SIMT;
-    'bf16': require the tensor-core path; 'fp32': always the exact SIMT path."""
+    """'auto': follow the tensors -- float32 tensors use the exact fp32 kernels, bfloat16 tensors (or float32 under
+    bf16 autocast) the tcgen05 tensor-core kernels when the geometry allows, else fp32;
+    'bf16': require the tensor-core path whatever the tensor dtype (tolerance rel <= 1e-2);
+    'fp32': always the exact fp32 path (rel <= 1e-4)."""
     global _MATH
     assert mode in ("auto", "bf16", "fp32")
     _MATH = mode
@@ -100,10 +107,19 @@ def _check_shapes(input, offset, mask, weight, bias, g, out_hw):
             raise RuntimeError("all tensors must be on the same CUDA device")
 
 
-def _pick_math(g, iod):
+def _bf16_autocast():
+    try:
+        return torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+    except Exception:  # pragma: no cover
+        return False
+
+
+def _pick_math(g, iod, autocast=False):
     lib = _lib.lib()
     if _MATH == "fp32":
         return _lib.SDB_MATH_FP32
+    if _MATH == "auto" and iod == _lib.SDB_F32 and not autocast:
+        return _lib.SDB_MATH_FP32     # a float32 model keeps the reference's fp32 numerics unless told otherwise
     ok = bool(lib.sdb_dcn_supported(ctypes.byref(g), iod, _lib.SDB_MATH_BF16))
     if ok:
         return _lib.SDB_MATH_BF16
@@ -113,8 +129,11 @@ def _pick_math(g, iod):
 
 
 def _compute_dtype(t):
-    """float32 / bfloat16 run natively; float16 (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF)
-    is computed in float32."""
+    """float32 / bfloat16 run natively; float16 (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF) is computed in
+    float32; float64 (which the reference computes in double) is refused rather than silently downcast."""
+    if t.dtype == torch.float64:
+        raise RuntimeError("slender_b200: float64 deformable convolution is not implemented (float32 / bfloat16 / "
+                           "float16 tensors only); cast the inputs explicitly")
     return t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.float32
 
 
@@ -126,14 +145,15 @@ def _plan(input, weight, g):
     bf16 tensors whose geometry the tensor-core path does not cover are computed in float32 on the SIMT
     path.  Cached per (geometry, dtype, math mode): the public-API step is host-bound, and these are six
     ctypes round trips per call otherwise."""
-    key = (tuple(getattr(g, f) for f, _ in g._fields_), input.dtype, _MATH)
+    autocast = _bf16_autocast()
+    key = (tuple(getattr(g, f) for f, _ in g._fields_), input.dtype, _MATH, autocast)
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
         return hit
     lib = _lib.lib()
     cdt = _compute_dtype(input)
     iod = _lib.SDB_F32 if cdt == torch.float32 else _lib.SDB_BF16
-    mth = _pick_math(g, iod)
+    mth = _pick_math(g, iod, autocast)
     if mth == _lib.SDB_MATH_FP32 and iod != _lib.SDB_F32:
         cdt, iod = torch.float32, _lib.SDB_F32
     ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
@@ -191,7 +211,7 @@ def _forward_impl(input, offset, mask, weight, bias, g):
     return (out if out.dtype == input.dtype else out.to(input.dtype)), packed
 
 
-def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias):
+def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias, scale=1.0):
     """-> grad_input, grad_offset, grad_mask, grad_weight, grad_bias (None where not requested)."""
     lib = _lib.lib()
     cdt, iod, mth, _, wsb, _ = _plan(input, weight, g)
@@ -218,7 +238,7 @@ def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_dat
             gb = torch.zeros((g.C_out,), dtype=torch.float32, device=dev) if with_bias else None
             ws = _ws(wsb[2], dev)
             _lib.check(lib.sdb_dcn_backward_weight(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(gy),
-                                                   _lib.ptr(gw), _lib.ptr(gb), 1.0, ctypes.byref(g), iod, mth,
+                                                   _lib.ptr(gw), _lib.ptr(gb), float(scale), ctypes.byref(g), iod, mth,
                                                    _lib.ptr(ws), wsb[2], _lib.ptr(packed), st))
             gw = _as(gw, weight.dtype)
             gb = _as(gb, weight.dtype) if gb is not None else None

@@ -3,10 +3,15 @@
 // bulk async copy from a pre-swizzled global image.  Not on the product path: it pins the
 // descriptor / swizzle / TMEM-lane conventions of tc_common.cuh against a plain matmul
 // (tests/test_gpu_umma_probe.py).
-#include "common.cuh"
-#include "tc_common.cuh"
+// TEST INFRASTRUCTURE: compiled by tests/test_gpu_umma_probe.py into tests/probe/libsdb_probe.so, never linked into
+// libslender_b200.so.
+#include "../../slenderobjdet_b200/csrc/common.cuh"
+#include "../../slenderobjdet_b200/csrc/tc_common.cuh"
 
 namespace sdb {
+// the two symbols common.cuh's macros expect from api.cu (this file is built on its own)
+long long g_launches = 0;
+void set_error(const char* fmt, ...) { fprintf(stderr, "sdb probe: %s\n", fmt); }
 namespace {
 using namespace tc;
 

@@ -2,6 +2,8 @@
 D[128,N] = A[128,K] @ B[N,K]^T in bf16 with fp32 accumulation, every operand major-ness the DCN
 kernels use, B optionally loaded by a bulk async copy of a pre-swizzled image."""
 import ctypes
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -10,6 +12,22 @@ import torch
 from slenderobjdet_b200 import _lib
 
 pytestmark = pytest.mark.gpu
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def probe():
+    """The probe is test infrastructure: built on demand next to its source, not part of the product library."""
+    src, so = os.path.join(_HERE, "probe", "debug_umma.cu"), os.path.join(_HERE, "probe", "libsdb_probe.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                        "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-cudart", "static", "-shared", "-o", so, src],
+                       check=True)
+    lib = ctypes.CDLL(so)
+    vp = ctypes.c_void_p
+    lib.sdb_debug_umma_gemm.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, vp]
+    return lib
 
 
 def _sw128(row, chunk):
@@ -34,7 +52,7 @@ def _b_image(B, b_mn):
 @pytest.mark.parametrize("b_mn", [0, 1])
 @pytest.mark.parametrize("N,K", [(256, 128), (64, 64), (128, 256)])
 @pytest.mark.parametrize("bulk", [0, 1])
-def test_umma_probe(a_mn, b_mn, N, K, bulk):
+def test_umma_probe(probe, a_mn, b_mn, N, K, bulk):
     g = torch.Generator().manual_seed(N + K + a_mn * 2 + b_mn)
     A = torch.randn(128, K, generator=g).to(torch.bfloat16)
     B = torch.randn(N, K, generator=g).to(torch.bfloat16)
@@ -42,8 +60,7 @@ def test_umma_probe(a_mn, b_mn, N, K, bulk):
     Ad, Bd = A.cuda(), B.cuda()
     img = _b_image(B, b_mn).cuda()
     D = torch.zeros(128, N, device="cuda")
-    lib = _lib.lib()
-    _lib.check(lib.sdb_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(img), _lib.ptr(D), N, K, a_mn, b_mn,
+    assert 0 == (probe.sdb_debug_umma_gemm(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(img), _lib.ptr(D), N, K, a_mn, b_mn,
                                        bulk, _lib.stream_ptr()))
     torch.cuda.synchronize()
     err = (D.cpu() - ref).abs().max().item()

@@ -39,6 +39,16 @@ def _worker(rank, world, port, out):
             exp = base[k] * scale + (1.0 if k == "cls_out.bias" else 0.0)
             assert torch.allclose(bucket.views[k], exp, atol=1e-6), k
         assert float(bucket.flat[bucket.used:].abs().sum()) == 0.0
+        # async + average: waiting on the handle leaves the MEAN in the buffer (the division is not skipped)
+        b2 = GradBucket(SHAPES, "cpu")
+        b2.pack(grads)
+        b2.all_reduce(average=True, async_op=True).wait()
+        assert torch.allclose(b2.views["cls_dcn.weight"], base["cls_dcn.weight"] * scale, atol=1e-6)
+        # producer already scaled by 1/world (sdb_dcn_backward's `scale`): no second division
+        b3 = GradBucket(SHAPES, "cpu")
+        b3.pack({k: v / world for k, v in grads.items()})
+        b3.all_reduce(average=True, prescaled=True)
+        assert torch.allclose(b3.views["cls_dcn.weight"], base["cls_dcn.weight"] * scale, atol=1e-6)
         params = {k: torch.nn.Parameter(torch.zeros(*s, dtype=torch.bfloat16)) for k, s in SHAPES.items()}
         bucket.unpack(params)
         assert all(p.grad.dtype == torch.bfloat16 for p in params.values())
