@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 1
+#define SDB_ABI_VERSION 2
 
 typedef enum {
   SDB_OK = 0,
@@ -105,6 +105,66 @@ int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mas
                             const void* grad_out, float* grad_weight, float* grad_bias, float scale,
                             const sdb_dcn_geom* g, int io_dtype, int math, void* workspace,
                             size_t workspace_bytes, const void* x_packed, void* stream);
+
+/* ---- whole-head calls: every FPN level x every deformable convolution in ONE launch per kernel --------------------
+ * The reference calls its native op once per (level, branch) from a Python loop (reppointsv2.py:728-752:
+ * 5 levels x {cls, refine} = 10 forward and 20 backward native calls per step, each re-laying-out the same weights).
+ * Here a call takes a TABLE of problems that share the channel counts and the kernel geometry (C_in, C_out, kH, kW,
+ * stride, padding, dilation of `g`; g->N/H/W are ignored) and differ in N, H, W and their tensors.  Every kernel runs
+ * once over the concatenated 128-pixel tiles of all problems (persistent grid, tile scheduler over the table), so the
+ * small pyramid levels fill the machine together instead of occupying 2..66 SMs each.
+ *   - weights are re-laid-out into the kernels' operand images ONCE per weight version (sdb_dcn_prepare_weights),
+ *     not once per call; a NULL `prepared` makes the call do it in its workspace;
+ *   - backward packs grad_out once and runs grad_offset / grad_mask, grad_input and grad_weight / grad_bias from it
+ *     (the reference's v2 entry point is one call too, deform_conv.h:314-375);
+ *   - problems with the same non-negative `offset_group` sample with the SAME offset (and mask) tensors -- the two
+ *     DCNs of a RepPoints level consume one dcn_offset (reppointsv2.py:744-748): the transposed sampling index of
+ *     grad_input is built once per group.
+ * Semantics: out, grad_offset, grad_mask AND grad_x are overwritten; grad_weight / grad_bias (float32) are
+ * accumulated into with `scale` (fold 1/world_size in here for data-parallel training).  Up to SDB_MAX_PROBLEMS
+ * problems and SDB_MAX_WEIGHTS weight tensors per call.  SDB_MATH_FP32 loops over the problems with the SIMT kernels. */
+#define SDB_MAX_PROBLEMS 16
+#define SDB_MAX_WEIGHTS 4
+typedef struct {
+  int32_t N, H, W;          /* input [N, C_in, H, W] of this problem                                              */
+  int32_t weight_id;        /* index into the weights table: the convolution this problem belongs to             */
+  int32_t offset_group;     /* >= 0: shares offset / mask (same pointers, same N, H, W) with equal values; -1: own */
+  int32_t reserved;
+  const void* x;            /* [N, C_in, H, W]                                                                    */
+  const float* offset;      /* [N, 2*kH*kW, Ho, Wo]                                                               */
+  const float* mask;        /* [N, kH*kW, Ho, Wo] or NULL (v1)                                                    */
+  void* out;                /* forward:  [N, C_out, Ho, Wo]                                                       */
+  void* x_packed;           /* optional NHWC-bf16 copy of x (sdb_dcn_packed_input_bytes): forward fills it,
+                               backward reads it instead of re-packing x; NULL = in the workspace                */
+  const void* grad_out;     /* backward: [N, C_out, Ho, Wo]                                                       */
+  void* grad_x;             /* backward: [N, C_in, H, W], overwritten; NULL = not wanted                         */
+  float* grad_offset;       /* backward: overwritten; NULL = not wanted                                           */
+  float* grad_mask;         /* backward: overwritten; NULL = not wanted                                           */
+} sdb_dcn_problem;
+typedef struct {
+  const void* weight;       /* [C_out, C_in, kH, kW]                                                              */
+  const void* bias;         /* [C_out] or NULL                                                                    */
+  const void* prepared;     /* operand images from sdb_dcn_prepare_weights, or NULL                               */
+  float* grad_weight;       /* backward: float32 [C_out, C_in, kH, kW], accumulated into; NULL = not wanted       */
+  float* grad_bias;         /* backward: float32 [C_out], accumulated into; NULL = not wanted                     */
+} sdb_dcn_weights;
+
+/* Bytes of / fill the operand images of one weight tensor (0 / no-op for SDB_MATH_FP32).  Call again whenever the
+ * weight values change (once per optimiser step); the images are read-only inputs of the calls below. */
+size_t sdb_dcn_prepared_weight_bytes(const sdb_dcn_geom* g, int io_dtype, int math);
+int sdb_dcn_prepare_weights(const void* weight, const void* bias, const sdb_dcn_geom* g, int io_dtype, int math,
+                            void* prepared, void* stream);
+/* Scratch bytes of a forward (backward == 0) or backward (backward != 0) call over this table (0 on error). */
+size_t sdb_dcn_multi_workspace_bytes(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
+                                     int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, int backward);
+/* Replaces the reference's loop of deform_conv_forward / modulated_deform_conv_forward calls over levels and branches. */
+int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
+                          int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* Replaces the loop of deform_conv_backward_input + deform_conv_backward_filter (or modulated_deform_conv_backward). */
+int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
+                           int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, float scale,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- label assignment (HBM/latency-bound; no tensor cores) ------------------------------------
  * Fuses pairwise_iou (d2/structures/boxes.py:316-348) with Matcher.__call__

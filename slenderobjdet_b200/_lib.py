@@ -21,7 +21,8 @@ SDB_BOX_LTRB, SDB_BOX_XYXY = 0, 1
 EXPORTED_SYMBOLS = [
     "sdb_last_error", "sdb_abi_version", "sdb_dcn_output_size", "sdb_dcn_supported",
     "sdb_dcn_workspace_bytes", "sdb_dcn_packed_input_bytes", "sdb_dcn_forward",
-    "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_assign_workspace_bytes",
+    "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
+    "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
     "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
 ]
@@ -33,6 +34,23 @@ class Geom(ctypes.Structure):
         "N", "C_in", "H", "W", "C_out", "kH", "kW", "sH", "sW", "pH", "pW", "dH", "dW", "groups",
         "deformable_groups")]
 
+
+class Problem(ctypes.Structure):
+    """sdb_dcn_problem: one row of a whole-head call (a FPN level of one convolution)"""
+    _fields_ = [("N", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("weight_id", ctypes.c_int32),
+                ("offset_group", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("x", ctypes.c_void_p), ("offset", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("x_packed", ctypes.c_void_p), ("grad_out", ctypes.c_void_p), ("grad_x", ctypes.c_void_p),
+                ("grad_offset", ctypes.c_void_p), ("grad_mask", ctypes.c_void_p)]
+
+
+class Weights(ctypes.Structure):
+    """sdb_dcn_weights: one weight tensor of a whole-head call"""
+    _fields_ = [("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("prepared", ctypes.c_void_p),
+                ("grad_weight", ctypes.c_void_p), ("grad_bias", ctypes.c_void_p)]
+
+
+SDB_MAX_PROBLEMS, SDB_MAX_WEIGHTS = 16, 4
 
 _lib = None
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -54,6 +72,14 @@ def _declare(lib):
                                           ctypes.c_int, _vp, _sz, _vp, _vp]
     lib.sdb_dcn_backward_weight.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _gp, ctypes.c_int,
                                             ctypes.c_int, _vp, _sz, _vp, _vp]
+    pp, wp = ctypes.POINTER(Problem), ctypes.POINTER(Weights)
+    lib.sdb_dcn_prepared_weight_bytes.restype = _sz
+    lib.sdb_dcn_prepared_weight_bytes.argtypes = [_gp, ctypes.c_int, ctypes.c_int]
+    lib.sdb_dcn_prepare_weights.argtypes = [_vp, _vp, _gp, ctypes.c_int, ctypes.c_int, _vp, _vp]
+    lib.sdb_dcn_multi_workspace_bytes.restype = _sz
+    lib.sdb_dcn_multi_workspace_bytes.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sdb_dcn_forward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _vp, _sz, _vp]
+    lib.sdb_dcn_backward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _f32, _vp, _sz, _vp]
     lib.sdb_assign_workspace_bytes.restype = _sz
     lib.sdb_assign_workspace_bytes.argtypes = [_i32, _i32, _i32]
     lib.sdb_iou_assign.argtypes = [_vp, _vp, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int8),
@@ -105,6 +131,11 @@ def check(rc):
 def ptr(t):
     """device pointer of a tensor (None -> NULL)"""
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def addr(t):
+    """device address of a tensor as an int for a ctypes struct field (None -> NULL)"""
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr(device=None):

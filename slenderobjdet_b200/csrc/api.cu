@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "dcn_tc_shared.cuh"
 
 namespace sdb {
 
@@ -167,9 +168,236 @@ int sdb_dcn_supported(const sdb_dcn_geom* g, int io_dtype, int math) {
   return 1;
 }
 
+}  // extern "C"
+
+// ---- multi-problem plumbing ---------------------------------------------------------------------------------------
+namespace {
+struct MultiCall {
+  TcProblem pb[tcshared::MAX_PROBS];
+  bool have_prep[tcshared::MAX_WEIGHTS];
+  float* gw[tcshared::MAX_WEIGHTS];
+  float* gb[tcshared::MAX_WEIGHTS];
+  TcPlan plan;
+};
+
+// validate the tables and translate them (workspace pointers are resolved later, by resolve())
+int build_call(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, int nw, const Geo& g, bool backward,
+               MultiCall& mc) {
+  SDB_REQUIRE(probs && n >= 1 && n <= tcshared::MAX_PROBS, SDB_ERR_INVALID, "need 1..%d problems, got %d", tcshared::MAX_PROBS, n);
+  SDB_REQUIRE(w && nw >= 1 && nw <= tcshared::MAX_WEIGHTS, SDB_ERR_INVALID, "need 1..%d weight tensors, got %d", tcshared::MAX_WEIGHTS, nw);
+  for (int k = 0; k < nw; ++k) {
+    mc.have_prep[k] = w[k].prepared != nullptr;
+    mc.gw[k] = backward ? w[k].grad_weight : nullptr;
+    mc.gb[k] = backward ? w[k].grad_bias : nullptr;
+  }
+  for (int i = 0; i < n; ++i) {
+    const sdb_dcn_problem& q = probs[i];
+    SDB_REQUIRE(q.N >= 0 && q.H > 0 && q.W > 0, SDB_ERR_INVALID, "problem %d: bad size N=%d H=%d W=%d", i, q.N, q.H, q.W);
+    SDB_REQUIRE(q.weight_id >= 0 && q.weight_id < nw, SDB_ERR_INVALID, "problem %d: weight_id %d out of range", i, q.weight_id);
+    Geo gi = g;
+    gi.N = q.N; gi.H = q.H; gi.W = q.W;
+    gi.Ho = (q.H + 2 * g.ph - (g.dh * (g.KH - 1) + 1)) / g.sh + 1;
+    gi.Wo = (q.W + 2 * g.pw - (g.dw * (g.KW - 1) + 1)) / g.sw + 1;
+    SDB_REQUIRE(gi.Ho > 0 && gi.Wo > 0, SDB_ERR_INVALID, "problem %d: output size (%d x %d) is too small", i, gi.Ho, gi.Wo);
+    const char* why = "";
+    SDB_REQUIRE(tc_supported(gi, &why), SDB_ERR_UNSUPPORTED, "problem %d: tensor-core path unsupported: %s", i, why);
+    TcProblem& t = mc.pb[i];
+    t = TcProblem{};
+    t.d = Dims{q.N, q.H, q.W, gi.Ho, gi.Wo};
+    t.weight_id = q.weight_id; t.group = q.offset_group;
+    t.x = q.x; t.off = q.offset; t.mask = q.mask; t.out = q.out; t.xp = q.x_packed;
+    t.gy = q.grad_out; t.gx = backward ? q.grad_x : nullptr; t.goff = backward ? q.grad_offset : nullptr;
+    t.gmask = backward ? q.grad_mask : nullptr;
+    if (q.offset_group >= 0)
+      for (int j = 0; j < i; ++j)
+        if (probs[j].offset_group == q.offset_group)
+          SDB_REQUIRE(probs[j].N == q.N && probs[j].H == q.H && probs[j].W == q.W && probs[j].offset == q.offset &&
+                          probs[j].mask == q.mask,
+                      SDB_ERR_INVALID, "problems %d and %d share offset_group %d but not their offset / mask / size", j, i,
+                      q.offset_group);
+  }
+  mc.plan = tc_plan(mc.pb, n, nw, mc.have_prep, g, backward);
+  return SDB_OK;
+}
+
+// point every problem at its workspace slices and weight images; prepare the images the call still needs
+int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g, int io_dtype, bool backward, uint8_t* base,
+            bool* packed_from_caller, cudaStream_t st) {
+  TcWeightImages img[tcshared::MAX_WEIGHTS];
+  for (int k = 0; k < nw; ++k) {
+    const void* prep = w[k].prepared;
+    if (!prep) {
+      int which = 0;   // only the images this call reads
+      if (!backward) which = 1;
+      else {
+        for (int i = 0; i < n; ++i)
+          if (mc.pb[i].weight_id == k) which |= ((mc.pb[i].goff || mc.pb[i].gmask) ? 2 : 0) | (mc.pb[i].gx ? 4 : 0);
+      }
+      int rc = tc_prepare_weights(w[k].weight, w[k].bias, g, io_dtype, base + mc.plan.prep_off[k], which, st);
+      if (rc) return rc;
+      prep = base + mc.plan.prep_off[k];
+    }
+    img[k] = tc_weight_images(g, prep, w[k].bias != nullptr);
+  }
+  *packed_from_caller = true;
+  for (int i = 0; i < n; ++i) {
+    TcProblem& t = mc.pb[i];
+    t.w = img[t.weight_id];
+    if (!t.xp) { t.xp = base + mc.plan.xp_off[i]; *packed_from_caller = false; }
+    if (backward) {
+      t.gy_img = base + mc.plan.gy_off[i];
+      t.gyn = base + mc.plan.gyn_off[i];
+    }
+  }
+  return SDB_OK;
+}
+
+int multi_fp32(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, const Geo& g, bool backward, float scale,
+               cudaStream_t st) {
+  for (int i = 0; i < n; ++i) {
+    const sdb_dcn_problem& q = probs[i];
+    const sdb_dcn_weights& ww = w[q.weight_id];
+    Geo gi = g;
+    gi.N = q.N; gi.H = q.H; gi.W = q.W;
+    gi.Ho = (q.H + 2 * g.ph - (g.dh * (g.KH - 1) + 1)) / g.sh + 1;
+    gi.Wo = (q.W + 2 * g.pw - (g.dw * (g.KW - 1) + 1)) / g.sw + 1;
+    SDB_REQUIRE(gi.Ho > 0 && gi.Wo > 0, SDB_ERR_INVALID, "problem %d: output size is too small", i);
+    if (gi.N == 0) continue;
+    int rc = SDB_OK;
+    if (!backward) {
+      rc = simt_forward((const float*)q.x, q.offset, q.mask, (const float*)ww.weight, (const float*)ww.bias, (float*)q.out, gi, st);
+    } else {
+      if (q.grad_x) SDB_CHECK_CUDA(cudaMemsetAsync(q.grad_x, 0, (size_t)gi.N * gi.C * gi.H * gi.W * 4, st));   // overwritten
+      if (q.grad_x || q.grad_offset || q.grad_mask)
+        rc = simt_backward_data((const float*)q.x, q.offset, q.mask, (const float*)ww.weight, (const float*)q.grad_out,
+                                (float*)q.grad_x, q.grad_offset, q.mask ? q.grad_mask : nullptr, gi, st);
+      if (!rc && (ww.grad_weight || ww.grad_bias))
+        rc = simt_backward_weight((const float*)q.x, q.offset, q.mask, (const float*)q.grad_out, ww.grad_weight,
+                                  ww.grad_bias, scale, gi, st);
+    }
+    if (rc) return rc;
+  }
+  return SDB_OK;
+}
+
+// the single-problem entry points are one-row tables
+struct Single {
+  sdb_dcn_problem p;
+  sdb_dcn_weights w;
+};
+Single single_of(const sdb_dcn_geom* g) {
+  Single s{};
+  s.p.N = g->N; s.p.H = g->H; s.p.W = g->W; s.p.weight_id = 0; s.p.offset_group = -1;
+  return s;
+}
+// the common geometry of a table call: N / H / W of `g` are ignored (every problem brings its own)
+sdb_dcn_geom common_geom(const sdb_dcn_geom* g) {
+  sdb_dcn_geom c = *g;
+  c.N = 1; c.H = 4096; c.W = 4096;
+  return c;
+}
+}  // namespace
+
+extern "C" {
+
+#define SDB_MULTI_PROLOGUE()                                                                       \
+  SDB_REQUIRE(g != nullptr, SDB_ERR_INVALID, "geometry pointer is NULL");                          \
+  const sdb_dcn_geom cg = common_geom(g);                                                          \
+  int rc = check_geom(&cg);                                                                        \
+  if (rc) return rc;                                                                               \
+  rc = check_io(io_dtype, math);                                                                   \
+  if (rc) return rc;                                                                               \
+  rc = require_device();                                                                           \
+  if (rc) return rc;                                                                               \
+  const Geo d = make_geo(cg);                                                                      \
+  cudaStream_t st = (cudaStream_t)stream;
+
+size_t sdb_dcn_prepared_weight_bytes(const sdb_dcn_geom* g, int io_dtype, int math) {
+  if (!g) return 0;
+  const sdb_dcn_geom cg = common_geom(g);
+  if (check_geom(&cg) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
+  return tc_prepared_weight_bytes(make_geo(cg));
+}
+
+int sdb_dcn_prepare_weights(const void* weight, const void* bias, const sdb_dcn_geom* g, int io_dtype, int math,
+                            void* prepared, void* stream) {
+  SDB_MULTI_PROLOGUE();
+  if (math == SDB_MATH_FP32) return SDB_OK;
+  SDB_REQUIRE(weight && prepared, SDB_ERR_INVALID, "weight and prepared must be non-NULL");
+  const char* why = "";
+  SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
+  return tc_prepare_weights(weight, bias, d, io_dtype, prepared, 7, st);
+}
+
+size_t sdb_dcn_multi_workspace_bytes(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights,
+                                     int32_t nw, const sdb_dcn_geom* g, int io_dtype, int math, int backward) {
+  if (!g) return 0;
+  const sdb_dcn_geom cg = common_geom(g);
+  if (check_geom(&cg) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
+  MultiCall mc;
+  if (build_call(problems, n, weights, nw, make_geo(cg), backward != 0, mc)) return 0;
+  return mc.plan.total;
+}
+
+int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
+                          const sdb_dcn_geom* g, int io_dtype, int math, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  SDB_MULTI_PROLOGUE();
+  SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
+  for (int i = 0; i < n; ++i)
+    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].out), SDB_ERR_INVALID,
+                "problem %d: x, offset and out must be non-NULL", i);
+  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, false, 1.f, st);
+  MultiCall mc;
+  rc = build_call(problems, n, weights, nw, d, false, mc);
+  if (rc) return rc;
+  SDB_REQUIRE(mc.plan.total == 0 || (workspace && workspace_bytes >= mc.plan.total), SDB_ERR_WORKSPACE,
+              "forward workspace too small: %zu < %zu", workspace_bytes, mc.plan.total);
+  bool from_caller;
+  rc = resolve(mc, n, weights, nw, d, io_dtype, false, (uint8_t*)workspace, &from_caller, st);
+  if (rc) return rc;
+  return tc_forward_all(mc.pb, n, d, io_dtype, st);
+}
+
+static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
+                               const Geo& d, int io_dtype, float scale, int accumulate_gx, void* workspace,
+                               size_t workspace_bytes, cudaStream_t st) {
+  MultiCall mc;
+  int rc = build_call(problems, n, weights, nw, d, true, mc);
+  if (rc) return rc;
+  SDB_REQUIRE(workspace && workspace_bytes >= mc.plan.total, SDB_ERR_WORKSPACE, "backward workspace too small: %zu < %zu",
+              workspace_bytes, mc.plan.total);
+  bool from_caller;
+  rc = resolve(mc, n, weights, nw, d, io_dtype, true, (uint8_t*)workspace, &from_caller, st);
+  if (rc) return rc;
+  // x_packed given for SOME problems only: the pack launch covers the ones that live in the workspace
+  bool pack_any = false;
+  for (int i = 0; i < n; ++i) {
+    const bool own = problems[i].x_packed == nullptr;
+    pack_any |= own;
+    if (!own) mc.pb[i].x = nullptr;   // pack_nhwc_multi skips NULL sources
+  }
+  return tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
+                         (uint8_t*)workspace, st);
+}
+
+int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
+                           const sdb_dcn_geom* g, int io_dtype, int math, float scale, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  SDB_MULTI_PROLOGUE();
+  SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
+  for (int i = 0; i < n; ++i)
+    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].grad_out), SDB_ERR_INVALID,
+                "problem %d: x, offset and grad_out must be non-NULL", i);
+  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, true, scale, st);
+  return backward_multi_impl(problems, n, weights, nw, d, io_dtype, scale, 0, workspace, workspace_bytes, st);
+}
+
+// ---- single-problem entry points (the reference's call granularity) --------------------------------------------
 size_t sdb_dcn_workspace_bytes(int op, const sdb_dcn_geom* g, int io_dtype, int math) {
   if (check_geom(g) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
-  return tc_workspace_bytes(op, make_geo(*g), io_dtype);
+  Single s = single_of(g);
+  return sdb_dcn_multi_workspace_bytes(&s.p, 1, &s.w, 1, g, io_dtype, math, op != SDB_OP_FORWARD);
 }
 
 size_t sdb_dcn_packed_input_bytes(const sdb_dcn_geom* g, int math) {
@@ -196,10 +424,10 @@ int sdb_dcn_forward(const void* x, const float* offset, const float* mask, const
   if (math == SDB_MATH_FP32)
     return simt_forward((const float*)x, offset, mask, (const float*)weight, (const float*)bias,
                         (float*)out, d, st);
-  const char* why = "";
-  SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
-  return tc_forward(x, offset, mask, weight, bias, out, d, io_dtype, workspace, workspace_bytes,
-                    x_packed_out, st);
+  Single s = single_of(g);
+  s.p.x = x; s.p.offset = offset; s.p.mask = mask; s.p.out = out; s.p.x_packed = x_packed_out;
+  s.w.weight = weight; s.w.bias = bias;
+  return sdb_dcn_forward_multi(&s.p, 1, &s.w, 1, g, io_dtype, math, workspace, workspace_bytes, stream);
 }
 
 int sdb_dcn_backward_data(const void* x, const float* offset, const float* mask, const void* weight,
@@ -212,10 +440,12 @@ int sdb_dcn_backward_data(const void* x, const float* offset, const float* mask,
   if (math == SDB_MATH_FP32)
     return simt_backward_data((const float*)x, offset, mask, (const float*)weight,
                               (const float*)grad_out, (float*)grad_x, grad_offset, grad_mask, d, st);
-  const char* why = "";
-  SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
-  return tc_backward_data(x, offset, mask, weight, grad_out, grad_x, grad_offset, grad_mask, d,
-                          io_dtype, workspace, workspace_bytes, x_packed, st);
+  Single s = single_of(g);
+  s.p.x = x; s.p.offset = offset; s.p.mask = mask; s.p.x_packed = (void*)x_packed; s.p.grad_out = grad_out;
+  s.p.grad_x = grad_x; s.p.grad_offset = grad_offset; s.p.grad_mask = grad_mask;
+  s.w.weight = weight;
+  // this entry point ACCUMULATES into grad_x (the reference's contract, deform_conv.py:89)
+  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, 1.f, 1, workspace, workspace_bytes, st);
 }
 
 int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mask,
@@ -227,10 +457,10 @@ int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mas
   if (math == SDB_MATH_FP32)
     return simt_backward_weight((const float*)x, offset, mask, (const float*)grad_out, grad_weight,
                                 grad_bias, scale, d, st);
-  const char* why = "";
-  SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
-  return tc_backward_weight(x, offset, mask, grad_out, grad_weight, grad_bias, scale, d, io_dtype,
-                            workspace, workspace_bytes, x_packed, st);
+  Single s = single_of(g);
+  s.p.x = x; s.p.offset = offset; s.p.mask = mask; s.p.x_packed = (void*)x_packed; s.p.grad_out = grad_out;
+  s.w.grad_weight = grad_weight; s.w.grad_bias = grad_bias;   // no operand image of the weights is read here
+  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, scale, 0, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

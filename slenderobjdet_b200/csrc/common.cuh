@@ -47,10 +47,6 @@ struct Geo {
 inline Geo make_geo(const sdb_dcn_geom& g) {
   Geo d{g.N, g.C_in, g.H, g.W, g.C_out, g.kH, g.kW, g.sH, g.sW, g.pH, g.pW, g.dH, g.dW,
         g.groups, g.deformable_groups, 0, 0, 8, 16};
-  if (const char* e = getenv("SDB_TC_TILE")) {   // "4x32", "8x16", "2x64": pixel walk patch of the tensor-core path
-    int a = 0, b = 0;
-    if (sscanf(e, "%dx%d", &a, &b) == 2 && a > 0 && b > 0 && a * b == 128) { d.th = a; d.tw = b; }
-  }
   d.Ho = (g.H + 2 * g.pH - (g.dH * (g.kH - 1) + 1)) / (g.sH > 0 ? g.sH : 1) + 1;
   d.Wo = (g.W + 2 * g.pW - (g.dW * (g.kW - 1) + 1)) / (g.sW > 0 ? g.sW : 1) + 1;
   return d;
@@ -85,18 +81,8 @@ int simt_backward_data(const float* x, const float* off, const float* mask, cons
 int simt_backward_weight(const float* x, const float* off, const float* mask, const float* gy,
                          float* gw, float* gb, float scale, const Geo& g, cudaStream_t st);
 
-// tcgen05 bf16 path (dcn_tc_*.cu)
+// tcgen05 bf16 path (dcn_tc.cu, dcn_tc_bwd.cu; multi-problem launchers declared in dcn_tc_shared.cuh)
 bool tc_supported(const Geo& g, const char** why);
-size_t tc_workspace_bytes(int op, const Geo& g, int io_dtype);
 size_t tc_packed_input_bytes(const Geo& g);
-int tc_forward(const void* x, const float* off, const float* mask, const void* w, const void* bias,
-               void* out, const Geo& g, int io_dtype, void* ws, size_t ws_bytes, void* x_packed_out,
-               cudaStream_t st);
-int tc_backward_data(const void* x, const float* off, const float* mask, const void* w,
-                     const void* gy, void* gx, float* goff, float* gmask, const Geo& g,
-                     int io_dtype, void* ws, size_t ws_bytes, const void* x_packed, cudaStream_t st);
-int tc_backward_weight(const void* x, const float* off, const float* mask, const void* gy,
-                       float* gw, float* gb, float scale, const Geo& g, int io_dtype, void* ws,
-                       size_t ws_bytes, const void* x_packed, cudaStream_t st);
 
 }  // namespace sdb

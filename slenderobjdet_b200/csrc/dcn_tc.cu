@@ -11,7 +11,9 @@
 //     double-buffered so the epilogue of tile i overlaps the main loop of tile i+1;
 //   * 4 epilogue warps drain TMEM with tcgen05.ld, add the bias and store NCHW (coalesced along
 //     the pixel dimension, which is the TMEM lane dimension).
-// The grid is persistent: one CTA per SM walking tiles round-robin.
+// The grid is persistent: one CTA per SM walking tiles round-robin, and ONE launch covers every problem
+// of a call (FPN levels x convolutions; problem table = kernel parameter, dcn_tc_shared.cuh): the small
+// pyramid levels are a handful of tiles each and would otherwise be separate launches of 2..66 CTAs.
 //
 // The same kernel, MODE_DX, computes grad_input as a second implicit GEMM instead of a scatter:
 //   dX[q, c] = sum_{tap, o} G[q, (tap,o)] * W[o, c, tap],   G[q, (tap,o)] = sum_e w_e * dY[p_e, o]
@@ -39,34 +41,73 @@ constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 constexpr size_t DX_STATIC_SMEM = 8192 + 1024 + 1024;   // MODE_DX: s_od, s_range, barriers
 
-// W [O][C][taps] -> per (channel chunk of `cps`, tap, 64-channel block) a K-major 128B-swizzled tile
-// [O rows][64 c] bf16, tiles ordered (chunk, tap, block-in-chunk) = the K order of the main loop;
-// also bias -> fp32.
+// Weight images.  W [O][C][taps] is re-laid-out ONCE per weight version (sdb_dcn_prepare_weights) into the three
+// operand images the kernels stream with cp.async.bulk, every tile already in the 128B-swizzled K-major layout
+// tcgen05.mma reads:
+//   image 0 (forward B operand)   per (channel chunk of `cps`, tap, 64-channel block): [O rows][64 c]
+//   image 1 (dcol = dY W^T)       per (tap, channel chunk of `nch`, 64-o block):       [nch rows (c)][64 o], o >= O zero
+//   image 2 (grad_input B operand) per column block nb: (o-chunk of 128, tap, 64-o block in chunk): [ncols rows (c)][64 o]
+// blockIdx.y selects the image; bias -> fp32 behind them.
+struct PrepLayout {
+  size_t fwd_off, dgrad_off, dx_off, bias_off, total;
+  int cps, nch, okb, ncols;
+  int which;   // images to write: 1 = forward, 2 = dcol (grad_offset), 4 = grad_input
+};
 template <typename T>
-__global__ void __launch_bounds__(256) prep_weight_fwd_kernel(const T* __restrict__ w, const T* __restrict__ bias,
-                                                              uint8_t* __restrict__ wimg,
-                                                              float* __restrict__ bias_f32, int O, int C, int taps, int cps) {
-  const int kbps = cps / 64;
-  const long long total = (long long)O * taps * (C / 8);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % (C / 8));
-    const int tap = (int)((i / (C / 8)) % taps);
-    const int o = (int)(i / ((long long)(C / 8) * taps));
-    const int c = c8 * 8;
+__global__ void __launch_bounds__(256) prep_weights_kernel(const T* __restrict__ w, const T* __restrict__ bias,
+                                                           uint8_t* __restrict__ img, const PrepLayout L, int O, int C,
+                                                           int taps) {
+  // blockIdx.y walks the requested images: bit i of L.which = image i
+  int which = 0;
+  for (int k = blockIdx.y; ; ++which)
+    if ((L.which >> which) & 1) { if (k == 0) break; --k; }
+  if (which == 0) {
+    const int kbps = L.cps / 64;
+    const long long total = (long long)O * taps * (C / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c8 = (int)(i % (C / 8));
+      const int tap = (int)((i / (C / 8)) % taps);
+      const int o = (int)(i / ((long long)(C / 8) * taps));
+      const int c = c8 * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = to_f32(w[((size_t)o * C + c + j) * taps + tap]);
+      uint4 pk;
+      pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+      pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+      const size_t tile = ((size_t)(c / L.cps) * taps + tap) * kbps + ((c % L.cps) >> 6);
+      *reinterpret_cast<uint4*>(img + L.fwd_off + tile * ((size_t)O * 128) + sw128_offset(o, (c & 63) >> 3)) = pk;
+    }
+    if (blockIdx.x == 0)
+      for (int o = threadIdx.x; o < O; o += blockDim.x)
+        reinterpret_cast<float*>(img + L.bias_off)[o] = bias ? to_f32(bias[o]) : 0.f;
+    return;
+  }
+  const int o8n = L.okb * 8;   // 8-wide o chunks incl. zero padding
+  const long long total = (long long)taps * C * o8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % o8n);
+    const int c = (int)((i / o8n) % C);
+    const int tap = (int)(i / ((long long)o8n * C));
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = to_f32(w[((size_t)o * C + c + j) * taps + tap]);
+    for (int j = 0; j < 8; ++j) {
+      const int o = o8 * 8 + j;
+      v[j] = o < O ? to_f32(w[((size_t)o * C + c) * taps + tap]) : 0.f;
+    }
     uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]);
-    pk.y = pack_bf16x2(v[2], v[3]);
-    pk.z = pack_bf16x2(v[4], v[5]);
-    pk.w = pack_bf16x2(v[6], v[7]);
-    const size_t tile = ((size_t)(c / cps) * taps + tap) * kbps + ((c % cps) >> 6);
-    *reinterpret_cast<uint4*>(wimg + tile * ((size_t)O * 128) + sw128_offset(o, (c & 63) >> 3)) = pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    if (which == 1) {
+      const size_t tile = ((size_t)tap * (C / L.nch) + c / L.nch) * L.okb + (o8 >> 3);
+      *reinterpret_cast<uint4*>(img + L.dgrad_off + tile * ((size_t)L.nch * 128) + sw128_offset(c % L.nch, o8 & 7)) = pk;
+    } else {
+      const int kb = o8 >> 3;                       // 64-o block
+      const int nb = c / L.ncols, cr = c % L.ncols;
+      const size_t tile = (size_t)nb * taps * L.okb + ((size_t)(kb >> 1) * taps + tap) * 2 + (kb & 1);
+      *reinterpret_cast<uint4*>(img + L.dx_off + tile * ((size_t)L.ncols * 128) + sw128_offset(cr, o8 & 7)) = pk;
+    }
   }
-  if (bias_f32 && blockIdx.x == 0)
-    for (int o = threadIdx.x; o < O; o += blockDim.x) bias_f32[o] = bias ? to_f32(bias[o]) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,32 +161,37 @@ __device__ __forceinline__ Sample make_sample(const Geo& g, const RawOff raw, bo
   return s;
 }
 
-struct FwdParams {
-  const __nv_bfloat16* xp;  // MODE_FWD: NHWC bf16 input
+// one problem of a launch (a FPN level of one convolution)
+struct FwdProb {
+  const __nv_bfloat16* xp;  // MODE_FWD: NHWC bf16 input; MODE_DX: NHWC bf16 dY [P][okb*64]
   const float* off;
   const float* mask;
   const GDesc* desc;        // MODE_DX: first four entries of every transposed list, key = (tile*taps + tap)*128 + row
-  const int* start;         // MODE_DX: first overflow descriptor of every key, nkeys + 1 values
+  const int* start;         // MODE_DX: first overflow descriptor of every key (nkeys + 1 values)
   const ODesc* odesc;       // MODE_DX: overflow descriptors (entries 5.. of a list, four per descriptor)
-  const uint8_t* wimg;
+  const uint8_t* wimg;      // weight image of this problem's convolution
   const float* bias;        // fp32 [ncols] or nullptr
   void* out;                // NCHW, f32 or bf16: [mN][out_ch][mH][mW]
-  Geo g;
+  Dims d;                   // N, H, W, Ho, Wo of this problem
   int mH, mW;               // pixel grid of the GEMM's M dimension (output grid fwd, input grid dx)
   long long mP;             // mN * mH * mW
+};
+struct FwdParams {
+  TileMap map;              // work item -> problem; a problem owns num_tiles * nnb consecutive work items
+  FwdProb pr[MAX_PROBS];
+  Geo g;                    // common geometry (N, H, W, Ho, Wo come from the problem)
   int ncols, nnb;           // GEMM N per column block, number of column blocks (dx with C_in > 256)
   int kch;                  // gathered channels per tap (C_in fwd, okb*64 dx)
   int out_ch;               // channel count of `out`
-  int okb;
-  int num_tiles, nsa, nsb;
-  int dbg;                  // SDB_TC_DEBUG: 1 = no weight streaming + no MMA issue, 2 = no gather loads (timing experiments)
+  int nsa, nsb;
+  int accumulate;           // MODE_DX: add to `out` (the single-call ABI accumulates into grad_x) instead of overwriting
 };
 
 constexpr int MODE_FWD = 0, MODE_DX = 1;
 
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
 template <int LPP, bool OUT_BF16, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   constexpr int CPS = LPP * 8;           // channels per A stage
   constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
   constexpr int A_BYTES = TILE_M * CPS * 2;
@@ -159,9 +205,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const Geo& g = p.g;
-  const int O = p.ncols, C = p.kch, taps = g.KH * g.KW, nchunks = C / CPS;
-  const int num_work = p.num_tiles * p.nnb;
+  const int O = p.ncols, C = p.kch, taps = p.g.KH * p.g.KW, nchunks = C / CPS;
+  const int num_work = p.map.start[p.map.n];
   const uint32_t B_BYTES = (uint32_t)O * 128u;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -199,16 +244,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     // ===== weight producer: bulk async copies of pre-swizzled [O x 64] tiles =====
     if (lane == 0) {
       uint32_t bs = 0, bp = 0;
+      const int nkb_total = taps * (C / 64);
       for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int nkb_total = taps * (C / 64);
-        const uint8_t* wsrc = p.wimg + (size_t)(work % p.nnb) * nkb_total * B_BYTES;
+        const int pi = find_range(p.map, work);
+        const int nb = (work - p.map.start[pi]) % p.nnb;
+        const uint8_t* wsrc = p.pr[pi].wimg + (size_t)nb * nkb_total * B_BYTES;
         for (int kb = 0; kb < nkb_total; ++kb) {
           mbar_wait(&b_empty[bs], bp ^ 1);
-          if (p.dbg & 1) { mbar_arrive(&b_full[bs]); }
-          else {
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
           bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
-          }
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
@@ -230,13 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           if (elect_one()) {
             const uint32_t a_addr = smem_base + as * A_BYTES + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + p.nsa * A_BYTES + bs * B_BYTES;
-            if (!(p.dbg & 1)) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
                         make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
               accumulate = 1;
-            }
             }
             umma_commit(&b_empty[bs]);
           }
@@ -254,33 +296,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   } else if (warp < FIRST_PW) {
     // ===== epilogue: TMEM -> registers -> NCHW global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int hw = p.mH * p.mW;
     uint32_t acc = 0, accp = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int tile = work / p.nnb, ob = (work % p.nnb) * O;
+      const int pi = find_range(p.map, work);
+      const FwdProb& pr = p.pr[pi];
+      const int local = work - p.map.start[pi];
+      const int tile = local / p.nnb, ob = (local % p.nnb) * O;
+      const int hw = pr.mH * pr.mW;
       mbar_wait(&acc_full[acc], accp);
       tc_fence_after_sync();
       const long long pix = (long long)tile * TILE_M + q * 32 + lane;
-      const bool valid = pix < p.mP;
+      const bool valid = pix < pr.mP;
       int n = 0, eho = 0, ewo = 0;
-      if (valid) decode_pos(p.mH, p.mW, g.th, g.tw, pix, n, eho, ewo);
-      const int rem = eho * p.mW + ewo;
+      if (valid) decode_pos(pr.mH, pr.mW, p.g.th, p.g.tw, pix, n, eho, ewo);
+      const int rem = eho * pr.mW + ewo;
+      const float* bias = pr.bias;
       for (int c0 = 0; c0 < O; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
         tmem_ld_wait();
-        if (valid && !(p.dbg & 4)) {
+        if (valid) {
           const size_t d0 = ((size_t)n * p.out_ch + ob + c0) * hw + rem;
-          if (MODE == MODE_DX) {
-            // grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it): fetch the 32 old values
-            // first (independent loads in flight together), then add and store
+          if (MODE == MODE_DX && p.accumulate) {
+            // single-call ABI: grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it): fetch the 32 old
+            // values first (independent loads in flight together), then add and store
             float old[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               old[j] = 0.f;
               if (c0 + j < O) {
-                if (OUT_BF16) old[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out)[d0 + (size_t)j * hw]);
-                else          old[j] = reinterpret_cast<const float*>(p.out)[d0 + (size_t)j * hw];
+                if (OUT_BF16) old[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.out)[d0 + (size_t)j * hw]);
+                else          old[j] = reinterpret_cast<const float*>(pr.out)[d0 + (size_t)j * hw];
               }
             }
 #pragma unroll
@@ -291,10 +337,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
             const int o = c0 + j;
             if (o < O) {
               float v = __uint_as_float(r[j]);
-              if (MODE == MODE_FWD && p.bias) v += __ldg(p.bias + o);
+              if (MODE == MODE_FWD && bias) v += __ldg(bias + o);
               const size_t di = d0 + (size_t)j * hw;
-              if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[di] = __float2bfloat16_rn(v);
-              else          reinterpret_cast<float*>(p.out)[di] = v;
+              if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(pr.out)[di] = __float2bfloat16_rn(v);
+              else          reinterpret_cast<float*>(pr.out)[di] = v;
             }
           }
         }
@@ -325,15 +371,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
     GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
-    const uint4* xbase = reinterpret_cast<const uint4*>(p.xp) + lig;
     const int nstages = taps * nchunks;
     uint32_t as = 0, ap = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int tile = work / p.nnb;
+      const int pi = find_range(p.map, work);
+      const FwdProb& pr = p.pr[pi];
+      const int tile = (work - p.map.start[pi]) / p.nnb;
+      const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
       if constexpr (MODE == MODE_FWD) {
+        const Geo g = with_dims(p.g, pr.d);
         const int px = lane % PIX_PER_WARP;
         const long long pix = (long long)tile * TILE_M + r0 + px;
-        const bool valid = pix < g.P();
+        const bool valid = pix < pr.mP;
         int n = 0, ho = 0, wo = 0;
         if (valid) decode_q(g, pix, n, ho, wo);
         __syncwarp();  // every lane is done reading the previous tile's descriptors
@@ -345,19 +394,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
           const int tap = lane / PIX_PER_WARP + r * TPR;
-          raw[r] = fetch_raw(g, p.off, p.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
+          raw[r] = fetch_raw(g, pr.off, pr.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
         }
         {
-          const long long npix = (long long)(work + gridDim.x) / p.nnb * TILE_M + r0 + px;
-          if (npix < g.P()) {
-            int nn, nho, nwo;
-            decode_q(g, npix, nn, nho, nwo);
-            const int hwo = g.Ho * g.Wo;
-            for (int tap = lane / PIX_PER_WARP; tap < taps; tap += TPR) {
-              const float* o = p.off + ((size_t)nn * 2 * taps + 2 * tap) * hwo + nho * g.Wo + nwo;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(o));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(o + hwo));
-              if (p.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + ((size_t)nn * taps + tap) * hwo + nho * g.Wo + nwo));
+          const int nwork = work + gridDim.x;
+          if (nwork < num_work) {
+            const int npi = find_range(p.map, nwork);
+            const FwdProb& npr = p.pr[npi];
+            const long long npix = (long long)((nwork - p.map.start[npi]) / p.nnb) * TILE_M + r0 + px;
+            if (npix < npr.mP) {
+              const Geo ng = with_dims(p.g, npr.d);
+              int nn, nho, nwo;
+              decode_q(ng, npix, nn, nho, nwo);
+              const int hwo = ng.Ho * ng.Wo;
+              for (int tap = lane / PIX_PER_WARP; tap < taps; tap += TPR) {
+                const float* o = npr.off + ((size_t)nn * 2 * taps + 2 * tap) * hwo + nho * ng.Wo + nwo;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o + hwo));
+                if (npr.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(npr.mask + ((size_t)nn * taps + tap) * hwo + nho * ng.Wo + nwo));
+              }
             }
           }
         }
@@ -382,13 +437,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         constexpr int U16 = PIX_PER_WARP * (int)sizeof(GDesc) / 16;   // 16-byte units per (warp, tap) slice
         for (int i = lane; i < taps * U16; i += 32) {
           const int tap = i / U16, u = i - tap * U16;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.desc + ((size_t)tile * taps + tap) * TILE_M + r0) + u * 16;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.desc + ((size_t)tile * taps + tap) * TILE_M + r0) + u * 16;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sD + tap * TILE_M + r0) + u * 16)),
                        "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (lane < taps) {   // this warp's slice of the overflow descriptor list, per tap: [begin, count]
-          const int* sp = p.start + ((size_t)tile * taps + lane) * TILE_M + r0;
+          const int* sp = pr.start + ((size_t)tile * taps + lane) * TILE_M + r0;
           const int b0 = __ldg(sp);
           s_range[pw][lane][0] = b0;
           s_range[pw][lane][1] = __ldg(sp + PIX_PER_WARP) - b0;
@@ -402,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
           const int ob = s_range[pw][tap_][0];
           int n16 = s_range[pw][tap_][1];
           n16 = (n16 < OD_CAP ? n16 : OD_CAP) * 2;   // 16-byte units
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.odesc + ob);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.odesc + ob);
           for (int i = lane; i < n16; i += 32)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(&s_od[pw][buf_][0]) + i * 16)),
                          "l"(src + i * 16) : "memory");
@@ -468,13 +523,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
         }
         mbar_wait(&a_empty[as], ap ^ 1);
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
-        if (p.dbg & 2) {   // timing experiment: publish the stage without gathering
-          fence_proxy_async_smem();
-          mbar_arrive_warp(&a_full[as]);
-          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
-          tap = ntap; ch = nch;
-          continue;
-        }
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
           const int slot = it % RING;
@@ -531,7 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
               ODesc od;
               od.o = make_uint4(0u, 0u, 0u, 0u);
               od.m = make_uint4(0u, 0u, 0u, 0u);
-              if (have) od = p.odesc[s_range[pw][tap][0] + d];
+              if (have) od = pr.odesc[s_range[pw][tap][0] + d];
               const int row = (int)od.m.z;
               const bool flush = acc_row >= 0 && (!have || row != acc_row);
               __syncwarp();
@@ -582,34 +630,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const FwdParams
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
-int lanes_per_pixel(const Geo& g) {
-  const char* e = getenv("SDB_TC_LPP");
-  if (e) {
-    const int v = atoi(e);
-    if ((v == 8 || v == 16 || v == 32) && g.C % (v * 8) == 0) return v;
-  }
-  if (g.C % 128 == 0) return 16;
-  return 8;
-}
-
-struct FwdWs {
-  size_t xp_off, wimg_off, bias_off, total;
-};
-FwdWs fwd_ws(const Geo& g) {
-  FwdWs w;
-  size_t o = 0;
-  w.xp_off = o;   o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 2, 1024);
-  w.wimg_off = o; o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
-  w.bias_off = o; o = align_up(o + (size_t)g.O * 4, 1024);
-  w.total = o;
-  return w;
-}
-
 template <int LPP, bool OUT_BF16, int MODE>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
   SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>), smem);
-  if (const char* e = getenv("SDB_TC_CARVEOUT"))   // timing experiment: percent of the unified L1/smem array given to shared memory
-    SDB_CHECK_CUDA(cudaFuncSetAttribute(dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
   ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : 3, st);   // slot 3 = grad_input GEMM
   dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
@@ -618,14 +641,8 @@ int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
 
 // stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit)
 size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
-  size_t budget = 200 * 1024;
-  if (const char* e = getenv("SDB_TC_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
-  if (budget > 222 * 1024) budget = 222 * 1024;
+  const size_t budget = 200 * 1024;
   p.nsa = 2;
-  if (const char* e = getenv("SDB_TC_NSA")) p.nsa = atoi(e);
-  if (p.nsa < 2) p.nsa = 2;
-  if (p.nsa > MAX_A_STAGES) p.nsa = MAX_A_STAGES;
-  while (p.nsa > 2 && p.nsa * a_bytes + 2 * b_bytes + d_bytes + 1024 > budget) --p.nsa;
   long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
   if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
   if (nsb < 2) return 0;
@@ -634,6 +651,14 @@ size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
 }
 
 }  // namespace
+
+int tc_lanes_per_pixel(const Geo& g) { return g.C % 128 == 0 ? 16 : 8; }
+// column blocking of the grad_input GEMM: N = C_in split into nnb equal blocks of <= 256 columns
+int tc_dx_col_blocks(const Geo& g) {
+  int nnb = (g.C + 255) / 256;
+  while (g.C % (nnb * 16) != 0) ++nnb;
+  return nnb;
+}
 
 bool tc_supported(const Geo& g, const char** why) {
   *why = "";
@@ -651,115 +676,103 @@ bool tc_supported(const Geo& g, const char** why) {
 
 size_t tc_packed_input_bytes(const Geo& g) { return align_up((size_t)g.N * g.H * g.W * g.C * 2, 1024); }
 
-size_t tc_workspace_bytes(int op, const Geo& g, int io_dtype) {
-  (void)io_dtype;
-  if (op == SDB_OP_FORWARD) return fwd_ws(g).total;
-  return tc_bwd_workspace_bytes(op, g);
+// ---- prepared weights -------------------------------------------------------------------------------------------
+static PrepLayout prep_layout(const Geo& g) {
+  PrepLayout L{};
+  L.cps = tc_lanes_per_pixel(g) * 8;
+  L.nch = g.C % 128 == 0 ? 128 : 64;
+  L.okb = 2 * ((g.O + 127) / 128);
+  L.ncols = g.C / tc_dx_col_blocks(g);
+  size_t o = 0;
+  L.fwd_off = o;   o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
+  L.dgrad_off = o; o = align_up(o + (size_t)g.taps() * g.C * L.okb * 64 * 2, 1024);
+  L.dx_off = o;    o = align_up(o + (size_t)g.taps() * g.C * L.okb * 64 * 2, 1024);
+  L.bias_off = o;  o = align_up(o + (size_t)g.O * 4, 1024);
+  L.total = o;
+  return L;
 }
-
-int tc_forward(const void* x, const float* off, const float* mask, const void* w, const void* bias,
-               void* out, const Geo& g, int io_dtype, void* ws, size_t ws_bytes, void* x_packed_out,
-               cudaStream_t st) {
-  const FwdWs L = fwd_ws(g);
-  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "forward workspace too small: %zu < %zu", ws_bytes, L.total);
-  uint8_t* base = (uint8_t*)ws;
-  __nv_bfloat16* xp = (__nv_bfloat16*)(x_packed_out ? x_packed_out : base + L.xp_off);
-  uint8_t* wimg = base + L.wimg_off;
-  float* bias32 = bias ? (float*)(base + L.bias_off) : nullptr;
-  int rc = io_dtype == SDB_F32 ? pack_input<float>(x, xp, g, st) : pack_input<__nv_bfloat16>(x, xp, g, st);
-  if (rc) return rc;
-  if (tc_win_supported(g)) return tc_forward_win(xp, off, mask, w, bias, wimg, bias32, out, g, io_dtype, st);
-  const long long wtotal = (long long)g.O * g.taps() * (g.C / 8);
-  const int wblocks = (int)((wtotal + 255) / 256 < 1184 ? (wtotal + 255) / 256 : 1184);
+size_t tc_prepared_weight_bytes(const Geo& g) { return prep_layout(g).total; }
+TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bias) {
+  const PrepLayout L = prep_layout(g);
+  const uint8_t* b = (const uint8_t*)prepared;
+  TcWeightImages w;
+  w.fwd = b + L.fwd_off; w.dgrad = b + L.dgrad_off; w.dx = b + L.dx_off;
+  w.bias = has_bias ? (const float*)(b + L.bias_off) : nullptr;
+  return w;
+}
+int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
+                       cudaStream_t st) {
+  PrepLayout L = prep_layout(g);
+  L.which = which & 7;
+  const int nimg = (which & 1) + ((which >> 1) & 1) + ((which >> 2) & 1);
+  if (nimg == 0) return SDB_OK;
+  const long long total = (long long)g.taps() * g.C * L.okb * 8;
+  const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+  dim3 grid(blocks, nimg);
   if (io_dtype == SDB_F32)
-    prep_weight_fwd_kernel<float><<<wblocks, 256, 0, st>>>((const float*)w, (const float*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8);
+    prep_weights_kernel<float><<<grid, 256, 0, st>>>((const float*)w, (const float*)bias, (uint8_t*)prepared, L, g.O, g.C, g.taps());
   else
-    prep_weight_fwd_kernel<__nv_bfloat16><<<wblocks, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, wimg, bias32, g.O, g.C, g.taps(), lanes_per_pixel(g) * 8);
+    prep_weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (uint8_t*)prepared, L, g.O, g.C, g.taps());
   SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
 
+// ---- forward, all problems in one launch -----------------------------------------------------------------------
+int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st) {
   FwdParams p{};
-  p.xp = xp; p.off = off; p.mask = mask; p.wimg = wimg; p.bias = bias32; p.out = out; p.g = g;
-  p.mH = g.Ho; p.mW = g.Wo; p.mP = g.P(); p.ncols = g.O; p.nnb = 1; p.kch = g.C; p.out_ch = g.O;
-  p.num_tiles = cdiv(g.P(), TILE_M);
-  if (const char* e = getenv("SDB_TC_DEBUG")) p.dbg = atoi(e);
-  const int lpp = lanes_per_pixel(g);
+  p.g = g;
+  p.ncols = g.O; p.nnb = 1; p.kch = g.C; p.out_ch = g.O; p.accumulate = 0;
+  p.map.n = n;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    const Geo gi = with_dims(g, pb[i].d);
+    FwdProb& q = p.pr[i];
+    q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.wimg = pb[i].w.fwd;
+    q.bias = pb[i].w.bias; q.out = pb[i].out; q.d = pb[i].d;
+    q.mH = gi.Ho; q.mW = gi.Wo; q.mP = gi.P();
+    p.map.start[i] = total;
+    total += cdiv(gi.P(), TILE_M);
+  }
+  p.map.start[n] = total;
+  if (total == 0) return SDB_OK;
+  const int lpp = tc_lanes_per_pixel(g);
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
   const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int grid = total < num_sms() ? total : num_sms();
   const bool obf = io_dtype == SDB_BF16;
-  if (lpp == 32) return obf ? launch_fwd<32, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<32, false, MODE_FWD>(p, smem, grid, st);
   if (lpp == 16) return obf ? launch_fwd<16, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<16, false, MODE_FWD>(p, smem, grid, st);
   return obf ? launch_fwd<8, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<8, false, MODE_FWD>(p, smem, grid, st);
 }
 
-// column blocking of the grad_input GEMM: N = C_in split into nnb equal blocks of <= 256 columns
-int dx_col_blocks(const Geo& g) {
-  int nnb = (g.C + 255) / 256;
-  while (g.C % (nnb * 16) != 0) ++nnb;
-  return nnb;
-}
-size_t tc_dx_weight_bytes(const Geo& g, int okb) { return align_up((size_t)g.taps() * g.C * okb * 64 * 2, 1024); }
-
-// W [O][C][taps] -> B operand of the grad_input GEMM: per column block nb, tiles ordered
-// (o-chunk of 128, tap, 64-o block in chunk), each [ncols rows (c)][64 o] bf16 K-major 128B-swizzled;
-// o >= O zero padded.
-template <typename T>
-__global__ void __launch_bounds__(256) prep_weight_dx_kernel(const T* __restrict__ w, uint8_t* __restrict__ img,
-                                                             int O, int C, int taps, int okb, int ncols) {
-  const int o8n = okb * 8;
-  const long long total = (long long)taps * C * o8n;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int o8 = (int)(i % o8n);
-    const int c = (int)((i / o8n) % C);
-    const int tap = (int)(i / ((long long)o8n * C));
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int o = o8 * 8 + j;
-      v[j] = o < O ? to_f32(w[((size_t)o * C + c) * taps + tap]) : 0.f;
-    }
-    uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]);
-    pk.y = pack_bf16x2(v[2], v[3]);
-    pk.z = pack_bf16x2(v[4], v[5]);
-    pk.w = pack_bf16x2(v[6], v[7]);
-    const int kb = o8 >> 3;                       // 64-o block
-    const int nb = c / ncols, cr = c % ncols;
-    const size_t tile = (size_t)nb * taps * okb + ((size_t)(kb >> 1) * taps + tap) * 2 + (kb & 1);
-    *reinterpret_cast<uint4*>(img + tile * ((size_t)ncols * 128) + sw128_offset(cr, o8 & 7)) = pk;
-  }
-}
-
-int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start, const void* entries,
-          uint8_t* wimg, void* gx, const Geo& g, int okb, int io_dtype, cudaStream_t st) {
-  const int nnb = dx_col_blocks(g), ncols = g.C / nnb;
-  {
-    const long long total = (long long)g.taps() * g.C * okb * 8;
-    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    if (io_dtype == SDB_F32)
-      prep_weight_dx_kernel<float><<<blocks, 256, 0, st>>>((const float*)w, wimg, g.O, g.C, g.taps(), okb, ncols);
-    else
-      prep_weight_dx_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wimg, g.O, g.C, g.taps(), okb, ncols);
-    SDB_LAUNCHED(1);
-    SDB_CHECK_CUDA(cudaGetLastError());
-  }
+// ---- grad_input, all problems in one launch ----------------------------------------------------------------------
+int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype, int accumulate, cudaStream_t st) {
+  const int nnb = tc_dx_col_blocks(g), ncols = g.C / nnb;
   FwdParams p{};
-  p.xp = (const __nv_bfloat16*)gy_nhwc; p.desc = (const GDesc*)desc; p.start = start;
-  p.odesc = (const ODesc*)entries; p.wimg = wimg; p.out = gx; p.g = g;
-  p.mH = g.H; p.mW = g.W; p.mP = (long long)g.N * g.H * g.W; p.ncols = ncols; p.nnb = nnb;
-  p.kch = okb * 64; p.out_ch = g.C; p.okb = okb;
-  p.num_tiles = cdiv(p.mP, TILE_M);
+  p.g = g;
+  p.ncols = ncols; p.nnb = nnb; p.kch = okb * 64; p.out_ch = g.C; p.accumulate = accumulate;
+  int total = 0, m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!pb[i].gx) continue;
+    FwdProb& q = p.pr[m];
+    q.xp = (const __nv_bfloat16*)pb[i].gyn; q.desc = (const GDesc*)pb[i].desc; q.start = pb[i].start;
+    q.odesc = (const ODesc*)pb[i].odesc; q.wimg = pb[i].w.dx; q.out = pb[i].gx; q.d = pb[i].d;
+    q.mH = pb[i].d.H; q.mW = pb[i].d.W; q.mP = (long long)pb[i].d.N * pb[i].d.H * pb[i].d.W;
+    p.map.start[m] = total;
+    total += cdiv(q.mP, TILE_M) * nnb;
+    ++m;
+  }
+  p.map.n = m;
+  p.map.start[m] = total;
+  if (total == 0) return SDB_OK;
   constexpr int lpp = 16;   // 128-channel stages: okb is even, so kch % 128 == 0
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)ncols * 128;
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);
   const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes + DX_STATIC_SMEM) - DX_STATIC_SMEM;  // static arrays come out of the same budget
   SDB_REQUIRE(smem > 0 && smem < (1u << 20), SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  const int work = p.num_tiles * nnb;
-  const int grid = work < num_sms() ? work : num_sms();
+  const int grid = total < num_sms() ? total : num_sms();
   return io_dtype == SDB_BF16 ? launch_fwd<lpp, true, MODE_DX>(p, smem, grid, st)
                               : launch_fwd<lpp, false, MODE_DX>(p, smem, grid, st);
 }

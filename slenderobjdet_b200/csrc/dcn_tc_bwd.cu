@@ -49,12 +49,21 @@ inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 // ------------------------------------------------------------------------------------------------
 // dY [N][O][HWo] (T) -> image of 128-pixel tiles: tile t, o-block kb -> [128 rows][64 o] bf16,
 // 128B-swizzled (K-major for dgrad's A operand, MN-major for wgrad's A operand).  Zero padded.
+// one entry per problem: grid.x walks the tiles of all entries (TileMap), grid.y the 64-o blocks
+struct PackGyTable {
+  TileMap map;
+  struct E { const void* gy; uint8_t* img; Dims d; } e[MAX_PROBS];
+  Geo g;
+};
 template <typename T>
-__global__ void __launch_bounds__(256) pack_gy_kernel(const T* __restrict__ gy, uint8_t* __restrict__ img,
-                                                      const Geo g, int okb) {
+__global__ void __launch_bounds__(256) pack_gy_kernel(const __grid_constant__ PackGyTable t, int okb) {
+  const int ei = find_range(t.map, blockIdx.x);
+  const Geo g = with_dims(t.g, t.e[ei].d);
+  const T* __restrict__ gy = (const T*)t.e[ei].gy;
+  uint8_t* __restrict__ img = t.e[ei].img;
   const int O = g.O, hw = g.Ho * g.Wo;
   __shared__ float s[64][129];
-  const int tile = blockIdx.x, kb = blockIdx.y;
+  const int tile = blockIdx.x - t.map.start[ei], kb = blockIdx.y;
   const int tid = threadIdx.x;
   {
     const int px = tid & 127;
@@ -86,11 +95,14 @@ __global__ void __launch_bounds__(256) pack_gy_kernel(const T* __restrict__ gy, 
 // bf16 source whose row segments are 8-byte aligned (Wo, tw, Ho*Wo multiples of 4): a lane loads FOUR pixels of
 // one channel with one 8-byte load -- a whole 128-pixel tile row per warp instruction, 8 per lane instead of 32
 // two-byte loads -- and one pixel decode per thread.
-__global__ void __launch_bounds__(256) pack_gy_bf16v_kernel(const __nv_bfloat16* __restrict__ gy, uint8_t* __restrict__ img,
-                                                            const Geo g, int okb) {
+__global__ void __launch_bounds__(256) pack_gy_bf16v_kernel(const __grid_constant__ PackGyTable t, int okb) {
+  const int ei = find_range(t.map, blockIdx.x);
+  const Geo g = with_dims(t.g, t.e[ei].d);
+  const __nv_bfloat16* __restrict__ gy = (const __nv_bfloat16*)t.e[ei].gy;
+  uint8_t* __restrict__ img = t.e[ei].img;
   const int O = g.O, hw = g.Ho * g.Wo;
   __shared__ __align__(8) __nv_bfloat16 s[64][136];   // [o][pixel (column ^ 32 for o >= 32)], 8 spare columns
-  const int tile = blockIdx.x, kb = blockIdx.y;
+  const int tile = blockIdx.x - t.map.start[ei], kb = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const long long p0 = (long long)tile * TILE_M + 4 * lane;
@@ -124,49 +136,33 @@ __global__ void __launch_bounds__(256) pack_gy_bf16v_kernel(const __nv_bfloat16*
   }
 }
 
-// W [O][C][taps] -> tiles ordered (tap, cchunk, okb): [NCH rows (c)][64 o] bf16 K-major swizzled.
-template <typename T, int NCH>
-__global__ void __launch_bounds__(256) prep_weight_dgrad_kernel(const T* __restrict__ w, uint8_t* __restrict__ img,
-                                                                int O, int C, int taps, int okb) {
-  const int o8n = okb * 8;  // 8-wide o chunks incl. zero padding
-  const long long total = (long long)taps * C * o8n;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int o8 = (int)(i % o8n);
-    const int c = (int)((i / o8n) % C);
-    const int tap = (int)(i / ((long long)o8n * C));
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int o = o8 * 8 + j;
-      v[j] = o < O ? to_f32(w[((size_t)o * C + c) * taps + tap]) : 0.f;
-    }
-    uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]);
-    pk.y = pack_bf16x2(v[2], v[3]);
-    pk.z = pack_bf16x2(v[4], v[5]);
-    pk.w = pack_bf16x2(v[6], v[7]);
-    const size_t tile = ((size_t)tap * (C / NCH) + c / NCH) * okb + (o8 >> 3);
-    *reinterpret_cast<uint4*>(img + tile * ((size_t)NCH * 128) + sw128_offset(c % NCH, o8 & 7)) = pk;
-  }
-}
-
+// grad_bias[o] += scale * sum over the problems of one weight tensor of sum_{n,h,w} dY; grid (O, weights)
+struct BiasGradTable {
+  int n;
+  struct E { const void* gy; int N, hw, weight; } e[MAX_PROBS];
+  float* gb[MAX_WEIGHTS];
+};
 template <typename T>
-__global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ gy, float* __restrict__ gb,
-                                                        float scale, int N, int O, int hw) {
-  const int o = blockIdx.x;
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasGradTable t, float scale, int O) {
+  const int o = blockIdx.x, wid = blockIdx.y;
+  if (!t.gb[wid]) return;
   float sum = 0.f;
-  for (int n = 0; n < N; ++n)
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) sum += to_f32(gy[((size_t)n * O + o) * hw + i]);
+  for (int e = 0; e < t.n; ++e) {
+    if (t.e[e].weight != wid) continue;
+    const T* gy = (const T*)t.e[e].gy;
+    const int hw = t.e[e].hw;
+    for (int n = 0; n < t.e[e].N; ++n)
+      for (int i = threadIdx.x; i < hw; i += blockDim.x) sum += to_f32(gy[((size_t)n * O + o) * hw + i]);
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   __shared__ float part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += part[i];
-    atomicAdd(gb + o, scale * t);
+    float tt = 0.f;
+    for (int i = 0; i < 8; ++i) tt += part[i];
+    atomicAdd(t.gb[wid] + o, scale * tt);
   }
 }
 
@@ -266,15 +262,25 @@ __device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) csr_count_kernel(const float* __restrict__ off, const float* __restrict__ mask,
-                                                        int* __restrict__ cnt, const Geo g) {
+// One transposed index per OFFSET GROUP (problems that sample with the same offsets, e.g. the two DCNs of a
+// RepPoints level, share it).  All groups live in one key space: group i owns keys [key_base, key_base + nkeys_i),
+// so a single scan serves the whole call.  grid (blocks of 256 output pixels over all groups, taps).
+struct CsrTable {
+  TileMap map;   // blocks of 256 output pixels
+  struct G { const float* off; const float* mask; Dims d; int key_base; } gr[MAX_PROBS];
+  Geo g;
+};
+__global__ void __launch_bounds__(256) csr_count_kernel(const __grid_constant__ CsrTable t, int* __restrict__ cnt) {
+  const int gi = find_range(t.map, blockIdx.x);
+  const Geo g = with_dims(t.g, t.gr[gi].d);
   const int tap = blockIdx.y;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = (long long)(blockIdx.x - t.map.start[gi]) * blockDim.x + threadIdx.x;
   if (p >= g.P()) return;
   const int hw = g.Ho * g.Wo;
   const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
-  for_each_hit(g, off, mask, n, r / g.Wo, r % g.Wo, tap,
-               [&](long long key, uint32_t, uint32_t) { atomicAdd(cnt + key, 1); });
+  int* c = cnt + t.gr[gi].key_base;
+  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap,
+               [&](long long key, uint32_t, uint32_t) { atomicAdd(c + key, 1); });
 }
 
 constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block
@@ -373,17 +379,21 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
 }
 
 // row_units = 16-byte units per pixel row of the NHWC dY (okb * 8)
-__global__ void __launch_bounds__(256) csr_fill_kernel(const float* __restrict__ off, const float* __restrict__ mask,
-                                                       int* __restrict__ cnt, const int* __restrict__ start,
-                                                       GDesc* __restrict__ desc, ODesc* __restrict__ odesc,
-                                                       const Geo g, int row_units) {
+__global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ CsrTable t, int* __restrict__ cnt_all,
+                                                       const int* __restrict__ start_all, GDesc* __restrict__ desc_all,
+                                                       ODesc* __restrict__ odesc, int row_units) {
+  const int gi = find_range(t.map, blockIdx.x);
+  const Geo g = with_dims(t.g, t.gr[gi].d);
   const int tap = blockIdx.y;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = (long long)(blockIdx.x - t.map.start[gi]) * blockDim.x + threadIdx.x;
   if (p >= g.P()) return;
   const int hw = g.Ho * g.Wo;
   const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
   const uint32_t poff = (uint32_t)p * (uint32_t)row_units;
-  for_each_hit(g, off, mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb, uint32_t row) {
+  int* cnt = cnt_all + t.gr[gi].key_base;
+  const int* start = start_all + t.gr[gi].key_base;
+  GDesc* desc = desc_all + t.gr[gi].key_base;
+  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb, uint32_t row) {
     const int pos = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
     if (pos < DESC_W) {
       desc[key].off[pos] = poff;
@@ -397,6 +407,110 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const float* __restrict__
   });
 }
 
+// Canonical order.  csr_fill hands out list slots with atomics, so WHICH entries of a list sit in the four-wide
+// descriptor and in what order the bf16 partial sums are formed would change from run to run.  This pass sorts the
+// entries of every list by their source row (an output pixel reaches an (input pixel, tap) at most once, so the
+// keys are unique): grad_input becomes bit-reproducible.  One thread per key; lists of up to four entries (the
+// common case) are a 5-exchange network in registers, longer ones go through a small local array.
+__global__ void __launch_bounds__(256) csr_sort_kernel(GDesc* __restrict__ desc, const int* __restrict__ start,
+                                                       ODesc* __restrict__ odesc, int nkeys) {
+  const int key = blockIdx.x * blockDim.x + threadIdx.x;
+  if (key >= nkeys) return;
+  const int ob = start[key], nod = start[key + 1] - ob;
+  uint4 o4 = *reinterpret_cast<const uint4*>(desc[key].off);
+  uint4 w4 = *reinterpret_cast<const uint4*>(desc[key].w2);
+  if (nod == 0) {
+    uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#define SDB_CX(a_, b_)                                                                             \
+    {                                                                                              \
+      const uint32_t ka_ = w[a_] ? o[a_] : 0xffffffffu, kb_ = w[b_] ? o[b_] : 0xffffffffu;         \
+      if (kb_ < ka_) { const uint32_t to_ = o[a_], tw_ = w[a_]; o[a_] = o[b_]; w[a_] = w[b_]; o[b_] = to_; w[b_] = tw_; } \
+    }
+    SDB_CX(0, 1) SDB_CX(2, 3) SDB_CX(0, 2) SDB_CX(1, 3) SDB_CX(1, 2)
+#undef SDB_CX
+    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
+  constexpr int CAP = 68;   // 4 + 16 overflow descriptors; longer lists are sorted in place in global memory
+  const int total_slots = DESC_W + 4 * nod;
+  if (total_slots <= CAP) {
+    uint32_t o[CAP];
+    uint16_t w[CAP];
+    int n = 0;
+    const uint32_t od0[4] = {o4.x, o4.y, o4.z, o4.w}, wd0[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int k = 0; k < 4; ++k)
+      if (wd0[k]) { o[n] = od0[k]; w[n] = (uint16_t)(wd0[k] & 0xffffu); ++n; }
+    for (int d = 0; d < nod; ++d) {
+      const ODesc od = odesc[ob + d];
+      const uint32_t oo[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
+      const uint32_t ww[4] = {od.m.x & 0xffffu, od.m.x >> 16, od.m.y & 0xffffu, od.m.y >> 16};
+      for (int k = 0; k < 4; ++k)
+        if (ww[k]) { o[n] = oo[k]; w[n] = (uint16_t)ww[k]; ++n; }
+    }
+    for (int i = 1; i < n; ++i) {   // insertion sort by source row
+      const uint32_t oi = o[i];
+      const uint16_t wi = w[i];
+      int j = i - 1;
+      while (j >= 0 && o[j] > oi) { o[j + 1] = o[j]; w[j + 1] = w[j]; --j; }
+      o[j + 1] = oi; w[j + 1] = wi;
+    }
+    uint32_t od[4], wd[4];
+    for (int k = 0; k < 4; ++k) { od[k] = k < n ? o[k] : 0u; wd[k] = k < n ? ((uint32_t)w[k] << 16) | w[k] : 0u; }
+    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    const uint32_t row = odesc[ob].m.z;
+    for (int d = 0; d < nod; ++d) {
+      uint32_t oo[4], ww[4];
+      for (int k = 0; k < 4; ++k) {
+        const int e = DESC_W + 4 * d + k;
+        oo[k] = e < n ? o[e] : 0u;
+        ww[k] = e < n ? w[e] : 0u;
+      }
+      ODesc out;
+      out.o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+      out.m = make_uint4(ww[0] | (ww[1] << 16), ww[2] | (ww[3] << 16), row, 0u);
+      odesc[ob + d] = out;
+    }
+    return;
+  }
+  // very long list (hundreds of taps colliding on one input pixel): selection sort over the slots in place
+  auto get = [&](int e, uint32_t& oo, uint32_t& ww) {
+    if (e < DESC_W) { oo = desc[key].off[e]; ww = desc[key].w2[e] & 0xffffu; }
+    else {
+      const ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
+      oo = reinterpret_cast<const uint32_t*>(&od->o)[(e - DESC_W) & 3];
+      ww = reinterpret_cast<const uint16_t*>(&od->m)[(e - DESC_W) & 3];
+    }
+  };
+  auto set = [&](int e, uint32_t oo, uint32_t ww) {
+    if (e < DESC_W) { desc[key].off[e] = oo; desc[key].w2[e] = (ww << 16) | ww; }
+    else {
+      ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
+      reinterpret_cast<uint32_t*>(&od->o)[(e - DESC_W) & 3] = oo;
+      reinterpret_cast<uint16_t*>(&od->m)[(e - DESC_W) & 3] = (uint16_t)ww;
+    }
+  };
+  for (int i = 0; i < total_slots; ++i) {
+    uint32_t bo, bw;
+    get(i, bo, bw);
+    uint32_t bk = bw ? bo : 0xffffffffu;
+    int bi = i;
+    for (int j = i + 1; j < total_slots; ++j) {
+      uint32_t oo, ww;
+      get(j, oo, ww);
+      const uint32_t kk = ww ? oo : 0xffffffffu;
+      if (kk < bk) { bk = kk; bi = j; bo = oo; bw = ww; }
+    }
+    if (bi != i) {
+      uint32_t oi, wi;
+      get(i, oi, wi);
+      set(bi, oi, wi);
+      set(i, bo, bw);
+    }
+  }
+}
+
 // byte offset of 16-byte chunk `chunk` of row `row` in the bf16 staging tile [128][NCH]
 template <int NCH>
 __device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
@@ -406,20 +520,25 @@ __device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
 // ------------------------------------------------------------------------------------------------
 // backward data kernel
 // ------------------------------------------------------------------------------------------------
-struct DgradParams {
+struct DgradProb {
   const __nv_bfloat16* xp;   // NHWC bf16 input
   const float* off;
   const float* mask;
   const uint8_t* gy_img;     // dY tiles
-  const uint8_t* wt_img;     // W^T tiles
-  float* goff;               // [N][2*taps][HWo] fp32, pre-zeroed, or nullptr
-  float* gmask;              // [N][taps][HWo] fp32, pre-zeroed, or nullptr
-  Geo g;
-  int num_tiles, nsb, okb;
+  const uint8_t* wt_img;     // W^T tiles of this problem's convolution
+  float* goff;               // [N][2*taps][HWo] fp32, or nullptr
+  float* gmask;              // [N][taps][HWo] fp32, or nullptr
+  Dims d;
+};
+struct DgradParams {
+  TileMap map;               // tiles of all problems
+  DgradProb pr[MAX_PROBS];
+  Geo g;                     // common geometry
+  int nsb, okb;
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const DgradParams p) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
   constexpr int LPB = NCH / 8, PPI = 32 / LPB;
   constexpr uint32_t B_BYTES = NCH * 128;            // one [NCH c][64 o] weight tile
   constexpr uint32_t STG_BYTES = TILE_M * NCH * 2;   // bf16 staging tile
@@ -429,8 +548,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], stg_full[2], stg_empty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const Geo& g = p.g;
-  const int C = g.C, taps = g.KH * g.KW, nch = C / NCH, units = taps * nch, okb = p.okb;
+  const int C = p.g.C, taps = p.g.KH * p.g.KW, nch = C / NCH, units = taps * nch, okb = p.okb;
+  const int num_tiles = p.map.start[p.map.n];
   const uint32_t A_BYTES = (uint32_t)okb * (TILE_M * 128);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -467,15 +586,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     // ===== bulk producer: dY tile once per tile, W^T tiles per (tap, chunk, o-block) =====
     if (lane == 0) {
       uint32_t bs = 0, bp = 0, ap = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int pi = find_range(p.map, work);
+        const DgradProb& pr = p.pr[pi];
+        const int tile = work - p.map.start[pi];
         mbar_wait(&a_empty, ap ^ 1);
         mbar_arrive_expect_tx(&a_full, A_BYTES);
-        bulk_g2s(sA, p.gy_img + (size_t)tile * A_BYTES, A_BYTES, &a_full);
+        bulk_g2s(sA, pr.gy_img + (size_t)tile * A_BYTES, A_BYTES, &a_full);
         ap ^= 1;
         for (int i = 0; i < units * okb; ++i) {
           mbar_wait(&b_empty[bs], bp ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-          bulk_g2s(sB + (size_t)bs * B_BYTES, p.wt_img + (size_t)i * B_BYTES, B_BYTES, &b_full[bs]);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, pr.wt_img + (size_t)i * B_BYTES, B_BYTES, &b_full[bs]);
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
@@ -484,7 +606,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     // ===== MMA issuer: dcol[128 x NCH] = dY_tile[128 x O] * W^T =====
     const uint32_t idesc = make_idesc_bf16(TILE_M, NCH, 0, 0);
     uint32_t bs = 0, bp = 0, acc = 0, accp = 0, ap = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       mbar_wait(&a_full, ap);
       ap ^= 1;
       for (int u = 0; u < units; ++u) {
@@ -518,7 +640,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     const int q = warp & 3;
     const uint32_t row = q * 32 + lane;
     uint32_t acc = 0, accp = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
       for (int u = 0; u < units; ++u) {
         mbar_wait(&acc_full[acc], accp);
         tc_fence_after_sync();
@@ -561,10 +683,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
     __shared__ int2 s_px[NSW][PIX_PER_WARP];          // (n, ho*Wo+wo) of the warp's pixels, n = -1 when padded
     const int sw = warp - FIRST_SW, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
-    const int hw = g.Ho * g.Wo;
-    const uint4* xbase = reinterpret_cast<const uint4*>(p.xp) + lig;
     uint32_t sb = 0, sp = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      const int pi = find_range(p.map, work);
+      const DgradProb& pr = p.pr[pi];
+      const int tile = work - p.map.start[pi];
+      const Geo g = with_dims(p.g, pr.d);
+      const int hw = g.Ho * g.Wo;
+      const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
       const long long pix = (long long)tile * TILE_M + r0 + lane;
       const bool valid = lane < PIX_PER_WARP && pix < g.P();
       int n = 0, ho = 0, wo = 0;
@@ -586,8 +712,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
           s_od[sw][tap_ & 1][lane][1] = f;
         }
       };
-      build_desc(0, fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, 0));
-      RawB raw_next = fetch_rawb(g, p.off, p.mask, valid && taps > 1, n, ho, wo, 1);   // raw offsets run two taps ahead
+      build_desc(0, fetch_rawb(g, pr.off, pr.mask, valid, n, ho, wo, 0));
+      RawB raw_next = fetch_rawb(g, pr.off, pr.mask, valid && taps > 1, n, ho, wo, 1);   // raw offsets run two taps ahead
       __syncwarp();
       uint4 v[RING][4];
 #define SDB_ISSUE(tap_, ch_, it_, slot_)                                                         \
@@ -604,7 +730,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
       for (int tap = 0; tap < taps; ++tap) {
         __syncwarp();
         if (tap + 1 < taps) build_desc(tap + 1, raw_next);   // buffer (tap+1)&1 was last read during tap-1
-        raw_next = fetch_rawb(g, p.off, p.mask, valid && tap + 2 < taps, n, ho, wo, tap + 2);
+        raw_next = fetch_rawb(g, pr.off, pr.mask, valid && tap + 2 < taps, n, ho, wo, tap + 2);
         __syncwarp();
         float racc[ITERS];
 #pragma unroll
@@ -663,12 +789,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
           if ((lig % Q) == 0 && quant < 3) {
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-              const int2 pi = s_px[sw][it * PPI + grp];
-              if (pi.x >= 0) {
+              const int2 pxy = s_px[sw][it * PPI + grp];
+              if (pxy.x >= 0) {
                 if (quant < 2) {
-                  if (p.goff) p.goff[((size_t)pi.x * 2 * taps + 2 * tap + quant) * hw + pi.y] = racc[it];
-                } else if (p.gmask) {
-                  p.gmask[((size_t)pi.x * taps + tap) * hw + pi.y] = racc[it];
+                  if (pr.goff) pr.goff[((size_t)pxy.x * 2 * taps + 2 * tap + quant) * hw + pxy.y] = racc[it];
+                } else if (pr.gmask) {
+                  pr.gmask[((size_t)pxy.x * taps + tap) * hw + pxy.y] = racc[it];
                 }
               }
             }
@@ -686,18 +812,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const D
 // ------------------------------------------------------------------------------------------------
 // backward weight kernel
 // ------------------------------------------------------------------------------------------------
-struct WgradParams {
+struct WgradProb {
   const __nv_bfloat16* xp;
   const float* off;
   const float* mask;
   const uint8_t* gy_img;
-  float* part;               // [splits][taps][O][C] fp32 partial sums
+  Dims d;
+};
+// The weight gradient of a convolution sums over ALL its problems (FPN levels): a CTA owns one (weight, tap,
+// channel chunk, pixel split) and walks its share of the concatenated tile list of that weight's problems.
+struct WgradParams {
+  WgradProb pr[MAX_PROBS];
+  TileMap wmap[MAX_WEIGHTS];         // per weight: tile ranges of its problems
+  int pidx[MAX_WEIGHTS][MAX_PROBS];  // per weight: problem index of each range
+  float* part[MAX_WEIGHTS];          // per weight: [splits][taps][O][C] fp32 partial sums
+  int splits[MAX_WEIGHTS], tiles_per_split[MAX_WEIGHTS];
+  int cta_start[MAX_WEIGHTS + 1];    // first CTA of each weight
+  int nweights;
   Geo g;
-  int num_tiles, tiles_per_split, splits, okb, nsg, nsy;
+  int okb, nsg, nsy;
 };
 
 template <int NCH>
-__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const __grid_constant__ WgradParams p) {
   constexpr int LPB = NCH / 8;
   constexpr uint32_t G_BYTES = TILE_M * NCH * 2;   // gathered col tile [NCH/64 blocks][128 px][64 c]
   extern __shared__ uint8_t smem_raw[];
@@ -705,8 +842,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   __shared__ uint32_t tmem_base_s;
   __shared__ GDesc sdesc[NSW][2][PIX_PER_WARP];   // per gather warp, double buffered over tiles
 
-  const Geo& g = p.g;
-  const int C = g.C, O = g.O, taps = g.KH * g.KW, nch = C / NCH, okb = p.okb, mh_n = okb / 2;
+  const int C = p.g.C, O = p.g.O, taps = p.g.KH * p.g.KW, nch = C / NCH, okb = p.okb, mh_n = okb / 2;
   const uint32_t Y_BYTES = (uint32_t)okb * (TILE_M * 128);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -716,11 +852,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   // so tcgen05.mma takes its descriptors from the uniform datapath without an ELECT/R2UR waterfall per instruction
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // work item of this CTA
-  const int split = blockIdx.x % p.splits;
-  const int ch = (blockIdx.x / p.splits) % nch;
-  const int tap = blockIdx.x / (p.splits * nch);
-  const int t0 = split * p.tiles_per_split;
-  const int t1 = min(p.num_tiles, t0 + p.tiles_per_split);
+  int wid = 0;
+  while (wid + 1 < p.nweights && (int)blockIdx.x >= p.cta_start[wid + 1]) ++wid;
+  const int lcta = blockIdx.x - p.cta_start[wid];
+  const int nsplit = p.splits[wid];
+  const int split = lcta % nsplit;
+  const int ch = (lcta / nsplit) % nch;
+  const int tap = lcta / (nsplit * nch);
+  const TileMap& wm = p.wmap[wid];
+  const int t0 = split * p.tiles_per_split[wid];
+  const int t1 = min(wm.start[wm.n], t0 + p.tiles_per_split[wid]);
   uint32_t ncols = 32;
   while ((int)ncols < mh_n * NCH) ncols <<= 1;
 
@@ -746,9 +887,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
     if (lane == 0) {
       uint32_t ys = 0, yp = 0;
       for (int tile = t0; tile < t1; ++tile) {
+        const int r = find_range(wm, tile);
+        const uint8_t* gy_img = p.pr[p.pidx[wid][r]].gy_img;
         mbar_wait(&y_empty[ys], yp ^ 1);
         mbar_arrive_expect_tx(&y_full[ys], Y_BYTES);
-        bulk_g2s(sY + (size_t)ys * Y_BYTES, p.gy_img + (size_t)tile * Y_BYTES, Y_BYTES, &y_full[ys]);
+        bulk_g2s(sY + (size_t)ys * Y_BYTES, gy_img + (size_t)(tile - wm.start[r]) * Y_BYTES, Y_BYTES, &y_full[ys]);
         if (++ys == (uint32_t)p.nsy) { ys = 0; yp ^= 1; }
       }
     }
@@ -793,7 +936,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
         tmem_ld_32x32(tmem_base + mh * NCH + ((uint32_t)(q * 32) << 16) + c0, r);
         tmem_ld_wait();
         if (o < O && t1 > t0) {
-          float4* dst = reinterpret_cast<float4*>(p.part + (((size_t)split * taps + tap) * O + o) * C + ch * NCH + c0);
+          float4* dst = reinterpret_cast<float4*>(p.part[wid] + (((size_t)split * taps + tap) * O + o) * C + ch * NCH + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -811,17 +954,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
     const int sw = warp - FIRST_SW, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
     uint32_t gs = 0, gp = 0;
-    const uint4* x16 = reinterpret_cast<const uint4*>(p.xp + ch * NCH + lig * 8);
-    auto locate = [&](int tile_, bool& valid_, int& n_, int& ho_, int& wo_) {
-      const long long pix = (long long)tile_ * TILE_M + r0 + lane;
-      valid_ = lane < PIX_PER_WARP && tile_ < t1 && pix < g.P();
-      n_ = ho_ = wo_ = 0;
-      if (valid_) decode_q(g, pix, n_, ho_, wo_);
+    // problem of concatenated tile `tile_`, its geometry and this lane's pixel in it
+    struct Loc { bool valid; int n, ho, wo, pi; };
+    auto locate = [&](int tile_) {
+      Loc L = {false, 0, 0, 0, 0};
+      if (tile_ >= t1) return L;
+      const int r = find_range(wm, tile_);
+      L.pi = p.pidx[wid][r];
+      const Geo g = with_dims(p.g, p.pr[L.pi].d);
+      const long long pix = (long long)(tile_ - wm.start[r]) * TILE_M + r0 + lane;
+      L.valid = lane < PIX_PER_WARP && pix < g.P();
+      if (L.valid) decode_q(g, pix, L.n, L.ho, L.wo);
+      return L;
     };
+    auto fetch = [&](const Loc& L) {
+      const Geo g = with_dims(p.g, p.pr[L.pi].d);
+      return fetch_rawb(g, p.pr[L.pi].off, p.pr[L.pi].mask, L.valid, L.n, L.ho, L.wo, tap);
+    };
+    auto xptr = [&](int pi_) { return reinterpret_cast<const uint4*>(p.pr[pi_].xp + ch * NCH + lig * 8); };
     // forward-style descriptor (weights already x mask, zero outside) of this lane's pixel -> sdesc[buf_]
-    auto build_desc = [&](const RawB raw_, bool valid_, int n_, int ho_, int wo_, int buf_) {
+    auto build_desc = [&](const RawB raw_, const Loc& L, int buf_) {
       if (lane < PIX_PER_WARP) {
-        const BSample bs = make_bsample_raw(g, raw_, valid_, n_, ho_, wo_, tap);
+        const Geo g = with_dims(p.g, p.pr[L.pi].d);
+        const BSample bs = make_bsample_raw(g, raw_, L.valid, L.n, L.ho, L.wo, tap);
         const float wk[4] = {(1.f - bs.lh) * (1.f - bs.lw), (1.f - bs.lh) * bs.lw, bs.lh * (1.f - bs.lw), bs.lh * bs.lw};
         uint4 o, w;
         uint32_t* op = &o.x;
@@ -837,35 +992,36 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
         *reinterpret_cast<uint4*>(sdesc[sw][buf_][lane].w2) = w;
       }
     };
-    bool valid;
-    int n, ho, wo;
-    locate(t0, valid, n, ho, wo);
-    build_desc(fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap), valid, n, ho, wo, t0 & 1);
-    locate(t0 + 1, valid, n, ho, wo);
-    RawB raw = fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap);   // of tile t0 + 1
+    Loc loc = locate(t0);
+    build_desc(fetch(loc), loc, t0 & 1);
+    const uint4* x_cur = xptr(loc.pi);        // input of the tile being gathered
+    loc = locate(t0 + 1);
+    RawB raw = fetch(loc);                    // of tile t0 + 1
+    const uint4* x_next = xptr(loc.pi);       // input of the tile after it (its loads are issued during this tile)
     __syncwarp();
     uint4 v[RING][4], wq[RING];
-#define SDB_WISSUE(tile_, it_, slot_)                                                            \
+#define SDB_WISSUE(x16_, tile_, it_, slot_)                                                      \
     {                                                                                            \
       const GDesc* d_ = &sdesc[sw][(tile_) & 1][(it_) * PPI + grp];                              \
       const uint4 o_ = *reinterpret_cast<const uint4*>(d_->off);                                 \
       wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                       \
-      v[slot_][0] = __ldg(x16 + o_.x);                                                           \
-      v[slot_][1] = __ldg(x16 + o_.y);                                                           \
-      v[slot_][2] = __ldg(x16 + o_.z);                                                           \
-      v[slot_][3] = __ldg(x16 + o_.w);                                                           \
+      v[slot_][0] = __ldg((x16_) + o_.x);                                                        \
+      v[slot_][1] = __ldg((x16_) + o_.y);                                                        \
+      v[slot_][2] = __ldg((x16_) + o_.z);                                                        \
+      v[slot_][3] = __ldg((x16_) + o_.w);                                                        \
     }
     if (t0 < t1) {
 #pragma unroll
-      for (int u = 0; u < RING; ++u) SDB_WISSUE(t0, u, u)
+      for (int u = 0; u < RING; ++u) SDB_WISSUE(x_cur, t0, u, u)
     }
     for (int tile = t0; tile < t1; ++tile) {
       const bool has_next = tile + 1 < t1;
       // descriptors of tile+1 (its raw offsets arrived during the previous tile), then raw offsets of tile+2
       __syncwarp();   // buffer (tile+1)&1 was read while tile-1 was gathered
-      build_desc(raw, valid, n, ho, wo, (tile + 1) & 1);
-      locate(tile + 2, valid, n, ho, wo);
-      raw = fetch_rawb(g, p.off, p.mask, valid, n, ho, wo, tap);
+      build_desc(raw, loc, (tile + 1) & 1);
+      loc = locate(tile + 2);
+      raw = fetch(loc);
+      const uint4* x_after = xptr(loc.pi);
       __syncwarp();
       mbar_wait(&g_empty[gs], gp ^ 1);
       uint8_t* dst = sG + (size_t)gs * G_BYTES + (lig >> 3) * (TILE_M * 128);
@@ -879,14 +1035,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
         a.w = bf2_fma(wq[slot].w, v[slot][3].w, bf2_fma(wq[slot].z, v[slot][2].w, bf2_fma(wq[slot].y, v[slot][1].w, bf2_mul(wq[slot].x, v[slot][0].w))));
         *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
         if (it + RING < ITERS) {
-          SDB_WISSUE(tile, it + RING, slot)
+          SDB_WISSUE(x_cur, tile, it + RING, slot)
         } else if (has_next) {
-          SDB_WISSUE(tile + 1, it + RING - ITERS, slot)
+          SDB_WISSUE(x_next, tile + 1, it + RING - ITERS, slot)
         }
       }
       fence_proxy_async_smem();
       mbar_arrive_warp(&g_full[gs]);
       if (++gs == (uint32_t)p.nsg) { gs = 0; gp ^= 1; }
+      x_cur = x_next;
+      x_next = x_after;
     }
 #undef SDB_WISSUE
   }
@@ -895,9 +1053,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
-// grad_weight[o][c][tap] += scale * sum_split part[split][tap][o][c]
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw,
-                                                           float scale, int splits, int taps, int O, int C) {
+// grad_weight[o][c][tap] += scale * sum_split part[split][tap][o][c]; grid.y = weight
+struct WgradReduceTable {
+  const float* part[MAX_WEIGHTS];
+  float* gw[MAX_WEIGHTS];
+  int splits[MAX_WEIGHTS];
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceTable t, float scale, int taps,
+                                                           int O, int C) {
+  const int wid = blockIdx.y;
+  const float* __restrict__ part = t.part[wid];
+  float* __restrict__ gw = t.gw[wid];
+  const int splits = t.splits[wid];
+  if (!gw || splits == 0) return;
   const long long total = (long long)O * C * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -910,201 +1078,284 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// ---- workspace layouts ----------------------------------------------------------------------
-struct BwdWs {
-  size_t xp_off, gy_off, wt_off, part_off, cnt_off, start_off, bsum_off, ent_off, wdx_off, desc_off, gyn_off, total;
-  long long nkeys, max_entries;
-  int scan_blocks;
-};
-int wgrad_splits(const Geo& g, int num_tiles) {
-  int s = num_sms() / (g.taps() * nch_chunks(g));
-  if (s < 1) s = 1;
-  if (s > num_tiles) s = num_tiles;
-  if (s > 64) s = 64;
-  return s;
-}
-BwdWs bwd_ws(int op, const Geo& g) {
-  BwdWs w{};
-  const int okb = okb_of(g);
-  const size_t tiles = (size_t)cdiv(g.P(), TILE_M);
-  size_t o = 0;
-  w.xp_off = o; o = align_up(o + (size_t)g.N * g.H * g.W * g.C * 2, 1024);
-  w.gy_off = o; o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
-  if (op == SDB_OP_BACKWARD_DATA) {
-    w.wt_off = o; o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
-    const long long tiles_in = cdiv((long long)g.N * g.H * g.W, TILE_M);
-    w.nkeys = tiles_in * g.taps() * TILE_M;
-    w.max_entries = g.P() * g.taps() + 1;   // overflow descriptors: a key with c > 4 entries needs ceil((c-4)/4) <= c/4
-    w.scan_blocks = cdiv(w.nkeys, SCAN_PER_BLOCK);
-    w.cnt_off = o;   o = align_up(o + (size_t)w.nkeys * 4, 1024);
-    w.start_off = o; o = align_up(o + (size_t)(w.nkeys + 1) * 4, 1024);
-    w.bsum_off = o;  o = align_up(o + (size_t)w.scan_blocks * 4, 1024);
-    w.ent_off = o;   o = align_up(o + (size_t)w.max_entries * sizeof(ODesc), 1024);
-    w.wdx_off = o;   o = align_up(o + (size_t)g.taps() * g.C * okb * 64 * 2, 1024);
-    w.desc_off = o;  o = align_up(o + (size_t)w.nkeys * sizeof(GDesc), 1024);
-    w.gyn_off = o;   o = align_up(o + (size_t)g.P() * okb * 64 * 2, 1024);
-  } else {
-    w.part_off = o; o = align_up(o + (size_t)wgrad_splits(g, (int)tiles) * g.taps() * g.O * g.C * 4, 1024);
-  }
-  w.total = o;
-  return w;
-}
-
-template <typename T>
-int pack_gy(const void* gy, uint8_t* img, const Geo& g, cudaStream_t st) {
-  dim3 grid(cdiv(g.P(), TILE_M), okb_of(g));
-  const int hw = g.Ho * g.Wo;
-  if (sizeof(T) == 2 && g.Wo % 4 == 0 && g.tw % 4 == 0 && hw % 4 == 0 && ((size_t)gy & 7) == 0)
-    pack_gy_bf16v_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)gy, img, g, okb_of(g));
-  else
-    pack_gy_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, img, g, okb_of(g));
-  SDB_LAUNCHED(1);
-  SDB_CHECK_CUDA(cudaGetLastError());
-  return SDB_OK;
-}
-
 }  // namespace
 
-size_t tc_bwd_workspace_bytes(int op, const Geo& g) { return bwd_ws(op, g).total; }
-
-int tc_backward_data(const void* x, const float* off, const float* mask, const void* w, const void* gy,
-                     void* gx, float* goff, float* gmask, const Geo& g, int io_dtype, void* ws,
-                     size_t ws_bytes, const void* x_packed, cudaStream_t st) {
-  const int NCH = nch_of(g);
-  const BwdWs L = bwd_ws(SDB_OP_BACKWARD_DATA, g);
-  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "backward_data workspace too small: %zu < %zu", ws_bytes, L.total);
-  uint8_t* base = (uint8_t*)ws;
-  const bool f32 = io_dtype == SDB_F32;
-  if (!mask) gmask = nullptr;
-  int rc;
-  uint8_t* gy_img = base + L.gy_off;
-  rc = f32 ? pack_gy<float>(gy, gy_img, g, st) : pack_gy<__nv_bfloat16>(gy, gy_img, g, st);
-  if (rc) return rc;
+// ---- workspace plan of a multi-problem call ------------------------------------------------------------------------
+// Everything a call needs beyond its tensors lives in ONE caller-provided workspace, laid out as a pure function of
+// the problem dimensions (so sdb_dcn_multi_workspace_bytes and the call agree):
+//   per problem : xp (NHWC bf16 input, unless the caller passes x_packed), and for the backward gy_img (dY as
+//                 swizzled tiles) + gyn (dY NHWC);
+//   per group   : its slice of the transposed index (cnt / start / desc share one key space, odesc one pool);
+//   per weight  : the prepared operand images (unless the caller passes them) and the split-K partials of dW.
+TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward) {
+  TcPlan P{};
   const int okb = okb_of(g);
-
-  if (goff || gmask) {
-    // ---- (1) grad_offset / grad_mask: dcol GEMM + channel reduction ----
-    const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
-    if (!xp) {
-      rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
-               : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
-      if (rc) return rc;
-      xp = (const __nv_bfloat16*)(base + L.xp_off);
+  size_t o = 0;
+  for (int i = 0; i < n; ++i) {
+    const Geo gi = with_dims(g, pb[i].d);
+    P.xp_off[i] = o;
+    if (!pb[i].xp) o = align_up(o + tc_packed_input_bytes(gi), 1024);
+    if (backward) {
+      const size_t tiles = (size_t)cdiv(gi.P(), TILE_M);
+      P.gy_off[i] = o;  o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
+      P.gyn_off[i] = o; o = align_up(o + (size_t)gi.P() * okb * 64 * 2, 1024);
     }
-    uint8_t* wt_img = base + L.wt_off;
-    const long long total = (long long)g.taps() * g.C * okb * 8;
-    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    if (NCH == 128) {
-      if (f32) prep_weight_dgrad_kernel<float, 128><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
-      else prep_weight_dgrad_kernel<__nv_bfloat16, 128><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
-    } else {
-      if (f32) prep_weight_dgrad_kernel<float, 64><<<blocks, 256, 0, st>>>((const float*)w, wt_img, g.O, g.C, g.taps(), okb);
-      else prep_weight_dgrad_kernel<__nv_bfloat16, 64><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w, wt_img, g.O, g.C, g.taps(), okb);
-    }
-    SDB_LAUNCHED(1);
-    SDB_CHECK_CUDA(cudaGetLastError());
-
-    DgradParams p;
-    p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.wt_img = wt_img;
-    p.goff = goff; p.gmask = gmask; p.g = g;
-    p.num_tiles = cdiv(g.P(), TILE_M);
-    p.okb = okb;
-    const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
-    long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
-    if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
-    SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
-    p.nsb = (int)nsb;
-    const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
-    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<128>, smem);
-    else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
-    {
-      ProfScope prof(SDB_OP_BACKWARD_DATA, st);
-      if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-      else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
-      SDB_LAUNCHED(1);
-    }
-    SDB_CHECK_CUDA(cudaGetLastError());
   }
-
-  if (gx) {
-    // ---- (2) grad_input: transposed sampling index + gathered implicit GEMM ----
-    int* cnt = (int*)(base + L.cnt_off);
-    int* start = (int*)(base + L.start_off);
-    int* bsum = (int*)(base + L.bsum_off);
-    ODesc* odesc = (ODesc*)(base + L.ent_off);
-    GDesc* desc = (GDesc*)(base + L.desc_off);
-    __nv_bfloat16* gyn = (__nv_bfloat16*)(base + L.gyn_off);
-    const int nkeys = (int)L.nkeys;
-    rc = f32 ? pack_grad_nhwc<float>(gy, gyn, g, okb * 64, st) : pack_grad_nhwc<__nv_bfloat16>(gy, gyn, g, okb * 64, st);
-    if (rc) return rc;
-    SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nkeys * 4, st));
-    SDB_CHECK_CUDA(cudaMemsetAsync(desc, 0, (size_t)nkeys * sizeof(GDesc), st));
-    dim3 hgrid(cdiv(g.P(), 256), g.taps());
-    csr_count_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, g);
-    csr_block_sums_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
-    csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, L.scan_blocks);
-    csr_scan_final_kernel<<<L.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
-    csr_fill_kernel<<<hgrid, 256, 0, st>>>(off, mask, cnt, start, desc, odesc, g, okb * 8);
-    SDB_LAUNCHED(5);
-    SDB_CHECK_CUDA(cudaGetLastError());
-    rc = tc_dx(w, gyn, desc, start, odesc, base + L.wdx_off, gx, g, okb, io_dtype, st);
-    if (rc) return rc;
+  for (int w = 0; w < nweights; ++w) {
+    P.prep_off[w] = o;
+    if (!have_prepared[w]) o = align_up(o + tc_prepared_weight_bytes(g), 1024);
   }
-  return SDB_OK;
+  if (backward) {
+    // offset groups: canonical index = order of first appearance; problems with group < 0 are their own group
+    int ng = 0;
+    for (int i = 0; i < n; ++i) {
+      int gi = -1;
+      if (pb[i].group >= 0)
+        for (int j = 0; j < i; ++j)
+          if (pb[j].group == pb[i].group) { gi = P.group_of[j]; break; }
+      if (gi < 0) { gi = ng; P.group_rep[ng++] = i; }
+      P.group_of[i] = gi;
+    }
+    P.ngroups = ng;
+    long long keys = 0, ods = 1;
+    for (int k = 0; k < ng; ++k) {
+      const Geo gk = with_dims(g, pb[P.group_rep[k]].d);
+      P.key_base[k] = keys;
+      keys += (long long)cdiv((long long)gk.N * gk.H * gk.W, TILE_M) * g.taps() * TILE_M;
+      ods += gk.P() * g.taps();   // a key with c > 4 entries needs ceil((c-4)/4) <= c/4 overflow descriptors
+    }
+    P.nkeys = keys;
+    P.scan_blocks = cdiv(keys, SCAN_PER_BLOCK);
+    // cnt and desc are cleared by ONE memset: keep them adjacent
+    P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
+    P.desc_off = o;  o = align_up(o + (size_t)keys * sizeof(GDesc), 1024);
+    P.clear_bytes = o - P.cnt_off;
+    P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
+    P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
+    P.od_off = o;    o = align_up(o + (size_t)ods * sizeof(ODesc), 1024);
+    // weight-gradient split-K: all weights share the machine
+    int tiles_w[MAX_WEIGHTS] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) tiles_w[pb[i].weight_id] += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
+    int s = num_sms() / ((nweights > 0 ? nweights : 1) * g.taps() * nch_chunks(g));
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    for (int w = 0; w < nweights; ++w) {
+      int sw = s < tiles_w[w] ? s : tiles_w[w];
+      if (sw < 1) sw = 1;
+      P.tiles_per_split[w] = tiles_w[w] > 0 ? cdiv(tiles_w[w], sw) : 1;
+      P.splits[w] = tiles_w[w] > 0 ? cdiv(tiles_w[w], P.tiles_per_split[w]) : 0;   // no empty split
+      P.part_off[w] = o;
+      o = align_up(o + (size_t)P.splits[w] * g.taps() * g.O * g.C * 4, 1024);
+    }
+  }
+  P.total = o;
+  return P;
 }
 
-int tc_backward_weight(const void* x, const float* off, const float* mask, const void* gy, float* gw,
-                       float* gb, float scale, const Geo& g, int io_dtype, void* ws, size_t ws_bytes,
-                       const void* x_packed, cudaStream_t st) {
-  const int NCH = nch_of(g);
-  const BwdWs L = bwd_ws(SDB_OP_BACKWARD_WEIGHT, g);
-  SDB_REQUIRE(ws && ws_bytes >= L.total, SDB_ERR_WORKSPACE, "backward_weight workspace too small: %zu < %zu", ws_bytes, L.total);
-  uint8_t* base = (uint8_t*)ws;
-  const bool f32 = io_dtype == SDB_F32;
+// ---- forward: pack every input once, one kernel over all problems -----------------------------------------------
+int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st) {
+  PackJob jobs[MAX_PROBS];
+  for (int i = 0; i < n; ++i) jobs[i] = PackJob{pb[i].x, pb[i].xp, pb[i].d.N, pb[i].d.H * pb[i].d.W};
+  int rc = pack_nhwc_multi(jobs, n, g.C, g.C, io_dtype == SDB_BF16, st);
+  if (rc) return rc;
+  return tc_forward_multi(pb, n, g, io_dtype, st);
+}
+
+// ---- backward: grad_offset / grad_mask, grad_input, grad_weight / grad_bias of all problems ------------------------
+// dY is packed once per problem (tile image + NHWC rows) and serves the three kernels; the transposed index is built
+// once per offset group; one launch per kernel over all problems.
+int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
+                    int io_dtype, float scale, bool pack_x, int accumulate_gx, uint8_t* base, cudaStream_t st) {
+  const int NCH = nch_of(g), okb = okb_of(g);
+  const bool bf = io_dtype == SDB_BF16;
   int rc;
-  if (gw) {
-    const __nv_bfloat16* xp = (const __nv_bfloat16*)x_packed;
-    if (!xp) {
-      rc = f32 ? pack_input<float>(x, (__nv_bfloat16*)(base + L.xp_off), g, st)
-               : pack_input<__nv_bfloat16>(x, (__nv_bfloat16*)(base + L.xp_off), g, st);
-      if (rc) return rc;
-      xp = (const __nv_bfloat16*)(base + L.xp_off);
-    }
-    uint8_t* gy_img = base + L.gy_off;
-    rc = f32 ? pack_gy<float>(gy, gy_img, g, st) : pack_gy<__nv_bfloat16>(gy, gy_img, g, st);
+  bool any_goff = false, any_gx = false, any_gw = false, any_gb = false;
+  for (int i = 0; i < n; ++i) { any_goff |= pb[i].goff || pb[i].gmask; any_gx |= pb[i].gx != nullptr; }
+  for (int w = 0; w < nweights; ++w) { any_gw |= gw[w] != nullptr; any_gb |= gb[w] != nullptr; }
+
+  // (0) layouts: x -> NHWC (unless the forward exported it), dY -> tile image and NHWC rows
+  if (pack_x && (any_goff || any_gw)) {
+    PackJob jobs[MAX_PROBS];
+    for (int i = 0; i < n; ++i) jobs[i] = PackJob{pb[i].x, pb[i].xp, pb[i].d.N, pb[i].d.H * pb[i].d.W};
+    rc = pack_nhwc_multi(jobs, n, g.C, g.C, bf, st);
     if (rc) return rc;
-    WgradParams p;
-    p.xp = xp; p.off = off; p.mask = mask; p.gy_img = gy_img; p.part = (float*)(base + L.part_off); p.g = g;
-    p.num_tiles = cdiv(g.P(), TILE_M);
-    p.tiles_per_split = cdiv(p.num_tiles, wgrad_splits(g, p.num_tiles));
-    p.splits = cdiv(p.num_tiles, p.tiles_per_split);   // no empty split
-    p.okb = okb_of(g);
-    const size_t g_bytes = (size_t)TILE_M * NCH * 2, y_bytes = (size_t)p.okb * TILE_M * 128;
-    p.nsy = 2;
-    long long nsg = ((long long)(208 * 1024) - 1024 - (long long)(p.nsy * y_bytes)) / (long long)g_bytes;
-    if (nsg > 4) nsg = 4;
-    SDB_REQUIRE(nsg >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_weight");
-    p.nsg = (int)nsg;
-    const size_t smem = p.nsg * g_bytes + p.nsy * y_bytes + 1024;
-    const int grid = g.taps() * nch_chunks(g) * p.splits;
-    if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<128>, smem);
-    else SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<64>, smem);
-    {
-      ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
-      if (NCH == 128) dcn_bwd_weight_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-      else dcn_bwd_weight_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
-      SDB_LAUNCHED(1);
-    }
-    SDB_CHECK_CUDA(cudaGetLastError());
-    const long long total = (long long)g.O * g.C * g.taps();
-    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.part, gw, scale, p.splits, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
-    SDB_CHECK_CUDA(cudaGetLastError());
   }
-  if (gb) {
-    if (f32) bias_grad_kernel<float><<<g.O, 256, 0, st>>>((const float*)gy, gb, scale, g.N, g.O, g.HWo());
-    else bias_grad_kernel<__nv_bfloat16><<<g.O, 256, 0, st>>>((const __nv_bfloat16*)gy, gb, scale, g.N, g.O, g.HWo());
+  if (any_goff || any_gw) {
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0: vectorised bf16 kernel, pass 1: generic
+      PackGyTable t{};
+      t.g = g;
+      int m = 0, total = 0;
+      for (int i = 0; i < n; ++i) {
+        const Geo gi = with_dims(g, pb[i].d);
+        const int hw = gi.Ho * gi.Wo;
+        const bool fast = bf && gi.Wo % 4 == 0 && g.tw % 4 == 0 && hw % 4 == 0 && ((size_t)pb[i].gy & 7) == 0;
+        if (fast != (pass == 0) || gi.P() == 0) continue;
+        t.e[m].gy = pb[i].gy; t.e[m].img = pb[i].gy_img; t.e[m].d = pb[i].d;
+        t.map.start[m] = total;
+        total += cdiv(gi.P(), TILE_M);
+        ++m;
+      }
+      t.map.n = m; t.map.start[m] = total;
+      if (total == 0) continue;
+      dim3 grid(total, okb);
+      if (pass == 0) pack_gy_bf16v_kernel<<<grid, 256, 0, st>>>(t, okb);
+      else if (bf) pack_gy_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(t, okb);
+      else pack_gy_kernel<float><<<grid, 256, 0, st>>>(t, okb);
+      SDB_LAUNCHED(1);
+      SDB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+
+  // (1) grad_offset / grad_mask: dcol GEMM + channel reduction
+  if (any_goff) {
+    DgradParams p{};
+    p.g = g; p.okb = okb;
+    int m = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!pb[i].goff && !pb[i].gmask) continue;
+      DgradProb& q = p.pr[m];
+      q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.gy_img = pb[i].gy_img;
+      q.wt_img = pb[i].w.dgrad; q.goff = pb[i].goff; q.gmask = pb[i].mask ? pb[i].gmask : nullptr; q.d = pb[i].d;
+      p.map.start[m] = total;
+      total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
+      ++m;
+    }
+    p.map.n = m; p.map.start[m] = total;
+    if (total > 0) {
+      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
+      long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
+      if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+      SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
+      p.nsb = (int)nsb;
+      const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
+      const int grid = total < num_sms() ? total : num_sms();
+      if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<128>, smem);
+      else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
+      {
+        ProfScope prof(SDB_OP_BACKWARD_DATA, st);
+        if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
+        else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+        SDB_LAUNCHED(1);
+      }
+      SDB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+
+  // (2) grad_input: transposed sampling index (one per offset group) + gathered implicit GEMM
+  if (any_gx) {
+    {
+      PackJob jobs[MAX_PROBS];
+      for (int i = 0; i < n; ++i)
+        jobs[i] = PackJob{pb[i].gx ? pb[i].gy : nullptr, pb[i].gyn, pb[i].d.N, pb[i].d.Ho * pb[i].d.Wo};
+      rc = pack_nhwc_multi(jobs, n, g.O, okb * 64, bf, st);
+      if (rc) return rc;
+    }
+    int* cnt = (int*)(base + P.cnt_off);
+    int* start = (int*)(base + P.start_off);
+    int* bsum = (int*)(base + P.bsum_off);
+    ODesc* odesc = (ODesc*)(base + P.od_off);
+    GDesc* desc = (GDesc*)(base + P.desc_off);
+    CsrTable t{};
+    t.g = g;
+    int total = 0, m = 0;
+    for (int k = 0; k < P.ngroups; ++k) {
+      bool wanted = false;
+      for (int i = 0; i < n; ++i) wanted |= P.group_of[i] == k && pb[i].gx;
+      if (!wanted) continue;
+      const TcProblem& r = pb[P.group_rep[k]];
+      t.gr[m].off = r.off; t.gr[m].mask = r.mask; t.gr[m].d = r.d; t.gr[m].key_base = (int)P.key_base[k];
+      t.map.start[m] = total;
+      total += cdiv(with_dims(g, r.d).P(), 256);
+      ++m;
+    }
+    t.map.n = m; t.map.start[m] = total;
+    const int nkeys = (int)P.nkeys;
+    SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and desc in one fill
+    dim3 hgrid(total, g.taps());
+    csr_count_kernel<<<hgrid, 256, 0, st>>>(t, cnt);
+    csr_block_sums_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
+    csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, P.scan_blocks);
+    csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
+    csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, desc, odesc, okb * 8);
+    csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(desc, start, odesc, nkeys);
+    SDB_LAUNCHED(6);
+    SDB_CHECK_CUDA(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+      const long long kb = P.key_base[P.group_of[i]];
+      pb[i].desc = desc + kb; pb[i].start = start + kb; pb[i].odesc = odesc;
+    }
+    rc = tc_dx_multi(pb, n, g, okb, io_dtype, accumulate_gx, st);
+    if (rc) return rc;
+  }
+
+  // (3) grad_weight (+ grad_bias): one CTA per (weight, tap, channel chunk, pixel split) over that weight's tiles
+  if (any_gw) {
+    WgradParams p{};
+    p.g = g; p.okb = okb; p.nweights = nweights;
+    int cta = 0, m = 0;
+    int slot_of[MAX_PROBS];
+    for (int i = 0; i < n; ++i) {
+      slot_of[i] = -1;
+      if (!gw[pb[i].weight_id] || with_dims(g, pb[i].d).P() == 0) continue;
+      WgradProb& q = p.pr[m];
+      q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.gy_img = pb[i].gy_img; q.d = pb[i].d;
+      slot_of[i] = m++;
+    }
+    WgradReduceTable rt{};
+    for (int w = 0; w < nweights; ++w) {
+      TileMap& wm = p.wmap[w];
+      int total = 0, r = 0;
+      for (int i = 0; i < n; ++i) {
+        if (pb[i].weight_id != w || slot_of[i] < 0) continue;
+        p.pidx[w][r] = slot_of[i];
+        wm.start[r++] = total;
+        total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
+      }
+      wm.n = r; wm.start[r] = total;
+      p.part[w] = (float*)(base + P.part_off[w]);
+      p.tiles_per_split[w] = P.tiles_per_split[w];
+      p.splits[w] = (gw[w] && total > 0) ? P.splits[w] : 0;
+      p.cta_start[w] = cta;
+      cta += g.taps() * nch_chunks(g) * p.splits[w];
+      rt.part[w] = p.part[w]; rt.gw[w] = gw[w]; rt.splits[w] = p.splits[w];
+    }
+    p.cta_start[nweights] = cta;
+    if (cta > 0) {
+      const size_t g_bytes = (size_t)TILE_M * NCH * 2, y_bytes = (size_t)okb * TILE_M * 128;
+      p.nsy = 2;
+      long long nsg = ((long long)(208 * 1024) - 1024 - (long long)(p.nsy * y_bytes)) / (long long)g_bytes;
+      if (nsg > 4) nsg = 4;
+      SDB_REQUIRE(nsg >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_weight");
+      p.nsg = (int)nsg;
+      const size_t smem = p.nsg * g_bytes + p.nsy * y_bytes + 1024;
+      if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<128>, smem);
+      else SDB_ENSURE_SMEM(dcn_bwd_weight_tc_kernel<64>, smem);
+      {
+        ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
+        if (NCH == 128) dcn_bwd_weight_tc_kernel<128><<<cta, BWD_THREADS, smem, st>>>(p);
+        else dcn_bwd_weight_tc_kernel<64><<<cta, BWD_THREADS, smem, st>>>(p);
+        SDB_LAUNCHED(1);
+      }
+      SDB_CHECK_CUDA(cudaGetLastError());
+      const long long total = (long long)g.O * g.C * g.taps();
+      const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+      // weights with no tile contribute nothing: the reduce of a weight with splits == 0 adds zero
+      wgrad_reduce_kernel<<<dim3(blocks, nweights), 256, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      SDB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  if (any_gb) {
+    BiasGradTable t{};
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!gb[pb[i].weight_id]) continue;
+      t.e[m].gy = pb[i].gy; t.e[m].N = pb[i].d.N; t.e[m].hw = pb[i].d.Ho * pb[i].d.Wo; t.e[m].weight = pb[i].weight_id;
+      ++m;
+    }
+    t.n = m;
+    for (int w = 0; w < nweights; ++w) t.gb[w] = gb[w];
+    if (bf) bias_grad_kernel<__nv_bfloat16><<<dim3(g.O, nweights), 256, 0, st>>>(t, scale, g.O);
+    else bias_grad_kernel<float><<<dim3(g.O, nweights), 256, 0, st>>>(t, scale, g.O);
     SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }

@@ -8,20 +8,88 @@
 
 namespace sdb {
 
-size_t tc_bwd_workspace_bytes(int op, const Geo& g);
-// grad_input as a gathered implicit GEMM over the transposed sampling index (dcn_tc.cu, MODE_DX)
-int tc_dx(const void* w, const void* gy_nhwc, const void* desc, const int* start, const void* entries,
-          uint8_t* wimg, void* gx, const Geo& g, int okb, int io_dtype, cudaStream_t st);
-
-// forward with the sampling window of each tile staged in shared memory by TMA (dcn_tc_win.cu)
-bool tc_win_supported(const Geo& g);
-int tc_forward_win(const __nv_bfloat16* xp, const float* off, const float* mask, const void* w, const void* bias,
-                   uint8_t* wimg, float* bias32, void* out, const Geo& g, int io_dtype, cudaStream_t st);
+// operand images of one prepared weight tensor (dcn_tc.cu: prep_weights_kernel)
+struct TcWeightImages {
+  const uint8_t* fwd;     // forward B operand
+  const uint8_t* dgrad;   // W^T tiles of the dcol GEMM (grad_offset / grad_mask)
+  const uint8_t* dx;      // B operand of the grad_input GEMM
+  const float* bias;      // fp32 [O] or nullptr
+};
+// host-side description of one problem of a multi-problem call, pointers resolved into the workspace
+// spatial geometry of one problem (the rest of Geo is common to the launch)
+struct Dims {
+  int N, H, W, Ho, Wo;
+};
+__host__ __device__ __forceinline__ Geo with_dims(Geo g, const Dims& d) {
+  g.N = d.N; g.H = d.H; g.W = d.W; g.Ho = d.Ho; g.Wo = d.Wo;
+  return g;
+}
+struct TcProblem {
+  Dims d;
+  int weight_id, group;         // convolution this problem belongs to; offset group (shared transposed index)
+  const void* x;                // NCHW input (io dtype)
+  const float* off;
+  const float* mask;
+  void* out;
+  const void* gy;               // NCHW grad_out (io dtype)
+  void* gx;                     // NCHW grad_input or nullptr
+  float* goff;
+  float* gmask;
+  TcWeightImages w;
+  void* xp;                     // NHWC bf16 input
+  uint8_t* gy_img;              // dY as swizzled 128-pixel tiles
+  void* gyn;                    // dY NHWC bf16 [P][okb*64]
+  const void* desc;             // transposed index of this problem's group
+  const int* start;
+  const void* odesc;
+};
+// workspace layout of a multi-problem call (dcn_tc_bwd.cu: tc_plan)
+struct TcPlan {
+  size_t xp_off[16], gy_off[16], gyn_off[16];
+  size_t prep_off[4], part_off[4];
+  int group_of[16], group_rep[16], ngroups;
+  long long key_base[16], nkeys;
+  int scan_blocks;
+  size_t cnt_off, desc_off, clear_bytes, start_off, bsum_off, od_off;
+  int tiles_per_split[4], splits[4];
+  size_t total;
+};
+TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward);
+int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
+int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype, int accumulate, cudaStream_t st);
+int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
+int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
+                    int io_dtype, float scale, bool pack_x, int accumulate_gx, uint8_t* base, cudaStream_t st);
+size_t tc_prepared_weight_bytes(const Geo& g);
+TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bias);
+int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
+                       cudaStream_t st);   // which: 1 = forward image, 2 = dcol image, 4 = grad_input image (7 = all)
+int tc_lanes_per_pixel(const Geo& g);
+int tc_dx_col_blocks(const Geo& g);
 
 namespace tcshared {
 using namespace tc;
 
 constexpr int TILE_M = 128;
+
+// ------------------------------------------------------------------------------------------------
+// Multi-problem launches.  One launch of every tensor-core kernel covers ALL problems of a call
+// (the FPN levels x the convolutions of a head: RepPoints = 5 x 2), which share the channel counts
+// and the kernel geometry and differ in N, H, W and their tensors.  The problem table travels as a
+// kernel parameter (no device allocation, safe under CUDA-graph capture); a work item (128-pixel
+// tile) is mapped to (problem, tile) through the prefix array below -- at most MAX_PROBS entries.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_PROBS = 16;     // problems per launch
+constexpr int MAX_WEIGHTS = 4;    // distinct weight tensors (convolutions) per launch
+struct TileMap {
+  int n;                      // ranges in use
+  int start[MAX_PROBS + 1];   // first work item of range i; start[n] = total
+};
+__device__ __forceinline__ int find_range(const TileMap& m, int work) {
+  int i = 0;
+  while (i + 1 < m.n && work >= m.start[i + 1]) ++i;
+  return i;
+}
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -70,21 +138,30 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// NCHW -> NHWC bf16 for every problem of a call in one launch: grid.x walks (entry, image, pixel block) through
+// the TileMap (entry i owns N_i * nblk_i blocks), grid.y the 64-channel blocks.
+struct PackTable {
+  TileMap map;
+  struct E { const void* src; __nv_bfloat16* dst; int HW, nblk; } e[MAX_PROBS];
+  int C, Cd;
+};
 // [N][C][HW] (T) -> [N][HW][Cd] bf16, Cd >= C (channels C..Cd-1 zero).  Tile 64 channels x 32 pixels.
 template <typename T>
-__global__ void __launch_bounds__(256) pack_nhwc_kernel(const T* __restrict__ src,
-                                                        __nv_bfloat16* __restrict__ dst, int C, int HW, int Cd) {
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const __grid_constant__ PackTable t) {
   __shared__ float s[64][33];
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int ei = find_range(t.map, blockIdx.x);
+  const int local = blockIdx.x - t.map.start[ei];
+  const int HW = t.e[ei].HW, C = t.C, Cd = t.Cd;
+  const int n = local / t.e[ei].nblk, c0 = blockIdx.y * 64, p0 = (local % t.e[ei].nblk) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const T* sp = src + ((size_t)n * C + c0) * HW;
+  const T* sp = (const T*)t.e[ei].src + ((size_t)n * C + c0) * HW;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = ty + 8 * j;
     s[c][tx] = (c0 + c < C && p0 + tx < HW) ? to_f32(sp[(size_t)c * HW + p0 + tx]) : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* dp = dst + ((size_t)n * HW + p0) * Cd + c0;
+  __nv_bfloat16* dp = t.e[ei].dst + ((size_t)n * HW + p0) * Cd + c0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int p = ty + 8 * j;
@@ -97,12 +174,15 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const T* __restrict__ sr
 // bf16 source with an even pixel count per plane: 64 channels x 64 pixels per block, bf16x2 loads (128 B per
 // warp instruction), one 16-byte store (8 channels of one pixel) per thread and round -- half the load and a
 // quarter of the store instructions of the generic kernel.  Requires HW % 2 == 0 and Cd % 8 == 0.
-static __global__ void __launch_bounds__(256) pack_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ src,
-                                                             __nv_bfloat16* __restrict__ dst, int C, int HW, int Cd) {
+static __global__ void __launch_bounds__(256) pack_nhwc_bf16_kernel(const __grid_constant__ PackTable t) {
   __shared__ uint32_t s[64][33];   // [channel][pixel pair]
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int ei = find_range(t.map, blockIdx.x);
+  const int local = blockIdx.x - t.map.start[ei];
+  const int HW = t.e[ei].HW, C = t.C, Cd = t.Cd;
+  const int n = local / t.e[ei].nblk, c0 = blockIdx.y * 64, p0 = (local % t.e[ei].nblk) * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const __nv_bfloat16* sp = src + ((size_t)n * C + c0) * HW;
+  const __nv_bfloat16* sp = (const __nv_bfloat16*)t.e[ei].src + ((size_t)n * C + c0) * HW;
+  __nv_bfloat16* dst = t.e[ei].dst;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = ty + 8 * j, px = p0 + 2 * tx;
@@ -215,33 +295,33 @@ __device__ __forceinline__ void gather_stage_bf16(const uint4* __restrict__ x16,
   }
 }
 
-template <typename T>
-inline int pack_input(const void* x, __nv_bfloat16* xp, const Geo& g, cudaStream_t st) {
-  const int HW = g.H * g.W;
-  if (sizeof(T) == 2 && HW % 2 == 0 && g.C % 8 == 0) {
-    dim3 grid2(cdiv(HW, 64), cdiv(g.C, 64), g.N);
-    pack_nhwc_bf16_kernel<<<grid2, 256, 0, st>>>((const __nv_bfloat16*)x, xp, g.C, HW, g.C); SDB_LAUNCHED(1);
+// NCHW (io dtype) -> NHWC bf16 [N][HW][Cd] for `n` tensors in at most two launches (the bf16 fast path needs an even
+// plane size; entries that do not qualify go through the generic kernel)
+struct PackJob { const void* src; void* dst; int N, HW; };
+inline int pack_nhwc_multi(const PackJob* jobs, int n, int C, int Cd, bool src_bf16, cudaStream_t st) {
+  for (int pass = 0; pass < 2; ++pass) {   // pass 0: fast bf16 kernel, pass 1: generic
+    PackTable t{};
+    t.C = C; t.Cd = Cd;
+    int m = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!jobs[i].src || jobs[i].N * jobs[i].HW == 0) continue;
+      const bool fast = src_bf16 && jobs[i].HW % 2 == 0 && Cd % 8 == 0;
+      if (fast != (pass == 0)) continue;
+      const int nblk = (jobs[i].HW + (fast ? 63 : 31)) / (fast ? 64 : 32);
+      t.e[m].src = jobs[i].src; t.e[m].dst = (__nv_bfloat16*)jobs[i].dst; t.e[m].HW = jobs[i].HW; t.e[m].nblk = nblk;
+      t.map.start[m] = total;
+      total += jobs[i].N * nblk;
+      ++m;
+    }
+    t.map.n = m; t.map.start[m] = total;
+    if (total == 0) continue;
+    dim3 grid(total, (Cd + 63) / 64);
+    if (pass == 0) pack_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(t);
+    else if (src_bf16) pack_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(t);
+    else pack_nhwc_kernel<float><<<grid, 256, 0, st>>>(t);
+    SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
-    return SDB_OK;
   }
-  dim3 grid(cdiv(HW, 32), cdiv(g.C, 64), g.N);
-  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, xp, g.C, HW, g.C); SDB_LAUNCHED(1);
-  SDB_CHECK_CUDA(cudaGetLastError());
-  return SDB_OK;
-}
-// grad_out [N][O][HWo] -> [N][HWo][Od] bf16 (Od = okb*64 >= O, zero padded)
-template <typename T>
-inline int pack_grad_nhwc(const void* gy, __nv_bfloat16* gyp, const Geo& g, int Od, cudaStream_t st) {
-  const int HW = g.Ho * g.Wo;
-  if (sizeof(T) == 2 && HW % 2 == 0 && Od % 8 == 0) {
-    dim3 grid2(cdiv(HW, 64), cdiv(Od, 64), g.N);
-    pack_nhwc_bf16_kernel<<<grid2, 256, 0, st>>>((const __nv_bfloat16*)gy, gyp, g.O, HW, Od); SDB_LAUNCHED(1);
-    SDB_CHECK_CUDA(cudaGetLastError());
-    return SDB_OK;
-  }
-  dim3 grid(cdiv(HW, 32), cdiv(Od, 64), g.N);
-  pack_nhwc_kernel<T><<<grid, 256, 0, st>>>((const T*)gy, gyp, g.O, HW, Od); SDB_LAUNCHED(1);
-  SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 

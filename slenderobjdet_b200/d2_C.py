@@ -129,7 +129,8 @@ def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, colu
     g = _geom(input, weight, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
               deformable_group)
     _dc._check_shapes(input, offset, mask, weight, bias if with_bias else None, g, _out_hw(g))
-    gi, go, gm, gw, gb = _dc._backward_impl(input, offset, mask, weight, grad_output, g, None, True, True, bool(with_bias))
+    gi, go, gm, gw, gb = _dc._backward_impl(input, offset, mask, weight, grad_output, g, None, True, True, bool(with_bias),
+                                            bias=bias if with_bias else None)
     _store(grad_input, gi, True)
     _store(grad_offset, go, False)
     _store(grad_mask, gm, False)

@@ -196,52 +196,135 @@ class _on_device(object):
         return False
 
 
-def _forward_impl(input, offset, mask, weight, bias, g):
+# ---- prepared weights ---------------------------------------------------------------------------------------------
+# The tensor-core kernels read the weights as pre-swizzled operand images (sdb_dcn_prepare_weights).  They depend on
+# the weight VALUES only, so they are built once per weight version -- every forward / backward of every FPN level
+# until the next optimiser step reuses them -- instead of once per native call.
+_PREPARED = {}
+
+
+def invalidate_prepared_weights():
+    """Drop the cached operand images.  Only needed after mutating a weight through ``.data`` IN PLACE (which does
+    not bump the tensor's version counter); optimiser steps, ``copy_`` / ``load_state_dict`` and ``.data = ...`` are
+    detected automatically."""
+    _PREPARED.clear()
+
+
+def _prepared_weights(weight, bias, g, iod, mth):
+    """-> uint8 tensor with the operand images of (weight, bias), cached on (tensor identity, version)."""
+    if mth != _lib.SDB_MATH_BF16:
+        return None
+    key = (id(weight), weight.device.index)
+    ver = (weight._version, weight.data_ptr(), None if bias is None else (id(bias), bias._version, bias.data_ptr()),
+           iod, g.C_in, g.C_out, g.kH, g.kW)
+    hit = _PREPARED.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == ver:
+        return hit[2]
     lib = _lib.lib()
-    cdt, iod, mth, (ho, wo), wsb, pkb = _plan(input, weight, g)
+    nbytes = int(lib.sdb_dcn_prepared_weight_bytes(ctypes.byref(g), iod, mth))
+    buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=weight.device)
+    _lib.check(lib.sdb_dcn_prepare_weights(_lib.ptr(weight), _lib.ptr(bias), ctypes.byref(g), iod, mth, _lib.ptr(buf),
+                                           _lib.stream_ptr(weight.device)))
+    if len(_PREPARED) > 64:
+        for k in [k for k, v in _PREPARED.items() if v[0]() is None]:
+            del _PREPARED[k]
+    import weakref
+    _PREPARED[key] = (weakref.ref(weight), ver, buf)
+    return buf
+
+
+def _problem(x, off, m, wid=0, group=-1, out=None, packed=None, gy=None, gx=None, goff=None, gmask=None):
+    return _lib.Problem(x.shape[0], x.shape[2], x.shape[3], wid, group, 0, _lib.addr(x), _lib.addr(off), _lib.addr(m),
+                        _lib.addr(out), _lib.addr(packed), _lib.addr(gy), _lib.addr(gx), _lib.addr(goff), _lib.addr(gmask))
+
+
+def _multi_forward(xs, offs, masks, weights, biases, wids, groups, g, iod, mth, cdt):
+    """One sdb_dcn_forward_multi call.  xs / offs / masks: per-problem tensors already in the compute dtype;
+    weights / biases: per-weight tensors.  -> (outputs, packed inputs | None)."""
+    lib = _lib.lib()
+    n, dev = len(xs), xs[0].device
+    tc = mth == _lib.SDB_MATH_BF16
+    gp = ctypes.byref(g)
+    outs, packed = [], []
+    for x in xs:
+        gi = _lib.Geom(x.shape[0], g.C_in, x.shape[2], x.shape[3], g.C_out, g.kH, g.kW, g.sH, g.sW, g.pH, g.pW, g.dH,
+                       g.dW, g.groups, g.deformable_groups)
+        ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.check(lib.sdb_dcn_output_size(ctypes.byref(gi), ho, wo))
+        outs.append(torch.empty((x.shape[0], g.C_out, ho.value, wo.value), dtype=cdt, device=dev))
+        packed.append(_ws(lib.sdb_dcn_packed_input_bytes(ctypes.byref(gi), mth), dev) if tc else None)
+    probs = (_lib.Problem * n)(*[_problem(xs[i], offs[i], masks[i], wids[i], groups[i], outs[i], packed[i]) for i in range(n)])
+    prep = [_prepared_weights(w, b, g, iod, mth) for w, b in zip(weights, biases)]
+    wts = (_lib.Weights * len(weights))(*[_lib.Weights(_lib.addr(w), _lib.addr(b), _lib.addr(p), None, None)
+                                          for w, b, p in zip(weights, biases, prep)])
+    wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 0)) if tc else 0
+    ws = _ws(wsb, dev)
+    with _on_device(dev):
+        _lib.check(lib.sdb_dcn_forward_multi(probs, n, wts, len(weights), gp, iod, mth, _lib.ptr(ws), wsb,
+                                             _lib.stream_ptr(dev)))
+    return outs, packed
+
+
+def _multi_backward(xs, offs, masks, weights, biases, wids, groups, gys, packed, g, iod, mth, cdt, need_x, need_off,
+                    need_mask, need_w, need_b, scale=1.0):
+    """One sdb_dcn_backward_multi call: grad_offset / grad_mask, grad_input and grad_weight / grad_bias of every
+    problem from one packed copy of grad_out.  need_*: per-problem (x, offset, mask) / per-weight (w, b) flags.
+    -> (grad_x list, grad_offset list, grad_mask list, grad_weight list (fp32), grad_bias list (fp32))."""
+    lib = _lib.lib()
+    n, dev = len(xs), xs[0].device
+    tc = mth == _lib.SDB_MATH_BF16
+    gp = ctypes.byref(g)
+    # v1 computes grad_input and grad_offset together if either is needed (deform_conv.py:88); the kernels can skip either
+    gxs = [torch.empty_like(xs[i]) if need_x[i] else None for i in range(n)]
+    gos = [torch.empty_like(offs[i]) if need_off[i] else None for i in range(n)]
+    gms = [torch.empty_like(masks[i]) if (masks[i] is not None and need_mask[i]) else None for i in range(n)]
+    gws = [torch.zeros(w.shape, dtype=torch.float32, device=dev) if need_w[k] else None for k, w in enumerate(weights)]
+    gbs = [torch.zeros((g.C_out,), dtype=torch.float32, device=dev) if (need_b[k] and biases[k] is not None) else None
+           for k in range(len(weights))]
+    probs = (_lib.Problem * n)(*[_problem(xs[i], offs[i], masks[i], wids[i], groups[i], None,
+                                          packed[i] if packed is not None else None, gys[i], gxs[i], gos[i], gms[i])
+                                 for i in range(n)])
+    # the weight VALUES are read only by grad_input / grad_offset / grad_mask; a grad_weight-only call needs no image
+    reads = [any(wids[i] == k and (need_x[i] or need_off[i] or need_mask[i]) for i in range(n)) for k in range(len(weights))]
+    prep = [_prepared_weights(w, b, g, iod, mth) if r else None for w, b, r in zip(weights, biases, reads)]
+    wts = (_lib.Weights * len(weights))(*[_lib.Weights(_lib.addr(w), _lib.addr(b), _lib.addr(p), _lib.addr(gw), _lib.addr(gb))
+                                          for w, b, p, gw, gb in zip(weights, biases, prep, gws, gbs)])
+    wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 1)) if tc else 0
+    ws = _ws(wsb, dev)
+    with _on_device(dev):
+        _lib.check(lib.sdb_dcn_backward_multi(probs, n, wts, len(weights), gp, iod, mth, float(scale), _lib.ptr(ws), wsb,
+                                              _lib.stream_ptr(dev)))
+    return gxs, gos, gms, gws, gbs
+
+
+def _forward_impl(input, offset, mask, weight, bias, g):
+    cdt, iod, mth, _, _, _ = _plan(input, weight, g)
     x, w, b = _as(input, cdt), _as(weight, cdt), _as(bias, cdt)
     off, m = _as(offset, torch.float32), _as(mask, torch.float32)
-    out = torch.empty((g.N, g.C_out, ho, wo), dtype=cdt, device=input.device)
-    ws = _ws(wsb[0], input.device)
-    packed = _ws(pkb, input.device) if pkb else None
-    with _on_device(input.device):
-        _lib.check(lib.sdb_dcn_forward(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w), _lib.ptr(b),
-                                       _lib.ptr(out), ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb[0],
-                                       _lib.ptr(packed), _lib.stream_ptr(input.device)))
-    return (out if out.dtype == input.dtype else out.to(input.dtype)), packed
+    outs, packed = _multi_forward([x], [off], [m], [w if w is not weight else weight], [b], [0], [-1], g, iod, mth, cdt)
+    out = outs[0]
+    return (out if out.dtype == input.dtype else out.to(input.dtype)), packed[0]
 
 
-def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias, scale=1.0):
+def _backward_impl(input, offset, mask, weight, grad_output, g, packed, need_data, need_weight, with_bias, scale=1.0,
+                   bias=None):
     """-> grad_input, grad_offset, grad_mask, grad_weight, grad_bias (None where not requested)."""
-    lib = _lib.lib()
-    cdt, iod, mth, _, wsb, _ = _plan(input, weight, g)
+    cdt, iod, mth, _, _, _ = _plan(input, weight, g)
     x, w, gy = _as(input, cdt), _as(weight, cdt), _as(grad_output, cdt)
     off, m = _as(offset, torch.float32), _as(mask, torch.float32)
-    dev = input.device
-    gi = go = gm = gw = gb = None
-    with _on_device(dev):
-        st = _lib.stream_ptr(dev)
-        if need_data:
-            gi = torch.zeros_like(x)  # accumulated into (deform_conv.py:89)
-            go = torch.empty_like(off)
-            gm = torch.empty_like(m) if m is not None else None
-            ws = _ws(wsb[1], dev)
-            _lib.check(lib.sdb_dcn_backward_data(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(w),
-                                                 _lib.ptr(gy), _lib.ptr(gi), _lib.ptr(go), _lib.ptr(gm),
-                                                 ctypes.byref(g), iod, mth, _lib.ptr(ws), wsb[1],
-                                                 _lib.ptr(packed), st))
-            gi = _as(gi, input.dtype)
-            go = _as(go, offset.dtype)
-            gm = _as(gm, mask.dtype) if gm is not None else None
-        if need_weight:
-            gw = torch.zeros(weight.shape, dtype=torch.float32, device=dev)  # deform_conv.py:113
-            gb = torch.zeros((g.C_out,), dtype=torch.float32, device=dev) if with_bias else None
-            ws = _ws(wsb[2], dev)
-            _lib.check(lib.sdb_dcn_backward_weight(_lib.ptr(x), _lib.ptr(off), _lib.ptr(m), _lib.ptr(gy),
-                                                   _lib.ptr(gw), _lib.ptr(gb), float(scale), ctypes.byref(g), iod, mth,
-                                                   _lib.ptr(ws), wsb[2], _lib.ptr(packed), st))
-            gw = _as(gw, weight.dtype)
-            gb = _as(gb, weight.dtype) if gb is not None else None
+    if with_bias and bias is None:   # only "is there a bias" matters to the backward
+        bias = torch.zeros(g.C_out, dtype=cdt, device=input.device)
+    b = _as(bias, cdt) if with_bias else None
+    gxs, gos, gms, gws, gbs = _multi_backward([x], [off], [m], [w], [b], [0], [-1], [gy],
+                                              [packed] if packed is not None else None, g, iod, mth, cdt,
+                                              [need_data], [need_data], [need_data], [need_weight], [need_weight and with_bias],
+                                              scale)
+    gi, go, gm, gw, gb = gxs[0], gos[0], gms[0], gws[0], gbs[0]
+    gi = _as(gi, input.dtype) if gi is not None else None
+    go = _as(go, offset.dtype) if go is not None else None
+    gm = _as(gm, mask.dtype) if gm is not None else None
+    gw = _as(gw, weight.dtype) if gw is not None else None
+    gb = _as(gb, weight.dtype) if gb is not None else None
     return gi, go, gm, gw, gb
 
 
@@ -336,6 +419,7 @@ class _ModulatedDeformConv(Function):
         if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
             ctx.save_for_backward(input, offset, mask, weight)
             ctx.packed_ = packed
+            ctx.bias_ = bias.detach() if bias is not None else None
         return output
 
     @staticmethod
@@ -347,7 +431,7 @@ class _ModulatedDeformConv(Function):
         g = _geom(input, weight, _pair(ctx.stride), _pair(ctx.padding), _pair(ctx.dilation), ctx.groups,
                   ctx.deformable_groups)
         gi, go, gm, gw, gb = _backward_impl(input, offset, mask, weight, grad_output, g, ctx.packed_,
-                                            True, True, ctx.with_bias)
+                                            True, True, ctx.with_bias, bias=ctx.bias_)
         return gi, go, gm, gw, gb, None, None, None, None, None
 
     @staticmethod

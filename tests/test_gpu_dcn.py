@@ -288,51 +288,3 @@ def test_auto_mode_falls_back_to_fp32_kernels_for_unsupported_geometry():
     assert rel_err(y.cpu().numpy(), yo) < TOL["fp32"]
     with sdb.dcn_math("bf16"), pytest.raises(RuntimeError):
         sdb.deform_conv(x.cuda(), off.cuda(), w.cuda(), 1, 2, 1, 1, 1)
-
-
-# ---- window-staged forward kernel (csrc/dcn_tc_win.cu, opt-in with SDB_TC_WIN=1) -----------------------
-@pytest.mark.parametrize("cl", ["1", "2"])
-@pytest.mark.parametrize("modulated", [False, True])
-@pytest.mark.parametrize("shape", [(2, 64, 13, 21, 64, 2.0), (1, 128, 25, 42, 256, 0.5), (2, 256, 7, 11, 256, 8.0),
-                                   (3, 256, 20, 19, 128, 30.0), (1, 256, 37, 50, 256, 3.0)])
-def test_window_forward_vs_oracle(monkeypatch, cl, modulated, shape):
-    """The TMA-window forward (every tile's sampling window staged in shared memory; samples outside it go
-    through global memory) against the CPU oracle: in-window offsets (sigma 0.5), mixed (2-3), mostly
-    out-of-window / out-of-image (8, 30); with and without the 2-CTA weight multicast; ragged tile edges."""
-    monkeypatch.setenv("SDB_TC_WIN", "1")
-    monkeypatch.setenv("SDB_TC_WIN_CL", cl)
-    N, C, H, W, O, sigma = shape
-    c = _random_case(131 + N + C, N, C, H, W, O, modulated, sigma)
-    y, *_ = _run(c, "bf16", need_grads=False)
-    yo = odcn.forward(c["x"], c["offset"], c["weight"], mask=c.get("mask"), bias=c.get("bias"), stride=(1, 1),
-                      padding=(1, 1), dilation=(1, 1), groups=1, deformable_groups=1)
-    assert rel_err(y.detach().cpu().numpy(), yo) < TOL["bf16"]
-
-
-@pytest.mark.parametrize("cfg", [(2, 2, 2, 2, 2, 2), (2, 1, 1, 1, 1, 1), (1, 1, 2, 2, 2, 2), (1, 2, 0, 1, 1, 1)])
-def test_window_forward_strided_dilated(monkeypatch, cfg):
-    """Window geometry with stride / dilation / asymmetric padding (the window origin and extent depend on all
-    three): forward against the CPU oracle."""
-    monkeypatch.setenv("SDB_TC_WIN", "1")
-    sh, sw, ph, pw, dh, dw = cfg
-    g = torch.Generator().manual_seed(9)
-    N, C, H, W, O, k = 2, 64, 23, 31, 64, 3
-    Ho = (H + 2 * ph - (dh * (k - 1) + 1)) // sh + 1
-    Wo = (W + 2 * pw - (dw * (k - 1) + 1)) // sw + 1
-    c = dict(x=torch.randn(N, C, H, W, generator=g).numpy(), weight=(torch.randn(O, C, k, k, generator=g) * 0.05).numpy(),
-             offset=(torch.randn(N, 2 * k * k, Ho, Wo, generator=g) * 1.5).numpy(),
-             grad_out=torch.randn(N, O, Ho, Wo, generator=g).numpy(), cfg=np.array([sh, sw, ph, pw, dh, dw, 1, 1]))
-    y, *_ = _run(c, "bf16", need_grads=False)
-    yo = odcn.forward(c["x"], c["offset"], c["weight"], stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw),
-                      groups=1, deformable_groups=1)
-    assert rel_err(y.detach().cpu().numpy(), yo) < TOL["bf16"]
-
-
-def test_window_forward_matches_l2_gather_kernel(monkeypatch):
-    """Both forward kernels on the RepPoints P4 shape: same bf16 operands, so they agree far inside the tolerance."""
-    c = _random_case(5, 2, 256, 50, 84, 256, False, 2.0)
-    monkeypatch.setenv("SDB_TC_WIN", "0")
-    y0, *_ = _run(c, "bf16", need_grads=False)
-    monkeypatch.setenv("SDB_TC_WIN", "1")
-    y1, *_ = _run(c, "bf16", need_grads=False)
-    assert rel_err(y1.detach().cpu().numpy(), y0.detach().cpu().numpy()) < 2e-3
