@@ -161,9 +161,15 @@ size_t sdb_dcn_multi_workspace_bytes(const sdb_dcn_problem* problems, int32_t n_
 int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
                           int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, void* workspace,
                           size_t workspace_bytes, void* stream);
-/* Replaces the loop of deform_conv_backward_input + deform_conv_backward_filter (or modulated_deform_conv_backward). */
+/* Replaces the loop of deform_conv_backward_input + deform_conv_backward_filter (or modulated_deform_conv_backward).
+ * `flags` (0 = everything in one go) lets a data-parallel trainer start the weight-gradient all-reduce early:
+ *   SDB_BWD_WEIGHT_ONLY  only grad_weight / grad_bias (first call: packs grad_out into the workspace);
+ *   SDB_BWD_DATA_ONLY    only grad_x / grad_offset / grad_mask;
+ *   SDB_BWD_GRAD_PACKED  the workspace still holds the packed grad_out of a previous call on the SAME table
+ *                        (second call: SDB_BWD_DATA_ONLY | SDB_BWD_GRAD_PACKED while NCCL reduces the weight grads). */
+enum { SDB_BWD_WEIGHT_ONLY = 1, SDB_BWD_DATA_ONLY = 2, SDB_BWD_GRAD_PACKED = 4 };
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
-                           int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, float scale,
+                           int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags,
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- label assignment (HBM/latency-bound; no tensor cores) ------------------------------------

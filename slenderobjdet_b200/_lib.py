@@ -51,6 +51,7 @@ class Weights(ctypes.Structure):
 
 
 SDB_MAX_PROBLEMS, SDB_MAX_WEIGHTS = 16, 4
+SDB_BWD_WEIGHT_ONLY, SDB_BWD_DATA_ONLY, SDB_BWD_GRAD_PACKED = 1, 2, 4
 
 _lib = None
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -79,7 +80,7 @@ def _declare(lib):
     lib.sdb_dcn_multi_workspace_bytes.restype = _sz
     lib.sdb_dcn_multi_workspace_bytes.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.sdb_dcn_forward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _vp, _sz, _vp]
-    lib.sdb_dcn_backward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _f32, _vp, _sz, _vp]
+    lib.sdb_dcn_backward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _f32, ctypes.c_int, _vp, _sz, _vp]
     lib.sdb_assign_workspace_bytes.restype = _sz
     lib.sdb_assign_workspace_bytes.argtypes = [_i32, _i32, _i32]
     lib.sdb_iou_assign.argtypes = [_vp, _vp, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int8),

@@ -253,7 +253,7 @@ int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g
 }
 
 int multi_fp32(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, const Geo& g, bool backward, float scale,
-               cudaStream_t st) {
+               int flags, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     const sdb_dcn_problem& q = probs[i];
     const sdb_dcn_weights& ww = w[q.weight_id];
@@ -267,11 +267,12 @@ int multi_fp32(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, co
     if (!backward) {
       rc = simt_forward((const float*)q.x, q.offset, q.mask, (const float*)ww.weight, (const float*)ww.bias, (float*)q.out, gi, st);
     } else {
-      if (q.grad_x) SDB_CHECK_CUDA(cudaMemsetAsync(q.grad_x, 0, (size_t)gi.N * gi.C * gi.H * gi.W * 4, st));   // overwritten
-      if (q.grad_x || q.grad_offset || q.grad_mask)
+      const bool do_data = !(flags & SDB_BWD_WEIGHT_ONLY), do_w = !(flags & SDB_BWD_DATA_ONLY);
+      if (do_data && q.grad_x) SDB_CHECK_CUDA(cudaMemsetAsync(q.grad_x, 0, (size_t)gi.N * gi.C * gi.H * gi.W * 4, st));   // overwritten
+      if (do_data && (q.grad_x || q.grad_offset || q.grad_mask))
         rc = simt_backward_data((const float*)q.x, q.offset, q.mask, (const float*)ww.weight, (const float*)q.grad_out,
                                 (float*)q.grad_x, q.grad_offset, q.mask ? q.grad_mask : nullptr, gi, st);
-      if (!rc && (ww.grad_weight || ww.grad_bias))
+      if (!rc && do_w && (ww.grad_weight || ww.grad_bias))
         rc = simt_backward_weight((const float*)q.x, q.offset, q.mask, (const float*)q.grad_out, ww.grad_weight,
                                   ww.grad_bias, scale, gi, st);
     }
@@ -347,7 +348,7 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_
   for (int i = 0; i < n; ++i)
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].out), SDB_ERR_INVALID,
                 "problem %d: x, offset and out must be non-NULL", i);
-  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, false, 1.f, st);
+  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, false, 1.f, 0, st);
   MultiCall mc;
   rc = build_call(problems, n, weights, nw, d, false, mc);
   if (rc) return rc;
@@ -360,7 +361,7 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_
 }
 
 static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
-                               const Geo& d, int io_dtype, float scale, int accumulate_gx, void* workspace,
+                               const Geo& d, int io_dtype, float scale, int accumulate_gx, int flags, void* workspace,
                                size_t workspace_bytes, cudaStream_t st) {
   MultiCall mc;
   int rc = build_call(problems, n, weights, nw, d, true, mc);
@@ -377,20 +378,25 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     pack_any |= own;
     if (!own) mc.pb[i].x = nullptr;   // pack_nhwc_multi skips NULL sources
   }
+  if (flags & SDB_BWD_DATA_ONLY)
+    for (int k = 0; k < nw; ++k) mc.gw[k] = mc.gb[k] = nullptr;
+  if (flags & SDB_BWD_WEIGHT_ONLY)
+    for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
   return tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
-                         (uint8_t*)workspace, st);
+                         (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st);
 }
 
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
-                           const sdb_dcn_geom* g, int io_dtype, int math, float scale, void* workspace,
+                           const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags, void* workspace,
                            size_t workspace_bytes, void* stream) {
   SDB_MULTI_PROLOGUE();
+  SDB_REQUIRE((flags & ~7) == 0 && (flags & 3) != 3, SDB_ERR_INVALID, "bad backward flags %d", flags);
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].grad_out), SDB_ERR_INVALID,
                 "problem %d: x, offset and grad_out must be non-NULL", i);
-  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, true, scale, st);
-  return backward_multi_impl(problems, n, weights, nw, d, io_dtype, scale, 0, workspace, workspace_bytes, st);
+  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, true, scale, flags, st);
+  return backward_multi_impl(problems, n, weights, nw, d, io_dtype, scale, 0, flags, workspace, workspace_bytes, st);
 }
 
 // ---- single-problem entry points (the reference's call granularity) --------------------------------------------
@@ -445,7 +451,7 @@ int sdb_dcn_backward_data(const void* x, const float* offset, const float* mask,
   s.p.grad_x = grad_x; s.p.grad_offset = grad_offset; s.p.grad_mask = grad_mask;
   s.w.weight = weight;
   // this entry point ACCUMULATES into grad_x (the reference's contract, deform_conv.py:89)
-  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, 1.f, 1, workspace, workspace_bytes, st);
+  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, 1.f, 1, 0, workspace, workspace_bytes, st);
 }
 
 int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mask,
@@ -460,7 +466,7 @@ int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mas
   Single s = single_of(g);
   s.p.x = x; s.p.offset = offset; s.p.mask = mask; s.p.x_packed = (void*)x_packed; s.p.grad_out = grad_out;
   s.w.grad_weight = grad_weight; s.w.grad_bias = grad_bias;   // no operand image of the weights is read here
-  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, scale, 0, workspace, workspace_bytes, st);
+  return backward_multi_impl(&s.p, 1, &s.w, 1, d, io_dtype, scale, 0, 0, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

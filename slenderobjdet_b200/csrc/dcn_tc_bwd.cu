@@ -1165,7 +1165,8 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
 // dY is packed once per problem (tile image + NHWC rows) and serves the three kernels; the transposed index is built
 // once per offset group; one launch per kernel over all problems.
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
-                    int io_dtype, float scale, bool pack_x, int accumulate_gx, uint8_t* base, cudaStream_t st) {
+                    int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
+                    cudaStream_t st) {
   const int NCH = nch_of(g), okb = okb_of(g);
   const bool bf = io_dtype == SDB_BF16;
   int rc;
@@ -1174,13 +1175,13 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   for (int w = 0; w < nweights; ++w) { any_gw |= gw[w] != nullptr; any_gb |= gb[w] != nullptr; }
 
   // (0) layouts: x -> NHWC (unless the forward exported it), dY -> tile image and NHWC rows
-  if (pack_x && (any_goff || any_gw)) {
+  if (pack_x && !grad_packed && (any_goff || any_gw)) {
     PackJob jobs[MAX_PROBS];
     for (int i = 0; i < n; ++i) jobs[i] = PackJob{pb[i].x, pb[i].xp, pb[i].d.N, pb[i].d.H * pb[i].d.W};
     rc = pack_nhwc_multi(jobs, n, g.C, g.C, bf, st);
     if (rc) return rc;
   }
-  if (any_goff || any_gw) {
+  if (!grad_packed && (any_goff || any_gw)) {
     for (int pass = 0; pass < 2; ++pass) {   // pass 0: vectorised bf16 kernel, pass 1: generic
       PackGyTable t{};
       t.g = g;

@@ -59,7 +59,8 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
 int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype, int accumulate, cudaStream_t st);
 int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
-                    int io_dtype, float scale, bool pack_x, int accumulate_gx, uint8_t* base, cudaStream_t st);
+                    int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
+                    cudaStream_t st);
 size_t tc_prepared_weight_bytes(const Geo& g);
 TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bias);
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,

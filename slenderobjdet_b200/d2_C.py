@@ -19,11 +19,12 @@ Arithmetic follows ``set_dcn_math`` (slenderobjdet_b200.layers.deform_conv): flo
 kernels unless bf16 / tf32 tensor-core math was selected explicitly; bfloat16 tensors use the tcgen05 kernels.
 """
 import ctypes
-
-import torch
+import importlib
 
 from . import _lib
-from .layers import deform_conv as _dc
+
+# the MODULE (the package re-exports a function of the same name)
+_dc = importlib.import_module(".layers.deform_conv", __package__)
 
 
 def _geom(input, weight, kH, kW, sH, sW, pH, pW, dH, dW, group, deformable_group):

@@ -109,7 +109,7 @@ def _check_shapes(input, offset, mask, weight, bias, g, out_hw):
 
 def _bf16_autocast():
     try:
-        return torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        return torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
     except Exception:  # pragma: no cover
         return False
 
@@ -292,7 +292,7 @@ def _multi_backward(xs, offs, masks, weights, biases, wids, groups, gys, packed,
     wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 1)) if tc else 0
     ws = _ws(wsb, dev)
     with _on_device(dev):
-        _lib.check(lib.sdb_dcn_backward_multi(probs, n, wts, len(weights), gp, iod, mth, float(scale), _lib.ptr(ws), wsb,
+        _lib.check(lib.sdb_dcn_backward_multi(probs, n, wts, len(weights), gp, iod, mth, float(scale), 0, _lib.ptr(ws), wsb,
                                               _lib.stream_ptr(dev)))
     return gxs, gos, gms, gws, gbs
 
@@ -445,6 +445,129 @@ class _ModulatedDeformConv(Function):
         return n, channels_out, height_out, width_out
 
 
+class _DeformConvMulti(Function):
+    """All deformable convolutions of a dense head in one native call per pass (sdb_dcn_forward_multi /
+    sdb_dcn_backward_multi): every FPN level x every convolution.  Tensor arguments arrive flattened as
+    inputs[n] + offsets[n] + masks[n or 0] + weights[k] + biases[k or 0]; ``meta`` describes the split."""
+
+    @staticmethod
+    def forward(ctx, meta, *tensors):
+        n, k, has_mask, has_bias, wids, groups, stride, padding, dilation = meta
+        groups = list(groups)
+        xs = list(tensors[:n])
+        offs = list(tensors[n:2 * n])
+        pos = 2 * n
+        masks = list(tensors[pos:pos + n]) if has_mask else [None] * n
+        pos += n if has_mask else 0
+        ws = list(tensors[pos:pos + k])
+        pos += k
+        bs = list(tensors[pos:pos + k]) if has_bias else [None] * k
+        for t in xs:
+            if t.dim() != 4:
+                raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(t.dim()))
+            if not t.is_cuda:
+                raise NotImplementedError("Deformable Conv is not supported on CPUs!")
+        w0 = ws[0]
+        for w in ws:
+            if tuple(w.shape) != tuple(w0.shape) or w.dtype != w0.dtype:
+                raise RuntimeError("the convolutions of one multi call must share their weight shape and dtype")
+        g = _geom(xs[0], w0, stride, padding, dilation, 1, 1)
+        cdt, iod, mth, _, _, _ = _plan(xs[0], w0, g)
+        for i in range(n):
+            gi = _geom(xs[i], w0, stride, padding, dilation, 1, 1)
+            ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
+            try:
+                _lib.check(_lib.lib().sdb_dcn_output_size(ctypes.byref(gi), ho, wo))
+            except RuntimeError as e:
+                raise ValueError(str(e))
+            _check_shapes(xs[i], offs[i], masks[i], ws[wids[i]], bs[wids[i]], gi, (ho.value, wo.value))
+        cx = [_as(t, cdt) for t in xs]
+        co = [_as(t, torch.float32) for t in offs]
+        cm = [_as(t, torch.float32) for t in masks]
+        cw = [_as(t, cdt) for t in ws]
+        cb = [_as(t, cdt) for t in bs]
+        outs, packed = _multi_forward(cx, co, cm, cw, cb, wids, groups, g, iod, mth, cdt)
+        ctx.save_for_backward(*tensors)
+        ctx.meta_, ctx.groups_, ctx.packed_, ctx.g_ = meta, groups, packed, g
+        return tuple(o if o.dtype == xs[i].dtype else o.to(xs[i].dtype) for i, o in enumerate(outs))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grad_outputs):
+        n, k, has_mask, has_bias, wids, _, stride, padding, dilation = ctx.meta_
+        tensors = ctx.saved_tensors
+        xs, offs = list(tensors[:n]), list(tensors[n:2 * n])
+        pos = 2 * n
+        masks = list(tensors[pos:pos + n]) if has_mask else [None] * n
+        pos += n if has_mask else 0
+        ws = list(tensors[pos:pos + k])
+        pos += k
+        bs = list(tensors[pos:pos + k]) if has_bias else [None] * k
+        g = ctx.g_
+        cdt, iod, mth, _, _, _ = _plan(xs[0], ws[0], g)
+        need = ctx.needs_input_grad[1:]
+        need_x = [bool(need[i]) for i in range(n)]
+        need_off = [bool(need[n + i]) for i in range(n)]
+        pos = 2 * n
+        need_mask = [bool(need[pos + i]) for i in range(n)] if has_mask else [False] * n
+        pos += n if has_mask else 0
+        need_w = [bool(need[pos + j]) for j in range(k)]
+        pos += k
+        need_b = [bool(need[pos + j]) for j in range(k)] if has_bias else [False] * k
+        gys = [_as(gy, cdt) for gy in grad_outputs]
+        gxs, gos, gms, gws, gbs = _multi_backward(
+            [_as(t, cdt) for t in xs], [_as(t, torch.float32) for t in offs], [_as(t, torch.float32) for t in masks],
+            [_as(t, cdt) for t in ws], [_as(t, cdt) for t in bs], wids, ctx.groups_, gys, ctx.packed_, g, iod, mth, cdt,
+            need_x, need_off, need_mask, need_w, need_b)
+        out = [None]
+        out += [None if t is None else _as(t, xs[i].dtype) for i, t in enumerate(gxs)]
+        out += [None if t is None else _as(t, offs[i].dtype) for i, t in enumerate(gos)]
+        if has_mask:
+            out += [None if t is None else _as(t, masks[i].dtype) for i, t in enumerate(gms)]
+        out += [None if t is None else _as(t, ws[j].dtype) for j, t in enumerate(gws)]
+        if has_bias:
+            out += [None if t is None else _as(t, bs[j].dtype) for j, t in enumerate(gbs)]
+        return tuple(out)
+
+
+def deform_conv_multi(inputs, offsets, weights, stride=1, padding=0, dilation=1, masks=None, biases=None,
+                      weight_ids=None):
+    """Every deformable convolution of a dense head in ONE native call per pass.
+
+    The reference loops ``deform_conv`` over FPN levels and branches (reppointsv2.py:728-752: 10 forward and 20
+    backward native calls per step for the RepPoints head).  Here ``inputs`` / ``offsets`` (and ``masks`` for DCNv2)
+    list one entry per (level, branch) problem, ``weights`` is one tensor or a list of up to four that share their
+    shape (e.g. ``[cls_conv.weight, refine_conv.weight]``) and ``weight_ids[i]`` says which of them problem ``i``
+    uses.  Problems that are given the SAME offset tensor object (the two DCNs of a RepPoints level consume one
+    ``dcn_offset``) share the transposed sampling index in the backward.  Semantics per problem are exactly those of
+    ``deform_conv`` / ``modulated_deform_conv``; groups = deformable_groups = 1.  Returns the list of outputs."""
+    single_w = torch.is_tensor(weights)
+    ws = [weights] if single_w else list(weights)
+    n = len(inputs)
+    if n == 0:
+        return []
+    if len(offsets) != n or (masks is not None and len(masks) != n):
+        raise ValueError("inputs, offsets and masks must have one entry per problem")
+    if n > _lib.SDB_MAX_PROBLEMS or len(ws) > _lib.SDB_MAX_WEIGHTS:
+        raise ValueError("at most %d problems and %d weight tensors per call" % (_lib.SDB_MAX_PROBLEMS, _lib.SDB_MAX_WEIGHTS))
+    wids = [0] * n if weight_ids is None else [int(v) for v in weight_ids]
+    if biases is not None and torch.is_tensor(biases):
+        biases = [biases]
+    if biases is not None and any(b is None for b in biases):
+        raise ValueError("biases: give one tensor per weight, or None for no bias at all")
+    # offsets that are the same tensor object (with the same mask and input size) form one offset group: the backward
+    # builds their transposed sampling index once
+    groups, seen = [], {}
+    for i in range(n):
+        key = (id(offsets[i]), None if masks is None else id(masks[i]), tuple(inputs[i].shape))
+        groups.append(seen.setdefault(key, len(seen)))
+    meta = (n, len(ws), masks is not None, biases is not None, tuple(wids), tuple(groups), _pair(stride), _pair(padding),
+            _pair(dilation))
+    tensors = list(inputs) + list(offsets) + (list(masks) if masks is not None else []) + ws + \
+        (list(biases) if biases is not None else [])
+    return list(_DeformConvMulti.apply(meta, *tensors))
+
+
 deform_conv = _DeformConv.apply
 modulated_deform_conv = _ModulatedDeformConv.apply
 
@@ -491,6 +614,18 @@ class DeformConv(nn.Module):
         if self.activation is not None:
             x = self.activation(x)
         return x
+
+    def forward_multi(self, xs, offsets):
+        """``[self(x, offset) for x, offset in zip(xs, offsets)]`` for all FPN levels in one native call per pass
+        (``deform_conv_multi``); norm / activation are applied per level as in ``forward``."""
+        if self.groups != 1 or self.deformable_groups != 1 or any(x.numel() == 0 for x in xs):
+            return [self(x, o) for x, o in zip(xs, offsets)]
+        ys = deform_conv_multi(xs, offsets, self.weight, self.stride, self.padding, self.dilation)
+        if self.norm is not None:
+            ys = [self.norm(y) for y in ys]
+        if self.activation is not None:
+            ys = [self.activation(y) for y in ys]
+        return ys
 
     def extra_repr(self):
         tmpstr = "in_channels=" + str(self.in_channels)
