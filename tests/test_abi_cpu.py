@@ -99,3 +99,62 @@ def test_matcher_constructor_contract():
         sdb.Matcher([0.0, 0.7], [0, -1, 1])
     with pytest.raises(RuntimeError):
         t(torch.zeros(3, 20))  # CPU tensors: no fallback
+
+
+def _table(levels, batch=2, groups=True):
+    rows = []
+    for li, (h, w) in enumerate(levels):
+        for b in range(2):
+            rows.append(_lib.Problem(batch, h, w, b, li if groups else -1, 0, 0x1000, 0x2000 + li, None, 0x3000, None,
+                                     0x4000, 0x5000, 0x6000, None))
+    return (_lib.Problem * len(rows))(*rows), len(rows)
+
+
+def test_multi_problem_table_host_logic_without_gpu():
+    """sdb_dcn_multi_workspace_bytes plans the workspace on the host: sizes, sharing of the transposed index between
+    the two convolutions of a level, and table validation -- no kernel is launched."""
+    lib = _lib.lib()
+    g = _lib.Geom(1, 256, 8, 8, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)    # N / H / W of the common geometry are ignored
+    gp = ctypes.byref(g)
+    wts = (_lib.Weights * 2)(_lib.Weights(0x7000, None, None, 0x8000, None), _lib.Weights(0x7100, None, None, 0x8100, None))
+    levels = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    probs, n = _table(levels)
+    fwd = lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 0)
+    bwd = lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1)
+    px = 2 * sum(h * w for h, w in levels)
+    assert fwd >= 2 * px * 256 * 2          # an NHWC bf16 copy of every input
+    assert bwd > fwd
+    # both branches of a level share one transposed index: without the groups the plan needs one per problem
+    probs_ng, _ = _table(levels, groups=False)
+    bwd_ng = lib.sdb_dcn_multi_workspace_bytes(probs_ng, n, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1)
+    assert bwd_ng > bwd + px * 9 * 32 // 2
+    # prepared weights passed by the caller are not planned into the workspace
+    wts_p = (_lib.Weights * 2)(_lib.Weights(0x7000, None, 0x9000, 0x8000, None), _lib.Weights(0x7100, None, 0x9100, 0x8100, None))
+    assert lib.sdb_dcn_multi_workspace_bytes(probs, n, wts_p, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 0) == \
+        fwd - 2 * lib.sdb_dcn_prepared_weight_bytes(gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16)
+    # fp32 math needs no workspace; a bad weight_id, too many problems, or a group whose members differ are refused
+    assert lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, 2, gp, _lib.SDB_F32, _lib.SDB_MATH_FP32, 1) == 0
+    probs[3].weight_id = 5
+    assert lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1) == 0
+    assert b"weight_id" in lib.sdb_last_error()
+    probs[3].weight_id = 1
+    probs[1].offset = 0x2fff                 # same group as problem 0, different offset tensor
+    assert lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1) == 0
+    assert b"offset_group" in lib.sdb_last_error()
+    big, nb = _table(levels * 2)
+    assert nb == 20 and lib.sdb_dcn_multi_workspace_bytes(big, nb, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 0) == 0
+    # the single-problem entry points are one-row tables
+    g1 = _lib.Geom(2, 256, 100, 168, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
+    one = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_DATA, ctypes.byref(g1), _lib.SDB_BF16, _lib.SDB_MATH_BF16)
+    assert one > 0 and one == lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_WEIGHT, ctypes.byref(g1), _lib.SDB_BF16, _lib.SDB_MATH_BF16)
+
+
+def test_deform_conv_multi_argument_checks():
+    w = torch.zeros(4, 4, 3, 3)
+    with pytest.raises(ValueError):
+        sdb.deform_conv_multi([torch.zeros(1, 4, 5, 5)], [], w)
+    with pytest.raises(ValueError):
+        sdb.deform_conv_multi([torch.zeros(1, 4, 5, 5)] * 17, [torch.zeros(1, 18, 5, 5)] * 17, w)
+    with pytest.raises(NotImplementedError):   # CPU tensors, like the reference (deform_conv.py:48-49)
+        sdb.deform_conv_multi([torch.zeros(1, 4, 5, 5)], [torch.zeros(1, 18, 5, 5)], w, 1, 1, 1)
+    assert sdb.deform_conv_multi([], [], w) == []

@@ -4,7 +4,7 @@
 //   warp 1 : optionally issues back-to-back 128x256x16 bf16 MMAs from fixed smem operands (mode bit 0)
 //   warps 2..9 : optionally run conflict-free LDS.128 x4 + STS.128 loops (mode bit 1)
 // and the kernel time for each combination tells whether the three add or overlap.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I slenderobjdet_b200/csrc scratch/smem_port_bench.cu -o scratch/smem_port_bench
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I slenderobjdet_b200/csrc tools/smem_port_bench.cu -o tools/smem_port_bench
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "tc_common.cuh"
