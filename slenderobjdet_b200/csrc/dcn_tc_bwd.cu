@@ -1080,6 +1080,34 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
 
 }  // namespace
 
+// ---- fork / join onto a library-owned side stream -----------------------------------------------------------------
+// The transposed-index build (a chain of seven small launches) depends only on the offsets and on grad_out, not on
+// the grad_offset kernel, so it runs BESIDE that kernel on a side stream and joins before grad_input.  Event
+// record / wait pairs are the fork-join pattern CUDA-graph capture understands, so the same code is captured into
+// the caller's graph when the caller's stream is capturing.  One (stream, events) set per device, created lazily.
+namespace {
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+Side* side_of_device() {
+  static Side tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Side& d = tab[dev];
+  if (!d.s) {
+    if (cudaStreamCreateWithFlags(&d.s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming) != cudaSuccess) {
+      d.s = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &d;
+}
+}  // namespace
+
 // ---- workspace plan of a multi-problem call ------------------------------------------------------------------------
 // Everything a call needs beyond its tensors lives in ONE caller-provided workspace, laid out as a pure function of
 // the problem dimensions (so sdb_dcn_multi_workspace_bytes and the call agree):
@@ -1161,6 +1189,54 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
   return tc_forward_multi(pb, n, g, io_dtype, st);
 }
 
+// dY -> NHWC rows and the transposed sampling index (one per offset group) of a call, on stream `st`
+static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, int okb, bool bf, uint8_t* base,
+                                  cudaStream_t st) {
+  int rc;
+  {
+    PackJob jobs[MAX_PROBS];
+    for (int i = 0; i < n; ++i)
+      jobs[i] = PackJob{pb[i].gx ? pb[i].gy : nullptr, pb[i].gyn, pb[i].d.N, pb[i].d.Ho * pb[i].d.Wo};
+    rc = pack_nhwc_multi(jobs, n, g.O, okb * 64, bf, st);
+    if (rc) return rc;
+  }
+  int* cnt = (int*)(base + P.cnt_off);
+  int* start = (int*)(base + P.start_off);
+  int* bsum = (int*)(base + P.bsum_off);
+  ODesc* odesc = (ODesc*)(base + P.od_off);
+  GDesc* desc = (GDesc*)(base + P.desc_off);
+  CsrTable t{};
+  t.g = g;
+  int total = 0, m = 0;
+  for (int k = 0; k < P.ngroups; ++k) {
+    bool wanted = false;
+    for (int i = 0; i < n; ++i) wanted |= P.group_of[i] == k && pb[i].gx;
+    if (!wanted) continue;
+    const TcProblem& r = pb[P.group_rep[k]];
+    t.gr[m].off = r.off; t.gr[m].mask = r.mask; t.gr[m].d = r.d; t.gr[m].key_base = (int)P.key_base[k];
+    t.map.start[m] = total;
+    total += cdiv(with_dims(g, r.d).P(), 256);
+    ++m;
+  }
+  t.map.n = m; t.map.start[m] = total;
+  const int nkeys = (int)P.nkeys;
+  SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and desc in one fill
+  dim3 hgrid(total, g.taps());
+  csr_count_kernel<<<hgrid, 256, 0, st>>>(t, cnt);
+  csr_block_sums_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
+  csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, P.scan_blocks);
+  csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
+  csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, desc, odesc, okb * 8);
+  csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(desc, start, odesc, nkeys);
+  SDB_LAUNCHED(6);
+  SDB_CHECK_CUDA(cudaGetLastError());
+  for (int i = 0; i < n; ++i) {
+    const long long kb = P.key_base[P.group_of[i]];
+    pb[i].desc = desc + kb; pb[i].start = start + kb; pb[i].odesc = odesc;
+  }
+  return SDB_OK;
+}
+
 // ---- backward: grad_offset / grad_mask, grad_input, grad_weight / grad_bias of all problems ------------------------
 // dY is packed once per problem (tile image + NHWC rows) and serves the three kernels; the transposed index is built
 // once per offset group; one launch per kernel over all problems.
@@ -1207,6 +1283,20 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     }
   }
 
+  // (2a) transposed sampling index for grad_input, on the side stream, beside the grad_offset kernel
+  Side* side = (any_gx && any_goff) ? side_of_device() : nullptr;
+  cudaStream_t ist = st;   // stream of the index build
+  if (side) {
+    SDB_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    SDB_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    ist = side->s;
+  }
+  if (any_gx) {
+    rc = build_transposed_index(pb, n, P, g, okb, bf, base, ist);
+    if (rc) return rc;
+    if (side) SDB_CHECK_CUDA(cudaEventRecord(side->join, side->s));
+  }
+
   // (1) grad_offset / grad_mask: dcol GEMM + channel reduction
   if (any_goff) {
     DgradParams p{};
@@ -1242,49 +1332,9 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     }
   }
 
-  // (2) grad_input: transposed sampling index (one per offset group) + gathered implicit GEMM
+  // (2b) grad_input: gathered implicit GEMM over the transposed index
   if (any_gx) {
-    {
-      PackJob jobs[MAX_PROBS];
-      for (int i = 0; i < n; ++i)
-        jobs[i] = PackJob{pb[i].gx ? pb[i].gy : nullptr, pb[i].gyn, pb[i].d.N, pb[i].d.Ho * pb[i].d.Wo};
-      rc = pack_nhwc_multi(jobs, n, g.O, okb * 64, bf, st);
-      if (rc) return rc;
-    }
-    int* cnt = (int*)(base + P.cnt_off);
-    int* start = (int*)(base + P.start_off);
-    int* bsum = (int*)(base + P.bsum_off);
-    ODesc* odesc = (ODesc*)(base + P.od_off);
-    GDesc* desc = (GDesc*)(base + P.desc_off);
-    CsrTable t{};
-    t.g = g;
-    int total = 0, m = 0;
-    for (int k = 0; k < P.ngroups; ++k) {
-      bool wanted = false;
-      for (int i = 0; i < n; ++i) wanted |= P.group_of[i] == k && pb[i].gx;
-      if (!wanted) continue;
-      const TcProblem& r = pb[P.group_rep[k]];
-      t.gr[m].off = r.off; t.gr[m].mask = r.mask; t.gr[m].d = r.d; t.gr[m].key_base = (int)P.key_base[k];
-      t.map.start[m] = total;
-      total += cdiv(with_dims(g, r.d).P(), 256);
-      ++m;
-    }
-    t.map.n = m; t.map.start[m] = total;
-    const int nkeys = (int)P.nkeys;
-    SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and desc in one fill
-    dim3 hgrid(total, g.taps());
-    csr_count_kernel<<<hgrid, 256, 0, st>>>(t, cnt);
-    csr_block_sums_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
-    csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, P.scan_blocks);
-    csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
-    csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, desc, odesc, okb * 8);
-    csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(desc, start, odesc, nkeys);
-    SDB_LAUNCHED(6);
-    SDB_CHECK_CUDA(cudaGetLastError());
-    for (int i = 0; i < n; ++i) {
-      const long long kb = P.key_base[P.group_of[i]];
-      pb[i].desc = desc + kb; pb[i].start = start + kb; pb[i].odesc = odesc;
-    }
+    if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     rc = tc_dx_multi(pb, n, g, okb, io_dtype, accumulate_gx, st);
     if (rc) return rc;
   }
