@@ -639,14 +639,12 @@ int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
   return SDB_OK;
 }
 
-// tuning overrides for measurement sessions (sdb_debug_tune; 0 = default): lanes per pixel of the forward gather,
-// shared-memory budget in KB (the rest of the 228 KB array is L1), A stages
-int g_tune_lpp = 0, g_tune_smem_kb = 0, g_tune_nsa = 0;
-
-// stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit)
-size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes, bool tunable = false) {
-  const size_t budget = (size_t)(tunable && g_tune_smem_kb > 0 ? g_tune_smem_kb : 200) * 1024;
-  p.nsa = g_tune_nsa > 1 && g_tune_nsa <= MAX_A_STAGES ? g_tune_nsa : 2;
+// Stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit).  200 KB of the 228 KB
+// array go to shared memory: giving the L1 more (budgets of 140 / 170 KB, 64- instead of 128-channel stages) was
+// measured to change the forward by -1 .. +7 % (profiles/r2_tuning.md) -- the gather is not bound by L1 capacity.
+size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
+  const size_t budget = 200 * 1024;
+  p.nsa = 2;
   long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
   if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
   if (nsb < 2) return 0;
@@ -656,10 +654,7 @@ size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes, b
 
 }  // namespace
 
-int tc_lanes_per_pixel(const Geo& g) {
-  if (g_tune_lpp == 8 || (g_tune_lpp == 16 && g.C % 128 == 0)) return g_tune_lpp;
-  return g.C % 128 == 0 ? 16 : 8;
-}
+int tc_lanes_per_pixel(const Geo& g) { return g.C % 128 == 0 ? 16 : 8; }
 // column blocking of the grad_input GEMM: N = C_in split into nnb equal blocks of <= 256 columns
 int tc_dx_col_blocks(const Geo& g) {
   int nnb = (g.C + 255) / 256;
@@ -746,7 +741,7 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   const int lpp = tc_lanes_per_pixel(g);
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)g.O * 128;
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
-  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes, true);
+  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   const int grid = total < num_sms() ? total : num_sms();
   const bool obf = io_dtype == SDB_BF16;
@@ -785,9 +780,3 @@ int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype,
 }
 
 }  // namespace sdb
-
-// measurement tooling, not part of the public ABI (tools/tune_fwd.py)
-extern "C" int sdb_debug_tune(int lpp, int smem_kb, int nsa) {
-  sdb::g_tune_lpp = lpp; sdb::g_tune_smem_kb = smem_kb; sdb::g_tune_nsa = nsa;
-  return 0;
-}
