@@ -297,6 +297,35 @@ int sdb_fcos_location_targets_batched(const float* locations, const float* sizes
                                       int32_t centerness_kind, int64_t* out_classes, float* out_reg, uint8_t* out_topk,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- inference post-processing of a dense point head ---------------------------------------
+ * Replaces RepPointsV2.inference / inference_single_image (reppointsv2.py:486-603) for a whole batch, with no host
+ * round trip between its steps: per (image, level) score = sigmoid(logit) over the H*W*K cells, the `topk` best cells
+ * with score > score_thresh, their boxes decoded from the refined point sets (pts_to_bbox :328-366: transform 0 =
+ * "minmax", 1 = "partial_minmax" (first 4 points), 2 = "moment" (mean +- std * exp(moment_transfer[0|1])); x stride,
+ * + centre, clamped to [0, w] x [0, h] :558-564); per image the candidates of all levels go through class-aware
+ * greedy NMS (IoU > nms_thresh suppresses; detectron2/layers/nms.py:10-29) and the first `max_det` survivors are
+ * written in decreasing score order.  Equal scores: lower flat cell index / lower level first (the reference's
+ * torch.sort leaves ties implementation-defined).
+ *   levels[l].cls [N, K, H, W], .pts [N, 2*num_points, H, W] (the head's NCHW outputs, read in place),
+ *   .centers [H*W, 2] (x, y) float32 device tensors; image_sizes: HOST int32 [N][2] = (height, width);
+ *   out_boxes [N, max_det, 4], out_scores [N, max_det] float32, out_classes [N, max_det] int64, out_count [N] int32
+ *   (device).  out_overflow (device int32, optional): set when more than 4096 cells of one (image, level) tie in the
+ *   top 19 bits of their score with the topk-th cell -- the cut is then approximate (never seen on real heads).
+ * Limits: n_levels <= 8, n_images <= 64, topk <= 2048, n_levels * topk <= 8192. */
+typedef struct {
+  const float* cls;
+  const float* pts;
+  const float* centers;
+  int32_t H, W;
+  float stride;
+} sdb_pp_level;
+size_t sdb_points_postprocess_workspace_bytes(int32_t n_levels, int32_t n_images, int32_t topk, float score_thresh);
+int sdb_points_postprocess(const sdb_pp_level* levels, int32_t n_levels, int32_t n_images, int32_t num_classes,
+                           int32_t num_points, int32_t transform, const float* moment_transfer, const int32_t* image_sizes,
+                           float score_thresh, int32_t topk, float nms_thresh, int32_t max_det, float* out_boxes,
+                           float* out_scores, int64_t* out_classes, int32_t* out_count, int32_t* out_overflow,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Per-kernel timing for bench.py's roofline line.  While enabled, each DCN entry point records a
  * CUDA event pair on ITS stream around its dominant kernel only (the tcgen05 / SIMT main kernel,

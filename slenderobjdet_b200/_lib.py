@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
     "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
-    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
+    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
 ]
 
 
@@ -48,6 +48,12 @@ class Weights(ctypes.Structure):
     """sdb_dcn_weights: one weight tensor of a whole-head call"""
     _fields_ = [("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("prepared", ctypes.c_void_p),
                 ("grad_weight", ctypes.c_void_p), ("grad_bias", ctypes.c_void_p)]
+
+
+class PPLevel(ctypes.Structure):
+    """sdb_pp_level: one FPN level of the inference post-processing"""
+    _fields_ = [("cls", ctypes.c_void_p), ("pts", ctypes.c_void_p), ("centers", ctypes.c_void_p), ("H", ctypes.c_int32),
+                ("W", ctypes.c_int32), ("stride", ctypes.c_float)]
 
 
 SDB_MAX_PROBLEMS, SDB_MAX_WEIGHTS = 16, 4
@@ -81,6 +87,10 @@ def _declare(lib):
     lib.sdb_dcn_multi_workspace_bytes.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.sdb_dcn_forward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _vp, _sz, _vp]
     lib.sdb_dcn_backward_multi.argtypes = [pp, _i32, wp, _i32, _gp, ctypes.c_int, ctypes.c_int, _f32, ctypes.c_int, _vp, _sz, _vp]
+    lib.sdb_points_postprocess_workspace_bytes.restype = _sz
+    lib.sdb_points_postprocess_workspace_bytes.argtypes = [_i32, _i32, _i32, _f32]
+    lib.sdb_points_postprocess.argtypes = [ctypes.POINTER(PPLevel), _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_f32),
+                                           ctypes.POINTER(_i32), _f32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     lib.sdb_assign_workspace_bytes.restype = _sz
     lib.sdb_assign_workspace_bytes.argtypes = [_i32, _i32, _i32]
     lib.sdb_iou_assign.argtypes = [_vp, _vp, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int8),
