@@ -189,6 +189,7 @@ struct FwdParams {
 
 constexpr int MODE_FWD = 0, MODE_DX = 1;
 
+
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
 template <int LPP, bool OUT_BF16, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
