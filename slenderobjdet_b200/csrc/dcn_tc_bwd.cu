@@ -540,8 +540,19 @@ struct DgradParams {
   int nsb, okb;
 };
 
+// Warp roles are aligned to warpgroups so that the register file can be re-split with setmaxnreg: warps 0-3 = bulk
+// producer, MMA issuer and two idle warps (40 registers each), warps 4-7 = TMEM drain (96), warps 8-15 = the reduce
+// warps (184), which are the critical path of this kernel: at the 128 registers a 512-thread launch gives everybody
+// ptxas could not overlap the dependent shuffle / FMA chains of two iterations and the drain warps waited for them
+// 80 % of the time (profiles/r2_dcn_kernels_ncu_v1.txt).
+constexpr int G_DRAIN0 = 4, G_SW0 = 8, G_THREADS = (G_SW0 + NSW) * 32;
+template <int R>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+
 template <int NCH>
-__global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
+__global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
   constexpr int LPB = NCH / 8, PPI = 32 / LPB;
   constexpr uint32_t B_BYTES = NCH * 128;            // one [NCH c][64 o] weight tile
   constexpr uint32_t STG_BYTES = TILE_M * NCH * 2;   // bf16 staging tile
@@ -585,6 +596,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const _
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
+  if (warp < G_DRAIN0) {
+    setmaxnreg_dec<40>();
+  }
   if (warp == 0) {
     // ===== bulk producer: dY tile once per tile, W^T tiles per (tap, chunk, o-block) =====
     if (lane == 0) {
@@ -638,8 +652,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const _
       if (elect_one()) umma_commit(&a_empty);
       __syncwarp();
     }
-  } else if (warp < FIRST_SW) {
+  } else if (warp < G_DRAIN0) {
+    // idle warps of the first warpgroup (they only take part in the register re-split and the final barrier)
+  } else if (warp < G_SW0) {
     // ===== drain: TMEM accumulator -> bf16 staging tile (row = pixel, swizzled 16-byte chunks) =====
+    setmaxnreg_dec<96>();
     const int q = warp & 3;
     const uint32_t row = q * 32 + lane;
     uint32_t acc = 0, accp = 0;
@@ -679,12 +696,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const _
     // combined in fp32 into this lane's share of d/dy, d/dx and d/dmask, then a 5-shuffle
     // reduce-scatter over the pixel's lane group.  The sums over channel chunks stay in registers;
     // one plain store per (pixel, tap, quantity) at the end of the tap.
+    setmaxnreg_inc<184>();
     constexpr int ITERS = PIX_PER_WARP / PPI;
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-unit iteration count");
     __shared__ uint4 s_od[NSW][2][PIX_PER_WARP][2];   // {off[4]}, {lh, lw, m, flags}
     __shared__ int2 s_px[NSW][PIX_PER_WARP];          // (n, ho*Wo+wo) of the warp's pixels, n = -1 when padded
-    const int sw = warp - FIRST_SW, r0 = sw * PIX_PER_WARP;
+    const int sw = warp - G_SW0, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
     uint32_t sb = 0, sp = 0;
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
@@ -735,9 +753,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const _
         if (tap + 1 < taps) build_desc(tap + 1, raw_next);   // buffer (tap+1)&1 was last read during tap-1
         raw_next = fetch_rawb(g, pr.off, pr.mask, valid && tap + 2 < taps, n, ho, wo, tap + 2);
         __syncwarp();
-        float racc[ITERS];
+        // this lane's share of d/dy, d/dx and d/dmask of every pixel it serves, summed over the channel chunks in
+        // registers: the cross-lane reduction runs once per (pixel, tap), not once per chunk
+        float qA[ITERS], qB[ITERS], qC[ITERS];
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) racc[it] = 0.f;
+        for (int it = 0; it < ITERS; ++it) qA[it] = qB[it] = qC[it] = 0.f;
         for (int ch = 0; ch < nch; ++ch) {
           int ntap = tap, nchk = ch + 1;
           if (nchk == nch) { nchk = 0; ++ntap; }
@@ -765,25 +785,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_data_tc_kernel(const _
             }
             const float lh = __uint_as_float(f.x), lw = __uint_as_float(f.y), m = __uint_as_float(f.z);
             // d(bilinear)/dh, /dw (get_coordinate_weight :185-211) and the unmasked sample value
-            float qa = m * ((1.f - lw) * (S[2] - S[0]) + lw * (S[3] - S[1]));
-            float qb = m * ((1.f - lh) * (S[1] - S[0]) + lh * (S[3] - S[2]));
-            float qc = (1.f - lh) * ((1.f - lw) * S[0] + lw * S[1]) + lh * ((1.f - lw) * S[2] + lw * S[3]);
-            // reduce-scatter over the LPB lanes of this pixel: lanes [0,Q) end with sum(qa), [Q,2Q) sum(qb),
-            // [2Q,3Q) sum(qc)
-            constexpr int H = LPB / 2, Q = LPB / 4;
-            const bool up = (lig & H) != 0;
-            const float r0_ = __shfl_xor_sync(0xffffffffu, up ? qa : qc, H);
-            const float r1_ = __shfl_xor_sync(0xffffffffu, up ? qb : 0.f, H);
-            const float k0 = (up ? qc : qa) + r0_;
-            const float k1 = (up ? 0.f : qb) + r1_;
-            const bool uq = (lig & Q) != 0;
-            float kk = (uq ? k1 : k0) + __shfl_xor_sync(0xffffffffu, uq ? k0 : k1, Q);
-#pragma unroll
-            for (int dlt = Q / 2; dlt > 0; dlt >>= 1) kk += __shfl_xor_sync(0xffffffffu, kk, dlt);
-            racc[it] += kk;
+            qA[it] += m * ((1.f - lw) * (S[2] - S[0]) + lw * (S[3] - S[1]));
+            qB[it] += m * ((1.f - lh) * (S[1] - S[0]) + lh * (S[3] - S[2]));
+            qC[it] += (1.f - lh) * ((1.f - lw) * S[0] + lw * S[1]) + lh * ((1.f - lw) * S[2] + lw * S[3]);
           }
           mbar_arrive_warp(&stg_empty[sb]);
           if (++sb == 2) { sb = 0; sp ^= 1; }
+        }
+        float racc[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          // reduce-scatter over the LPB lanes of this pixel: lanes [0,Q) end with sum(qa), [Q,2Q) sum(qb),
+          // [2Q,3Q) sum(qc)
+          constexpr int H = LPB / 2, Q = LPB / 4;
+          const float qa = qA[it], qb = qB[it], qc = qC[it];
+          const bool up = (lig & H) != 0;
+          const float r0_ = __shfl_xor_sync(0xffffffffu, up ? qa : qc, H);
+          const float r1_ = __shfl_xor_sync(0xffffffffu, up ? qb : 0.f, H);
+          const float k0 = (up ? qc : qa) + r0_;
+          const float k1 = (up ? 0.f : qb) + r1_;
+          const bool uq = (lig & Q) != 0;
+          float kk = (uq ? k1 : k0) + __shfl_xor_sync(0xffffffffu, uq ? k0 : k1, Q);
+#pragma unroll
+          for (int dlt = Q / 2; dlt > 0; dlt >>= 1) kk += __shfl_xor_sync(0xffffffffu, kk, dlt);
+          racc[it] = kk;
         }
         // lanes lig == 0, Q, 2Q hold d/dy, d/dx, d/dmask of pixel it*PPI+grp
         {
@@ -1327,8 +1352,8 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
       else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
       {
         ProfScope prof(SDB_OP_BACKWARD_DATA, st);
-        if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, BWD_THREADS, smem, st>>>(p);
-        else dcn_bwd_data_tc_kernel<64><<<grid, BWD_THREADS, smem, st>>>(p);
+        if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, G_THREADS, smem, st>>>(p);
+        else dcn_bwd_data_tc_kernel<64><<<grid, G_THREADS, smem, st>>>(p);
         SDB_LAUNCHED(1);
       }
       SDB_CHECK_CUDA(cudaGetLastError());
