@@ -363,8 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     //     + the row they belong to).  A stage's overflow descriptors of this warp are staged in smem one
     //     stage ahead and processed as extra iterations of the SAME ring after the 8 regular ones, ending
     //     in a read-modify-write of the row instead of a store - no load latency is exposed.
-    constexpr int DW = MODE == MODE_DX ? 2 : 1;          // descriptors per (row, tap): MODE_DX lists have eight fixed slots
-    constexpr int ITERS = PIX_PER_WARP / PPI * DW;       // warp iterations per stage (MODE_DX: two per row pair)
+    constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
     constexpr int OD_CAP = 16;                  // MODE_DX: overflow descriptors staged per warp and stage
@@ -436,11 +435,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         __syncwarp();
       } else {
         __syncwarp();
-        constexpr int U16 = PIX_PER_WARP * DW * (int)sizeof(GDesc) / 16;   // 16-byte units per (warp, tap) slice
+        constexpr int U16 = PIX_PER_WARP * (int)sizeof(GDesc) / 16;   // 16-byte units per (warp, tap) slice
         for (int i = lane; i < taps * U16; i += 32) {
           const int tap = i / U16, u = i - tap * U16;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.desc + (((size_t)tile * taps + tap) * TILE_M + r0) * DW) + u * 16;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sD + (tap * TILE_M + r0) * DW) + u * 16)),
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.desc + ((size_t)tile * taps + tap) * TILE_M + r0) + u * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sD + tap * TILE_M + r0) + u * 16)),
                        "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -468,25 +467,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       };
       uint4 v[RING][4], wq[RING];
       // issue the loads of iteration `it` of the stage (tap_, ch_) into ring slot `slot`
-      // (iteration it_ covers rows (it_ / DW) * PPI + grp, descriptor it_ % DW of each; MODE_DX skips empty slots)
 #define SDB_ISSUE(tap_, ch_, it_, slot_)                                                     \
       {                                                                                          \
-        const GDesc* d_ = sD + ((tap_) * TILE_M + r0 + ((it_) / DW) * PPI + grp) * DW + ((it_) % DW); \
+        const GDesc* d_ = sD + (tap_) * TILE_M + r0 + (it_) * PPI + grp;                         \
         const uint4 o_ = *reinterpret_cast<const uint4*>(d_->off);                               \
         wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                     \
         const uint4* xb_ = xbase + (ch_) * (CPS / 8);                                            \
-        if (MODE == MODE_DX) {                                                                   \
-          const uint4 z_ = make_uint4(0u, 0u, 0u, 0u);                                           \
-          v[slot_][0] = wq[slot_].x ? __ldg(xb_ + o_.x) : z_;                                    \
-          v[slot_][1] = wq[slot_].y ? __ldg(xb_ + o_.y) : z_;                                    \
-          v[slot_][2] = wq[slot_].z ? __ldg(xb_ + o_.z) : z_;                                    \
-          v[slot_][3] = wq[slot_].w ? __ldg(xb_ + o_.w) : z_;                                    \
-        } else {                                                                                 \
-          v[slot_][0] = __ldg(xb_ + o_.x);                                                       \
-          v[slot_][1] = __ldg(xb_ + o_.y);                                                       \
-          v[slot_][2] = __ldg(xb_ + o_.z);                                                       \
-          v[slot_][3] = __ldg(xb_ + o_.w);                                                       \
-        }                                                                                        \
+        v[slot_][0] = __ldg(xb_ + o_.x);                                                         \
+        v[slot_][1] = __ldg(xb_ + o_.y);                                                         \
+        v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
+        v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
       }
       // MODE_DX: overflow iteration j_ of the current stage = overflow descriptors j_*PPI + grp of this
       // warp's staged list (up to four more entries of one row); same ring slots, same loads
@@ -534,21 +524,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         }
         mbar_wait(&a_empty[as], ap ^ 1);
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
-        uint4 part = make_uint4(0u, 0u, 0u, 0u);   // MODE_DX: sum of the row's first descriptor
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
           const int slot = it % RING;
           uint4 a;
           SDB_INTERP(a, slot)
-          if (DW == 2 && (it & 1) == 0) {
-            part = a;
-          } else {
-            if (DW == 2) {
-              a.x = bf2_add(part.x, a.x); a.y = bf2_add(part.y, a.y);
-              a.z = bf2_add(part.z, a.z); a.w = bf2_add(part.w, a.w);
-            }
-            *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + (it / DW) * PPI + grp, lig & 7)) = a;
-          }
+          *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
           if (it + RING < ITERS) {
             SDB_ISSUE(tap, ch, it + RING, slot)
           } else if (MODE == MODE_DX && m_ov > 0) {
@@ -662,7 +643,8 @@ int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
 // Stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit).  200 KB of the 228 KB
 // array go to shared memory: giving the L1 more (budgets of 140 / 170 KB, 64- instead of 128-channel stages) was
 // measured to change the forward by -1 .. +7 % (profiles/r2_tuning.md) -- the gather is not bound by L1 capacity.
-size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes, size_t budget = 200 * 1024) {
+size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
+  const size_t budget = 200 * 1024;
   p.nsa = 2;
   long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)b_bytes;
   if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
@@ -688,11 +670,6 @@ bool tc_supported(const Geo& g, const char** why) {
   if (g.C % 64 != 0) { *why = "C_in not a multiple of 64"; return false; }
   if (g.O % 16 != 0 || g.O < 16 || g.O > 256) { *why = "C_out must be a multiple of 16 in [16,256]"; return false; }
   if (g.taps() > 16) { *why = "more than 16 kernel taps (per-tile descriptors would not fit in shared memory)"; return false; }
-  {   // grad_input stages two descriptors per (row, tap): they, two A stages and two weight stages must fit
-    const size_t ncols = (size_t)g.C / tc_dx_col_blocks(g);
-    const size_t need = (size_t)g.taps() * TILE_M * 2 * sizeof(GDesc) + DX_STATIC_SMEM + 2 * (size_t)TILE_M * 256 + 2 * ncols * 128 + 1024;
-    if (need > 214 * 1024) { *why = "kernel taps x input channels too large for the grad_input descriptors in shared memory"; return false; }
-  }
   const long long pin = (long long)g.N * g.H * g.W;
   if (pin * (g.C / 8) >= (1LL << 32) || g.P() * g.O >= (1LL << 40) ||
       (4 * g.P() + pin + TILE_M) * g.taps() >= (1LL << 31) ||
@@ -795,9 +772,8 @@ int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype,
   if (total == 0) return SDB_OK;
   constexpr int lpp = 16;   // 128-channel stages: okb is even, so kch % 128 == 0
   const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)ncols * 128;
-  const size_t d_bytes = (size_t)g.taps() * TILE_M * 2 * sizeof(GDesc);   // two descriptors per (row, tap)
-  // static arrays come out of the same budget; the doubled descriptors leave room for two weight stages at C_in = 256
-  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes + DX_STATIC_SMEM, 214 * 1024) - DX_STATIC_SMEM;
+  const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);
+  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes + DX_STATIC_SMEM) - DX_STATIC_SMEM;  // static arrays come out of the same budget
   SDB_REQUIRE(smem > 0 && smem < (1u << 20), SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   const int grid = total < num_sms() ? total : num_sms();
   return io_dtype == SDB_BF16 ? launch_fwd<lpp, true, MODE_DX>(p, smem, grid, st)

@@ -235,16 +235,13 @@ __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // key(q, tap) = (tile(q) * taps + tap) * 128 + row(q), q = band-order position of the INPUT pixel.
 // The list of (output pixel p, weight w = bilinear x mask) that reach q through `tap` is stored as
-//   desc[2*key + h] : its first eight entries, four per descriptor, in the forward gather's format (row offset of
-//                p in the NHWC bf16 dY in 16 B units + bf16x2 weight; unused slots are zero), and
-//   overflow   : entries nine and up, four per ODesc (same fields + the row), descriptors of a key
+//   desc[key]  : its first four entries in the forward gather's descriptor format (row offset of p in
+//                the NHWC bf16 dY in 16 B units + bf16x2 weight; unused slots are zero), and
+//   overflow   : entries five and up, four per ODesc (same fields + the row), descriptors of a key
 //                contiguous (start[key] .. start[key+1]) and keys in (tile, tap, row) order, so the
 //                descriptors of one (tile, tap, 16-row warp slice) are one contiguous run.
-// With stride 1 a list holds four entries on average (Poisson-like spread for irregular offsets): the fixed-width part
-// is EIGHT entries = two descriptors per key, which covers 98 % of the lists (P(n > 8) = 2 % at mean 4); the gather
-// skips the loads of empty slots.  (Round 1 kept four and sent 37 % of the lists through the overflow path, whose
-// serialised read-modify-write of the operand row made grad_input 1.6x the forward.)
-constexpr int DESC_W = 8;
+// With stride 1 a list holds four entries on average, so most of the work takes the fixed-width path.
+constexpr int DESC_W = 4;
 template <typename F>
 __device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restrict__ off,
                                              const float* __restrict__ mask, int n, int ho, int wo, int tap,
@@ -395,13 +392,12 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ C
   const uint32_t poff = (uint32_t)p * (uint32_t)row_units;
   int* cnt = cnt_all + t.gr[gi].key_base;
   const int* start = start_all + t.gr[gi].key_base;
-  GDesc* desc = desc_all + 2 * (size_t)t.gr[gi].key_base;
+  GDesc* desc = desc_all + t.gr[gi].key_base;
   for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb, uint32_t row) {
     const int pos = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
     if (pos < DESC_W) {
-      GDesc& d = desc[2 * key + (pos >> 2)];
-      d.off[pos & 3] = poff;
-      d.w2[pos & 3] = (wb << 16) | wb;
+      desc[key].off[pos] = poff;
+      desc[key].w2[pos] = (wb << 16) | wb;
     } else {
       ODesc* od = odesc + start[key] + ((pos - DESC_W) >> 2);
       const int sl = (pos - DESC_W) & 3;
@@ -421,21 +417,30 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(GDesc* __restrict__ desc,
   const int key = blockIdx.x * blockDim.x + threadIdx.x;
   if (key >= nkeys) return;
   const int ob = start[key], nod = start[key + 1] - ob;
-  GDesc* dk = desc + 2 * (size_t)key;
-  constexpr int CAP = 72;   // 8 + 16 overflow descriptors; longer lists are sorted in place in global memory
+  uint4 o4 = *reinterpret_cast<const uint4*>(desc[key].off);
+  uint4 w4 = *reinterpret_cast<const uint4*>(desc[key].w2);
+  if (nod == 0) {
+    uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#define SDB_CX(a_, b_)                                                                             \
+    {                                                                                              \
+      const uint32_t ka_ = w[a_] ? o[a_] : 0xffffffffu, kb_ = w[b_] ? o[b_] : 0xffffffffu;         \
+      if (kb_ < ka_) { const uint32_t to_ = o[a_], tw_ = w[a_]; o[a_] = o[b_]; w[a_] = w[b_]; o[b_] = to_; w[b_] = tw_; } \
+    }
+    SDB_CX(0, 1) SDB_CX(2, 3) SDB_CX(0, 2) SDB_CX(1, 3) SDB_CX(1, 2)
+#undef SDB_CX
+    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
+  constexpr int CAP = 68;   // 4 + 16 overflow descriptors; longer lists are sorted in place in global memory
   const int total_slots = DESC_W + 4 * nod;
   if (total_slots <= CAP) {
     uint32_t o[CAP];
     uint16_t w[CAP];
     int n = 0;
-    for (int h = 0; h < 2; ++h) {
-      const uint4 o4 = *reinterpret_cast<const uint4*>(dk[h].off);
-      const uint4 w4 = *reinterpret_cast<const uint4*>(dk[h].w2);
-      const uint32_t od0[4] = {o4.x, o4.y, o4.z, o4.w}, wd0[4] = {w4.x, w4.y, w4.z, w4.w};
-      for (int k = 0; k < 4; ++k)
-        if (wd0[k]) { o[n] = od0[k]; w[n] = (uint16_t)(wd0[k] & 0xffffu); ++n; }
-    }
-    if (n <= 1 && nod == 0) return;   // nothing to order
+    const uint32_t od0[4] = {o4.x, o4.y, o4.z, o4.w}, wd0[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int k = 0; k < 4; ++k)
+      if (wd0[k]) { o[n] = od0[k]; w[n] = (uint16_t)(wd0[k] & 0xffffu); ++n; }
     for (int d = 0; d < nod; ++d) {
       const ODesc od = odesc[ob + d];
       const uint32_t oo[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
@@ -450,36 +455,28 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(GDesc* __restrict__ desc,
       while (j >= 0 && o[j] > oi) { o[j + 1] = o[j]; w[j + 1] = w[j]; --j; }
       o[j + 1] = oi; w[j + 1] = wi;
     }
-    for (int h = 0; h < 2; ++h) {
-      uint32_t od[4], wd[4];
+    uint32_t od[4], wd[4];
+    for (int k = 0; k < 4; ++k) { od[k] = k < n ? o[k] : 0u; wd[k] = k < n ? ((uint32_t)w[k] << 16) | w[k] : 0u; }
+    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    const uint32_t row = odesc[ob].m.z;
+    for (int d = 0; d < nod; ++d) {
+      uint32_t oo[4], ww[4];
       for (int k = 0; k < 4; ++k) {
-        const int e = 4 * h + k;
-        od[k] = e < n ? o[e] : 0u;
-        wd[k] = e < n ? ((uint32_t)w[e] << 16) | w[e] : 0u;
+        const int e = DESC_W + 4 * d + k;
+        oo[k] = e < n ? o[e] : 0u;
+        ww[k] = e < n ? w[e] : 0u;
       }
-      *reinterpret_cast<uint4*>(dk[h].off) = make_uint4(od[0], od[1], od[2], od[3]);
-      *reinterpret_cast<uint4*>(dk[h].w2) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-    }
-    if (nod > 0) {
-      const uint32_t row = odesc[ob].m.z;
-      for (int d = 0; d < nod; ++d) {
-        uint32_t oo[4], ww[4];
-        for (int k = 0; k < 4; ++k) {
-          const int e = DESC_W + 4 * d + k;
-          oo[k] = e < n ? o[e] : 0u;
-          ww[k] = e < n ? w[e] : 0u;
-        }
-        ODesc out;
-        out.o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-        out.m = make_uint4(ww[0] | (ww[1] << 16), ww[2] | (ww[3] << 16), row, 0u);
-        odesc[ob + d] = out;
-      }
+      ODesc out;
+      out.o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+      out.m = make_uint4(ww[0] | (ww[1] << 16), ww[2] | (ww[3] << 16), row, 0u);
+      odesc[ob + d] = out;
     }
     return;
   }
   // very long list (hundreds of taps colliding on one input pixel): selection sort over the slots in place
   auto get = [&](int e, uint32_t& oo, uint32_t& ww) {
-    if (e < DESC_W) { oo = dk[e >> 2].off[e & 3]; ww = dk[e >> 2].w2[e & 3] & 0xffffu; }
+    if (e < DESC_W) { oo = desc[key].off[e]; ww = desc[key].w2[e] & 0xffffu; }
     else {
       const ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
       oo = reinterpret_cast<const uint32_t*>(&od->o)[(e - DESC_W) & 3];
@@ -487,7 +484,7 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(GDesc* __restrict__ desc,
     }
   };
   auto set = [&](int e, uint32_t oo, uint32_t ww) {
-    if (e < DESC_W) { dk[e >> 2].off[e & 3] = oo; dk[e >> 2].w2[e & 3] = (ww << 16) | ww; }
+    if (e < DESC_W) { desc[key].off[e] = oo; desc[key].w2[e] = (ww << 16) | ww; }
     else {
       ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
       reinterpret_cast<uint32_t*>(&od->o)[(e - DESC_W) & 3] = oo;
@@ -1184,7 +1181,7 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     P.scan_blocks = cdiv(keys, SCAN_PER_BLOCK);
     // cnt and desc are cleared by ONE memset: keep them adjacent
     P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
-    P.desc_off = o;  o = align_up(o + (size_t)keys * 2 * sizeof(GDesc), 1024);   // two descriptors (eight entries) per key
+    P.desc_off = o;  o = align_up(o + (size_t)keys * sizeof(GDesc), 1024);
     P.clear_bytes = o - P.cnt_off;
     P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
     P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
@@ -1260,7 +1257,7 @@ static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const G
   SDB_CHECK_CUDA(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     const long long kb = P.key_base[P.group_of[i]];
-    pb[i].desc = desc + 2 * kb; pb[i].start = start + kb; pb[i].odesc = odesc;
+    pb[i].desc = desc + kb; pb[i].start = start + kb; pb[i].odesc = odesc;
   }
   return SDB_OK;
 }
