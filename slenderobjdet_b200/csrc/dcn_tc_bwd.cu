@@ -1084,23 +1084,30 @@ struct WgradReduceTable {
   float* gw[MAX_WEIGHTS];
   int splits[MAX_WEIGHTS];
 };
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceTable t, float scale, int taps,
+// One block per (o, 128-channel chunk): the split sums are formed with coalesced reads along c, transposed through
+// shared memory and added to grad_weight [O][C][taps] as one contiguous run of 128 * taps floats (the direct write has
+// a stride of `taps` floats between lanes: 9x the sectors).
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const __grid_constant__ WgradReduceTable t, float scale, int taps,
                                                            int O, int C) {
+  __shared__ float s[128 * 16];   // taps <= 16
   const int wid = blockIdx.y;
   const float* __restrict__ part = t.part[wid];
   float* __restrict__ gw = t.gw[wid];
   const int splits = t.splits[wid];
   if (!gw || splits == 0) return;
-  const long long total = (long long)O * C * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int o = (int)((i / C) % O);
-    const int tap = (int)(i / ((long long)C * O));
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += part[(((size_t)sp * taps + tap) * O + o) * C + c];
-    gw[((size_t)o * C + c) * taps + tap] += scale * s;
-  }
+  const int cchunks = (C + 127) / 128;
+  const int o = blockIdx.x / cchunks, c0 = (blockIdx.x % cchunks) * 128;
+  const int c = c0 + threadIdx.x;
+  if (c < C)
+    for (int tap = 0; tap < taps; ++tap) {
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += part[(((size_t)sp * taps + tap) * O + o) * C + c];
+      s[threadIdx.x * taps + tap] = acc;
+    }
+  __syncthreads();
+  const int n = min(128, C - c0) * taps;
+  float* dst = gw + ((size_t)o * C + c0) * taps;
+  for (int i = threadIdx.x; i < n; i += 128) dst[i] += scale * s[i];
 }
 
 }  // namespace
@@ -1413,10 +1420,8 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
         SDB_LAUNCHED(1);
       }
       SDB_CHECK_CUDA(cudaGetLastError());
-      const long long total = (long long)g.O * g.C * g.taps();
-      const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
-      // weights with no tile contribute nothing: the reduce of a weight with splits == 0 adds zero
-      wgrad_reduce_kernel<<<dim3(blocks, nweights), 256, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      // weights with no tile contribute nothing: the reduce of a weight with splits == 0 returns at once
+      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
       SDB_CHECK_CUDA(cudaGetLastError());
     }
   }
