@@ -231,7 +231,7 @@ int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g
       if (!backward) which = 1;
       else {
         for (int i = 0; i < n; ++i)
-          if (mc.pb[i].weight_id == k) which |= ((mc.pb[i].goff || mc.pb[i].gmask) ? 2 : 0) | (mc.pb[i].gx ? 4 : 0);
+          if (mc.pb[i].weight_id == k && (mc.pb[i].goff || mc.pb[i].gmask || mc.pb[i].gx)) which |= 2;
       }
       int rc = tc_prepare_weights(w[k].weight, w[k].bias, g, io_dtype, base + mc.plan.prep_off[k], which, st);
       if (rc) return rc;
@@ -246,7 +246,7 @@ int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g
     if (!t.xp) { t.xp = base + mc.plan.xp_off[i]; *packed_from_caller = false; }
     if (backward) {
       t.gy_img = base + mc.plan.gy_off[i];
-      t.gyn = base + mc.plan.gyn_off[i];
+      t.dcol = base + mc.plan.dcol_off[i];
     }
   }
   return SDB_OK;
@@ -294,7 +294,7 @@ Single single_of(const sdb_dcn_geom* g) {
 // the common geometry of a table call: N / H / W of `g` are ignored (every problem brings its own)
 sdb_dcn_geom common_geom(const sdb_dcn_geom* g) {
   sdb_dcn_geom c = *g;
-  c.N = 1; c.H = 4096; c.W = 4096;
+  c.N = 1; c.H = 1024; c.W = 1024;   // placeholder extent that passes every size limit
   return c;
 }
 }  // namespace
@@ -327,7 +327,7 @@ int sdb_dcn_prepare_weights(const void* weight, const void* bias, const sdb_dcn_
   SDB_REQUIRE(weight && prepared, SDB_ERR_INVALID, "weight and prepared must be non-NULL");
   const char* why = "";
   SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
-  return tc_prepare_weights(weight, bias, d, io_dtype, prepared, 7, st);
+  return tc_prepare_weights(weight, bias, d, io_dtype, prepared, 3, st);
 }
 
 size_t sdb_dcn_multi_workspace_bytes(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights,

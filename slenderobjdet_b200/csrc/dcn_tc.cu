@@ -15,13 +15,6 @@
 // of a call (FPN levels x convolutions; problem table = kernel parameter, dcn_tc_shared.cuh): the small
 // pyramid levels are a handful of tiles each and would otherwise be separate launches of 2..66 CTAs.
 //
-// The same kernel, MODE_DX, computes grad_input as a second implicit GEMM instead of a scatter:
-//   dX[q, c] = sum_{tap, o} G[q, (tap,o)] * W[o, c, tap],   G[q, (tap,o)] = sum_e w_e * dY[p_e, o]
-// where the list of (output pixel p_e, bilinear weight x mask w_e) that touch input pixel q through
-// tap `tap` comes from a CSR index built per call (dcn_tc_bwd.cu: count / scan / fill).  The gather
-// warps walk that list instead of four fixed corners; everything else (weights by bulk copy, tcgen05
-// into TMEM, NCHW epilogue) is shared with the forward pass.  No atomics touch grad_input.
-//
 // Reference semantics being reproduced: d2/layers/csrc/deformable/deform_conv_cuda_kernel.cu
 // :96-130 (bilinear), :216-288 (im2col + validity), :785-868 (mask), deform_conv_cuda.cu:397-409 (GEMM).
 #include <stdlib.h>
@@ -39,19 +32,17 @@ constexpr int NPW = 8;                       // gather producer warps
 constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
 constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
-constexpr size_t DX_STATIC_SMEM = 8192 + 1024 + 1024;   // MODE_DX: s_od, s_range, barriers
 
-// Weight images.  W [O][C][taps] is re-laid-out ONCE per weight version (sdb_dcn_prepare_weights) into the three
+// Weight images.  W [O][C][taps] is re-laid-out ONCE per weight version (sdb_dcn_prepare_weights) into the two
 // operand images the kernels stream with cp.async.bulk, every tile already in the 128B-swizzled K-major layout
 // tcgen05.mma reads:
 //   image 0 (forward B operand)   per (channel chunk of `cps`, tap, 64-channel block): [O rows][64 c]
 //   image 1 (dcol = dY W^T)       per (tap, channel chunk of `nch`, 64-o block):       [nch rows (c)][64 o], o >= O zero
-//   image 2 (grad_input B operand) per column block nb: (o-chunk of 128, tap, 64-o block in chunk): [ncols rows (c)][64 o]
 // blockIdx.y selects the image; bias -> fp32 behind them.
 struct PrepLayout {
-  size_t fwd_off, dgrad_off, dx_off, bias_off, total;
-  int cps, nch, okb, ncols;
-  int which;   // images to write: 1 = forward, 2 = dcol (grad_offset), 4 = grad_input
+  size_t fwd_off, dgrad_off, bias_off, total;
+  int cps, nch, okb;
+  int which;   // images to write: 1 = forward, 2 = dcol (backward data)
 };
 template <typename T>
 __global__ void __launch_bounds__(256) prep_weights_kernel(const T* __restrict__ w, const T* __restrict__ bias,
@@ -98,15 +89,8 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const T* __restrict__
     uint4 pk;
     pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
     pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-    if (which == 1) {
-      const size_t tile = ((size_t)tap * (C / L.nch) + c / L.nch) * L.okb + (o8 >> 3);
-      *reinterpret_cast<uint4*>(img + L.dgrad_off + tile * ((size_t)L.nch * 128) + sw128_offset(c % L.nch, o8 & 7)) = pk;
-    } else {
-      const int kb = o8 >> 3;                       // 64-o block
-      const int nb = c / L.ncols, cr = c % L.ncols;
-      const size_t tile = (size_t)nb * taps * L.okb + ((size_t)(kb >> 1) * taps + tap) * 2 + (kb & 1);
-      *reinterpret_cast<uint4*>(img + L.dx_off + tile * ((size_t)L.ncols * 128) + sw128_offset(cr, o8 & 7)) = pk;
-    }
+    const size_t tile = ((size_t)tap * (C / L.nch) + c / L.nch) * L.okb + (o8 >> 3);
+    *reinterpret_cast<uint4*>(img + L.dgrad_off + tile * ((size_t)L.nch * 128) + sw128_offset(c % L.nch, o8 & 7)) = pk;
   }
 }
 
@@ -163,35 +147,25 @@ __device__ __forceinline__ Sample make_sample(const Geo& g, const RawOff raw, bo
 
 // one problem of a launch (a FPN level of one convolution)
 struct FwdProb {
-  const __nv_bfloat16* xp;  // MODE_FWD: NHWC bf16 input; MODE_DX: NHWC bf16 dY [P][okb*64]
+  const __nv_bfloat16* xp;  // NHWC bf16 input
   const float* off;
   const float* mask;
-  const GDesc* desc;        // MODE_DX: first four entries of every transposed list, key = (tile*taps + tap)*128 + row
-  const int* start;         // MODE_DX: first overflow descriptor of every key (nkeys + 1 values)
-  const ODesc* odesc;       // MODE_DX: overflow descriptors (entries 5.. of a list, four per descriptor)
   const uint8_t* wimg;      // weight image of this problem's convolution
-  const float* bias;        // fp32 [ncols] or nullptr
-  void* out;                // NCHW, f32 or bf16: [mN][out_ch][mH][mW]
+  const float* bias;        // fp32 [O] or nullptr
+  void* out;                // NCHW, f32 or bf16: [N][O][Ho][Wo]
   Dims d;                   // N, H, W, Ho, Wo of this problem
-  int mH, mW;               // pixel grid of the GEMM's M dimension (output grid fwd, input grid dx)
-  long long mP;             // mN * mH * mW
+  long long mP;             // N * Ho * Wo
 };
 struct FwdParams {
-  TileMap map;              // work item -> problem; a problem owns num_tiles * nnb consecutive work items
+  TileMap map;              // work item (128-pixel tile) -> problem
   FwdProb pr[MAX_PROBS];
   Geo g;                    // common geometry (N, H, W, Ho, Wo come from the problem)
-  int ncols, nnb;           // GEMM N per column block, number of column blocks (dx with C_in > 256)
-  int kch;                  // gathered channels per tap (C_in fwd, okb*64 dx)
-  int out_ch;               // channel count of `out`
   int nsa, nsb;
-  int accumulate;           // MODE_DX: add to `out` (the single-call ABI accumulates into grad_x) instead of overwriting
 };
-
-constexpr int MODE_FWD = 0, MODE_DX = 1;
 
 
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
-template <int LPP, bool OUT_BF16, int MODE>
+template <int LPP, bool OUT_BF16>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   constexpr int CPS = LPP * 8;           // channels per A stage
   constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
@@ -206,7 +180,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int O = p.ncols, C = p.kch, taps = p.g.KH * p.g.KW, nchunks = C / CPS;
+  const int O = p.g.O, C = p.g.C, taps = p.g.KH * p.g.KW, nchunks = C / CPS;
   const int num_work = p.map.start[p.map.n];
   const uint32_t B_BYTES = (uint32_t)O * 128u;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -247,9 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       uint32_t bs = 0, bp = 0;
       const int nkb_total = taps * (C / 64);
       for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int pi = find_range(p.map, work);
-        const int nb = (work - p.map.start[pi]) % p.nnb;
-        const uint8_t* wsrc = p.pr[pi].wimg + (size_t)nb * nkb_total * B_BYTES;
+        const uint8_t* wsrc = p.pr[find_range(p.map, work)].wimg;
         for (int kb = 0; kb < nkb_total; ++kb) {
           mbar_wait(&b_empty[bs], bp ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
@@ -301,44 +273,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int pi = find_range(p.map, work);
       const FwdProb& pr = p.pr[pi];
-      const int local = work - p.map.start[pi];
-      const int tile = local / p.nnb, ob = (local % p.nnb) * O;
-      const int hw = pr.mH * pr.mW;
+      const int tile = work - p.map.start[pi];
+      const int hw = pr.d.Ho * pr.d.Wo;
       mbar_wait(&acc_full[acc], accp);
       tc_fence_after_sync();
       const long long pix = (long long)tile * TILE_M + q * 32 + lane;
       const bool valid = pix < pr.mP;
       int n = 0, eho = 0, ewo = 0;
-      if (valid) decode_pos(pr.mH, pr.mW, p.g.th, p.g.tw, pix, n, eho, ewo);
-      const int rem = eho * pr.mW + ewo;
+      if (valid) decode_pos(pr.d.Ho, pr.d.Wo, p.g.th, p.g.tw, pix, n, eho, ewo);
+      const int rem = eho * pr.d.Wo + ewo;
       const float* bias = pr.bias;
       for (int c0 = 0; c0 < O; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16) + c0, r);
         tmem_ld_wait();
         if (valid) {
-          const size_t d0 = ((size_t)n * p.out_ch + ob + c0) * hw + rem;
-          if (MODE == MODE_DX && p.accumulate) {
-            // single-call ABI: grad_input is accumulated into (deform_conv.py:89-90 pre-zeroes it): fetch the 32 old
-            // values first (independent loads in flight together), then add and store
-            float old[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              old[j] = 0.f;
-              if (c0 + j < O) {
-                if (OUT_BF16) old[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.out)[d0 + (size_t)j * hw]);
-                else          old[j] = reinterpret_cast<const float*>(pr.out)[d0 + (size_t)j * hw];
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + old[j]);
-          }
+          const size_t d0 = ((size_t)n * O + c0) * hw + rem;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int o = c0 + j;
             if (o < O) {
               float v = __uint_as_float(r[j]);
-              if (MODE == MODE_FWD && bias) v += __ldg(bias + o);
+              if (bias) v += __ldg(bias + o);
               const size_t di = d0 + (size_t)j * hw;
               if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(pr.out)[di] = __float2bfloat16_rn(v);
               else          reinterpret_cast<float*>(pr.out)[di] = v;
@@ -353,22 +309,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   } else {
     // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
     // (1) per tile, the descriptors (4 source rows + 4 weights) of this warp's 16 pixels for EVERY tap
-    //     go to shared memory once: MODE_FWD computes them from the offsets, MODE_DX copies the first
-    //     four entries of each transposed list (built by csr_fill_kernel) with cp.async;
+    //     are computed from the offsets and go to shared memory once;
     // (2) the gather then runs as one continuous stream over (chunk, tap, pixel pair) with a 4-slot
     //     register ring: the four 16-byte loads of iteration i+4 are issued right after iteration i
     //     is consumed, across stage boundaries, so 16 loads per warp stay in flight instead of every
-    //     warp paying the full memory latency once per stage in lock-step;
-    // (3) MODE_DX only: lists longer than four entries continue in overflow descriptors (four more entries
-    //     + the row they belong to).  A stage's overflow descriptors of this warp are staged in smem one
-    //     stage ahead and processed as extra iterations of the SAME ring after the 8 regular ones, ending
-    //     in a read-modify-write of the row instead of a store - no load latency is exposed.
+    //     warp paying the full memory latency once per stage in lock-step.
     constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
-    constexpr int OD_CAP = 16;                  // MODE_DX: overflow descriptors staged per warp and stage
-    __shared__ int s_range[MODE == MODE_DX ? NPW : 1][16][2];         // per warp, tap: [first overflow descriptor, count]
-    __shared__ ODesc s_od[MODE == MODE_DX ? NPW : 1][2][OD_CAP];      // staged overflow descriptors, double buffered
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
     GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
@@ -377,9 +325,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int pi = find_range(p.map, work);
       const FwdProb& pr = p.pr[pi];
-      const int tile = (work - p.map.start[pi]) / p.nnb;
+      const int tile = work - p.map.start[pi];
       const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
-      if constexpr (MODE == MODE_FWD) {
+      {
         const Geo g = with_dims(p.g, pr.d);
         const int px = lane % PIX_PER_WARP;
         const long long pix = (long long)tile * TILE_M + r0 + px;
@@ -402,7 +350,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           if (nwork < num_work) {
             const int npi = find_range(p.map, nwork);
             const FwdProb& npr = p.pr[npi];
-            const long long npix = (long long)((nwork - p.map.start[npi]) / p.nnb) * TILE_M + r0 + px;
+            const long long npix = (long long)(nwork - p.map.start[npi]) * TILE_M + r0 + px;
             if (npix < npr.mP) {
               const Geo ng = with_dims(p.g, npr.d);
               int nn, nho, nwo;
@@ -433,38 +381,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           }
         }
         __syncwarp();
-      } else {
-        __syncwarp();
-        constexpr int U16 = PIX_PER_WARP * (int)sizeof(GDesc) / 16;   // 16-byte units per (warp, tap) slice
-        for (int i = lane; i < taps * U16; i += 32) {
-          const int tap = i / U16, u = i - tap * U16;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.desc + ((size_t)tile * taps + tap) * TILE_M + r0) + u * 16;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sD + tap * TILE_M + r0) + u * 16)),
-                       "l"(src) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (lane < taps) {   // this warp's slice of the overflow descriptor list, per tap: [begin, count]
-          const int* sp = pr.start + ((size_t)tile * taps + lane) * TILE_M + r0;
-          const int b0 = __ldg(sp);
-          s_range[pw][lane][0] = b0;
-          s_range[pw][lane][1] = __ldg(sp + PIX_PER_WARP) - b0;
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
       }
-      // MODE_DX: copy the warp's overflow descriptors of tap `tap_` into staging buffer `buf_` (async)
-      auto stage_overflow = [&](int tap_, int buf_) {
-        if constexpr (MODE == MODE_DX) {
-          const int ob = s_range[pw][tap_][0];
-          int n16 = s_range[pw][tap_][1];
-          n16 = (n16 < OD_CAP ? n16 : OD_CAP) * 2;   // 16-byte units
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(pr.odesc + ob);
-          for (int i = lane; i < n16; i += 32)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(&s_od[pw][buf_][0]) + i * 16)),
-                         "l"(src + i * 16) : "memory");
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-      };
       uint4 v[RING][4], wq[RING];
       // issue the loads of iteration `it` of the stage (tap_, ch_) into ring slot `slot`
 #define SDB_ISSUE(tap_, ch_, it_, slot_)                                                     \
@@ -478,25 +395,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
         v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
       }
-      // MODE_DX: overflow iteration j_ of the current stage = overflow descriptors j_*PPI + grp of this
-      // warp's staged list (up to four more entries of one row); same ring slots, same loads
-#define SDB_ISSUE_OV(j_, slot_)                                                                  \
-      {                                                                                          \
-        const int d_ = (j_) * PPI + grp;                                                         \
-        wq[slot_] = make_uint4(0u, 0u, 0u, 0u);                                                  \
-        if (d_ < nod) {                                                                          \
-          const uint4 o_ = sod[d_].o;                                                            \
-          const uint4 m_ = sod[d_].m;                                                            \
-          wq[slot_].x = __byte_perm(m_.x, m_.x, 0x1010); wq[slot_].y = __byte_perm(m_.x, m_.x, 0x3232); \
-          wq[slot_].z = __byte_perm(m_.y, m_.y, 0x1010); wq[slot_].w = __byte_perm(m_.y, m_.y, 0x3232); \
-          const uint4* xb_ = xbase + ch * (CPS / 8);                                             \
-          const uint4 z_ = make_uint4(0u, 0u, 0u, 0u);                                           \
-          v[slot_][0] = wq[slot_].x ? __ldg(xb_ + o_.x) : z_;                                    \
-          v[slot_][1] = wq[slot_].y ? __ldg(xb_ + o_.y) : z_;                                    \
-          v[slot_][2] = wq[slot_].z ? __ldg(xb_ + o_.z) : z_;                                    \
-          v[slot_][3] = wq[slot_].w ? __ldg(xb_ + o_.w) : z_;                                    \
-        }                                                                                        \
-      }
 #define SDB_INTERP(a_, slot_)                                                                    \
         a_.x = bf2_fma(wq[slot_].w, v[slot_][3].x, bf2_fma(wq[slot_].z, v[slot_][2].x, bf2_fma(wq[slot_].y, v[slot_][1].x, bf2_mul(wq[slot_].x, v[slot_][0].x)))); \
         a_.y = bf2_fma(wq[slot_].w, v[slot_][3].y, bf2_fma(wq[slot_].z, v[slot_][2].y, bf2_fma(wq[slot_].y, v[slot_][1].y, bf2_mul(wq[slot_].x, v[slot_][0].y)))); \
@@ -504,24 +402,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         a_.w = bf2_fma(wq[slot_].w, v[slot_][3].w, bf2_fma(wq[slot_].z, v[slot_][2].w, bf2_fma(wq[slot_].y, v[slot_][1].w, bf2_mul(wq[slot_].x, v[slot_][0].w))));
 #pragma unroll
       for (int u = 0; u < RING; ++u) SDB_ISSUE(0, 0, u, u)
-      if constexpr (MODE == MODE_DX) stage_overflow(0, 0);
       int tap = 0, ch = 0;
       for (int st = 0; st < nstages; ++st) {
         int ntap = tap + 1, nch = ch;   // K order: chunk outermost, taps inside (L1-friendly)
         if (ntap == taps) { ntap = 0; ++nch; }
         const bool has_next = st + 1 < nstages;
-        // MODE_DX: overflow descriptors of this stage (staged one stage ahead), ring iterations they need
-        int nod = 0, m_ov = 0, ocount = 0;
-        const ODesc* sod = nullptr;
-        if constexpr (MODE == MODE_DX) {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
-          if (has_next) stage_overflow(ntap, (st + 1) & 1);
-          ocount = s_range[pw][tap][1];
-          nod = ocount < OD_CAP ? ocount : OD_CAP;
-          m_ov = ((nod + PPI - 1) / PPI + RING - 1) / RING * RING;
-          sod = &s_od[pw][st & 1][0];
-        }
         mbar_wait(&a_empty[as], ap ^ 1);
         uint8_t* dst = sA + (size_t)as * A_BYTES + (lig >> 3) * (TILE_M * 128);
 #pragma unroll
@@ -532,87 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
           if (it + RING < ITERS) {
             SDB_ISSUE(tap, ch, it + RING, slot)
-          } else if (MODE == MODE_DX && m_ov > 0) {
-            SDB_ISSUE_OV(it + RING - ITERS, slot)
           } else if (has_next) {
             SDB_ISSUE(ntap, nch, it + RING - ITERS, slot)
-          }
-        }
-        if constexpr (MODE == MODE_DX) {
-          if (m_ov > 0) {
-            __syncwarp();   // rows written above by other lanes of this warp
-            for (int j0 = 0; j0 < m_ov; j0 += RING) {
-#pragma unroll
-              for (int u = 0; u < RING; ++u) {
-                const int d = (j0 + u) * PPI + grp;
-                uint4 add;
-                SDB_INTERP(add, u)
-#pragma unroll
-                for (int gs = 0; gs < PPI; ++gs) {   // one lane group at a time: two descriptors may share a row
-                  if (grp == gs && d < nod) {
-                    uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(sod[d].m.z, lig & 7));
-                    uint4 a = *rp;
-                    a.x = bf2_add(a.x, add.x); a.y = bf2_add(a.y, add.y);
-                    a.z = bf2_add(a.z, add.z); a.w = bf2_add(a.w, add.w);
-                    *rp = a;
-                  }
-                  __syncwarp();
-                }
-                if (j0 + u + RING < m_ov) {
-                  SDB_ISSUE_OV(j0 + u + RING, u)
-                } else if (has_next) {
-                  SDB_ISSUE(ntap, nch, u, u)
-                }
-              }
-            }
-          }
-          // lists so long that the warp's descriptors did not fit the staging buffer: the tail is summed in
-          // fp32 per lane group while consecutive descriptors stay on the same row, and added to the operand
-          // row once per run (a bf16 read-modify-write per descriptor lost ~1e-2 on ~140-entry lists)
-          if (ocount > OD_CAP) {
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-            int acc_row = -1;
-            for (int d0 = OD_CAP; d0 < ocount + PPI; d0 += PPI) {   // the extra round flushes the last rows
-              const int d = d0 + grp;
-              const bool have = d < ocount;
-              ODesc od;
-              od.o = make_uint4(0u, 0u, 0u, 0u);
-              od.m = make_uint4(0u, 0u, 0u, 0u);
-              if (have) od = pr.odesc[s_range[pw][tap][0] + d];
-              const int row = (int)od.m.z;
-              const bool flush = acc_row >= 0 && (!have || row != acc_row);
-              __syncwarp();
-#pragma unroll
-              for (int gs = 0; gs < PPI; ++gs) {   // one lane group at a time: two groups may hold the same row
-                if (grp == gs && flush) {
-                  uint4* rp = reinterpret_cast<uint4*>(dst + sw128_offset(acc_row, lig & 7));
-                  const uint4 a = *rp;
-                  uint4 r;
-                  r.x = pack_bf16x2(__uint_as_float(a.x << 16) + acc[0], __uint_as_float(a.x & 0xffff0000u) + acc[1]);
-                  r.y = pack_bf16x2(__uint_as_float(a.y << 16) + acc[2], __uint_as_float(a.y & 0xffff0000u) + acc[3]);
-                  r.z = pack_bf16x2(__uint_as_float(a.z << 16) + acc[4], __uint_as_float(a.z & 0xffff0000u) + acc[5]);
-                  r.w = pack_bf16x2(__uint_as_float(a.w << 16) + acc[6], __uint_as_float(a.w & 0xffff0000u) + acc[7]);
-                  *rp = r;
-                }
-                __syncwarp();
-              }
-              if (flush) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-                acc_row = -1;
-              }
-              if (have) {
-                const uint4* xb = xbase + ch * (CPS / 8);
-                const uint32_t wbits[4] = {od.m.x << 16, od.m.x & 0xffff0000u, od.m.y << 16, od.m.y & 0xffff0000u};
-                const uint32_t o[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (wbits[k]) fma8(acc, __ldg(xb + o[k]), __uint_as_float(wbits[k]));
-                acc_row = row;
-              }
-            }
           }
         }
         fence_proxy_async_smem();
@@ -622,7 +428,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         ch = nch;
       }
 #undef SDB_ISSUE
-#undef SDB_ISSUE_OV
 #undef SDB_INTERP
     }
   }
@@ -631,11 +436,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
-template <int LPP, bool OUT_BF16, int MODE>
+template <int LPP, bool OUT_BF16>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE>), smem);
-  ProfScope prof(MODE == MODE_FWD ? SDB_OP_FORWARD : 3, st);   // slot 3 = grad_input GEMM
-  dcn_fwd_tc_kernel<LPP, OUT_BF16, MODE><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16>), smem);
+  ProfScope prof(SDB_OP_FORWARD, st);
+  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -656,12 +461,6 @@ size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
 }  // namespace
 
 int tc_lanes_per_pixel(const Geo& g) { return g.C % 128 == 0 ? 16 : 8; }
-// column blocking of the grad_input GEMM: N = C_in split into nnb equal blocks of <= 256 columns
-int tc_dx_col_blocks(const Geo& g) {
-  int nnb = (g.C + 255) / 256;
-  while (g.C % (nnb * 16) != 0) ++nnb;
-  return nnb;
-}
 
 bool tc_supported(const Geo& g, const char** why) {
   *why = "";
@@ -671,9 +470,9 @@ bool tc_supported(const Geo& g, const char** why) {
   if (g.O % 16 != 0 || g.O < 16 || g.O > 256) { *why = "C_out must be a multiple of 16 in [16,256]"; return false; }
   if (g.taps() > 16) { *why = "more than 16 kernel taps (per-tile descriptors would not fit in shared memory)"; return false; }
   const long long pin = (long long)g.N * g.H * g.W;
-  if (pin * (g.C / 8) >= (1LL << 32) || g.P() * g.O >= (1LL << 40) ||
-      (4 * g.P() + pin + TILE_M) * g.taps() >= (1LL << 31) ||
-      g.P() * (((g.O + 127) / 128) * 16) >= (1LL << 32)) { *why = "tensor too large"; return false; }
+  // 32-bit row offsets (input rows, dcol rows in 16-byte units), int key / entry counts of the transposed index
+  if (pin * (g.C / 8) >= (1LL << 32) || g.P() * g.O >= (1LL << 40) || (g.P() + TILE_M) * g.taps() * (g.C / 8) >= (1LL << 32) ||
+      4 * g.P() * g.taps() + (pin + TILE_M) * (g.taps() + 9) >= (1LL << 31) || g.P() + TILE_M >= (1LL << 31)) { *why = "tensor too large"; return false; }
   return true;
 }
 
@@ -685,11 +484,9 @@ static PrepLayout prep_layout(const Geo& g) {
   L.cps = tc_lanes_per_pixel(g) * 8;
   L.nch = g.C % 128 == 0 ? 128 : 64;
   L.okb = 2 * ((g.O + 127) / 128);
-  L.ncols = g.C / tc_dx_col_blocks(g);
   size_t o = 0;
   L.fwd_off = o;   o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
   L.dgrad_off = o; o = align_up(o + (size_t)g.taps() * g.C * L.okb * 64 * 2, 1024);
-  L.dx_off = o;    o = align_up(o + (size_t)g.taps() * g.C * L.okb * 64 * 2, 1024);
   L.bias_off = o;  o = align_up(o + (size_t)g.O * 4, 1024);
   L.total = o;
   return L;
@@ -699,15 +496,15 @@ TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bia
   const PrepLayout L = prep_layout(g);
   const uint8_t* b = (const uint8_t*)prepared;
   TcWeightImages w;
-  w.fwd = b + L.fwd_off; w.dgrad = b + L.dgrad_off; w.dx = b + L.dx_off;
+  w.fwd = b + L.fwd_off; w.dgrad = b + L.dgrad_off;
   w.bias = has_bias ? (const float*)(b + L.bias_off) : nullptr;
   return w;
 }
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
                        cudaStream_t st) {
   PrepLayout L = prep_layout(g);
-  L.which = which & 7;
-  const int nimg = (which & 1) + ((which >> 1) & 1) + ((which >> 2) & 1);
+  L.which = which & 3;
+  const int nimg = (which & 1) + ((which >> 1) & 1);
   if (nimg == 0) return SDB_OK;
   const long long total = (long long)g.taps() * g.C * L.okb * 8;
   const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
@@ -725,7 +522,6 @@ int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dty
 int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st) {
   FwdParams p{};
   p.g = g;
-  p.ncols = g.O; p.nnb = 1; p.kch = g.C; p.out_ch = g.O; p.accumulate = 0;
   p.map.n = n;
   int total = 0;
   for (int i = 0; i < n; ++i) {
@@ -733,7 +529,7 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
     FwdProb& q = p.pr[i];
     q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.wimg = pb[i].w.fwd;
     q.bias = pb[i].w.bias; q.out = pb[i].out; q.d = pb[i].d;
-    q.mH = gi.Ho; q.mW = gi.Wo; q.mP = gi.P();
+    q.mP = gi.P();
     p.map.start[i] = total;
     total += cdiv(gi.P(), TILE_M);
   }
@@ -746,38 +542,8 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   const int grid = total < num_sms() ? total : num_sms();
   const bool obf = io_dtype == SDB_BF16;
-  if (lpp == 16) return obf ? launch_fwd<16, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<16, false, MODE_FWD>(p, smem, grid, st);
-  return obf ? launch_fwd<8, true, MODE_FWD>(p, smem, grid, st) : launch_fwd<8, false, MODE_FWD>(p, smem, grid, st);
-}
-
-// ---- grad_input, all problems in one launch ----------------------------------------------------------------------
-int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype, int accumulate, cudaStream_t st) {
-  const int nnb = tc_dx_col_blocks(g), ncols = g.C / nnb;
-  FwdParams p{};
-  p.g = g;
-  p.ncols = ncols; p.nnb = nnb; p.kch = okb * 64; p.out_ch = g.C; p.accumulate = accumulate;
-  int total = 0, m = 0;
-  for (int i = 0; i < n; ++i) {
-    if (!pb[i].gx) continue;
-    FwdProb& q = p.pr[m];
-    q.xp = (const __nv_bfloat16*)pb[i].gyn; q.desc = (const GDesc*)pb[i].desc; q.start = pb[i].start;
-    q.odesc = (const ODesc*)pb[i].odesc; q.wimg = pb[i].w.dx; q.out = pb[i].gx; q.d = pb[i].d;
-    q.mH = pb[i].d.H; q.mW = pb[i].d.W; q.mP = (long long)pb[i].d.N * pb[i].d.H * pb[i].d.W;
-    p.map.start[m] = total;
-    total += cdiv(q.mP, TILE_M) * nnb;
-    ++m;
-  }
-  p.map.n = m;
-  p.map.start[m] = total;
-  if (total == 0) return SDB_OK;
-  constexpr int lpp = 16;   // 128-channel stages: okb is even, so kch % 128 == 0
-  const size_t a_bytes = (size_t)TILE_M * lpp * 8 * 2, b_bytes = (size_t)ncols * 128;
-  const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);
-  const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes + DX_STATIC_SMEM) - DX_STATIC_SMEM;  // static arrays come out of the same budget
-  SDB_REQUIRE(smem > 0 && smem < (1u << 20), SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  const int grid = total < num_sms() ? total : num_sms();
-  return io_dtype == SDB_BF16 ? launch_fwd<lpp, true, MODE_DX>(p, smem, grid, st)
-                              : launch_fwd<lpp, false, MODE_DX>(p, smem, grid, st);
+  if (lpp == 16) return obf ? launch_fwd<16, true>(p, smem, grid, st) : launch_fwd<16, false>(p, smem, grid, st);
+  return obf ? launch_fwd<8, true>(p, smem, grid, st) : launch_fwd<8, false>(p, smem, grid, st);
 }
 
 }  // namespace sdb

@@ -9,14 +9,14 @@
 //   reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels with warp
 //   shuffles -> grad_offset / grad_mask, plain stores (one owner per (pixel, tap)).
 //  (2) grad_input -- the reference scatters w * dcol with fp32 atomics (K3/K6); here the scatter is
-//   inverted once per call into a CSR index "which (output pixel, tap, weight) touch input pixel q"
-//   (count -> scan -> fill, ~36 eight-byte entries per output pixel) and grad_input becomes a second
-//   gathered implicit GEMM  dX[q,c] = sum_{tap,o} (sum_e w_e dY[p_e,o]) W[o,c,tap]  run by the
-//   forward kernel in MODE_DX (dcn_tc.cu).  Tensor work goes up by one GEMM, HBM/L2 atomic traffic
-//   (36 KB per output pixel at C=256) goes to zero, and the fp32 NHWC accumulation buffer, its
-//   memset and the NHWC->NCHW conversion pass disappear.
+//   inverted once per offset group into a CSR index "which (output pixel, tap, weight) touch input
+//   pixel q" (count -> scan -> fill -> sort, ~36 entries per output pixel), kernel (1) writes its bf16
+//   dcol staging tiles to HBM with one bulk copy each (the only pass over dY W^T: no second GEMM), and
+//   grad_input becomes a pure gather  dX[q,c] = sum_{(p,tap,w) in list(q)} w * dcol[p,tap,c]  with fp32
+//   accumulation in a fixed (sorted) order: deterministic, no atomics, no fp32 NHWC accumulation buffer,
+//   no memset, no NHWC->NCHW pass.  (dcn_dx_gather_kernel below.)
 //   Replaces G2 + K2/K5 + K3/K6 of the reference (deform_conv_cuda.cu:553-559,
-//   deform_conv_cuda_kernel.cu:291-452, :870-1066); `columns` is never written to HBM.
+//   deform_conv_cuda_kernel.cu:291-452, :870-1066).
 //
 // backward_weight: dW[o, c, tap] = sum_p dY[p,o] col[p,(tap,c)]  -- tcgen05 GEMM with BOTH operands
 //   MN-major: A = dY^T tiles (bulk-copied), B = re-gathered col tile (same producer as forward),
@@ -24,6 +24,8 @@
 //   accumulate in TMEM for the CTA's whole pixel range; split partials are reduced (and permuted to
 //   [O][C][kH][kW]) by a second tiny kernel -- deterministic, no atomics.
 //   Replaces K1' + G3 of the reference (deform_conv_cuda.cu:738-778).
+#include <type_traits>
+
 #include "dcn_tc_shared.cuh"
 
 namespace sdb {
@@ -41,7 +43,7 @@ constexpr int PIX_PER_WARP = TILE_M / NSW;   // 16
 constexpr int MAX_B_STAGES = 8;
 
 inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wide o blocks, even count
-inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
+__host__ __device__ inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
 inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,25 +225,22 @@ __device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __res
   return make_bsample_raw(g, fetch_rawb(g, off, mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
 }
 
-__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
-  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
-  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
-  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
-  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
-}
-
 // ------------------------------------------------------------------------------------------------
 // index of the transposed sampling pattern (grad_input as a gather, see file header)
 // ------------------------------------------------------------------------------------------------
-// key(q, tap) = (tile(q) * taps + tap) * 128 + row(q), q = band-order position of the INPUT pixel.
-// The list of (output pixel p, weight w = bilinear x mask) that reach q through `tap` is stored as
-//   desc[key]  : its first four entries in the forward gather's descriptor format (row offset of p in
-//                the NHWC bf16 dY in 16 B units + bf16x2 weight; unused slots are zero), and
-//   overflow   : entries five and up, four per ODesc (same fields + the row), descriptors of a key
-//                contiguous (start[key] .. start[key+1]) and keys in (tile, tap, row) order, so the
-//                descriptors of one (tile, tap, 16-row warp slice) are one contiguous run.
-// With stride 1 a list holds four entries on average, so most of the work takes the fixed-width path.
-constexpr int DESC_W = 4;
+// key(q, tap) = q * (taps + 1) + tap, q = band-order position of the INPUT pixel (tile = q >> 7, row = q & 127).
+// Plain CSR: the (output pixel p, weight w = bilinear x mask) pairs that reach q through `tap` are the entries
+// start[key] .. start[key + 1]; because the keys of one input pixel are adjacent, the whole list of q -- every tap --
+// is one contiguous run, which is what the gather walks.  The extra key q * (taps + 1) + taps holds 0..7 zero entries
+// that pad the run to a multiple of eight entries (64 bytes), so the gather reads whole groups of eight with aligned
+// 16-byte loads and no per-entry bounds test (a zero entry = row 0 with weight 0).  An entry is 8 bytes: the row of
+// dcol it names, as an offset in 16-byte units into the problem's dcol tiles (channel chunk 0), and tap << 16 | bf16
+// weight.  With stride 1 a key holds four entries on average (36 per input pixel for 3x3).
+struct __align__(8) CEntry {
+  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (16 * NCH) + (pos & 127) * (NCH / 8), pos = band-order position of p
+  uint32_t tw;      // tap << 16 | weight (bf16 bits; zero only in padding)
+};
+constexpr int LIST_ALIGN = 8;   // entries
 template <typename F>
 __device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restrict__ off,
                                              const float* __restrict__ mask, int n, int ho, int wo, int tap,
@@ -257,8 +256,7 @@ __device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restri
     const int pixel = s.idx[k] - n * g.H * g.W;    // y * W + x
     const int y = pixel / g.W, x = pixel - y * g.W;
     const long long q = encode_pos(g.H, g.W, g.th, g.tw, n, y, x);
-    const long long key = ((q >> 7) * g.taps() + tap) * TILE_M + (q & 127);
-    f(key, wb, (uint32_t)(q & 127));
+    f(q * (g.taps() + 1) + tap, wb);
   }
 }
 
@@ -280,18 +278,27 @@ __global__ void __launch_bounds__(256) csr_count_kernel(const __grid_constant__ 
   const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
   int* c = cnt + t.gr[gi].key_base;
   for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap,
-               [&](long long key, uint32_t, uint32_t) { atomicAdd(c + key, 1); });
+               [&](long long key, uint32_t) { atomicAdd(c + key, 1); });
+}
+
+// pad key of every input pixel: the number of zero entries that round its list up to LIST_ALIGN entries
+__global__ void __launch_bounds__(256) csr_pad_kernel(int* __restrict__ cnt, int npix, int taps) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npix) return;
+  int* c = cnt + (size_t)q * (taps + 1);
+  int s = 0;
+  for (int t = 0; t < taps; ++t) s += c[t];
+  c[taps] = (-s) & (LIST_ALIGN - 1);
 }
 
 constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block
-__device__ __forceinline__ int overflow_of(int c) { return c > DESC_W ? (c - DESC_W + 3) >> 2 : 0; }   // descriptors
 __global__ void __launch_bounds__(256) csr_block_sums_kernel(const int* __restrict__ cnt, int* __restrict__ bsum,
                                                              int nkeys) {
   const int base = blockIdx.x * SCAN_PER_BLOCK;
   int s = 0;
   for (int i = threadIdx.x; i < SCAN_PER_BLOCK; i += 256) {
     const int k = base + i;
-    if (k < nkeys) s += overflow_of(cnt[k]);
+    if (k < nkeys) s += cnt[k];
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -339,11 +346,9 @@ __global__ void __launch_bounds__(1024) csr_scan_top_kernel(int* __restrict__ bs
     __syncthreads();
   }
 }
-// start[k] = exclusive scan of the overflow descriptor counts; start[nkeys] = total; the descriptors of
-// key k are cleared and tagged with their row here
+// start[k] = exclusive scan of the entry counts; start[nkeys] = total
 __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restrict__ cnt, const int* __restrict__ bsum,
-                                                             int* __restrict__ start, ODesc* __restrict__ odesc,
-                                                             int nkeys) {
+                                                             int* __restrict__ start, int nkeys) {
   __shared__ int wsum[8];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = bsum[blockIdx.x];
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
   const int base = blockIdx.x * SCAN_PER_BLOCK;
   for (int i0 = 0; i0 < SCAN_PER_BLOCK; i0 += 256) {
     const int k = base + i0 + threadIdx.x;
-    const int v = k < nkeys ? overflow_of(cnt[k]) : 0;
+    const int v = k < nkeys ? cnt[k] : 0;
     int incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -367,10 +372,6 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
     if (k < nkeys) {
       start[k] = excl;
       if (k == nkeys - 1) start[nkeys] = excl + v;
-      for (int d = 0; d < v; ++d) {
-        odesc[excl + d].o = make_uint4(0u, 0u, 0u, 0u);
-        odesc[excl + d].m = make_uint4(0u, 0u, (uint32_t)(k & (TILE_M - 1)), 0u);
-      }
     }
     __syncthreads();
     if (threadIdx.x == 255) carry_s = carry + wbase + incl;
@@ -378,10 +379,8 @@ __global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restri
   }
 }
 
-// row_units = 16-byte units per pixel row of the NHWC dY (okb * 8)
 __global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ CsrTable t, int* __restrict__ cnt_all,
-                                                       const int* __restrict__ start_all, GDesc* __restrict__ desc_all,
-                                                       ODesc* __restrict__ odesc, int row_units) {
+                                                       const int* __restrict__ start_all, CEntry* __restrict__ ent) {
   const int gi = find_range(t.map, blockIdx.x);
   const Geo g = with_dims(t.g, t.gr[gi].d);
   const int tap = blockIdx.y;
@@ -389,132 +388,57 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ C
   if (p >= g.P()) return;
   const int hw = g.Ho * g.Wo;
   const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
-  const uint32_t poff = (uint32_t)p * (uint32_t)row_units;
+  const uint32_t pos = (uint32_t)encode_pos(g.Ho, g.Wo, g.th, g.tw, n, r / g.Wo, r % g.Wo);
+  const uint32_t nchv = (uint32_t)nch_of(g), nchunks = (uint32_t)g.C / nchv;
+  const uint32_t row16 = ((pos >> 7) * (uint32_t)g.taps() * nchunks + (uint32_t)tap * nchunks) * (16u * nchv) + (pos & 127u) * (nchv / 8u);
   int* cnt = cnt_all + t.gr[gi].key_base;
   const int* start = start_all + t.gr[gi].key_base;
-  GDesc* desc = desc_all + t.gr[gi].key_base;
-  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb, uint32_t row) {
-    const int pos = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
-    if (pos < DESC_W) {
-      desc[key].off[pos] = poff;
-      desc[key].w2[pos] = (wb << 16) | wb;
-    } else {
-      ODesc* od = odesc + start[key] + ((pos - DESC_W) >> 2);
-      const int sl = (pos - DESC_W) & 3;
-      reinterpret_cast<uint32_t*>(&od->o)[sl] = poff;
-      reinterpret_cast<uint16_t*>(&od->m)[sl] = (uint16_t)wb;
-    }
+  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb) {
+    const int slot = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
+    CEntry e;
+    e.row16 = row16;
+    e.tw = ((uint32_t)tap << 16) | wb;
+    ent[start[key] + slot] = e;
   });
 }
 
-// Canonical order.  csr_fill hands out list slots with atomics, so WHICH entries of a list sit in the four-wide
-// descriptor and in what order the bf16 partial sums are formed would change from run to run.  This pass sorts the
-// entries of every list by their source row (an output pixel reaches an (input pixel, tap) at most once, so the
-// keys are unique): grad_input becomes bit-reproducible.  One thread per key; lists of up to four entries (the
-// common case) are a 5-exchange network in registers, longer ones go through a small local array.
-__global__ void __launch_bounds__(256) csr_sort_kernel(GDesc* __restrict__ desc, const int* __restrict__ start,
-                                                       ODesc* __restrict__ odesc, int nkeys) {
+// Canonical order.  csr_fill hands out list slots with atomics, so the order in which the fp32 sums of grad_input are
+// formed would change from run to run.  This pass sorts the entries of every key by their output pixel (an output
+// pixel reaches an (input pixel, tap) at most once, so the sort keys are unique): grad_input becomes
+// bit-reproducible.  One thread per key; a key holds ~4 entries.
+__global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ start, CEntry* __restrict__ ent, int nkeys,
+                                                       int taps) {
   const int key = blockIdx.x * blockDim.x + threadIdx.x;
-  if (key >= nkeys) return;
-  const int ob = start[key], nod = start[key + 1] - ob;
-  uint4 o4 = *reinterpret_cast<const uint4*>(desc[key].off);
-  uint4 w4 = *reinterpret_cast<const uint4*>(desc[key].w2);
-  if (nod == 0) {
-    uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
-#define SDB_CX(a_, b_)                                                                             \
-    {                                                                                              \
-      const uint32_t ka_ = w[a_] ? o[a_] : 0xffffffffu, kb_ = w[b_] ? o[b_] : 0xffffffffu;         \
-      if (kb_ < ka_) { const uint32_t to_ = o[a_], tw_ = w[a_]; o[a_] = o[b_]; w[a_] = w[b_]; o[b_] = to_; w[b_] = tw_; } \
-    }
-    SDB_CX(0, 1) SDB_CX(2, 3) SDB_CX(0, 2) SDB_CX(1, 3) SDB_CX(1, 2)
-#undef SDB_CX
-    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(w[0], w[1], w[2], w[3]);
-    return;
-  }
-  constexpr int CAP = 68;   // 4 + 16 overflow descriptors; longer lists are sorted in place in global memory
-  const int total_slots = DESC_W + 4 * nod;
-  if (total_slots <= CAP) {
-    uint32_t o[CAP];
-    uint16_t w[CAP];
-    int n = 0;
-    const uint32_t od0[4] = {o4.x, o4.y, o4.z, o4.w}, wd0[4] = {w4.x, w4.y, w4.z, w4.w};
-    for (int k = 0; k < 4; ++k)
-      if (wd0[k]) { o[n] = od0[k]; w[n] = (uint16_t)(wd0[k] & 0xffffu); ++n; }
-    for (int d = 0; d < nod; ++d) {
-      const ODesc od = odesc[ob + d];
-      const uint32_t oo[4] = {od.o.x, od.o.y, od.o.z, od.o.w};
-      const uint32_t ww[4] = {od.m.x & 0xffffu, od.m.x >> 16, od.m.y & 0xffffu, od.m.y >> 16};
-      for (int k = 0; k < 4; ++k)
-        if (ww[k]) { o[n] = oo[k]; w[n] = (uint16_t)ww[k]; ++n; }
-    }
-    for (int i = 1; i < n; ++i) {   // insertion sort by source row
-      const uint32_t oi = o[i];
-      const uint16_t wi = w[i];
-      int j = i - 1;
-      while (j >= 0 && o[j] > oi) { o[j + 1] = o[j]; w[j + 1] = w[j]; --j; }
-      o[j + 1] = oi; w[j + 1] = wi;
-    }
-    uint32_t od[4], wd[4];
-    for (int k = 0; k < 4; ++k) { od[k] = k < n ? o[k] : 0u; wd[k] = k < n ? ((uint32_t)w[k] << 16) | w[k] : 0u; }
-    *reinterpret_cast<uint4*>(desc[key].off) = make_uint4(od[0], od[1], od[2], od[3]);
-    *reinterpret_cast<uint4*>(desc[key].w2) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-    const uint32_t row = odesc[ob].m.z;
-    for (int d = 0; d < nod; ++d) {
-      uint32_t oo[4], ww[4];
-      for (int k = 0; k < 4; ++k) {
-        const int e = DESC_W + 4 * d + k;
-        oo[k] = e < n ? o[e] : 0u;
-        ww[k] = e < n ? w[e] : 0u;
+  if (key >= nkeys || key % (taps + 1) == taps) return;   // pad keys hold zeros
+  const int b = start[key], n = start[key + 1] - b;
+  if (n < 2) return;
+  unsigned long long* e = reinterpret_cast<unsigned long long*>(ent + b);   // row16 (monotonic in the output pixel) in the low word
+  constexpr int CAP = 8;
+  if (n <= CAP) {
+    unsigned long long v[CAP];
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) v[i] = i < n ? e[i] : ~0ull;
+    // odd-even transposition sort on the low word (fully unrolled: registers, no local memory)
+#pragma unroll
+    for (int r = 0; r < CAP; ++r) {
+#pragma unroll
+      for (int i = r & 1; i + 1 < CAP; i += 2) {
+        const bool sw = (uint32_t)v[i + 1] < (uint32_t)v[i] && v[i + 1] != ~0ull;
+        const unsigned long long lo = sw ? v[i + 1] : v[i], hi = sw ? v[i] : v[i + 1];
+        v[i] = lo; v[i + 1] = hi;
       }
-      ODesc out;
-      out.o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-      out.m = make_uint4(ww[0] | (ww[1] << 16), ww[2] | (ww[3] << 16), row, 0u);
-      odesc[ob + d] = out;
     }
+#pragma unroll
+    for (int i = 0; i < CAP; ++i)
+      if (i < n) e[i] = v[i];
     return;
   }
-  // very long list (hundreds of taps colliding on one input pixel): selection sort over the slots in place
-  auto get = [&](int e, uint32_t& oo, uint32_t& ww) {
-    if (e < DESC_W) { oo = desc[key].off[e]; ww = desc[key].w2[e] & 0xffffu; }
-    else {
-      const ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
-      oo = reinterpret_cast<const uint32_t*>(&od->o)[(e - DESC_W) & 3];
-      ww = reinterpret_cast<const uint16_t*>(&od->m)[(e - DESC_W) & 3];
-    }
-  };
-  auto set = [&](int e, uint32_t oo, uint32_t ww) {
-    if (e < DESC_W) { desc[key].off[e] = oo; desc[key].w2[e] = (ww << 16) | ww; }
-    else {
-      ODesc* od = odesc + ob + ((e - DESC_W) >> 2);
-      reinterpret_cast<uint32_t*>(&od->o)[(e - DESC_W) & 3] = oo;
-      reinterpret_cast<uint16_t*>(&od->m)[(e - DESC_W) & 3] = (uint16_t)ww;
-    }
-  };
-  for (int i = 0; i < total_slots; ++i) {
-    uint32_t bo, bw;
-    get(i, bo, bw);
-    uint32_t bk = bw ? bo : 0xffffffffu;
-    int bi = i;
-    for (int j = i + 1; j < total_slots; ++j) {
-      uint32_t oo, ww;
-      get(j, oo, ww);
-      const uint32_t kk = ww ? oo : 0xffffffffu;
-      if (kk < bk) { bk = kk; bi = j; bo = oo; bw = ww; }
-    }
-    if (bi != i) {
-      uint32_t oi, wi;
-      get(i, oi, wi);
-      set(bi, oi, wi);
-      set(i, bo, bw);
-    }
+  for (int i = 1; i < n; ++i) {   // long list (many taps colliding on one input pixel): insertion sort in place
+    const unsigned long long x = e[i];
+    int j = i - 1;
+    while (j >= 0 && (uint32_t)e[j] > (uint32_t)x) { e[j + 1] = e[j]; --j; }
+    e[j + 1] = x;
   }
-}
-
-// byte offset of 16-byte chunk `chunk` of row `row` in the bf16 staging tile [128][NCH]
-template <int NCH>
-__device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
-  return row * (NCH * 2) + (((chunk & ~7u) | ((chunk & 7u) ^ (row & 7u))) << 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -528,6 +452,7 @@ struct DgradProb {
   const uint8_t* wt_img;     // W^T tiles of this problem's convolution
   float* goff;               // [N][2*taps][HWo] fp32, or nullptr
   float* gmask;              // [N][taps][HWo] fp32, or nullptr
+  uint8_t* dcol;             // export of the bf16 dcol staging tiles [tile][tap][chunk][128][NCH] for grad_input, or nullptr
   Dims d;
 };
 struct DgradParams {
@@ -538,7 +463,7 @@ struct DgradParams {
 };
 
 // Warp roles are aligned to warpgroups so that the register file can be re-split with setmaxnreg: warps 0-3 = bulk
-// producer, MMA issuer and two idle warps (40 registers each), warps 4-7 = TMEM drain (96), warps 8-15 = the reduce
+// producer, MMA issuer, dcol exporter and one idle warp (40 registers each), warps 4-7 = TMEM drain (96), warps 8-15 = the reduce
 // warps (184), which are the critical path of this kernel: at the 128 registers a 512-thread launch gives everybody
 // ptxas could not overlap the dependent shuffle / FMA chains of two iterations and the drain warps waited for them
 // 80 % of the time (profiles/r2_dcn_kernels_ncu_v1.txt).
@@ -583,7 +508,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);        // one arrival per drain warp
       mbar_init(&stg_full[s], 4);
-      mbar_init(&stg_empty[s], NSW);      // one arrival per reduce warp
+      mbar_init(&stg_empty[s], NSW + 1);  // one arrival per reduce warp + the exporter
     }
     fence_barrier_init();
   }
@@ -649,8 +574,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
       if (elect_one()) umma_commit(&a_empty);
       __syncwarp();
     }
+  } else if (warp == 2) {
+    // ===== dcol exporter: every finished staging tile goes to HBM as one bulk copy (the grad_input gather reads it) =====
+    if (lane == 0) {
+      uint32_t sb = 0, sp = 0;
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int pi = find_range(p.map, work);
+        uint8_t* dst = p.pr[pi].dcol;
+        if (dst) dst += (size_t)(work - p.map.start[pi]) * units * STG_BYTES;
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(&stg_full[sb], sp);
+          if (dst) {
+            bulk_s2g(dst + (size_t)u * STG_BYTES, sS + (size_t)sb * STG_BYTES, STG_BYTES);
+            bulk_commit();
+            bulk_wait_read_all();
+          }
+          mbar_arrive(&stg_empty[sb]);
+          if (++sb == 2) { sb = 0; sp ^= 1; }
+        }
+      }
+      bulk_wait_all();
+    }
   } else if (warp < G_DRAIN0) {
-    // idle warps of the first warpgroup (they only take part in the register re-split and the final barrier)
+    // idle warp of the first warpgroup (takes part in the register re-split and the final barrier only)
   } else if (warp < G_SW0) {
     // ===== drain: TMEM accumulator -> bf16 staging tile (row = pixel, swizzled 16-byte chunks) =====
     setmaxnreg_dec<96>();
@@ -679,6 +625,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
           }
         }
         tc_fence_before_sync();
+        fence_proxy_async_smem();            // the exporter's bulk copy reads the tile through the async proxy
         mbar_arrive_warp(&acc_empty[acc]);   // TMEM buffer may be overwritten
         mbar_arrive_warp(&stg_full[acc]);    // staging tile is ready (release)
         if (++acc == 2) { acc = 0; accp ^= 1; }
@@ -706,6 +653,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
       const int pi = find_range(p.map, work);
       const DgradProb& pr = p.pr[pi];
       const int tile = work - p.map.start[pi];
+      if (!pr.goff && !pr.gmask) {   // problem that only wants dcol (grad_input without grad_offset): release the tiles
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(&stg_full[sb], sp);
+          mbar_arrive_warp(&stg_empty[sb]);
+          if (++sb == 2) { sb = 0; sp ^= 1; }
+        }
+        continue;
+      }
       const Geo g = with_dims(p.g, pr.d);
       const int hw = g.Ho * g.Wo;
       const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
@@ -832,6 +787,129 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, NCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grad_input: gather of the exported dcol tiles over the transposed index
+// ------------------------------------------------------------------------------------------------
+// dX[q, c] = sum over the list of q (all taps): w_e * dcol[p_e, tap_e, c], accumulated in fp32 in list order (sorted:
+// bit-reproducible).  A CTA owns (128 input pixels in band order = a compact patch, one NCH-channel chunk); a group of
+// LPB lanes serves one pixel with 8 channels per lane, so a list entry is one 16-byte load per lane and NCH*2
+// contiguous bytes per group.  The group reads eight entries of its list with one coalesced load, broadcasts them with
+// shuffles and issues the eight row loads together; latency is hidden by occupancy (one accumulator row of 8 floats
+// per thread, <= 64 registers, 32 warps per SM), not by a software pipeline.  The four input pixels that share a dcol
+// row (the four bilinear corners) sit in the same or a neighbouring warp and walk their lists in the same (tap,
+// position) order, so the repeats are L1 / L2 hits.  HBM-bound on paper (dcol is read once: taps * C * 2 bytes per
+// output pixel); the result leaves through a shared-memory transpose as NCHW rows.
+struct DxProb {
+  const uint8_t* dcol;
+  const int* start;          // transposed index of the problem's offset group
+  const CEntry* ent;
+  void* out;                 // NCHW grad_input (f32 or bf16)
+  Dims d;
+};
+struct DxParams {
+  TileMap map;               // work items: (input tile, channel chunk), chunk fastest
+  DxProb pr[MAX_PROBS];
+  Geo g;
+  int accumulate;            // add to `out` (the single-call ABI accumulates into grad_x) instead of overwriting
+};
+
+// acc[0..7] += w * (8 bf16 of v), fp32 accumulation: mixed-precision FMA (FHFMA.BF16) reads the bf16 halves in place
+__device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4 v, uint32_t w_lo16) {
+#define SDB_FH(a0_, a1_, r_)                                                                   \
+  asm("{ .reg .b16 lo, hi, wl, wh;\n mov.b32 {lo, hi}, %2;\n mov.b32 {wl, wh}, %3;\n"        \
+      "fma.rn.f32.bf16 %0, lo, wl, %0;\n fma.rn.f32.bf16 %1, hi, wl, %1;\n }"                 \
+      : "+f"(a0_), "+f"(a1_) : "r"(r_), "r"(w_lo16));
+  SDB_FH(acc[0], acc[1], v.x) SDB_FH(acc[2], acc[3], v.y) SDB_FH(acc[4], acc[5], v.z) SDB_FH(acc[6], acc[7], v.w)
+#undef SDB_FH
+}
+
+template <int NCH, bool OUT_BF16, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) dcn_dx_gather_kernel(const __grid_constant__ DxParams p) {
+  constexpr int LPB = NCH / 8, PPI = 32 / LPB;
+  constexpr int PIXW = TILE_M / (THREADS / 32), ROUNDS = PIXW / PPI;
+  static_assert(ROUNDS >= 1 && LIST_ALIGN == 8, "list walk is written for groups of eight entries");
+  constexpr size_t STG_BYTES = (size_t)TILE_M * NCH * 2;
+  using ST = typename std::conditional<OUT_BF16, __nv_bfloat16, float>::type;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  ST* s_t = reinterpret_cast<ST*>(s_raw);  // [NCH][128] transpose buffer in the output type, column rotated by PPI * (c >> 3)
+  __shared__ int2 s_px[TILE_M];            // (n, y*W + x) of the tile's pixels, n = -1 past the end
+
+  const int pi = find_range(p.map, blockIdx.x);
+  const DxProb& pr = p.pr[pi];
+  const int C = p.g.C, taps = p.g.KH * p.g.KW, nch = C / NCH;
+  const int local = blockIdx.x - p.map.start[pi];
+  const int tile = local / nch, ch = local - tile * nch;
+  const int H = pr.d.H, W = pr.d.W, hw = H * W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / LPB, lig = lane % LPB;
+  const int r0 = warp * PIXW;
+
+  if (threadIdx.x < TILE_M) {
+    const long long q = (long long)tile * TILE_M + threadIdx.x;
+    int n = -1, y = 0, x = 0;
+    if (q < (long long)pr.d.N * hw) decode_pos(H, W, p.g.th, p.g.tw, q, n, y, x);
+    s_px[threadIdx.x] = make_int2(n, y * W + x);
+  }
+
+  // this lane's 16-byte column of a dcol row: chunk lig of the row, 128B-swizzled by the row's low three bits
+  const uint4* cb = reinterpret_cast<const uint4*>(pr.dcol + (size_t)ch * STG_BYTES);
+  const uint32_t lig_hi = (uint32_t)lig & ~7u;
+#pragma unroll 1
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int px = r0 + r * PPI + grp;
+    const int* sp = pr.start + ((size_t)tile * TILE_M + px) * (taps + 1);
+    const int beg = __ldg(sp), end = __ldg(sp + taps + 1);   // multiples of eight entries
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent + beg);
+    for (int e0 = beg; e0 < end; e0 += 8, ep += 4) {
+      uint4 e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) e[k] = __ldg(ep + k);   // two entries each: (row16, tw, row16, tw)
+      uint4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t row16 = (k & 1) ? e[k >> 1].z : e[k >> 1].x;
+        v[k] = __ldg(cb + (row16 + (lig_hi | (((row16 / (NCH / 8)) ^ (uint32_t)lig) & 7u))));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fma8_bf16(acc, v[k], (k & 1) ? e[k >> 1].w : e[k >> 1].y);
+    }
+    // [pixel][channel] registers -> transpose buffer
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int si = (lig * 8 + j) * TILE_M + ((px + PPI * lig) & (TILE_M - 1));
+      if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(s_t)[si] = __float2bfloat16_rn(acc[j]);
+      else reinterpret_cast<float*>(s_t)[si] = acc[j];
+    }
+  }
+  __syncthreads();
+  // NCHW rows: a warp store = 32 consecutive tile pixels of one channel
+  {
+    const int px = threadIdx.x & (TILE_M - 1);
+    const int2 pxy = s_px[px];
+    if (pxy.x >= 0) {
+      const size_t o0 = ((size_t)pxy.x * C + (size_t)ch * NCH) * hw + pxy.y;
+      for (int c = threadIdx.x >> 7; c < NCH; c += THREADS / TILE_M) {
+        const int si = c * TILE_M + ((px + PPI * (c >> 3)) & (TILE_M - 1));
+        const size_t di = o0 + (size_t)c * hw;
+        if (OUT_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(pr.out) + di;
+          __nv_bfloat16 v = reinterpret_cast<const __nv_bfloat16*>(s_t)[si];
+          if (p.accumulate) v = __float2bfloat16_rn(__bfloat162float(v) + __bfloat162float(*o));
+          *o = v;
+        } else {
+          float* o = reinterpret_cast<float*>(pr.out) + di;
+          float v = reinterpret_cast<const float*>(s_t)[si];
+          if (p.accumulate) v += *o;
+          *o = v;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1144,8 +1222,9 @@ Side* side_of_device() {
 // Everything a call needs beyond its tensors lives in ONE caller-provided workspace, laid out as a pure function of
 // the problem dimensions (so sdb_dcn_multi_workspace_bytes and the call agree):
 //   per problem : xp (NHWC bf16 input, unless the caller passes x_packed), and for the backward gy_img (dY as
-//                 swizzled tiles) + gyn (dY NHWC);
-//   per group   : its slice of the transposed index (cnt / start / desc share one key space, odesc one pool);
+//                 swizzled tiles) + dcol (dY W^T as bf16 tiles, taps * C * 2 bytes per output pixel, written by the
+//                 grad_offset kernel and read by the grad_input gather);
+//   per group   : its slice of the transposed index (cnt / start share one key space, the entries one pool);
 //   per weight  : the prepared operand images (unless the caller passes them) and the split-K partials of dW.
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward) {
   TcPlan P{};
@@ -1158,7 +1237,7 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     if (backward) {
       const size_t tiles = (size_t)cdiv(gi.P(), TILE_M);
       P.gy_off[i] = o;  o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
-      P.gyn_off[i] = o; o = align_up(o + (size_t)gi.P() * okb * 64 * 2, 1024);
+      P.dcol_off[i] = o; o = align_up(o + tiles * g.taps() * TILE_M * g.C * 2, 1024);
     }
   }
   for (int w = 0; w < nweights; ++w) {
@@ -1177,22 +1256,23 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
       P.group_of[i] = gi;
     }
     P.ngroups = ng;
-    long long keys = 0, ods = 1;
+    long long keys = 0, ents = 1;
     for (int k = 0; k < ng; ++k) {
       const Geo gk = with_dims(g, pb[P.group_rep[k]].d);
       P.key_base[k] = keys;
-      keys += (long long)cdiv((long long)gk.N * gk.H * gk.W, TILE_M) * g.taps() * TILE_M;
-      ods += gk.P() * g.taps();   // a key with c > 4 entries needs ceil((c-4)/4) <= c/4 overflow descriptors
+      const long long pix_in = (long long)cdiv((long long)gk.N * gk.H * gk.W, TILE_M) * TILE_M;
+      keys += pix_in * (g.taps() + 1);
+      // every (output pixel, tap) reaches at most four input pixels; up to LIST_ALIGN - 1 pad entries per input pixel
+      ents += 4 * gk.P() * g.taps() + (LIST_ALIGN - 1) * pix_in;
     }
     P.nkeys = keys;
     P.scan_blocks = cdiv(keys, SCAN_PER_BLOCK);
-    // cnt and desc are cleared by ONE memset: keep them adjacent
+    // cnt and the entry pool are cleared by ONE memset (pad entries must read as zero): keep them adjacent
     P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
-    P.desc_off = o;  o = align_up(o + (size_t)keys * sizeof(GDesc), 1024);
+    P.ent_off = o;   o = align_up(o + (size_t)ents * sizeof(CEntry), 1024);
     P.clear_bytes = o - P.cnt_off;
     P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
     P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
-    P.od_off = o;    o = align_up(o + (size_t)ods * sizeof(ODesc), 1024);
     // weight-gradient split-K: all weights share the machine
     int tiles_w[MAX_WEIGHTS] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) tiles_w[pb[i].weight_id] += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
@@ -1221,22 +1301,12 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
   return tc_forward_multi(pb, n, g, io_dtype, st);
 }
 
-// dY -> NHWC rows and the transposed sampling index (one per offset group) of a call, on stream `st`
-static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, int okb, bool bf, uint8_t* base,
-                                  cudaStream_t st) {
-  int rc;
-  {
-    PackJob jobs[MAX_PROBS];
-    for (int i = 0; i < n; ++i)
-      jobs[i] = PackJob{pb[i].gx ? pb[i].gy : nullptr, pb[i].gyn, pb[i].d.N, pb[i].d.Ho * pb[i].d.Wo};
-    rc = pack_nhwc_multi(jobs, n, g.O, okb * 64, bf, st);
-    if (rc) return rc;
-  }
+// the transposed sampling index (one per offset group) of a call, on stream `st`
+static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st) {
   int* cnt = (int*)(base + P.cnt_off);
   int* start = (int*)(base + P.start_off);
   int* bsum = (int*)(base + P.bsum_off);
-  ODesc* odesc = (ODesc*)(base + P.od_off);
-  GDesc* desc = (GDesc*)(base + P.desc_off);
+  CEntry* ent = (CEntry*)(base + P.ent_off);
   CsrTable t{};
   t.g = g;
   int total = 0, m = 0;
@@ -1252,20 +1322,62 @@ static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const G
   }
   t.map.n = m; t.map.start[m] = total;
   const int nkeys = (int)P.nkeys;
-  SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and desc in one fill
+  SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and the entry pool in one fill
   dim3 hgrid(total, g.taps());
   csr_count_kernel<<<hgrid, 256, 0, st>>>(t, cnt);
+  csr_pad_kernel<<<cdiv(nkeys / (g.taps() + 1), 256), 256, 0, st>>>(cnt, nkeys / (g.taps() + 1), g.taps());
   csr_block_sums_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
   csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, P.scan_blocks);
-  csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, odesc, nkeys);
-  csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, desc, odesc, okb * 8);
-  csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(desc, start, odesc, nkeys);
-  SDB_LAUNCHED(6);
+  csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, nkeys);
+  csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, ent);
+  csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(start, ent, nkeys, g.taps());
+  SDB_LAUNCHED(7);
   SDB_CHECK_CUDA(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     const long long kb = P.key_base[P.group_of[i]];
-    pb[i].desc = desc + kb; pb[i].start = start + kb; pb[i].odesc = odesc;
+    pb[i].start = start + kb; pb[i].ent = ent;
   }
+  return SDB_OK;
+}
+
+// ---- grad_input of all problems that want it: one gather launch ---------------------------------------------------
+int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accumulate, cudaStream_t st) {
+  const int NCH = nch_of(g), nch = nch_chunks(g);
+  DxParams p{};
+  p.g = g; p.accumulate = accumulate;
+  int m = 0, total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!pb[i].gx) continue;
+    const long long pin = (long long)pb[i].d.N * pb[i].d.H * pb[i].d.W;
+    if (pin == 0) continue;
+    DxProb& q = p.pr[m];
+    q.dcol = pb[i].dcol; q.start = pb[i].start; q.ent = (const CEntry*)pb[i].ent;
+    q.out = pb[i].gx; q.d = pb[i].d;
+    p.map.start[m] = total;
+    total += cdiv(pin, TILE_M) * nch;
+    ++m;
+  }
+  p.map.n = m; p.map.start[m] = total;
+  if (total == 0) return SDB_OK;
+  const bool obf = io_dtype == SDB_BF16;
+  const size_t smem = (size_t)NCH * TILE_M * (obf ? 2 : 4);
+  ProfScope prof(3, st);   // slot 3 = grad_input (slender_b200.h)
+  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 512;
+#define SDB_DX_LAUNCH(NCH_, BF_)                                                                  \
+  {                                                                                               \
+    if (dx_threads == 1024) {                                                                     \
+      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 1024>), smem);                             \
+      dcn_dx_gather_kernel<NCH_, BF_, 1024><<<total, 1024, smem, st>>>(p);                        \
+    } else {                                                                                      \
+      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 512>), smem);                              \
+      dcn_dx_gather_kernel<NCH_, BF_, 512><<<total, 512, smem, st>>>(p);                          \
+    }                                                                                             \
+  }
+  if (NCH == 128) { if (obf) SDB_DX_LAUNCH(128, true) else SDB_DX_LAUNCH(128, false) }
+  else            { if (obf) SDB_DX_LAUNCH(64, true) else SDB_DX_LAUNCH(64, false) }
+#undef SDB_DX_LAUNCH
+  SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
@@ -1283,13 +1395,13 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   for (int w = 0; w < nweights; ++w) { any_gw |= gw[w] != nullptr; any_gb |= gb[w] != nullptr; }
 
   // (0) layouts: x -> NHWC (unless the forward exported it), dY -> tile image and NHWC rows
-  if (pack_x && !grad_packed && (any_goff || any_gw)) {
+  if (pack_x && !grad_packed && (any_goff || any_gw)) {   // grad_input alone does not read x
     PackJob jobs[MAX_PROBS];
     for (int i = 0; i < n; ++i) jobs[i] = PackJob{pb[i].x, pb[i].xp, pb[i].d.N, pb[i].d.H * pb[i].d.W};
     rc = pack_nhwc_multi(jobs, n, g.C, g.C, bf, st);
     if (rc) return rc;
   }
-  if (!grad_packed && (any_goff || any_gw)) {
+  if (!grad_packed && (any_goff || any_gx || any_gw)) {
     for (int pass = 0; pass < 2; ++pass) {   // pass 0: vectorised bf16 kernel, pass 1: generic
       PackGyTable t{};
       t.g = g;
@@ -1316,7 +1428,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   }
 
   // (2a) transposed sampling index for grad_input, on the side stream, beside the grad_offset kernel
-  Side* side = (any_gx && any_goff) ? side_of_device() : nullptr;
+  Side* side = any_gx ? side_of_device() : nullptr;
   cudaStream_t ist = st;   // stream of the index build
   if (side) {
     SDB_CHECK_CUDA(cudaEventRecord(side->fork, st));
@@ -1324,21 +1436,23 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     ist = side->s;
   }
   if (any_gx) {
-    rc = build_transposed_index(pb, n, P, g, okb, bf, base, ist);
+    rc = build_transposed_index(pb, n, P, g, base, ist);
     if (rc) return rc;
     if (side) SDB_CHECK_CUDA(cudaEventRecord(side->join, side->s));
   }
 
-  // (1) grad_offset / grad_mask: dcol GEMM + channel reduction
-  if (any_goff) {
+  // (1) grad_offset / grad_mask: dcol GEMM + channel reduction; the dcol tiles of the problems that want grad_input
+  //     are exported for the gather (2b)
+  if (any_goff || any_gx) {
     DgradParams p{};
     p.g = g; p.okb = okb;
     int m = 0, total = 0;
     for (int i = 0; i < n; ++i) {
-      if (!pb[i].goff && !pb[i].gmask) continue;
+      if (!pb[i].goff && !pb[i].gmask && !pb[i].gx) continue;
       DgradProb& q = p.pr[m];
       q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.gy_img = pb[i].gy_img;
       q.wt_img = pb[i].w.dgrad; q.goff = pb[i].goff; q.gmask = pb[i].mask ? pb[i].gmask : nullptr; q.d = pb[i].d;
+      q.dcol = pb[i].gx ? pb[i].dcol : nullptr;
       p.map.start[m] = total;
       total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
       ++m;
@@ -1364,10 +1478,10 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     }
   }
 
-  // (2b) grad_input: gathered implicit GEMM over the transposed index
+  // (2b) grad_input: gather of the dcol tiles over the transposed index
   if (any_gx) {
     if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    rc = tc_dx_multi(pb, n, g, okb, io_dtype, accumulate_gx, st);
+    rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
     if (rc) return rc;
   }
 

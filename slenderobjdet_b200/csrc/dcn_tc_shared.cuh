@@ -11,8 +11,7 @@ namespace sdb {
 // operand images of one prepared weight tensor (dcn_tc.cu: prep_weights_kernel)
 struct TcWeightImages {
   const uint8_t* fwd;     // forward B operand
-  const uint8_t* dgrad;   // W^T tiles of the dcol GEMM (grad_offset / grad_mask)
-  const uint8_t* dx;      // B operand of the grad_input GEMM
+  const uint8_t* dgrad;   // W^T tiles of the dcol GEMM (grad_offset / grad_mask / grad_input)
   const float* bias;      // fp32 [O] or nullptr
 };
 // host-side description of one problem of a multi-problem call, pointers resolved into the workspace
@@ -38,25 +37,24 @@ struct TcProblem {
   TcWeightImages w;
   void* xp;                     // NHWC bf16 input
   uint8_t* gy_img;              // dY as swizzled 128-pixel tiles
-  void* gyn;                    // dY NHWC bf16 [P][okb*64]
-  const void* desc;             // transposed index of this problem's group
-  const int* start;
-  const void* odesc;
+  uint8_t* dcol;                // dcol = dY W^T as bf16 staging tiles [tile][tap][chunk] (written by the grad_offset kernel)
+  const int* start;             // transposed index of this problem's group: CSR offsets (per input pixel and tap)
+  const void* ent;              // and the entry pool
 };
 // workspace layout of a multi-problem call (dcn_tc_bwd.cu: tc_plan)
 struct TcPlan {
-  size_t xp_off[16], gy_off[16], gyn_off[16];
+  size_t xp_off[16], gy_off[16], dcol_off[16];
   size_t prep_off[4], part_off[4];
   int group_of[16], group_rep[16], ngroups;
   long long key_base[16], nkeys;
   int scan_blocks;
-  size_t cnt_off, desc_off, clear_bytes, start_off, bsum_off, od_off;
+  size_t cnt_off, ent_off, clear_bytes, start_off, bsum_off;
   int tiles_per_split[4], splits[4];
   size_t total;
 };
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward);
 int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
-int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int okb, int io_dtype, int accumulate, cudaStream_t st);
+int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accumulate, cudaStream_t st);
 int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
                     int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
@@ -64,9 +62,8 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
 size_t tc_prepared_weight_bytes(const Geo& g);
 TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bias);
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
-                       cudaStream_t st);   // which: 1 = forward image, 2 = dcol image, 4 = grad_input image (7 = all)
+                       cudaStream_t st);   // which: 1 = forward image, 2 = dcol image (3 = both)
 int tc_lanes_per_pixel(const Geo& g);
-int tc_dx_col_blocks(const Geo& g);
 
 namespace tcshared {
 using namespace tc;
@@ -236,11 +233,12 @@ struct __align__(16) GDesc {
   uint32_t w2[4];   // bf16x2 (w, w); 0 for a corner that does not contribute
 };
 
-// overflow descriptor of the transposed index (MODE_DX): four more entries of the list of one row
-struct __align__(16) ODesc {
-  uint4 o;   // row offsets of dY, units of 16 bytes
-  uint4 m;   // x = w0 | w1 << 16, y = w2 | w3 << 16 (bf16 weights, 0 = unused slot), z = row in tile, w = 0
-};
+// byte offset of 16-byte chunk `chunk` of row `row` in a bf16 staging tile [128][NCH] (dcol tiles: written by the
+// grad_offset kernel's drain warps, read by its reduce warps and -- through HBM -- by the grad_input gather)
+template <int NCH>
+__host__ __device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
+  return row * (NCH * 2) + (((chunk & ~7u) | ((chunk & 7u) ^ (row & 7u))) << 4);
+}
 
 __device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
   uint32_t d;
