@@ -237,7 +237,7 @@ __device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __res
 // dcol it names, as an offset in 16-byte units into the problem's dcol tiles (channel chunk 0), and tap << 16 | bf16
 // weight.  With stride 1 a key holds four entries on average (36 per input pixel for 3x3).
 struct __align__(8) CEntry {
-  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (16 * NCH) + (pos & 127) * (NCH / 8), pos = band-order position of p
+  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (tile bytes / 16) + (pos & 127) * (row bytes / 16), pos = band-order position of p
   uint32_t tw;      // tap << 16 | weight (bf16 bits; zero only in padding)
 };
 constexpr int LIST_ALIGN = 8;   // entries
@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ C
   const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
   const uint32_t pos = (uint32_t)encode_pos(g.Ho, g.Wo, g.th, g.tw, n, r / g.Wo, r % g.Wo);
   const uint32_t nchv = (uint32_t)nch_of(g), nchunks = (uint32_t)g.C / nchv;
-  const uint32_t row16 = ((pos >> 7) * (uint32_t)g.taps() * nchunks + (uint32_t)tap * nchunks) * (16u * nchv) + (pos & 127u) * (nchv / 8u);
+  const uint32_t row16 = ((pos >> 7) * (uint32_t)g.taps() * nchunks + (uint32_t)tap * nchunks) * (stg_tile_bytes((int)nchv) / 16u) +
+                         (pos & 127u) * stg_row_units((int)nchv);
   int* cnt = cnt_all + t.gr[gi].key_base;
   const int* start = start_all + t.gr[gi].key_base;
   for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb) {
@@ -477,7 +478,7 @@ template <int NCH>
 __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
   constexpr int LPB = NCH / 8, PPI = 32 / LPB;
   constexpr uint32_t B_BYTES = NCH * 128;            // one [NCH c][64 o] weight tile
-  constexpr uint32_t STG_BYTES = TILE_M * NCH * 2;   // bf16 staging tile
+  constexpr uint32_t STG_BYTES = stg_tile_bytes(NCH);   // bf16 staging tile (padded rows)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full, a_empty;
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
@@ -826,11 +827,11 @@ __device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4 v, uint32
 }
 
 template <int NCH, bool OUT_BF16, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) dcn_dx_gather_kernel(const __grid_constant__ DxParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1024 / THREADS) dcn_dx_gather_kernel(const __grid_constant__ DxParams p) {
   constexpr int LPB = NCH / 8, PPI = 32 / LPB;
   constexpr int PIXW = TILE_M / (THREADS / 32), ROUNDS = PIXW / PPI;
   static_assert(ROUNDS >= 1 && LIST_ALIGN == 8, "list walk is written for groups of eight entries");
-  constexpr size_t STG_BYTES = (size_t)TILE_M * NCH * 2;
+  constexpr size_t STG_BYTES = stg_tile_bytes(NCH);
   using ST = typename std::conditional<OUT_BF16, __nv_bfloat16, float>::type;
   extern __shared__ __align__(16) uint8_t s_raw[];
   ST* s_t = reinterpret_cast<ST*>(s_raw);  // [NCH][128] transpose buffer in the output type, column rotated by PPI * (c >> 3)
@@ -853,30 +854,47 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) dcn_dx_gather_kernel(
     s_px[threadIdx.x] = make_int2(n, y * W + x);
   }
 
-  // this lane's 16-byte column of a dcol row: chunk lig of the row, 128B-swizzled by the row's low three bits
-  const uint4* cb = reinterpret_cast<const uint4*>(pr.dcol + (size_t)ch * STG_BYTES);
-  const uint32_t lig_hi = (uint32_t)lig & ~7u;
+  // list bounds of the tile's pixels (the first global-memory latency of every list, paid once per CTA)
+  __shared__ int s_beg[TILE_M + 1];
+  if (threadIdx.x <= TILE_M) s_beg[threadIdx.x] = __ldg(pr.start + ((size_t)tile * TILE_M + threadIdx.x) * (taps + 1));
+  __syncthreads();
+
+  // Pixel of (warp, round, lane group).  The pixels in flight at one time form a compact block of the 8 x 16 patch
+  // (4 x 8 with 16 warps, 4 x 4 with 8): the four input pixels sharing a dcol row are 2 x 2 neighbours, so most of
+  // them are in flight together and the repeats hit in L1.  Other shapes walk the tile linearly.
+  auto pixel_of = [&](int r) {
+    if (PPI == 2 && THREADS == 512) return ((r >> 1) * 4 + (warp >> 2)) * 16 + (r & 1) * 8 + (warp & 3) * 2 + grp;
+    if (PPI == 2 && THREADS == 256) return ((r >> 2) * 4 + (warp >> 1)) * 16 + (r & 3) * 4 + (warp & 1) * 2 + grp;
+    return r0 + r * PPI + grp;
+  };
+  // this lane's 16-byte column of the dcol rows of channel chunk `ch`
+  const uint4* cb = reinterpret_cast<const uint4*>(pr.dcol + (size_t)ch * STG_BYTES) + lig;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; ++r) {
-    const int px = r0 + r * PPI + grp;
-    const int* sp = pr.start + ((size_t)tile * TILE_M + px) * (taps + 1);
-    const int beg = __ldg(sp), end = __ldg(sp + taps + 1);   // multiples of eight entries
+    const int px = pixel_of(r);
+    const int beg = s_beg[px], nb = (s_beg[px + 1] - beg) >> 3;   // batches of eight entries
+    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent + beg);  // two entries per uint4: (row16, tw, row16, tw)
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent + beg);
-    for (int e0 = beg; e0 < end; e0 += 8, ep += 4) {
-      uint4 e[4];
+    uint4 e[4];   // entries of the batch being issued, fetched one batch ahead
 #pragma unroll
-      for (int k = 0; k < 4; ++k) e[k] = __ldg(ep + k);   // two entries each: (row16, tw, row16, tw)
+    for (int k = 0; k < 4; ++k) e[k] = nb > 0 ? __ldg(ep + k) : zero4;
+    for (int b = 0; b < nb; ++b) {
       uint4 v[8];
+      uint32_t tw[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t row16 = (k & 1) ? e[k >> 1].z : e[k >> 1].x;
-        v[k] = __ldg(cb + (row16 + (lig_hi | (((row16 / (NCH / 8)) ^ (uint32_t)lig) & 7u))));
+      for (int k = 0; k < 8; ++k) {   // zero entries (padding) load row 0 and contribute nothing
+        tw[k] = (k & 1) ? e[k >> 1].w : e[k >> 1].y;
+        v[k] = __ldg(cb + ((k & 1) ? e[k >> 1].z : e[k >> 1].x));
+      }
+      if (b + 1 < nb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = __ldg(ep + 4 * (b + 1) + k);
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) fma8_bf16(acc, v[k], (k & 1) ? e[k >> 1].w : e[k >> 1].y);
+      for (int k = 0; k < 8; ++k) fma8_bf16(acc, v[k], tw[k]);
     }
     // [pixel][channel] registers -> transpose buffer
 #pragma unroll
@@ -1237,7 +1255,7 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     if (backward) {
       const size_t tiles = (size_t)cdiv(gi.P(), TILE_M);
       P.gy_off[i] = o;  o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
-      P.dcol_off[i] = o; o = align_up(o + tiles * g.taps() * TILE_M * g.C * 2, 1024);
+      P.dcol_off[i] = o; o = align_up(o + tiles * g.taps() * nch_chunks(g) * stg_tile_bytes(nch_of(g)), 1024);
     }
   }
   for (int w = 0; w < nweights; ++w) {
@@ -1362,12 +1380,12 @@ int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accu
   const bool obf = io_dtype == SDB_BF16;
   const size_t smem = (size_t)NCH * TILE_M * (obf ? 2 : 4);
   ProfScope prof(3, st);   // slot 3 = grad_input (slender_b200.h)
-  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 512;
+  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 256;
 #define SDB_DX_LAUNCH(NCH_, BF_)                                                                  \
   {                                                                                               \
-    if (dx_threads == 1024) {                                                                     \
-      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 1024>), smem);                             \
-      dcn_dx_gather_kernel<NCH_, BF_, 1024><<<total, 1024, smem, st>>>(p);                        \
+    if (dx_threads == 256) {                                                                      \
+      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 256>), smem);                              \
+      dcn_dx_gather_kernel<NCH_, BF_, 256><<<total, 256, smem, st>>>(p);                          \
     } else {                                                                                      \
       SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 512>), smem);                              \
       dcn_dx_gather_kernel<NCH_, BF_, 512><<<total, 512, smem, st>>>(p);                          \
@@ -1459,7 +1477,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     }
     p.map.n = m; p.map.start[m] = total;
     if (total > 0) {
-      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)TILE_M * NCH * 2;
+      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)stg_tile_bytes(NCH);
       long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
       if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
       SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");

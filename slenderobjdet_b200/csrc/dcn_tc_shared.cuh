@@ -233,11 +233,16 @@ struct __align__(16) GDesc {
   uint32_t w2[4];   // bf16x2 (w, w); 0 for a corner that does not contribute
 };
 
-// byte offset of 16-byte chunk `chunk` of row `row` in a bf16 staging tile [128][NCH] (dcol tiles: written by the
-// grad_offset kernel's drain warps, read by its reduce warps and -- through HBM -- by the grad_input gather)
+// dcol tiles: bf16 [128 pixels][NCH channels], every row followed by 16 bytes of padding.  Written by the grad_offset
+// kernel's drain warps (one row per lane), read by its reduce warps (one row per lane group) and -- through HBM,
+// exported verbatim by one bulk copy per tile -- by the grad_input gather.  The padding shifts consecutive rows by one
+// 16-byte bank group, which makes the row-per-lane writes conflict-free without an XOR swizzle, so a gather lane's
+// address is simply (row base + lane): one multiply-add per list entry.
+__host__ __device__ constexpr uint32_t stg_row_units(int nch) { return (uint32_t)nch / 8u + 1u; }   // 16-byte units per row
+__host__ __device__ constexpr uint32_t stg_tile_bytes(int nch) { return 128u * 16u * stg_row_units(nch); }
 template <int NCH>
 __host__ __device__ __forceinline__ uint32_t stg_offset(uint32_t row, uint32_t chunk) {
-  return row * (NCH * 2) + (((chunk & ~7u) | ((chunk & 7u) ^ (row & 7u))) << 4);
+  return (row * stg_row_units(NCH) + chunk) * 16u;
 }
 
 __device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
