@@ -158,7 +158,8 @@ class Workload:
     """All device buffers of one step + the C-ABI call sequence (graph-capturable: no allocation, no synchronisation,
     fixed pointers).  Problems are ordered (level, branch); both branches of a level share the level's offsets."""
 
-    def __init__(self, torch, lib_mod, device, seed, batch, levels=LEVELS, modulated=False, scale=1.0, bucket=True):
+    def __init__(self, torch, lib_mod, device, seed, batch, levels=LEVELS, modulated=False, scale=1.0, bucket=True,
+                 save_columns=os.environ.get("SDB_DCN_SAVE_COLUMNS", "1") != "0"):
         self.torch, self._lib, self.device, self.batch, self.levels_hw = torch, lib_mod, device, batch, levels
         L, lib = lib_mod, lib_mod.lib()
         g = torch.Generator(device="cpu").manual_seed(seed)
@@ -185,6 +186,7 @@ class Workload:
         for li, (H, W) in enumerate(levels):
             gl = L.Geom(batch, C_IN, H, W, C_OUT, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
             pkb = lib.sdb_dcn_packed_input_bytes(ctypes.byref(gl), self.mth)
+            clb = lib.sdb_dcn_columns_bytes(ctypes.byref(gl), self.mth) if save_columns else 0
             lv = dict(H=H, W=W, off=(mk(batch, 18, H, W) * 2.0).to(device), br=[],
                       mask=torch.sigmoid(mk(batch, 9, H, W)).to(device) if modulated else None)
             for b in range(2):
@@ -193,11 +195,12 @@ class Workload:
                           gx=torch.empty(batch, C_IN, H, W, device=device, dtype=bf),
                           goff=torch.empty(batch, 18, H, W, device=device),
                           gmask=torch.empty(batch, 9, H, W, device=device) if modulated else None,
-                          pk=torch.empty(max(1, pkb), dtype=torch.uint8, device=device))
+                          pk=torch.empty(max(1, pkb), dtype=torch.uint8, device=device),
+                          cols=torch.empty(clb, dtype=torch.uint8, device=device) if clb else None)
                 lv["br"].append(br)
                 rows.append(L.Problem(batch, H, W, b, li, 0, L.addr(br["x"]), L.addr(lv["off"]), L.addr(lv["mask"]),
                                       L.addr(br["out"]), L.addr(br["pk"]), L.addr(br["gy"]), L.addr(br["gx"]),
-                                      L.addr(br["goff"]), L.addr(br["gmask"])))
+                                      L.addr(br["goff"]), L.addr(br["gmask"]), L.addr(br["cols"])))
             self.lv.append(lv)
         self.n = len(rows)
         self.probs = (L.Problem * self.n)(*rows)

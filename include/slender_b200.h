@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 2
+#define SDB_ABI_VERSION 3
 
 typedef enum {
   SDB_OK = 0,
@@ -77,6 +77,9 @@ size_t sdb_dcn_workspace_bytes(int op, const sdb_dcn_geom* g, int io_dtype, int 
 /* Bytes of the packed (NHWC bf16) copy of x that BF16 math uses; forward can export it
  * (`x_packed_out`) so the backward calls need not rebuild it (`x_packed`).  0 for FP32 math. */
 size_t sdb_dcn_packed_input_bytes(const sdb_dcn_geom* g, int math);
+/* Bytes of the saved sampled columns of one problem (sdb_dcn_problem.columns): kH*kW*C_in*2 per output pixel, rounded
+ * up to whole 128-pixel tiles.  0 for FP32 math. */
+size_t sdb_dcn_columns_bytes(const sdb_dcn_geom* g, int math);
 
 /* Replaces deform_conv_forward (deform_conv.h:116-161 -> deform_conv_cuda.cu:272-438) and
  * modulated_deform_conv_forward (deform_conv.h:263-312 -> deform_conv_cuda.cu:804-927).
@@ -140,6 +143,10 @@ typedef struct {
   void* grad_x;             /* backward: [N, C_in, H, W], overwritten; NULL = not wanted                         */
   float* grad_offset;       /* backward: overwritten; NULL = not wanted                                           */
   float* grad_mask;         /* backward: overwritten; NULL = not wanted                                           */
+  void* columns;            /* optional buffer of sdb_dcn_columns_bytes: forward saves the sampled columns (the bf16
+                               `columns` of deform_conv_cuda.cu:345-352, as tensor-core operand tiles) in it, backward
+                               streams them into the weight-gradient GEMM instead of sampling x again; NULL = not
+                               saved / sampled again.  Valid for the offsets / mask / x of the forward call only.    */
 } sdb_dcn_problem;
 typedef struct {
   const void* weight;       /* [C_out, C_in, kH, kW]                                                              */

@@ -20,7 +20,7 @@ SDB_BOX_LTRB, SDB_BOX_XYXY = 0, 1
 # every symbol include/slender_b200.h declares (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "sdb_last_error", "sdb_abi_version", "sdb_dcn_output_size", "sdb_dcn_supported",
-    "sdb_dcn_workspace_bytes", "sdb_dcn_packed_input_bytes", "sdb_dcn_forward",
+    "sdb_dcn_workspace_bytes", "sdb_dcn_packed_input_bytes", "sdb_dcn_columns_bytes", "sdb_dcn_forward",
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
     "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
@@ -41,7 +41,7 @@ class Problem(ctypes.Structure):
                 ("offset_group", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("x", ctypes.c_void_p), ("offset", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("out", ctypes.c_void_p),
                 ("x_packed", ctypes.c_void_p), ("grad_out", ctypes.c_void_p), ("grad_x", ctypes.c_void_p),
-                ("grad_offset", ctypes.c_void_p), ("grad_mask", ctypes.c_void_p)]
+                ("grad_offset", ctypes.c_void_p), ("grad_mask", ctypes.c_void_p), ("columns", ctypes.c_void_p)]
 
 
 class Weights(ctypes.Structure):
@@ -74,6 +74,8 @@ def _declare(lib):
     lib.sdb_dcn_workspace_bytes.argtypes = [ctypes.c_int, _gp, ctypes.c_int, ctypes.c_int]
     lib.sdb_dcn_packed_input_bytes.restype = _sz
     lib.sdb_dcn_packed_input_bytes.argtypes = [_gp, ctypes.c_int]
+    lib.sdb_dcn_columns_bytes.restype = _sz
+    lib.sdb_dcn_columns_bytes.argtypes = [_gp, ctypes.c_int]
     lib.sdb_dcn_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _gp, ctypes.c_int, ctypes.c_int, _vp, _sz, _vp, _vp]
     lib.sdb_dcn_backward_data.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _gp, ctypes.c_int,
                                           ctypes.c_int, _vp, _sz, _vp, _vp]

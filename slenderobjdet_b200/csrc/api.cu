@@ -205,7 +205,7 @@ int build_call(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, in
     t = TcProblem{};
     t.d = Dims{q.N, q.H, q.W, gi.Ho, gi.Wo};
     t.weight_id = q.weight_id; t.group = q.offset_group;
-    t.x = q.x; t.off = q.offset; t.mask = q.mask; t.out = q.out; t.xp = q.x_packed;
+    t.x = q.x; t.off = q.offset; t.mask = q.mask; t.out = q.out; t.xp = q.x_packed; t.col = (uint8_t*)q.columns;
     t.gy = q.grad_out; t.gx = backward ? q.grad_x : nullptr; t.goff = backward ? q.grad_offset : nullptr;
     t.gmask = backward ? q.grad_mask : nullptr;
     if (q.offset_group >= 0)
@@ -409,6 +409,11 @@ size_t sdb_dcn_workspace_bytes(int op, const sdb_dcn_geom* g, int io_dtype, int 
 size_t sdb_dcn_packed_input_bytes(const sdb_dcn_geom* g, int math) {
   if (check_geom(g) || math != SDB_MATH_BF16) return 0;
   return tc_packed_input_bytes(make_geo(*g));
+}
+
+size_t sdb_dcn_columns_bytes(const sdb_dcn_geom* g, int math) {
+  if (check_geom(g) || math != SDB_MATH_BF16) return 0;
+  return tc_columns_bytes(make_geo(*g));
 }
 
 #define SDB_PROLOGUE()                         \

@@ -84,5 +84,6 @@ int simt_backward_weight(const float* x, const float* off, const float* mask, co
 // tcgen05 bf16 path (dcn_tc.cu, dcn_tc_bwd.cu; multi-problem launchers declared in dcn_tc_shared.cuh)
 bool tc_supported(const Geo& g, const char** why);
 size_t tc_packed_input_bytes(const Geo& g);
+size_t tc_columns_bytes(const Geo& g);
 
 }  // namespace sdb

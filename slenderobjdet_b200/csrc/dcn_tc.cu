@@ -30,7 +30,8 @@ using namespace tcshared;
 
 constexpr int NPW = 8;                       // gather producer warps
 constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
-constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
+constexpr int EXPORT_WARP = FIRST_PW + NPW;    // last warp: exports the sampled A stages (columns) for the backward
+constexpr int NTHREADS = (EXPORT_WARP + 1) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 
 // Weight images.  W [O][C][taps] is re-laid-out ONCE per weight version (sdb_dcn_prepare_weights) into the two
@@ -153,6 +154,7 @@ struct FwdProb {
   const uint8_t* wimg;      // weight image of this problem's convolution
   const float* bias;        // fp32 [O] or nullptr
   void* out;                // NCHW, f32 or bf16: [N][O][Ho][Wo]
+  uint8_t* col;             // export of the sampled columns: the A stages [tile][chunk][tap][128 x CPS bf16], or nullptr
   Dims d;                   // N, H, W, Ho, Wo of this problem
   long long mP;             // N * Ho * Wo
 };
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsa; ++s) {
       mbar_init(&a_full[s], NPW);   // one arrival per gather warp
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], 2);    // the MMA issuer's commit + the exporter
     }
     for (int s = 0; s < p.nsb; ++s) {
       mbar_init(&b_full[s], 1);
@@ -305,6 +307,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       tc_fence_before_sync();
       mbar_arrive_warp(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; accp ^= 1; }
+    }
+  } else if (warp == EXPORT_WARP) {
+    // ===== column exporter: every finished A stage (128 pixels x CPS sampled channels of one tap, already in the
+    // swizzled operand layout) goes to HBM as one bulk copy when the caller wants the columns saved for the backward
+    // pass (the weight gradient then streams them back instead of sampling again) =====
+    if (lane == 0) {
+      uint32_t as = 0, ap = 0;
+      const int nstages = taps * nchunks;
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int pi = find_range(p.map, work);
+        uint8_t* dst = p.pr[pi].col;
+        if (dst) dst += (size_t)(work - p.map.start[pi]) * nstages * A_BYTES;
+        for (int st = 0; st < nstages; ++st) {
+          mbar_wait(&a_full[as], ap);
+          if (dst) {
+            bulk_s2g(dst + (size_t)st * A_BYTES, sA + (size_t)as * A_BYTES, A_BYTES);
+            bulk_commit();
+            bulk_wait_read_all();
+          }
+          mbar_arrive(&a_empty[as]);
+          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
+        }
+      }
+      bulk_wait_all();
     }
   } else {
     // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
@@ -477,6 +503,8 @@ bool tc_supported(const Geo& g, const char** why) {
 }
 
 size_t tc_packed_input_bytes(const Geo& g) { return align_up((size_t)g.N * g.H * g.W * g.C * 2, 1024); }
+// sampled columns of one problem: one 128-pixel x C bf16 tile per (output tile, tap)
+size_t tc_columns_bytes(const Geo& g) { return align_up((size_t)cdiv(g.P(), TILE_M) * g.taps() * TILE_M * g.C * 2, 1024); }
 
 // ---- prepared weights -------------------------------------------------------------------------------------------
 static PrepLayout prep_layout(const Geo& g) {
@@ -528,7 +556,7 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
     const Geo gi = with_dims(g, pb[i].d);
     FwdProb& q = p.pr[i];
     q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.wimg = pb[i].w.fwd;
-    q.bias = pb[i].w.bias; q.out = pb[i].out; q.d = pb[i].d;
+    q.bias = pb[i].w.bias; q.out = pb[i].out; q.col = pb[i].col; q.d = pb[i].d;
     q.mP = gi.P();
     p.map.start[i] = total;
     total += cdiv(gi.P(), TILE_M);

@@ -44,6 +44,8 @@ constexpr int MAX_B_STAGES = 8;
 
 inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wide o blocks, even count
 __host__ __device__ inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
+// channels per CTA of the weight-gradient kernel over saved columns (UMMA N, <= 256; O x CG fp32 must fit in TMEM)
+inline int wgrad_col_group(const Geo& g) { return g.C % 256 == 0 ? 256 : nch_of(g); }
 inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 
 // ------------------------------------------------------------------------------------------------
@@ -1174,6 +1176,147 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) dcn_bwd_weight_tc_kernel(const
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward weight kernel over SAVED columns
+// ------------------------------------------------------------------------------------------------
+// When the forward pass saved its sampled columns (sdb_dcn_problem.columns: the A stages of dcn_fwd_tc_kernel, already
+// in the 128B-swizzled operand layout), the weight gradient needs no sampling at all: dW[o, (tap, c)] = sum_p
+// dY[p, o] col[p, (tap, c)] is a plain GEMM whose two operands stream in by bulk copy.  A CTA owns one (weight, tap,
+// channel group of CG <= 256 channels, pixel split); the accumulators (O x CG fp32 = up to all 512 TMEM columns) stay
+// in TMEM for the CTA's whole pixel range.  A stage holds HALF a tile (64 pixels = 4 K-steps): dY [okb][64 px][64 o] +
+// col [CG/64][64 px][64 c], 8 KB per block, so three stages fit beside each other at O = C = 256.
+struct WcolProb {
+  const uint8_t* col;
+  const uint8_t* gy_img;
+};
+struct WcolParams {
+  WcolProb pr[MAX_PROBS];
+  TileMap wmap[MAX_WEIGHTS];         // per weight: tile ranges of its problems
+  int pidx[MAX_WEIGHTS][MAX_PROBS];  // per weight: problem index of each range
+  float* part[MAX_WEIGHTS];          // per weight: [splits][taps][O][C] fp32 partial sums
+  int splits[MAX_WEIGHTS], tiles_per_split[MAX_WEIGHTS];
+  int cta_start[MAX_WEIGHTS + 1];
+  int nweights;
+  Geo g;
+  int okb, cg, cps, ns;              // 64-o blocks of dY; channels per CTA; channels per saved A stage; stages
+};
+constexpr int WCOL_THREADS = 6 * 32;   // warps: 0 bulk producer, 1 mma, 2-5 epilogue
+constexpr int WCOL_MAX_STAGES = 6;
+constexpr uint32_t HALF_BLOCK = 64 * 128;   // bytes of one [64 px][64 ch] block
+
+__global__ void __launch_bounds__(WCOL_THREADS, 1) dcn_wgrad_col_tc_kernel(const __grid_constant__ WcolParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[WCOL_MAX_STAGES], empty[WCOL_MAX_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int C = p.g.C, O = p.g.O, taps = p.g.KH * p.g.KW, okb = p.okb, mh_n = okb / 2, CG = p.cg;
+  const int ncg = C / CG, cb_n = CG / 64;                      // channel groups; 64-channel blocks per group
+  const int nchunks = C / p.cps, kbps = p.cps / 64;            // layout of the saved columns: [tile][chunk][tap][kbps][128][64]
+  const uint32_t A_STAGE = (uint32_t)p.cps * TILE_M * 2;       // one saved A stage
+  const uint32_t Y_BYTES = (uint32_t)okb * (TILE_M * 128);     // one dY tile
+  const uint32_t S_Y = (uint32_t)okb * HALF_BLOCK, S_BYTES = S_Y + (uint32_t)cb_n * HALF_BLOCK;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  int wid = 0;
+  while (wid + 1 < p.nweights && (int)blockIdx.x >= p.cta_start[wid + 1]) ++wid;
+  const int lcta = blockIdx.x - p.cta_start[wid];
+  const int nsplit = p.splits[wid];
+  const int split = lcta % nsplit;
+  const int cgi = (lcta / nsplit) % ncg;
+  const int tap = lcta / (nsplit * ncg);
+  const TileMap& wm = p.wmap[wid];
+  const int t0 = split * p.tiles_per_split[wid];
+  const int t1 = min(wm.start[wm.n], t0 + p.tiles_per_split[wid]);
+  uint32_t ncols = 32;
+  while ((int)ncols < mh_n * CG) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.ns; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ss = 0, sp = 0;
+      for (int tile = t0; tile < t1; ++tile) {
+        const int r = find_range(wm, tile);
+        const WcolProb& pr = p.pr[p.pidx[wid][r]];
+        const int lt = tile - wm.start[r];
+        const uint8_t* ysrc = pr.gy_img + (size_t)lt * Y_BYTES;
+        const uint8_t* csrc = pr.col + ((size_t)lt * nchunks * taps + tap) * A_STAGE;
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&empty[ss], sp ^ 1);
+          mbar_arrive_expect_tx(&full[ss], S_BYTES);
+          uint8_t* dst = sm + (size_t)ss * S_BYTES;
+          for (int kb = 0; kb < okb; ++kb)
+            bulk_g2s(dst + kb * HALF_BLOCK, ysrc + (size_t)kb * (TILE_M * 128) + half * HALF_BLOCK, HALF_BLOCK, &full[ss]);
+          for (int b = 0; b < cb_n; ++b) {
+            const int cblk = cgi * cb_n + b;   // 64-channel block of C
+            const uint8_t* src = csrc + (size_t)(cblk / kbps) * taps * A_STAGE + (size_t)(cblk % kbps) * (TILE_M * 128);
+            bulk_g2s(dst + S_Y + b * HALF_BLOCK, src + half * HALF_BLOCK, HALF_BLOCK, &full[ss]);
+          }
+          if (++ss == (uint32_t)p.ns) { ss = 0; sp ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D[o, c] += sum_pixels dY[pix, o] * col[pix, c]; both operands MN-major, 64-element blocks HALF_BLOCK apart
+    const uint32_t idesc = make_idesc_bf16(128, CG, 1, 1);
+    uint32_t ss = 0, sp = 0, accumulate = 0;
+    for (int i = 0; i < 2 * (t1 - t0); ++i) {
+      mbar_wait(&full[ss], sp);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t y_addr = smem_base + ss * S_BYTES, c_addr = y_addr + S_Y;
+        for (int s = 0; s < 4; ++s) {
+          for (int mh = 0; mh < mh_n; ++mh)
+            umma_bf16(tmem_base + mh * CG, make_smem_desc_sw128(y_addr + (2 * mh) * HALF_BLOCK + s * 2048, HALF_BLOCK, 1024),
+                      make_smem_desc_sw128(c_addr + s * 2048, HALF_BLOCK, 1024), idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty[ss]);
+      }
+      __syncwarp();
+      if (++ss == (uint32_t)p.ns) { ss = 0; sp ^= 1; }
+    }
+    if (elect_one()) umma_commit(&acc_full);
+    __syncwarp();
+  } else {
+    // epilogue: partial dW tile -> workspace [split][tap][O][C]
+    const int q = warp & 3;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after_sync();
+    for (int mh = 0; mh < mh_n; ++mh) {
+      const int o = mh * 128 + q * 32 + lane;
+      for (int c0 = 0; c0 < CG; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + mh * CG + ((uint32_t)(q * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        if (o < O && t1 > t0) {
+          float4* dst = reinterpret_cast<float4*>(p.part[wid] + (((size_t)split * taps + tap) * O + o) * C + cgi * CG + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
 // grad_weight[o][c][tap] += scale * sum_split part[split][tap][o][c]; grid.y = weight
 struct WgradReduceTable {
   const float* part[MAX_WEIGHTS];
@@ -1294,16 +1437,26 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     // weight-gradient split-K: all weights share the machine
     int tiles_w[MAX_WEIGHTS] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) tiles_w[pb[i].weight_id] += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
-    int s = num_sms() / ((nweights > 0 ? nweights : 1) * g.taps() * nch_chunks(g));
-    if (s < 1) s = 1;
-    if (s > 64) s = 64;
+    // two variants: CTAs per (tap, NCH-channel chunk) for the re-sampling kernel, per (tap, wgrad_col_group channels)
+    // for the kernel over saved columns; the partials buffer is sized for the larger split count
+    for (int v = 0; v < 2; ++v) {
+      const int groups = v == 0 ? nch_chunks(g) : g.C / wgrad_col_group(g);
+      int s = num_sms() / ((nweights > 0 ? nweights : 1) * g.taps() * groups);
+      if (s < 1) s = 1;
+      if (s > 64) s = 64;
+      for (int w = 0; w < nweights; ++w) {
+        int sw = s < tiles_w[w] ? s : tiles_w[w];
+        if (sw < 1) sw = 1;
+        const int tps = tiles_w[w] > 0 ? cdiv(tiles_w[w], sw) : 1;
+        const int sp = tiles_w[w] > 0 ? cdiv(tiles_w[w], tps) : 0;   // no empty split
+        if (v == 0) { P.tiles_per_split[w] = tps; P.splits[w] = sp; }
+        else { P.tiles_per_split_col[w] = tps; P.splits_col[w] = sp; }
+      }
+    }
     for (int w = 0; w < nweights; ++w) {
-      int sw = s < tiles_w[w] ? s : tiles_w[w];
-      if (sw < 1) sw = 1;
-      P.tiles_per_split[w] = tiles_w[w] > 0 ? cdiv(tiles_w[w], sw) : 1;
-      P.splits[w] = tiles_w[w] > 0 ? cdiv(tiles_w[w], P.tiles_per_split[w]) : 0;   // no empty split
+      const int smax = P.splits[w] > P.splits_col[w] ? P.splits[w] : P.splits_col[w];
       P.part_off[w] = o;
-      o = align_up(o + (size_t)P.splits[w] * g.taps() * g.O * g.C * 4, 1024);
+      o = align_up(o + (size_t)smax * g.taps() * g.O * g.C * 4, 1024);
     }
   }
   P.total = o;
@@ -1504,7 +1657,57 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   }
 
   // (3) grad_weight (+ grad_bias): one CTA per (weight, tap, channel chunk, pixel split) over that weight's tiles
-  if (any_gw) {
+  bool all_col = any_gw;   // every problem that contributes to a wanted weight gradient brings its saved columns
+  for (int i = 0; i < n; ++i)
+    if (gw[pb[i].weight_id] && with_dims(g, pb[i].d).P() > 0 && !pb[i].col) all_col = false;
+  if (any_gw && all_col) {
+    WcolParams p{};
+    p.g = g; p.okb = okb; p.nweights = nweights; p.cg = wgrad_col_group(g); p.cps = tc_lanes_per_pixel(g) * 8;
+    int cta = 0, m = 0;
+    int slot_of[MAX_PROBS];
+    for (int i = 0; i < n; ++i) {
+      slot_of[i] = -1;
+      if (!gw[pb[i].weight_id] || with_dims(g, pb[i].d).P() == 0) continue;
+      p.pr[m].col = pb[i].col; p.pr[m].gy_img = pb[i].gy_img;
+      slot_of[i] = m++;
+    }
+    WgradReduceTable rt{};
+    for (int w = 0; w < nweights; ++w) {
+      TileMap& wm = p.wmap[w];
+      int total = 0, r = 0;
+      for (int i = 0; i < n; ++i) {
+        if (pb[i].weight_id != w || slot_of[i] < 0) continue;
+        p.pidx[w][r] = slot_of[i];
+        wm.start[r++] = total;
+        total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
+      }
+      wm.n = r; wm.start[r] = total;
+      p.part[w] = (float*)(base + P.part_off[w]);
+      p.tiles_per_split[w] = P.tiles_per_split_col[w];
+      p.splits[w] = (gw[w] && total > 0) ? P.splits_col[w] : 0;
+      p.cta_start[w] = cta;
+      cta += g.taps() * (g.C / p.cg) * p.splits[w];
+      rt.part[w] = p.part[w]; rt.gw[w] = gw[w]; rt.splits[w] = p.splits[w];
+    }
+    p.cta_start[nweights] = cta;
+    if (cta > 0) {
+      const size_t s_bytes = (size_t)(okb + p.cg / 64) * HALF_BLOCK;
+      long long ns = ((long long)(208 * 1024) - 1024) / (long long)s_bytes;
+      if (ns > WCOL_MAX_STAGES) ns = WCOL_MAX_STAGES;
+      SDB_REQUIRE(ns >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_weight");
+      p.ns = (int)ns;
+      const size_t smem = p.ns * s_bytes + 1024;
+      SDB_ENSURE_SMEM(dcn_wgrad_col_tc_kernel, smem);
+      {
+        ProfScope prof(SDB_OP_BACKWARD_WEIGHT, st);
+        dcn_wgrad_col_tc_kernel<<<cta, WCOL_THREADS, smem, st>>>(p);
+        SDB_LAUNCHED(1);
+      }
+      SDB_CHECK_CUDA(cudaGetLastError());
+      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      SDB_CHECK_CUDA(cudaGetLastError());
+    }
+  } else if (any_gw) {
     WgradParams p{};
     p.g = g; p.okb = okb; p.nweights = nweights;
     int cta = 0, m = 0;

@@ -37,6 +37,7 @@ struct TcProblem {
   TcWeightImages w;
   void* xp;                     // NHWC bf16 input
   uint8_t* gy_img;              // dY as swizzled 128-pixel tiles
+  uint8_t* col;                 // sampled columns saved by the forward (A stages [tile][chunk][tap]), or nullptr
   uint8_t* dcol;                // dcol = dY W^T as bf16 staging tiles [tile][tap][chunk] (written by the grad_offset kernel)
   const int* start;             // transposed index of this problem's group: CSR offsets (per input pixel and tap)
   const void* ent;              // and the entry pool
@@ -49,7 +50,8 @@ struct TcPlan {
   long long key_base[16], nkeys;
   int scan_blocks;
   size_t cnt_off, ent_off, clear_bytes, start_off, bsum_off;
-  int tiles_per_split[4], splits[4];
+  int tiles_per_split[4], splits[4];           // weight-gradient split-K of the re-sampling kernel
+  int tiles_per_split_col[4], splits_col[4];   // ... of the kernel over saved columns
   size_t total;
 };
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward);
