@@ -30,8 +30,7 @@ using namespace tcshared;
 
 constexpr int NPW = 8;                       // gather producer warps
 constexpr int FIRST_PW = 6;                  // warps: 0 weights, 1 mma, 2-5 epilogue, 6.. gather
-constexpr int EXPORT_WARP = FIRST_PW + NPW;    // last warp: exports the sampled A stages (columns) for the backward
-constexpr int NTHREADS = (EXPORT_WARP + 1) * 32;
+constexpr int NTHREADS = (FIRST_PW + NPW) * 32;
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 
 // Weight images.  W [O][C][taps] is re-laid-out ONCE per weight version (sdb_dcn_prepare_weights) into the two
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsa; ++s) {
       mbar_init(&a_full[s], NPW);   // one arrival per gather warp
-      mbar_init(&a_empty[s], 2);    // the MMA issuer's commit + the exporter
+      mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < p.nsb; ++s) {
       mbar_init(&b_full[s], 1);
@@ -308,30 +307,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       mbar_arrive_warp(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
-  } else if (warp == EXPORT_WARP) {
-    // ===== column exporter: every finished A stage (128 pixels x CPS sampled channels of one tap, already in the
-    // swizzled operand layout) goes to HBM as one bulk copy when the caller wants the columns saved for the backward
-    // pass (the weight gradient then streams them back instead of sampling again) =====
-    if (lane == 0) {
-      uint32_t as = 0, ap = 0;
-      const int nstages = taps * nchunks;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int pi = find_range(p.map, work);
-        uint8_t* dst = p.pr[pi].col;
-        if (dst) dst += (size_t)(work - p.map.start[pi]) * nstages * A_BYTES;
-        for (int st = 0; st < nstages; ++st) {
-          mbar_wait(&a_full[as], ap);
-          if (dst) {
-            bulk_s2g(dst + (size_t)st * A_BYTES, sA + (size_t)as * A_BYTES, A_BYTES);
-            bulk_commit();
-            bulk_wait_read_all();
-          }
-          mbar_arrive(&a_empty[as]);
-          if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
-        }
-      }
-      bulk_wait_all();
-    }
   } else {
     // ===== gather producers: bilinear sampling straight into the swizzled A stage =====
     // (1) per tile, the descriptors (4 source rows + 4 weights) of this warp's 16 pixels for EVERY tap
@@ -353,6 +328,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       const FwdProb& pr = p.pr[pi];
       const int tile = work - p.map.start[pi];
       const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
+      // saved columns (sdb_dcn_problem.columns): every sampled row also goes to HBM, in the operand layout of the stage
+      // it is stored to, so the weight-gradient GEMM of the backward pass streams it back instead of sampling again
+      uint8_t* colp = pr.col ? pr.col + (size_t)tile * nstages * A_BYTES + (lig >> 3) * (TILE_M * 128) : nullptr;
       {
         const Geo g = with_dims(p.g, pr.d);
         const int px = lane % PIX_PER_WARP;
@@ -440,7 +418,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           const int slot = it % RING;
           uint4 a;
           SDB_INTERP(a, slot)
-          *reinterpret_cast<uint4*>(dst + sw128_offset(r0 + it * PPI + grp, lig & 7)) = a;
+          const uint32_t soff = sw128_offset(r0 + it * PPI + grp, lig & 7);
+          *reinterpret_cast<uint4*>(dst + soff) = a;
+          if (colp) *reinterpret_cast<uint4*>(colp + (size_t)st * A_BYTES + soff) = a;
           if (it + RING < ITERS) {
             SDB_ISSUE(tap, ch, it + RING, slot)
           } else if (has_next) {

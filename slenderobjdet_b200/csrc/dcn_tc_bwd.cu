@@ -1533,7 +1533,7 @@ int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accu
   const bool obf = io_dtype == SDB_BF16;
   const size_t smem = (size_t)NCH * TILE_M * (obf ? 2 : 4);
   ProfScope prof(3, st);   // slot 3 = grad_input (slender_b200.h)
-  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 256;
+  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 512;
 #define SDB_DX_LAUNCH(NCH_, BF_)                                                                  \
   {                                                                                               \
     if (dx_threads == 256) {                                                                      \
