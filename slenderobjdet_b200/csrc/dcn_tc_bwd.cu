@@ -56,17 +56,15 @@ inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 // one entry per problem: grid.x walks the tiles of all entries (TileMap), grid.y the 64-o blocks
 struct PackGyTable {
   TileMap map;
-  struct E { const void* gy; uint8_t* img; Dims d; } e[MAX_PROBS];
+  struct E { const void* gy; uint8_t* img; Dims d; int fast; } e[MAX_PROBS];
   Geo g;
 };
 template <typename T>
-__global__ void __launch_bounds__(256) pack_gy_kernel(const __grid_constant__ PackGyTable t, int okb) {
-  const int ei = find_range(t.map, blockIdx.x);
+__device__ __forceinline__ void pack_gy_body(const PackGyTable& t, int ei, int okb, float (*s)[129]) {
   const Geo g = with_dims(t.g, t.e[ei].d);
   const T* __restrict__ gy = (const T*)t.e[ei].gy;
   uint8_t* __restrict__ img = t.e[ei].img;
   const int O = g.O, hw = g.Ho * g.Wo;
-  __shared__ float s[64][129];
   const int tile = blockIdx.x - t.map.start[ei], kb = blockIdx.y;
   const int tid = threadIdx.x;
   {
@@ -95,17 +93,28 @@ __global__ void __launch_bounds__(256) pack_gy_kernel(const __grid_constant__ Pa
     *reinterpret_cast<uint4*>(dst + sw128_offset(row, ch)) = pk;
   }
 }
+template <typename T>
+__global__ void __launch_bounds__(256) pack_gy_kernel(const __grid_constant__ PackGyTable t, int okb) {
+  __shared__ float s[64][129];
+  pack_gy_body<T>(t, find_range(t.map, blockIdx.x), okb, s);
+}
 
 // bf16 source whose row segments are 8-byte aligned (Wo, tw, Ho*Wo multiples of 4): a lane loads FOUR pixels of
 // one channel with one 8-byte load -- a whole 128-pixel tile row per warp instruction, 8 per lane instead of 32
-// two-byte loads -- and one pixel decode per thread.
+// two-byte loads -- and one pixel decode per thread.  Entries that do not qualify (`fast` == 0) take the generic body
+// in the same launch.
 __global__ void __launch_bounds__(256) pack_gy_bf16v_kernel(const __grid_constant__ PackGyTable t, int okb) {
+  __shared__ __align__(16) float s_gen[64][129];
   const int ei = find_range(t.map, blockIdx.x);
+  if (!t.e[ei].fast) {
+    pack_gy_body<__nv_bfloat16>(t, ei, okb, s_gen);
+    return;
+  }
   const Geo g = with_dims(t.g, t.e[ei].d);
   const __nv_bfloat16* __restrict__ gy = (const __nv_bfloat16*)t.e[ei].gy;
   uint8_t* __restrict__ img = t.e[ei].img;
   const int O = g.O, hw = g.Ho * g.Wo;
-  __shared__ __align__(8) __nv_bfloat16 s[64][136];   // [o][pixel (column ^ 32 for o >= 32)], 8 spare columns
+  __nv_bfloat16 (*s)[136] = reinterpret_cast<__nv_bfloat16(*)[136]>(s_gen);   // [o][pixel (column ^ 32 for o >= 32)], 8 spare columns
   const int tile = blockIdx.x - t.map.start[ei], kb = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
@@ -1573,25 +1582,23 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     if (rc) return rc;
   }
   if (!grad_packed && (any_goff || any_gx || any_gw)) {
-    for (int pass = 0; pass < 2; ++pass) {   // pass 0: vectorised bf16 kernel, pass 1: generic
-      PackGyTable t{};
-      t.g = g;
-      int m = 0, total = 0;
-      for (int i = 0; i < n; ++i) {
-        const Geo gi = with_dims(g, pb[i].d);
-        const int hw = gi.Ho * gi.Wo;
-        const bool fast = bf && gi.Wo % 4 == 0 && g.tw % 4 == 0 && hw % 4 == 0 && ((size_t)pb[i].gy & 7) == 0;
-        if (fast != (pass == 0) || gi.P() == 0) continue;
-        t.e[m].gy = pb[i].gy; t.e[m].img = pb[i].gy_img; t.e[m].d = pb[i].d;
-        t.map.start[m] = total;
-        total += cdiv(gi.P(), TILE_M);
-        ++m;
-      }
-      t.map.n = m; t.map.start[m] = total;
-      if (total == 0) continue;
+    PackGyTable t{};
+    t.g = g;
+    int m = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+      const Geo gi = with_dims(g, pb[i].d);
+      const int hw = gi.Ho * gi.Wo;
+      if (gi.P() == 0) continue;
+      t.e[m].gy = pb[i].gy; t.e[m].img = pb[i].gy_img; t.e[m].d = pb[i].d;
+      t.e[m].fast = bf && gi.Wo % 4 == 0 && g.tw % 4 == 0 && hw % 4 == 0 && ((size_t)pb[i].gy & 7) == 0;
+      t.map.start[m] = total;
+      total += cdiv(gi.P(), TILE_M);
+      ++m;
+    }
+    t.map.n = m; t.map.start[m] = total;
+    if (total > 0) {
       dim3 grid(total, okb);
-      if (pass == 0) pack_gy_bf16v_kernel<<<grid, 256, 0, st>>>(t, okb);
-      else if (bf) pack_gy_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(t, okb);
+      if (bf) pack_gy_bf16v_kernel<<<grid, 256, 0, st>>>(t, okb);
       else pack_gy_kernel<float><<<grid, 256, 0, st>>>(t, okb);
       SDB_LAUNCHED(1);
       SDB_CHECK_CUDA(cudaGetLastError());

@@ -142,15 +142,12 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return
 // the TileMap (entry i owns N_i * nblk_i blocks), grid.y the 64-channel blocks.
 struct PackTable {
   TileMap map;
-  struct E { const void* src; __nv_bfloat16* dst; int HW, nblk; } e[MAX_PROBS];
+  struct E { const void* src; __nv_bfloat16* dst; int HW, nblk, fast; } e[MAX_PROBS];
   int C, Cd;
 };
 // [N][C][HW] (T) -> [N][HW][Cd] bf16, Cd >= C (channels C..Cd-1 zero).  Tile 64 channels x 32 pixels.
 template <typename T>
-__global__ void __launch_bounds__(256) pack_nhwc_kernel(const __grid_constant__ PackTable t) {
-  __shared__ float s[64][33];
-  const int ei = find_range(t.map, blockIdx.x);
-  const int local = blockIdx.x - t.map.start[ei];
+__device__ __forceinline__ void pack_nhwc_body(const PackTable& t, int ei, int local, float (*s)[33]) {
   const int HW = t.e[ei].HW, C = t.C, Cd = t.Cd;
   const int n = local / t.e[ei].nblk, c0 = blockIdx.y * 64, p0 = (local % t.e[ei].nblk) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -170,14 +167,25 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const __grid_constant__ 
           __floats2bfloat162_rn(s[2 * tx][p], s[2 * tx + 1][p]);
   }
 }
+template <typename T>
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float s[64][33];
+  const int ei = find_range(t.map, blockIdx.x);
+  pack_nhwc_body<T>(t, ei, blockIdx.x - t.map.start[ei], s);
+}
 
 // bf16 source with an even pixel count per plane: 64 channels x 64 pixels per block, bf16x2 loads (128 B per
 // warp instruction), one 16-byte store (8 channels of one pixel) per thread and round -- half the load and a
-// quarter of the store instructions of the generic kernel.  Requires HW % 2 == 0 and Cd % 8 == 0.
+// quarter of the store instructions of the generic kernel.  Requires HW % 2 == 0 and Cd % 8 == 0; entries that do not
+// qualify (`fast` == 0: odd plane sizes, the small pyramid levels) take the generic body in the same launch.
 static __global__ void __launch_bounds__(256) pack_nhwc_bf16_kernel(const __grid_constant__ PackTable t) {
   __shared__ uint32_t s[64][33];   // [channel][pixel pair]
   const int ei = find_range(t.map, blockIdx.x);
   const int local = blockIdx.x - t.map.start[ei];
+  if (!t.e[ei].fast) {
+    pack_nhwc_body<__nv_bfloat16>(t, ei, local, reinterpret_cast<float(*)[33]>(s));
+    return;
+  }
   const int HW = t.e[ei].HW, C = t.C, Cd = t.Cd;
   const int n = local / t.e[ei].nblk, c0 = blockIdx.y * 64, p0 = (local % t.e[ei].nblk) * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -301,33 +309,29 @@ __device__ __forceinline__ void gather_stage_bf16(const uint4* __restrict__ x16,
   }
 }
 
-// NCHW (io dtype) -> NHWC bf16 [N][HW][Cd] for `n` tensors in at most two launches (the bf16 fast path needs an even
-// plane size; entries that do not qualify go through the generic kernel)
+// NCHW (io dtype) -> NHWC bf16 [N][HW][Cd] for `n` tensors in one launch
 struct PackJob { const void* src; void* dst; int N, HW; };
 inline int pack_nhwc_multi(const PackJob* jobs, int n, int C, int Cd, bool src_bf16, cudaStream_t st) {
-  for (int pass = 0; pass < 2; ++pass) {   // pass 0: fast bf16 kernel, pass 1: generic
-    PackTable t{};
-    t.C = C; t.Cd = Cd;
-    int m = 0, total = 0;
-    for (int i = 0; i < n; ++i) {
-      if (!jobs[i].src || jobs[i].N * jobs[i].HW == 0) continue;
-      const bool fast = src_bf16 && jobs[i].HW % 2 == 0 && Cd % 8 == 0;
-      if (fast != (pass == 0)) continue;
-      const int nblk = (jobs[i].HW + (fast ? 63 : 31)) / (fast ? 64 : 32);
-      t.e[m].src = jobs[i].src; t.e[m].dst = (__nv_bfloat16*)jobs[i].dst; t.e[m].HW = jobs[i].HW; t.e[m].nblk = nblk;
-      t.map.start[m] = total;
-      total += jobs[i].N * nblk;
-      ++m;
-    }
-    t.map.n = m; t.map.start[m] = total;
-    if (total == 0) continue;
-    dim3 grid(total, (Cd + 63) / 64);
-    if (pass == 0) pack_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(t);
-    else if (src_bf16) pack_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(t);
-    else pack_nhwc_kernel<float><<<grid, 256, 0, st>>>(t);
-    SDB_LAUNCHED(1);
-    SDB_CHECK_CUDA(cudaGetLastError());
+  PackTable t{};
+  t.C = C; t.Cd = Cd;
+  int m = 0, total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!jobs[i].src || jobs[i].N * jobs[i].HW == 0) continue;
+    const bool fast = src_bf16 && jobs[i].HW % 2 == 0 && Cd % 8 == 0;
+    const int nblk = (jobs[i].HW + (fast ? 63 : 31)) / (fast ? 64 : 32);
+    t.e[m].src = jobs[i].src; t.e[m].dst = (__nv_bfloat16*)jobs[i].dst; t.e[m].HW = jobs[i].HW; t.e[m].nblk = nblk;
+    t.e[m].fast = fast;
+    t.map.start[m] = total;
+    total += jobs[i].N * nblk;
+    ++m;
   }
+  t.map.n = m; t.map.start[m] = total;
+  if (total == 0) return SDB_OK;
+  dim3 grid(total, (Cd + 63) / 64);
+  if (src_bf16) pack_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(t);
+  else pack_nhwc_kernel<float><<<grid, 256, 0, st>>>(t);
+  SDB_LAUNCHED(1);
+  SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
