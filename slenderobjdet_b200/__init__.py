@@ -7,7 +7,8 @@ there is no CPU or eager-PyTorch fallback.
 """
 from . import _lib  # noqa: F401
 from .layers import (DeformConv, ModulatedDeformConv, DFConv2d, deform_conv, modulated_deform_conv,  # noqa: F401
-                     deform_conv_multi, set_dcn_math, get_dcn_math, dcn_math, invalidate_prepared_weights)
+                     deform_conv_multi, set_dcn_math, get_dcn_math, dcn_math, invalidate_prepared_weights,
+                     set_dcn_save_columns)
 from .matchers import Matcher, TopKMatcher, pairwise_iou  # noqa: F401
 
 __version__ = "0.1.0"

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           SDB_INTERP(a, slot)
           const uint32_t soff = sw128_offset(r0 + it * PPI + grp, lig & 7);
           *reinterpret_cast<uint4*>(dst + soff) = a;
-          if (colp) *reinterpret_cast<uint4*>(colp + (size_t)st * A_BYTES + soff) = a;
+          if (colp) __stcs(reinterpret_cast<uint4*>(colp + (size_t)st * A_BYTES + soff), a);   // streaming: keep x in L2
           if (it + RING < ITERS) {
             SDB_ISSUE(tap, ch, it + RING, slot)
           } else if (has_next) {

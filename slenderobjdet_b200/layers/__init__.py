@@ -1,6 +1,6 @@
 """Operator API mirroring ``detectron2.layers`` / ``slender_det.layers`` for the dense-head hot path."""
 from .deform_conv import (DeformConv, ModulatedDeformConv, deform_conv, modulated_deform_conv, deform_conv_multi,
-                          set_dcn_math, get_dcn_math, dcn_math, invalidate_prepared_weights)
+                          set_dcn_math, get_dcn_math, dcn_math, invalidate_prepared_weights, set_dcn_save_columns)
 from .df_conv import DFConv2d
 from .losses import (sigmoid_focal_loss, sigmoid_focal_loss_jit, sigmoid_focal_loss_from_class_idx,
                      iou_loss, box_iou_loss, smooth_l1_loss, smooth_l1_loss_with_weight, giou_loss,

@@ -258,6 +258,55 @@ def test_tensor_core_forward_vs_oracle(shape):
     assert rel_err(y.cpu().numpy(), yq) < 6e-3  # bf16 interpolation + bf16 operand rounding of the sample
 
 
+@pytest.mark.parametrize("save_columns", [True, False])
+@pytest.mark.parametrize("shape", [
+    # N, C, H, W, O, k, stride, pad, dil, modulated, sigma
+    (2, 192, 9, 10, 48, 3, 2, 1, 1, False, 1.0),      # stride 2, three 64-channel chunks, C_out not a multiple of 64
+    (1, 64, 12, 9, 16, 1, 1, 0, 1, False, 1.0),       # 1x1 kernel, no padding
+    (1, 512, 10, 13, 128, 3, 1, 2, 2, True, 3.0),     # dilation 2, pad 2, four 128-channel chunks, mask + bias
+    (3, 256, 20, 19, 240, 3, 1, 1, 1, False, 30.0),   # huge offsets (most taps outside), odd width
+    (1, 64, 11, 12, 32, (2, 4), 1, 1, 1, False, 1.0),  # non-square kernel
+    (2, 128, 16, 24, 80, 3, 2, 2, 2, True, 2.0),      # stride 2 + dilation 2, mask + bias
+    (2, 256, 13, 21, 256, 3, 1, 0, 1, False, 2.0),    # no padding: output grid smaller than the input grid
+])
+def test_tensor_core_backward_geometries(shape, save_columns):
+    """Every gradient of the tcgen05 backward (dcol GEMM + channel reduction, grad_input gather over the transposed
+    index, weight gradient over saved columns or by re-sampling) away from 3x3 / stride 1 / pad 1, vs the CPU oracle."""
+    N, C, H, W, O, k, st, pd, dl, mod, sigma = shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    g = torch.Generator().manual_seed(7 * C + O + H)
+    Ho = (H + 2 * pd - (dl * (kh - 1) + 1)) // st + 1
+    Wo = (W + 2 * pd - (dl * (kw - 1) + 1)) // st + 1
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(O, C, kh, kw, generator=g) * 0.05
+    off = torch.randn(N, 2 * kh * kw, Ho, Wo, generator=g) * sigma
+    m = torch.sigmoid(torch.randn(N, kh * kw, Ho, Wo, generator=g)) if mod else None
+    b = torch.randn(O, generator=g) if mod else None
+    gy = torch.randn(N, O, Ho, Wo, generator=g)
+    ref = odcn.backward(x.numpy(), off.numpy(), w.numpy(), gy.numpy(), mask=None if m is None else m.numpy(),
+                        with_bias=mod, stride=st, padding=pd, dilation=dl)
+    xd, od, wd = x.cuda().requires_grad_(), off.cuda().requires_grad_(), w.cuda().requires_grad_()
+    md = m.cuda().requires_grad_() if mod else None
+    bd = b.cuda().requires_grad_() if mod else None
+    sdb.set_dcn_save_columns(save_columns)
+    try:
+        with sdb.dcn_math("bf16"):
+            if mod:
+                y = sdb.modulated_deform_conv(xd, od, md, wd, bd, st, pd, dl, 1, 1)
+            else:
+                y = sdb.deform_conv(xd, od, wd, st, pd, dl, 1, 1)
+            y.backward(gy.cuda())
+        torch.cuda.synchronize()
+    finally:
+        sdb.set_dcn_save_columns(True)
+    got = dict(grad_x=xd.grad, grad_offset=od.grad, grad_weight=wd.grad)
+    if mod:
+        got.update(grad_mask=md.grad, grad_bias=bd.grad)
+    for name, t in got.items():
+        e = rel_err(t.float().cpu().numpy(), ref[name])
+        assert e < TOL["bf16"], (name, e)
+
+
 def test_auto_mode_keeps_float32_tensors_exact():
     """'auto' follows the tensors: a float32 model gets the reference's fp32 numerics (rel <= 1e-4) even where the
     tensor-core geometry would qualify; bf16 autocast or bfloat16 tensors select the tcgen05 kernels."""
