@@ -392,14 +392,18 @@ def run_ours(args):
             wl.step(stream)              # one stream: the event pairs time each tensor-core kernel alone
         lib.sdb_profile_enable(0)
         stream.synchronize()
-    names = ["dcn_fwd_tc_kernel<MODE_FWD>", "dcn_bwd_data_tc_kernel (grad_offset)", "dcn_bwd_weight_tc_kernel",
-             "dcn_fwd_tc_kernel<MODE_DX> (grad_input)"]
+    names = ["dcn_fwd_tc_kernel", "dcn_bwd_data_tc_kernel (grad_offset)", "dcn_wgrad_col_tc_kernel",
+             "dcn_dx_gather_kernel (grad_input)"]
+    # the first three are GEMM passes (tensor-bound on paper); grad_input is a gather of the exported dcol tiles over the
+    # transposed index (HBM-bound on paper): dcol read once (taps * C * 2 B per output pixel) + the index (36 entries of
+    # 8 B per input pixel, shared by the two branches of a level) + grad_x written (C * 2 B per input pixel)
+    gather_bytes = px_step * (9 * C_IN * 2 + C_IN * 2) + (px_step // 2) * 36 * 8
     kern = []
     for slot in range(4):
         ms, n = ctypes.c_float(0), ctypes.c_int(0)
         L.check(lib.sdb_profile_read(slot, ctypes.byref(ms), ctypes.byref(n)))
         kern.append((ms.value / reps, n.value // reps))
-    dom = max(range(4), key=lambda s: kern[s][0])
+    dom = max(range(3), key=lambda s: kern[s][0])   # dominant GEMM kernel
     dom_ms, dom_launches = kern[dom]
     # algorithmic FLOPs of one GEMM pass over every (level, branch) = FLOP_PER_PIXEL_PASS * pixels
     achieved = FLOP_PER_PIXEL_PASS * px_step / (dom_ms * 1e-3) / 1e12
@@ -408,10 +412,15 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4),
                 "launches_per_step": dom_launches, "avg_launch_us": round(dom_ms * 1e3 / max(dom_launches, 1), 2),
                 "algorithmic_flops_per_launch": FLOP_PER_PIXEL_PASS * px_step,
-                "algorithmic_flops_per_step": flops_step, "executed_gemm_flops_per_step": 4 * FLOP_PER_PIXEL_PASS * px_step,
+                "algorithmic_flops_per_step": flops_step, "executed_gemm_flops_per_step": 3 * FLOP_PER_PIXEL_PASS * px_step,
                 "per_kernel_ms_per_step": {names[s]: round(kern[s][0], 4) for s in range(4)},
                 "per_kernel_frac_of_peak": {names[s]: round(FLOP_PER_PIXEL_PASS * px_step / (kern[s][0] * 1e-3) / 1e12
-                                                            / peaks["bf16_tflops"], 4) for s in range(4) if kern[s][0] > 0},
+                                                            / peaks["bf16_tflops"], 4) for s in range(3) if kern[s][0] > 0},
+                "grad_input_gather": ({"bound": "hbm", "algorithmic_bytes_per_launch": gather_bytes,
+                                       "achieved": round(gather_bytes / (kern[3][0] * 1e-3) / 1e9, 1),
+                                       "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                       "frac": round(gather_bytes / (kern[3][0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)
+                                       if peaks.get("hbm_gbs") else None} if kern[3][0] > 0 else None),
                 "step_frac_of_peak": round(flops_step / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], 4),
                 "traffic": None}
     tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
