@@ -700,6 +700,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
       build_desc(0, fetch_rawb(g, pr.off, pr.mask, valid, n, ho, wo, 0));
       RawB raw_next = fetch_rawb(g, pr.off, pr.mask, valid && taps > 1, n, ho, wo, 1);   // raw offsets run two taps ahead
       __syncwarp();
+      // the pixel whose results this lane stores (see the transposing reduction below): its plane offsets
+      const int2 my_px = s_px[sw][(lig >> 1) * PPI + grp];
+      const int my_n = my_px.x;
+      const size_t my_goff = (size_t)my_n * 2 * taps * hw + my_px.y, my_gmask = (size_t)my_n * taps * hw + my_px.y;
       uint4 v[RING][4];
 #define SDB_ISSUE(tap_, ch_, it_, slot_)                                                         \
       {                                                                                          \
@@ -756,40 +760,35 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
           mbar_arrive_warp(&stg_empty[sb]);
           if (++sb == 2) { sb = 0; sp ^= 1; }
         }
-        float racc[ITERS];
+        // Transposing reduction over the LPB = 2 * ITERS lanes of a pixel group: every step sends half of the
+        // remaining per-pixel values to the partner lane and keeps the other half, so after log2(ITERS) steps lane
+        // `lig` holds ONE value per quantity -- that of pixel (lig >> 1) * PPI + grp -- summed over half the group, and
+        // a last exchange with lane lig ^ 1 completes it: ITERS shuffles per quantity, results spread over all
+        // lanes (one pixel per lane pair), so the stores below are one or two full-width instructions per tap.
+        static_assert(LPB == 2 * ITERS, "transposing reduction needs two lanes per pixel of the group");
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-          // reduce-scatter over the LPB lanes of this pixel: lanes [0,Q) end with sum(qa), [Q,2Q) sum(qb),
-          // [2Q,3Q) sum(qc)
-          constexpr int H = LPB / 2, Q = LPB / 4;
-          const float qa = qA[it], qb = qB[it], qc = qC[it];
-          const bool up = (lig & H) != 0;
-          const float r0_ = __shfl_xor_sync(0xffffffffu, up ? qa : qc, H);
-          const float r1_ = __shfl_xor_sync(0xffffffffu, up ? qb : 0.f, H);
-          const float k0 = (up ? qc : qa) + r0_;
-          const float k1 = (up ? 0.f : qb) + r1_;
-          const bool uq = (lig & Q) != 0;
-          float kk = (uq ? k1 : k0) + __shfl_xor_sync(0xffffffffu, uq ? k0 : k1, Q);
+        for (int m = ITERS, nn = ITERS; m >= 2; m >>= 1, nn >>= 1) {
+          const bool up = (lig & m) != 0;
 #pragma unroll
-          for (int dlt = Q / 2; dlt > 0; dlt >>= 1) kk += __shfl_xor_sync(0xffffffffu, kk, dlt);
-          racc[it] = kk;
+          for (int j = 0; j < nn / 2; ++j) {
+            const float sa = __shfl_xor_sync(0xffffffffu, up ? qA[j] : qA[j + nn / 2], m);
+            const float sb_ = __shfl_xor_sync(0xffffffffu, up ? qB[j] : qB[j + nn / 2], m);
+            const float sc = __shfl_xor_sync(0xffffffffu, up ? qC[j] : qC[j + nn / 2], m);
+            qA[j] = (up ? qA[j + nn / 2] : qA[j]) + sa;
+            qB[j] = (up ? qB[j + nn / 2] : qB[j]) + sb_;
+            qC[j] = (up ? qC[j + nn / 2] : qC[j]) + sc;
+          }
         }
-        // lanes lig == 0, Q, 2Q hold d/dy, d/dx, d/dmask of pixel it*PPI+grp
-        {
-          constexpr int Q = LPB / 4;
-          const int quant = lig / Q;
-          if ((lig % Q) == 0 && quant < 3) {
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-              const int2 pxy = s_px[sw][it * PPI + grp];
-              if (pxy.x >= 0) {
-                if (quant < 2) {
-                  if (pr.goff) pr.goff[((size_t)pxy.x * 2 * taps + 2 * tap + quant) * hw + pxy.y] = racc[it];
-                } else if (pr.gmask) {
-                  pr.gmask[((size_t)pxy.x * taps + tap) * hw + pxy.y] = racc[it];
-                }
-              }
-            }
+        const float SA = qA[0] + __shfl_xor_sync(0xffffffffu, qA[0], 1);
+        const float SB = qB[0] + __shfl_xor_sync(0xffffffffu, qB[0], 1);
+        const float SC = qC[0] + __shfl_xor_sync(0xffffffffu, qC[0], 1);
+        // even lane of a pair: d/dy and d/dmask, odd lane: d/dx of pixel (lig >> 1) * PPI + grp
+        if (my_n >= 0) {
+          if ((lig & 1) == 0) {
+            if (pr.goff) pr.goff[my_goff + (size_t)(2 * tap) * hw] = SA;
+            if (pr.gmask) pr.gmask[my_gmask + (size_t)tap * hw] = SC;
+          } else if (pr.goff) {
+            pr.goff[my_goff + (size_t)(2 * tap + 1) * hw] = SB;
           }
         }
       }
