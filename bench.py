@@ -456,7 +456,10 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        cb = cpu_reference(steps=1, warmup=0, shape=(2, 100, 152), budget_s=60.0)   # BASELINE.json configs[0] shape
+        if args.no_cpu:   # developer flag (A/B timing of two builds): never used for a reported line
+            cb = dict(value=0.0, cores=0, kind="skipped", sample="skipped (--no-cpu developer flag)")
+        else:
+            cb = cpu_reference(steps=1, warmup=0, shape=(2, 100, 152), budget_s=60.0)   # BASELINE.json configs[0] shape
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
@@ -612,6 +615,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager C-ABI launches instead of a CUDA graph")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[4] extra measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="developer flag: skip the CPU baseline sample (A/B timing of builds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -9,7 +9,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libslender_b200.so")
+# SDB_LIB_PATH: developer switch for A/B timing of two builds on the same GPU box (tools/ab_bench.sh)
+LIB_PATH = os.environ.get("SDB_LIB_PATH") or os.path.join(_PKG, "libslender_b200.so")
 
 SDB_F32, SDB_BF16 = 0, 1
 SDB_MATH_FP32, SDB_MATH_BF16 = 0, 1

@@ -4,28 +4,23 @@
 //  (1) grad_offset / grad_mask -- one fused persistent kernel:
 //   dcol[p, (tap,c)] = sum_o dY[p,o] W[o,c,tap]        tcgen05 GEMM, M=128 pixels, N=128 channels,
 //                                                      K = C_out, accumulator in TMEM (never in HBM)
-//   4 drain warps move each 128x128 fp32 accumulator to a swizzled bf16 staging tile in smem;
+//   4 drain warps move each 128x128 fp32 accumulator to a bf16 staging tile in smem (padded rows);
 //   reduce warps (16 lanes x 8 channels per pixel) re-read the 4 input corners of (pixel, tap) and
-//   reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels with warp
-//   shuffles -> grad_offset / grad_mask, plain stores (one owner per (pixel, tap)).
-//  (2) grad_input -- the reference scatters w * dcol with fp32 atomics (K3/K6); here the scatter is
-//   inverted once per offset group into a CSR index "which (output pixel, tap, weight) touch input
-//   pixel q" (count -> scan -> fill -> sort, ~36 entries per output pixel), kernel (1) writes its bf16
-//   dcol staging tiles to HBM with one bulk copy each (the only pass over dY W^T: no second GEMM), and
-//   grad_input becomes a pure gather  dX[q,c] = sum_{(p,tap,w) in list(q)} w * dcol[p,tap,c]  with fp32
-//   accumulation in a fixed (sorted) order: deterministic, no atomics, no fp32 NHWC accumulation buffer,
-//   no memset, no NHWC->NCHW pass.  (dcn_dx_gather_kernel below.)
+//   reduce  sum_c dcol * d(bilinear)/d(y|x)  and  sum_c dcol * bilinear  over channels (packed bf16 dot
+//   products, mixed-precision FMAs, a transposing shuffle reduction) -> grad_offset / grad_mask, plain
+//   full-width stores (one owner per (pixel, tap)).
+//  (2) grad_input -- the reference scatters w * dcol with fp32 atomics (K3/K6); here kernel (1) writes its
+//   bf16 dcol staging tiles to HBM with one bulk copy each (the only pass over dY W^T: no second GEMM) and
+//   grad_input is a gather of them over a transposed sampling index: dcn_tc_dx.cu.
 //   Replaces G2 + K2/K5 + K3/K6 of the reference (deform_conv_cuda.cu:553-559,
 //   deform_conv_cuda_kernel.cu:291-452, :870-1066).
 //
 // backward_weight: dW[o, c, tap] = sum_p dY[p,o] col[p,(tap,c)]  -- tcgen05 GEMM with BOTH operands
-//   MN-major: A = dY^T tiles (bulk-copied), B = re-gathered col tile (same producer as forward),
-//   K = pixels.  One CTA per (tap, 128-channel chunk, pixel split); both 128-row halves of C_out
-//   accumulate in TMEM for the CTA's whole pixel range; split partials are reduced (and permuted to
-//   [O][C][kH][kW]) by a second tiny kernel -- deterministic, no atomics.
-//   Replaces K1' + G3 of the reference (deform_conv_cuda.cu:738-778).
-#include <type_traits>
-
+//   MN-major, K = pixels, accumulators stationary in TMEM for a CTA's whole pixel range, split partials
+//   reduced (and permuted to [O][C][kH][kW]) by a second small kernel -- deterministic, no atomics.
+//   Two variants: over the columns the forward pass saved (dcn_wgrad_col_tc_kernel: both operands stream in
+//   by bulk copy, O x 256 accumulators) or, when they were not saved, re-sampling them with the forward's
+//   gather producer (dcn_bwd_weight_tc_kernel).  Replaces K1' + G3 of the reference (deform_conv_cuda.cu:738-778).
 #include "dcn_tc_shared.cuh"
 
 namespace sdb {
@@ -42,11 +37,8 @@ constexpr int BWD_THREADS = (FIRST_SW + NSW) * 32;
 constexpr int PIX_PER_WARP = TILE_M / NSW;   // 16
 constexpr int MAX_B_STAGES = 8;
 
-inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wide o blocks, even count
-__host__ __device__ inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
 // channels per CTA of the weight-gradient kernel over saved columns (UMMA N, <= 256; O x CG fp32 must fit in TMEM)
 inline int wgrad_col_group(const Geo& g) { return g.C % 256 == 0 ? 256 : nch_of(g); }
-inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 
 // ------------------------------------------------------------------------------------------------
 // packing kernels
@@ -180,280 +172,6 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// sampling descriptor for the backward pass
-// ------------------------------------------------------------------------------------------------
-struct BSample {
-  int idx[4];   // corner pixel index (n*H + y)*W + x, or -1 when that corner is outside the image
-  float lh, lw, m;
-};
-
-// raw (dy, dx, mask) of one (pixel, tap): fetched ahead of use so the loads overlap other work
-struct RawB {
-  float dy, dx, m;
-};
-__device__ __forceinline__ RawB fetch_rawb(const Geo& g, const float* __restrict__ off,
-                                           const float* __restrict__ mask, bool valid, int n, int ho, int wo,
-                                           int tap) {
-  RawB r = {0.f, 0.f, 1.f};
-  if (!valid) return r;
-  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
-  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
-  r.dy = __ldg(o);
-  r.dx = __ldg(o + hw);
-  if (mask) r.m = __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo);
-  return r;
-}
-
-__device__ __forceinline__ BSample make_bsample_raw(const Geo& g, const RawB raw, bool valid, int n, int ho,
-                                                    int wo, int tap) {
-  BSample s;
-  s.idx[0] = s.idx[1] = s.idx[2] = s.idx[3] = -1;
-  s.lh = s.lw = 0.f;
-  s.m = 0.f;
-  if (!valid) return s;
-  const int i = tap / g.KW, j = tap - i * g.KW;
-  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + raw.dy;
-  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + raw.dx;
-  // gradient-side validity test is the non-strict one (deform_conv_cuda_kernel.cu:140-144, :435-437)
-  if (h <= -1.f || w <= -1.f || h >= (float)g.H || w >= (float)g.W) return s;
-  s.m = raw.m;
-  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
-  const int h_high = h_low + 1, w_high = w_low + 1;
-  s.lh = h - h_low;
-  s.lw = w - w_low;
-  const bool t = h_low >= 0, b = h_high <= g.H - 1, l = w_low >= 0, r = w_high <= g.W - 1;
-  const int base = n * g.H;
-  if (t && l) s.idx[0] = (base + h_low) * g.W + w_low;
-  if (t && r) s.idx[1] = (base + h_low) * g.W + w_high;
-  if (b && l) s.idx[2] = (base + h_high) * g.W + w_low;
-  if (b && r) s.idx[3] = (base + h_high) * g.W + w_high;
-  return s;
-}
-
-__device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __restrict__ off,
-                                                const float* __restrict__ mask, bool valid, int n, int ho,
-                                                int wo, int tap) {
-  return make_bsample_raw(g, fetch_rawb(g, off, mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
-}
-
-// ------------------------------------------------------------------------------------------------
-// index of the transposed sampling pattern (grad_input as a gather, see file header)
-// ------------------------------------------------------------------------------------------------
-// key(q, tap) = q * (taps + 1) + tap, q = band-order position of the INPUT pixel (tile = q >> 7, row = q & 127).
-// Plain CSR: the (output pixel p, weight w = bilinear x mask) pairs that reach q through `tap` are the entries
-// start[key] .. start[key + 1]; because the keys of one input pixel are adjacent, the whole list of q -- every tap --
-// is one contiguous run, which is what the gather walks.  The extra key q * (taps + 1) + taps holds 0..7 zero entries
-// that pad the run to a multiple of eight entries (64 bytes), so the gather reads whole groups of eight with aligned
-// 16-byte loads and no per-entry bounds test (a zero entry = row 0 with weight 0).  An entry is 8 bytes: the row of
-// dcol it names, as an offset in 16-byte units into the problem's dcol tiles (channel chunk 0), and tap << 16 | bf16
-// weight.  With stride 1 a key holds four entries on average (36 per input pixel for 3x3).
-struct __align__(8) CEntry {
-  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (tile bytes / 16) + (pos & 127) * (row bytes / 16), pos = band-order position of p
-  uint32_t tw;      // tap << 16 | weight (bf16 bits; zero only in padding)
-};
-constexpr int LIST_ALIGN = 8;   // entries
-template <typename F>
-__device__ __forceinline__ void for_each_hit(const Geo& g, const float* __restrict__ off,
-                                             const float* __restrict__ mask, int n, int ho, int wo, int tap,
-                                             F f) {
-  const BSample s = make_bsample(g, off, mask, true, n, ho, wo, tap);
-  const float wk[4] = {(1.f - s.lh) * (1.f - s.lw), (1.f - s.lh) * s.lw, s.lh * (1.f - s.lw), s.lh * s.lw};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (s.idx[k] < 0) continue;
-    const float wv = wk[k] * s.m;
-    const uint32_t wb = pack_bf16x2(wv, wv) >> 16;
-    if (wb == 0u || wb == 0x8000u) continue;       // rounds to zero as a bf16 operand: contributes nothing
-    const int pixel = s.idx[k] - n * g.H * g.W;    // y * W + x
-    const int y = pixel / g.W, x = pixel - y * g.W;
-    const long long q = encode_pos(g.H, g.W, g.th, g.tw, n, y, x);
-    f(q * (g.taps() + 1) + tap, wb);
-  }
-}
-
-// One transposed index per OFFSET GROUP (problems that sample with the same offsets, e.g. the two DCNs of a
-// RepPoints level, share it).  All groups live in one key space: group i owns keys [key_base, key_base + nkeys_i),
-// so a single scan serves the whole call.  grid (blocks of 256 output pixels over all groups, taps).
-struct CsrTable {
-  TileMap map;   // blocks of 256 output pixels
-  struct G { const float* off; const float* mask; Dims d; int key_base; } gr[MAX_PROBS];
-  Geo g;
-};
-__global__ void __launch_bounds__(256) csr_count_kernel(const __grid_constant__ CsrTable t, int* __restrict__ cnt) {
-  const int gi = find_range(t.map, blockIdx.x);
-  const Geo g = with_dims(t.g, t.gr[gi].d);
-  const int tap = blockIdx.y;
-  const long long p = (long long)(blockIdx.x - t.map.start[gi]) * blockDim.x + threadIdx.x;
-  if (p >= g.P()) return;
-  const int hw = g.Ho * g.Wo;
-  const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
-  int* c = cnt + t.gr[gi].key_base;
-  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap,
-               [&](long long key, uint32_t) { atomicAdd(c + key, 1); });
-}
-
-// pad key of every input pixel: the number of zero entries that round its list up to LIST_ALIGN entries
-__global__ void __launch_bounds__(256) csr_pad_kernel(int* __restrict__ cnt, int npix, int taps) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= npix) return;
-  int* c = cnt + (size_t)q * (taps + 1);
-  int s = 0;
-  for (int t = 0; t < taps; ++t) s += c[t];
-  c[taps] = (-s) & (LIST_ALIGN - 1);
-}
-
-constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block
-__global__ void __launch_bounds__(256) csr_block_sums_kernel(const int* __restrict__ cnt, int* __restrict__ bsum,
-                                                             int nkeys) {
-  const int base = blockIdx.x * SCAN_PER_BLOCK;
-  int s = 0;
-  for (int i = threadIdx.x; i < SCAN_PER_BLOCK; i += 256) {
-    const int k = base + i;
-    if (k < nkeys) s += cnt[k];
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-  __shared__ int part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < 8; ++i) t += part[i];
-    bsum[blockIdx.x] = t;
-  }
-}
-// exclusive scan of the block sums in place (single block)
-__global__ void __launch_bounds__(1024) csr_scan_top_kernel(int* __restrict__ bsum, int nblocks) {
-  __shared__ int wsum[32];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
-    const int i = b0 + threadIdx.x;
-    const int v = i < nblocks ? bsum[i] : 0;
-    int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if ((threadIdx.x & 31) >= d) incl += t;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = wsum[threadIdx.x];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, d);
-        if (threadIdx.x >= d) w += t;
-      }
-      wsum[threadIdx.x] = w;   // inclusive over warps
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int wbase = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
-    if (i < nblocks) bsum[i] = carry + wbase + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
-    __syncthreads();
-  }
-}
-// start[k] = exclusive scan of the entry counts; start[nkeys] = total
-__global__ void __launch_bounds__(256) csr_scan_final_kernel(const int* __restrict__ cnt, const int* __restrict__ bsum,
-                                                             int* __restrict__ start, int nkeys) {
-  __shared__ int wsum[8];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = bsum[blockIdx.x];
-  __syncthreads();
-  const int base = blockIdx.x * SCAN_PER_BLOCK;
-  for (int i0 = 0; i0 < SCAN_PER_BLOCK; i0 += 256) {
-    const int k = base + i0 + threadIdx.x;
-    const int v = k < nkeys ? cnt[k] : 0;
-    int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if ((threadIdx.x & 31) >= d) incl += t;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
-    const int carry = carry_s;
-    const int excl = carry + wbase + incl - v;
-    if (k < nkeys) {
-      start[k] = excl;
-      if (k == nkeys - 1) start[nkeys] = excl + v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + wbase + incl;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ CsrTable t, int* __restrict__ cnt_all,
-                                                       const int* __restrict__ start_all, CEntry* __restrict__ ent) {
-  const int gi = find_range(t.map, blockIdx.x);
-  const Geo g = with_dims(t.g, t.gr[gi].d);
-  const int tap = blockIdx.y;
-  const long long p = (long long)(blockIdx.x - t.map.start[gi]) * blockDim.x + threadIdx.x;
-  if (p >= g.P()) return;
-  const int hw = g.Ho * g.Wo;
-  const int n = (int)(p / hw), r = (int)(p - (long long)n * hw);
-  const uint32_t pos = (uint32_t)encode_pos(g.Ho, g.Wo, g.th, g.tw, n, r / g.Wo, r % g.Wo);
-  const uint32_t nchv = (uint32_t)nch_of(g), nchunks = (uint32_t)g.C / nchv;
-  const uint32_t row16 = ((pos >> 7) * (uint32_t)g.taps() * nchunks + (uint32_t)tap * nchunks) * (stg_tile_bytes((int)nchv) / 16u) +
-                         (pos & 127u) * stg_row_units((int)nchv);
-  int* cnt = cnt_all + t.gr[gi].key_base;
-  const int* start = start_all + t.gr[gi].key_base;
-  for_each_hit(g, t.gr[gi].off, t.gr[gi].mask, n, r / g.Wo, r % g.Wo, tap, [&](long long key, uint32_t wb) {
-    const int slot = atomicSub(cnt + key, 1) - 1;   // slots are handed out from the back
-    CEntry e;
-    e.row16 = row16;
-    e.tw = ((uint32_t)tap << 16) | wb;
-    ent[start[key] + slot] = e;
-  });
-}
-
-// Canonical order.  csr_fill hands out list slots with atomics, so the order in which the fp32 sums of grad_input are
-// formed would change from run to run.  This pass sorts the entries of every key by their output pixel (an output
-// pixel reaches an (input pixel, tap) at most once, so the sort keys are unique): grad_input becomes
-// bit-reproducible.  One thread per key; a key holds ~4 entries.
-__global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ start, CEntry* __restrict__ ent, int nkeys,
-                                                       int taps) {
-  const int key = blockIdx.x * blockDim.x + threadIdx.x;
-  if (key >= nkeys || key % (taps + 1) == taps) return;   // pad keys hold zeros
-  const int b = start[key], n = start[key + 1] - b;
-  if (n < 2) return;
-  unsigned long long* e = reinterpret_cast<unsigned long long*>(ent + b);   // row16 (monotonic in the output pixel) in the low word
-  constexpr int CAP = 8;
-  if (n <= CAP) {
-    unsigned long long v[CAP];
-#pragma unroll
-    for (int i = 0; i < CAP; ++i) v[i] = i < n ? e[i] : ~0ull;
-    // odd-even transposition sort on the low word (fully unrolled: registers, no local memory)
-#pragma unroll
-    for (int r = 0; r < CAP; ++r) {
-#pragma unroll
-      for (int i = r & 1; i + 1 < CAP; i += 2) {
-        const bool sw = (uint32_t)v[i + 1] < (uint32_t)v[i] && v[i + 1] != ~0ull;
-        const unsigned long long lo = sw ? v[i + 1] : v[i], hi = sw ? v[i] : v[i + 1];
-        v[i] = lo; v[i + 1] = hi;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < CAP; ++i)
-      if (i < n) e[i] = v[i];
-    return;
-  }
-  for (int i = 1; i < n; ++i) {   // long list (many taps colliding on one input pixel): insertion sort in place
-    const unsigned long long x = e[i];
-    int j = i - 1;
-    while (j >= 0 && (uint32_t)e[j] > (uint32_t)x) { e[j + 1] = e[j]; --j; }
-    e[j + 1] = x;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // backward data kernel
 // ------------------------------------------------------------------------------------------------
 struct DgradProb {
@@ -484,6 +202,16 @@ template <int R>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// acc += (s2.lo + s2.hi) * c, c = low / high bf16 half of c2: two mixed-precision FMAs (FHFMA.BF16), fp32 accumulation
+__device__ __forceinline__ void fma_pair_lo(float& acc, uint32_t s2, uint32_t c2) {
+  asm("{ .reg .b16 sl, sh, cl, ch;\n mov.b32 {sl, sh}, %1;\n mov.b32 {cl, ch}, %2;\n"
+      "fma.rn.f32.bf16 %0, sl, cl, %0;\n fma.rn.f32.bf16 %0, sh, cl, %0;\n }" : "+f"(acc) : "r"(s2), "r"(c2));
+}
+__device__ __forceinline__ void fma_pair_hi(float& acc, uint32_t s2, uint32_t c2) {
+  asm("{ .reg .b16 sl, sh, cl, ch;\n mov.b32 {sl, sh}, %1;\n mov.b32 {cl, ch}, %2;\n"
+      "fma.rn.f32.bf16 %0, sl, ch, %0;\n fma.rn.f32.bf16 %0, sh, ch, %0;\n }" : "+f"(acc) : "r"(s2), "r"(c2));
+}
 
 template <int NCH>
 __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
@@ -645,18 +373,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     }
   } else {
     // ===== reduce warps: grad_offset / grad_mask = channel reductions of dcol against the corners =====
-    // Same load pipeline as the forward gather: per (pixel, tap) a descriptor in shared memory (corner
-    // offsets + lh, lw, mask, corner-valid flags, built one tap ahead by lanes 0..15), and a 4-slot
-    // register ring that keeps 16 sixteen-byte corner loads per lane in flight across unit boundaries.
-    // Per (pixel, tap, 8 channels): four packed-bf16 dot products S_k = <dcol, corner_k> (16 HFMA2),
-    // combined in fp32 into this lane's share of d/dy, d/dx and d/dmask, then a 5-shuffle
-    // reduce-scatter over the pixel's lane group.  The sums over channel chunks stay in registers;
-    // one plain store per (pixel, tap, quantity) at the end of the tap.
+    // Same load pipeline as the forward gather: per (pixel, tap) a descriptor in shared memory (corner offsets +
+    // the twelve bf16 coefficients with which the four corner dot products enter d/dy, d/dx and d/dmask, zero for a
+    // corner outside the image; built one tap ahead by lanes 0..15), and a 4-slot register ring that keeps 16
+    // sixteen-byte corner loads per lane in flight across unit boundaries.  Per (pixel, tap, 8 channels): four
+    // packed-bf16 dot products S_k = <dcol, corner_k> (16 HFMA2, two bf16 partial sums each) and 24 mixed-precision
+    // FMAs (bf16 partial sum x bf16 coefficient + fp32 accumulator) into this lane's share of the three quantities,
+    // then a transposing shuffle reduction over the pixel's lane group.  The sums over channel chunks stay in
+    // registers; one full-width store per quantity at the end of the tap.
     setmaxnreg_inc<184>();
     constexpr int ITERS = PIX_PER_WARP / PPI;
     constexpr int RING = 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-unit iteration count");
-    __shared__ uint4 s_od[NSW][2][PIX_PER_WARP][2];   // {off[4]}, {lh, lw, m, flags}
+    __shared__ uint4 s_od[NSW][2][PIX_PER_WARP][3];   // {off[4]}, {ay01, ay23, ax01, ax23}, {w01, w23, -, -}: bf16 pairs
     __shared__ int2 s_px[NSW][PIX_PER_WARP];          // (n, ho*Wo+wo) of the warp's pixels, n = -1 when padded
     const int sw = warp - G_SW0, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
@@ -686,15 +415,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
       auto build_desc = [&](int tap_, const RawB raw_) {
         if (lane < PIX_PER_WARP) {
           const BSample bs = make_bsample_raw(g, raw_, valid, n, ho, wo, tap_);
-          uint4 o, f;
-          uint32_t flags = 0;
-          o.x = bs.idx[0] >= 0 ? (flags |= 1u, (uint32_t)bs.idx[0] * (uint32_t)(C / 8)) : 0u;
-          o.y = bs.idx[1] >= 0 ? (flags |= 2u, (uint32_t)bs.idx[1] * (uint32_t)(C / 8)) : 0u;
-          o.z = bs.idx[2] >= 0 ? (flags |= 4u, (uint32_t)bs.idx[2] * (uint32_t)(C / 8)) : 0u;
-          o.w = bs.idx[3] >= 0 ? (flags |= 8u, (uint32_t)bs.idx[3] * (uint32_t)(C / 8)) : 0u;
-          f.x = __float_as_uint(bs.lh); f.y = __float_as_uint(bs.lw); f.z = __float_as_uint(bs.m); f.w = flags;
-          s_od[sw][tap_ & 1][lane][0] = o;
-          s_od[sw][tap_ & 1][lane][1] = f;
+          // d(bilinear)/dh, /dw (get_coordinate_weight, deform_conv_cuda_kernel.cu:163-214) and the bilinear weights
+          // themselves, as signed per-corner coefficients (x mask for the two coordinate gradients)
+          const float lh = bs.lh, lw = bs.lw, m = bs.m;
+          const float ay[4] = {-m * (1.f - lw), -m * lw, m * (1.f - lw), m * lw};
+          const float ax[4] = {-m * (1.f - lh), m * (1.f - lh), -m * lh, m * lh};
+          const float wk[4] = {(1.f - lh) * (1.f - lw), (1.f - lh) * lw, lh * (1.f - lw), lh * lw};
+          uint32_t off4[4];
+          float cy[4], cx[4], cw[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool on = bs.idx[k] >= 0;
+            off4[k] = on ? (uint32_t)bs.idx[k] * (uint32_t)(C / 8) : 0u;
+            cy[k] = on ? ay[k] : 0.f; cx[k] = on ? ax[k] : 0.f; cw[k] = on ? wk[k] : 0.f;
+          }
+          s_od[sw][tap_ & 1][lane][0] = make_uint4(off4[0], off4[1], off4[2], off4[3]);
+          s_od[sw][tap_ & 1][lane][1] = make_uint4(pack_bf16x2(cy[0], cy[1]), pack_bf16x2(cy[2], cy[3]),
+                                                   pack_bf16x2(cx[0], cx[1]), pack_bf16x2(cx[2], cx[3]));
+          s_od[sw][tap_ & 1][lane][2] = make_uint4(pack_bf16x2(cw[0], cw[1]), pack_bf16x2(cw[2], cw[3]), 0u, 0u);
         }
       };
       build_desc(0, fetch_rawb(g, pr.off, pr.mask, valid, n, ho, wo, 0));
@@ -736,26 +474,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
           for (int it = 0; it < ITERS; ++it) {
             const int slot = it % RING;
             const int px = it * PPI + grp;
-            const uint4 f = s_od[sw][tap & 1][px][1];
+            const uint4 cf = s_od[sw][tap & 1][px][1];
+            const uint2 cw = *reinterpret_cast<const uint2*>(&s_od[sw][tap & 1][px][2]);
             const uint4 d = *reinterpret_cast<const uint4*>(stg + stg_offset<NCH>(r0 + px, lig));
-            float S[4];
+            uint32_t S2[4];   // <dcol, corner_k> over this lane's 8 channels as two bf16 partial sums
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t a2 = bf2_fma(d.w, v[slot][k].w, bf2_fma(d.z, v[slot][k].z,
-                                  bf2_fma(d.y, v[slot][k].y, bf2_mul(d.x, v[slot][k].x))));
-              const float sk = __uint_as_float(a2 << 16) + __uint_as_float(a2 & 0xffff0000u);
-              S[k] = (f.w >> k) & 1u ? sk : 0.f;
-            }
+            for (int k = 0; k < 4; ++k)
+              S2[k] = bf2_fma(d.w, v[slot][k].w, bf2_fma(d.z, v[slot][k].z, bf2_fma(d.y, v[slot][k].y, bf2_mul(d.x, v[slot][k].x))));
             if (it + RING < ITERS) {
               SDB_ISSUE(tap, ch, it + RING, slot)
             } else if (has_next) {
               SDB_ISSUE(ntap, nchk, it + RING - ITERS, slot)
             }
-            const float lh = __uint_as_float(f.x), lw = __uint_as_float(f.y), m = __uint_as_float(f.z);
-            // d(bilinear)/dh, /dw (get_coordinate_weight :185-211) and the unmasked sample value
-            qA[it] += m * ((1.f - lw) * (S[2] - S[0]) + lw * (S[3] - S[1]));
-            qB[it] += m * ((1.f - lh) * (S[1] - S[0]) + lh * (S[3] - S[2]));
-            qC[it] += (1.f - lh) * ((1.f - lw) * S[0] + lw * S[1]) + lh * ((1.f - lw) * S[2] + lw * S[3]);
+            fma_pair_lo(qA[it], S2[0], cf.x); fma_pair_hi(qA[it], S2[1], cf.x);
+            fma_pair_lo(qA[it], S2[2], cf.y); fma_pair_hi(qA[it], S2[3], cf.y);
+            fma_pair_lo(qB[it], S2[0], cf.z); fma_pair_hi(qB[it], S2[1], cf.z);
+            fma_pair_lo(qB[it], S2[2], cf.w); fma_pair_hi(qB[it], S2[3], cf.w);
+            fma_pair_lo(qC[it], S2[0], cw.x); fma_pair_hi(qC[it], S2[1], cw.x);
+            fma_pair_lo(qC[it], S2[2], cw.y); fma_pair_hi(qC[it], S2[3], cw.y);
           }
           mbar_arrive_warp(&stg_empty[sb]);
           if (++sb == 2) { sb = 0; sp ^= 1; }
@@ -798,146 +534,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, NCOLS);
-}
-
-// ------------------------------------------------------------------------------------------------
-// grad_input: gather of the exported dcol tiles over the transposed index
-// ------------------------------------------------------------------------------------------------
-// dX[q, c] = sum over the list of q (all taps): w_e * dcol[p_e, tap_e, c], accumulated in fp32 in list order (sorted:
-// bit-reproducible).  A CTA owns (128 input pixels in band order = a compact patch, one NCH-channel chunk); a group of
-// LPB lanes serves one pixel with 8 channels per lane, so a list entry is one 16-byte load per lane and NCH*2
-// contiguous bytes per group.  The group reads eight entries of its list with one coalesced load, broadcasts them with
-// shuffles and issues the eight row loads together; latency is hidden by occupancy (one accumulator row of 8 floats
-// per thread, <= 64 registers, 32 warps per SM), not by a software pipeline.  The four input pixels that share a dcol
-// row (the four bilinear corners) sit in the same or a neighbouring warp and walk their lists in the same (tap,
-// position) order, so the repeats are L1 / L2 hits.  HBM-bound on paper (dcol is read once: taps * C * 2 bytes per
-// output pixel); the result leaves through a shared-memory transpose as NCHW rows.
-struct DxProb {
-  const uint8_t* dcol;
-  const int* start;          // transposed index of the problem's offset group
-  const CEntry* ent;
-  void* out;                 // NCHW grad_input (f32 or bf16)
-  Dims d;
-};
-struct DxParams {
-  TileMap map;               // work items: (input tile, channel chunk), chunk fastest
-  DxProb pr[MAX_PROBS];
-  Geo g;
-  int accumulate;            // add to `out` (the single-call ABI accumulates into grad_x) instead of overwriting
-};
-
-// acc[0..7] += w * (8 bf16 of v), fp32 accumulation: mixed-precision FMA (FHFMA.BF16) reads the bf16 halves in place
-__device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4 v, uint32_t w_lo16) {
-#define SDB_FH(a0_, a1_, r_)                                                                   \
-  asm("{ .reg .b16 lo, hi, wl, wh;\n mov.b32 {lo, hi}, %2;\n mov.b32 {wl, wh}, %3;\n"        \
-      "fma.rn.f32.bf16 %0, lo, wl, %0;\n fma.rn.f32.bf16 %1, hi, wl, %1;\n }"                 \
-      : "+f"(a0_), "+f"(a1_) : "r"(r_), "r"(w_lo16));
-  SDB_FH(acc[0], acc[1], v.x) SDB_FH(acc[2], acc[3], v.y) SDB_FH(acc[4], acc[5], v.z) SDB_FH(acc[6], acc[7], v.w)
-#undef SDB_FH
-}
-
-template <int NCH, bool OUT_BF16, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1024 / THREADS) dcn_dx_gather_kernel(const __grid_constant__ DxParams p) {
-  constexpr int LPB = NCH / 8, PPI = 32 / LPB;
-  constexpr int PIXW = TILE_M / (THREADS / 32), ROUNDS = PIXW / PPI;
-  static_assert(ROUNDS >= 1 && LIST_ALIGN == 8, "list walk is written for groups of eight entries");
-  constexpr size_t STG_BYTES = stg_tile_bytes(NCH);
-  using ST = typename std::conditional<OUT_BF16, __nv_bfloat16, float>::type;
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  ST* s_t = reinterpret_cast<ST*>(s_raw);  // [NCH][128] transpose buffer in the output type, column rotated by PPI * (c >> 3)
-  __shared__ int2 s_px[TILE_M];            // (n, y*W + x) of the tile's pixels, n = -1 past the end
-
-  const int pi = find_range(p.map, blockIdx.x);
-  const DxProb& pr = p.pr[pi];
-  const int C = p.g.C, taps = p.g.KH * p.g.KW, nch = C / NCH;
-  const int local = blockIdx.x - p.map.start[pi];
-  const int tile = local / nch, ch = local - tile * nch;
-  const int H = pr.d.H, W = pr.d.W, hw = H * W;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane / LPB, lig = lane % LPB;
-  const int r0 = warp * PIXW;
-
-  if (threadIdx.x < TILE_M) {
-    const long long q = (long long)tile * TILE_M + threadIdx.x;
-    int n = -1, y = 0, x = 0;
-    if (q < (long long)pr.d.N * hw) decode_pos(H, W, p.g.th, p.g.tw, q, n, y, x);
-    s_px[threadIdx.x] = make_int2(n, y * W + x);
-  }
-
-  // list bounds of the tile's pixels (the first global-memory latency of every list, paid once per CTA)
-  __shared__ int s_beg[TILE_M + 1];
-  if (threadIdx.x <= TILE_M) s_beg[threadIdx.x] = __ldg(pr.start + ((size_t)tile * TILE_M + threadIdx.x) * (taps + 1));
-  __syncthreads();
-
-  // Pixel of (warp, round, lane group).  The pixels in flight at one time form a compact block of the 8 x 16 patch
-  // (4 x 8 with 16 warps, 4 x 4 with 8): the four input pixels sharing a dcol row are 2 x 2 neighbours, so most of
-  // them are in flight together and the repeats hit in L1.  Other shapes walk the tile linearly.
-  auto pixel_of = [&](int r) {
-    if (PPI == 2 && THREADS == 512) return ((r >> 1) * 4 + (warp >> 2)) * 16 + (r & 1) * 8 + (warp & 3) * 2 + grp;
-    if (PPI == 2 && THREADS == 256) return ((r >> 2) * 4 + (warp >> 1)) * 16 + (r & 3) * 4 + (warp & 1) * 2 + grp;
-    return r0 + r * PPI + grp;
-  };
-  // this lane's 16-byte column of the dcol rows of channel chunk `ch`
-  const uint4* cb = reinterpret_cast<const uint4*>(pr.dcol + (size_t)ch * STG_BYTES) + lig;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-  for (int r = 0; r < ROUNDS; ++r) {
-    const int px = pixel_of(r);
-    const int beg = s_beg[px], nb = (s_beg[px + 1] - beg) >> 3;   // batches of eight entries
-    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent + beg);  // two entries per uint4: (row16, tw, row16, tw)
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    uint4 e[4];   // entries of the batch being issued, fetched one batch ahead
-#pragma unroll
-    for (int k = 0; k < 4; ++k) e[k] = nb > 0 ? __ldg(ep + k) : zero4;
-    for (int b = 0; b < nb; ++b) {
-      uint4 v[8];
-      uint32_t tw[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {   // zero entries (padding) load row 0 and contribute nothing
-        tw[k] = (k & 1) ? e[k >> 1].w : e[k >> 1].y;
-        v[k] = __ldg(cb + ((k & 1) ? e[k >> 1].z : e[k >> 1].x));
-      }
-      if (b + 1 < nb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = __ldg(ep + 4 * (b + 1) + k);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) fma8_bf16(acc, v[k], tw[k]);
-    }
-    // [pixel][channel] registers -> transpose buffer
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int si = (lig * 8 + j) * TILE_M + ((px + PPI * lig) & (TILE_M - 1));
-      if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(s_t)[si] = __float2bfloat16_rn(acc[j]);
-      else reinterpret_cast<float*>(s_t)[si] = acc[j];
-    }
-  }
-  __syncthreads();
-  // NCHW rows: a warp store = 32 consecutive tile pixels of one channel
-  {
-    const int px = threadIdx.x & (TILE_M - 1);
-    const int2 pxy = s_px[px];
-    if (pxy.x >= 0) {
-      const size_t o0 = ((size_t)pxy.x * C + (size_t)ch * NCH) * hw + pxy.y;
-      for (int c = threadIdx.x >> 7; c < NCH; c += THREADS / TILE_M) {
-        const int si = c * TILE_M + ((px + PPI * (c >> 3)) & (TILE_M - 1));
-        const size_t di = o0 + (size_t)c * hw;
-        if (OUT_BF16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(pr.out) + di;
-          __nv_bfloat16 v = reinterpret_cast<const __nv_bfloat16*>(s_t)[si];
-          if (p.accumulate) v = __float2bfloat16_rn(__bfloat162float(v) + __bfloat162float(*o));
-          *o = v;
-        } else {
-          float* o = reinterpret_cast<float*>(pr.out) + di;
-          float v = reinterpret_cast<const float*>(s_t)[si];
-          if (p.accumulate) v += *o;
-          *o = v;
-        }
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1480,86 +1076,6 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
   return tc_forward_multi(pb, n, g, io_dtype, st);
 }
 
-// the transposed sampling index (one per offset group) of a call, on stream `st`
-static int build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st) {
-  int* cnt = (int*)(base + P.cnt_off);
-  int* start = (int*)(base + P.start_off);
-  int* bsum = (int*)(base + P.bsum_off);
-  CEntry* ent = (CEntry*)(base + P.ent_off);
-  CsrTable t{};
-  t.g = g;
-  int total = 0, m = 0;
-  for (int k = 0; k < P.ngroups; ++k) {
-    bool wanted = false;
-    for (int i = 0; i < n; ++i) wanted |= P.group_of[i] == k && pb[i].gx;
-    if (!wanted) continue;
-    const TcProblem& r = pb[P.group_rep[k]];
-    t.gr[m].off = r.off; t.gr[m].mask = r.mask; t.gr[m].d = r.d; t.gr[m].key_base = (int)P.key_base[k];
-    t.map.start[m] = total;
-    total += cdiv(with_dims(g, r.d).P(), 256);
-    ++m;
-  }
-  t.map.n = m; t.map.start[m] = total;
-  const int nkeys = (int)P.nkeys;
-  SDB_CHECK_CUDA(cudaMemsetAsync(cnt, 0, P.clear_bytes, st));   // cnt and the entry pool in one fill
-  dim3 hgrid(total, g.taps());
-  csr_count_kernel<<<hgrid, 256, 0, st>>>(t, cnt);
-  csr_pad_kernel<<<cdiv(nkeys / (g.taps() + 1), 256), 256, 0, st>>>(cnt, nkeys / (g.taps() + 1), g.taps());
-  csr_block_sums_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, nkeys);
-  csr_scan_top_kernel<<<1, 1024, 0, st>>>(bsum, P.scan_blocks);
-  csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, nkeys);
-  csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, ent);
-  csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(start, ent, nkeys, g.taps());
-  SDB_LAUNCHED(7);
-  SDB_CHECK_CUDA(cudaGetLastError());
-  for (int i = 0; i < n; ++i) {
-    const long long kb = P.key_base[P.group_of[i]];
-    pb[i].start = start + kb; pb[i].ent = ent;
-  }
-  return SDB_OK;
-}
-
-// ---- grad_input of all problems that want it: one gather launch ---------------------------------------------------
-int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accumulate, cudaStream_t st) {
-  const int NCH = nch_of(g), nch = nch_chunks(g);
-  DxParams p{};
-  p.g = g; p.accumulate = accumulate;
-  int m = 0, total = 0;
-  for (int i = 0; i < n; ++i) {
-    if (!pb[i].gx) continue;
-    const long long pin = (long long)pb[i].d.N * pb[i].d.H * pb[i].d.W;
-    if (pin == 0) continue;
-    DxProb& q = p.pr[m];
-    q.dcol = pb[i].dcol; q.start = pb[i].start; q.ent = (const CEntry*)pb[i].ent;
-    q.out = pb[i].gx; q.d = pb[i].d;
-    p.map.start[m] = total;
-    total += cdiv(pin, TILE_M) * nch;
-    ++m;
-  }
-  p.map.n = m; p.map.start[m] = total;
-  if (total == 0) return SDB_OK;
-  const bool obf = io_dtype == SDB_BF16;
-  const size_t smem = (size_t)NCH * TILE_M * (obf ? 2 : 4);
-  ProfScope prof(3, st);   // slot 3 = grad_input (slender_b200.h)
-  static const int dx_threads = getenv("SDB_DX_THREADS") ? atoi(getenv("SDB_DX_THREADS")) : 512;
-#define SDB_DX_LAUNCH(NCH_, BF_)                                                                  \
-  {                                                                                               \
-    if (dx_threads == 256) {                                                                      \
-      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 256>), smem);                              \
-      dcn_dx_gather_kernel<NCH_, BF_, 256><<<total, 256, smem, st>>>(p);                          \
-    } else {                                                                                      \
-      SDB_ENSURE_SMEM((dcn_dx_gather_kernel<NCH_, BF_, 512>), smem);                              \
-      dcn_dx_gather_kernel<NCH_, BF_, 512><<<total, 512, smem, st>>>(p);                          \
-    }                                                                                             \
-  }
-  if (NCH == 128) { if (obf) SDB_DX_LAUNCH(128, true) else SDB_DX_LAUNCH(128, false) }
-  else            { if (obf) SDB_DX_LAUNCH(64, true) else SDB_DX_LAUNCH(64, false) }
-#undef SDB_DX_LAUNCH
-  SDB_LAUNCHED(1);
-  SDB_CHECK_CUDA(cudaGetLastError());
-  return SDB_OK;
-}
-
 // ---- backward: grad_offset / grad_mask, grad_input, grad_weight / grad_bias of all problems ------------------------
 // dY is packed once per problem (tile image + NHWC rows) and serves the three kernels; the transposed index is built
 // once per offset group; one launch per kernel over all problems.
@@ -1613,7 +1129,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     ist = side->s;
   }
   if (any_gx) {
-    rc = build_transposed_index(pb, n, P, g, base, ist);
+    rc = tc_build_transposed_index(pb, n, P, g, base, ist);
     if (rc) return rc;
     if (side) SDB_CHECK_CUDA(cudaEventRecord(side->join, side->s));
   }

@@ -57,6 +57,7 @@ struct TcPlan {
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward);
 int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
 int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accumulate, cudaStream_t st);
+int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st);
 int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
                     int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
@@ -334,6 +335,77 @@ inline int pack_nhwc_multi(const PackJob* jobs, int n, int C, int Cd, bool src_b
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
+
+// channel chunking of the backward kernels: NCH = channels per dcol accumulator / staging tile (128 or 64)
+inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wide o blocks, even count
+__host__ __device__ inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
+inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
+
+// entry of the transposed sampling index (dcn_tc_dx.cu)
+struct __align__(8) CEntry {
+  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (tile bytes / 16) + (pos & 127) * (row bytes / 16), pos = band-order position of p
+  uint32_t tw;      // tap << 16 | weight (bf16 bits; zero only in padding)
+};
+constexpr int LIST_ALIGN = 8;   // entries
+constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block of the index scan
+
+// ------------------------------------------------------------------------------------------------
+// sampling descriptor of the backward kernels
+// ------------------------------------------------------------------------------------------------
+struct BSample {
+  int idx[4];   // corner pixel index (n*H + y)*W + x, or -1 when that corner is outside the image
+  float lh, lw, m;
+};
+
+// raw (dy, dx, mask) of one (pixel, tap): fetched ahead of use so the loads overlap other work
+struct RawB {
+  float dy, dx, m;
+};
+__device__ __forceinline__ RawB fetch_rawb(const Geo& g, const float* __restrict__ off,
+                                           const float* __restrict__ mask, bool valid, int n, int ho, int wo,
+                                           int tap) {
+  RawB r = {0.f, 0.f, 1.f};
+  if (!valid) return r;
+  const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
+  const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
+  r.dy = __ldg(o);
+  r.dx = __ldg(o + hw);
+  if (mask) r.m = __ldg(mask + ((size_t)n * k2 + tap) * hw + ho * g.Wo + wo);
+  return r;
+}
+
+__device__ __forceinline__ BSample make_bsample_raw(const Geo& g, const RawB raw, bool valid, int n, int ho,
+                                                    int wo, int tap) {
+  BSample s;
+  s.idx[0] = s.idx[1] = s.idx[2] = s.idx[3] = -1;
+  s.lh = s.lw = 0.f;
+  s.m = 0.f;
+  if (!valid) return s;
+  const int i = tap / g.KW, j = tap - i * g.KW;
+  const float h = (float)(ho * g.sh - g.ph + i * g.dh) + raw.dy;
+  const float w = (float)(wo * g.sw - g.pw + j * g.dw) + raw.dx;
+  // gradient-side validity test is the non-strict one (deform_conv_cuda_kernel.cu:140-144, :435-437)
+  if (h <= -1.f || w <= -1.f || h >= (float)g.H || w >= (float)g.W) return s;
+  s.m = raw.m;
+  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
+  const int h_high = h_low + 1, w_high = w_low + 1;
+  s.lh = h - h_low;
+  s.lw = w - w_low;
+  const bool t = h_low >= 0, b = h_high <= g.H - 1, l = w_low >= 0, r = w_high <= g.W - 1;
+  const int base = n * g.H;
+  if (t && l) s.idx[0] = (base + h_low) * g.W + w_low;
+  if (t && r) s.idx[1] = (base + h_low) * g.W + w_high;
+  if (b && l) s.idx[2] = (base + h_high) * g.W + w_low;
+  if (b && r) s.idx[3] = (base + h_high) * g.W + w_high;
+  return s;
+}
+
+__device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __restrict__ off,
+                                                const float* __restrict__ mask, bool valid, int n, int ho,
+                                                int wo, int tap) {
+  return make_bsample_raw(g, fetch_rawb(g, off, mask, valid, n, ho, wo, tap), valid, n, ho, wo, tap);
+}
+
 
 inline int num_sms() {
   static int n = 0;
