@@ -154,6 +154,11 @@ def cpu_reference(steps, warmup, shape, budget_s):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+# offsets of the synthetic workload: dcn_offset ~ N(0, sigma^2) pixels (SURVEY 8d regime ii; 2 px = a trained RepPoints head).
+# SDB_BENCH_SIGMA is a developer knob for locality experiments, never set for a reported line.
+OFFSET_SIGMA = float(os.environ.get("SDB_BENCH_SIGMA", "2.0"))
+
+
 class Workload:
     """All device buffers of one step + the C-ABI call sequence (graph-capturable: no allocation, no synchronisation,
     fixed pointers).  Problems are ordered (level, branch); both branches of a level share the level's offsets."""
@@ -187,7 +192,7 @@ class Workload:
             gl = L.Geom(batch, C_IN, H, W, C_OUT, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
             pkb = lib.sdb_dcn_packed_input_bytes(ctypes.byref(gl), self.mth)
             clb = lib.sdb_dcn_columns_bytes(ctypes.byref(gl), self.mth) if save_columns else 0
-            lv = dict(H=H, W=W, off=(mk(batch, 18, H, W) * 2.0).to(device), br=[],
+            lv = dict(H=H, W=W, off=(mk(batch, 18, H, W) * OFFSET_SIGMA).to(device), br=[],
                       mask=torch.sigmoid(mk(batch, 9, H, W)).to(device) if modulated else None)
             for b in range(2):
                 br = dict(x=mk(batch, C_IN, H, W).to(device, bf), gy=mk(batch, C_OUT, H, W).to(device, bf),
