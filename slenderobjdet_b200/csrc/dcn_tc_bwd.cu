@@ -1034,10 +1034,12 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     P.scan_blocks = cdiv(keys, SCAN_PER_BLOCK);
     // cnt and the entry pool are cleared by ONE memset (pad entries must read as zero): keep them adjacent
     P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
-    P.ent_off = o;   o = align_up(o + (size_t)ents * sizeof(CEntry), 1024);
+    P.ent_cap = (long long)cdiv(ents, LIST_ALIGN) * LIST_ALIGN;
+    P.ent_off = o;   o = align_up(o + (size_t)P.ent_cap * sizeof(CEntry), 1024);
     P.clear_bytes = o - P.cnt_off;
     P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
     P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
+    P.blk_off = o;   o = align_up(o + (size_t)(P.ent_cap / LIST_ALIGN) * ENT_BLOCK_BYTES, 1024);
     // weight-gradient split-K: all weights share the machine
     int tiles_w[MAX_WEIGHTS] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) tiles_w[pb[i].weight_id] += cdiv(with_dims(g, pb[i].d).P(), TILE_M);

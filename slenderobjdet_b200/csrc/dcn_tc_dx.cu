@@ -228,6 +228,22 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ s
   }
 }
 
+// Final form read by the gather: the sorted 8-byte entries regrouped into blocks of eight (8 x u32 dcol row, then 8 x
+// bf16 weight: 48 bytes, dcn_tc_shared.cuh) -- three aligned 16-byte loads per batch in the gather and the weights
+// already packed in pairs for its mixed-precision FMAs.  One thread per block; lists are padded to whole blocks with
+// zero entries, so every block is written.
+__global__ void __launch_bounds__(256) csr_pack_kernel(const CEntry* __restrict__ ent, uint4* __restrict__ blocks, int nblocks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const uint4* src = reinterpret_cast<const uint4*>(ent + (size_t)b * 8);   // two entries per uint4: (row16, tw, row16, tw)
+  const uint4 e0 = src[0], e1 = src[1], e2 = src[2], e3 = src[3];
+  uint4* dst = blocks + (size_t)b * 3;
+  dst[0] = make_uint4(e0.x, e0.z, e1.x, e1.z);
+  dst[1] = make_uint4(e2.x, e2.z, e3.x, e3.z);
+  dst[2] = make_uint4((e0.y & 0xffffu) | (e0.w << 16), (e1.y & 0xffffu) | (e1.w << 16),
+                      (e2.y & 0xffffu) | (e2.w << 16), (e3.y & 0xffffu) | (e3.w << 16));
+}
+
 // ------------------------------------------------------------------------------------------------
 // grad_input: gather of the exported dcol tiles over the transposed index
 // ------------------------------------------------------------------------------------------------
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(256) csr_sort_kernel(const int* __restrict__ s
 struct DxProb {
   const uint8_t* dcol;
   const int* start;          // transposed index of the problem's offset group
-  const CEntry* ent;
+  const uint32_t* ent;       // entry pool (blocks of eight, dcn_tc_shared.cuh)
   void* out;                 // NCHW grad_input (f32 or bf16)
   Dims d;
 };
@@ -254,14 +270,27 @@ struct DxParams {
   int accumulate;            // add to `out` (the single-call ABI accumulates into grad_x) instead of overwriting
 };
 
-// acc[0..7] += w * (8 bf16 of v), fp32 accumulation: mixed-precision FMA (FHFMA.BF16) reads the bf16 halves in place
-__device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4 v, uint32_t w_lo16) {
+// acc[0..7] += w * (8 bf16 of v), w = bf16 half HI (0 = low, 1 = high) of w2, fp32 accumulation: mixed-precision FMA
+// (FHFMA.BF16) reads all bf16 halves in place
+template <int HI>
+__device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4 v, uint32_t w2) {
 #define SDB_FH(a0_, a1_, r_)                                                                   \
-  asm("{ .reg .b16 lo, hi, wl, wh;\n mov.b32 {lo, hi}, %2;\n mov.b32 {wl, wh}, %3;\n"        \
-      "fma.rn.f32.bf16 %0, lo, wl, %0;\n fma.rn.f32.bf16 %1, hi, wl, %1;\n }"                 \
-      : "+f"(a0_), "+f"(a1_) : "r"(r_), "r"(w_lo16));
+  if (HI)                                                                                      \
+    asm("{ .reg .b16 lo, hi, wl, wh;\n mov.b32 {lo, hi}, %2;\n mov.b32 {wl, wh}, %3;\n"      \
+        "fma.rn.f32.bf16 %0, lo, wh, %0;\n fma.rn.f32.bf16 %1, hi, wh, %1;\n }"               \
+        : "+f"(a0_), "+f"(a1_) : "r"(r_), "r"(w2));                                            \
+  else                                                                                         \
+    asm("{ .reg .b16 lo, hi, wl, wh;\n mov.b32 {lo, hi}, %2;\n mov.b32 {wl, wh}, %3;\n"      \
+        "fma.rn.f32.bf16 %0, lo, wl, %0;\n fma.rn.f32.bf16 %1, hi, wl, %1;\n }"               \
+        : "+f"(a0_), "+f"(a1_) : "r"(r_), "r"(w2));
   SDB_FH(acc[0], acc[1], v.x) SDB_FH(acc[2], acc[3], v.y) SDB_FH(acc[4], acc[5], v.z) SDB_FH(acc[6], acc[7], v.w)
 #undef SDB_FH
+}
+
+// 16-byte read-only load of row `row16` (16-byte units) behind this lane's base pointer, written so that the address
+// is ONE wide multiply-add (IMAD.WIDE.U32) instead of a 64-bit add + shift chain
+__device__ __forceinline__ uint4 ldg_row(const uint8_t* base, uint32_t row16) {
+  return __ldg(reinterpret_cast<const uint4*>(base + (unsigned long long)row16 * 16ull));
 }
 
 template <int NCH, bool OUT_BF16, int THREADS>
@@ -309,33 +338,29 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1024 / THREADS) 
     return r0 + r * PPI + grp;
   };
   // this lane's 16-byte column of the dcol rows of channel chunk `ch`
-  const uint4* cb = reinterpret_cast<const uint4*>(pr.dcol + (size_t)ch * STG_BYTES) + lig;
+  const uint8_t* cb = pr.dcol + (size_t)ch * STG_BYTES + (size_t)lig * 16;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; ++r) {
     const int px = pixel_of(r);
     const int beg = s_beg[px], nb = (s_beg[px + 1] - beg) >> 3;   // batches of eight entries
-    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent + beg);  // two entries per uint4: (row16, tw, row16, tw)
+    const uint4* ep = reinterpret_cast<const uint4*>(pr.ent) + (size_t)(beg >> 3) * 3;  // blocks: rows 0-3, rows 4-7, 8 weights
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    uint4 e[4];   // entries of the batch being issued, fetched one batch ahead
-#pragma unroll
-    for (int k = 0; k < 4; ++k) e[k] = nb > 0 ? __ldg(ep + k) : zero4;
+    uint4 ra = zero4, rb = zero4, wv = zero4;   // block of the batch being issued, fetched one batch ahead
+    if (nb > 0) { ra = __ldg(ep); rb = __ldg(ep + 1); wv = __ldg(ep + 2); }
     for (int b = 0; b < nb; ++b) {
       uint4 v[8];
-      uint32_t tw[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {   // zero entries (padding) load row 0 and contribute nothing
-        tw[k] = (k & 1) ? e[k >> 1].w : e[k >> 1].y;
-        v[k] = __ldg(cb + ((k & 1) ? e[k >> 1].z : e[k >> 1].x));
-      }
-      if (b + 1 < nb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = __ldg(ep + 4 * (b + 1) + k);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) fma8_bf16(acc, v[k], tw[k]);
+      // zero entries (padding) load row 0 and contribute nothing
+      v[0] = ldg_row(cb, ra.x); v[1] = ldg_row(cb, ra.y); v[2] = ldg_row(cb, ra.z); v[3] = ldg_row(cb, ra.w);
+      v[4] = ldg_row(cb, rb.x); v[5] = ldg_row(cb, rb.y); v[6] = ldg_row(cb, rb.z); v[7] = ldg_row(cb, rb.w);
+      const uint4 w = wv;
+      if (b + 1 < nb) { ra = __ldg(ep + 3 * (b + 1)); rb = __ldg(ep + 3 * (b + 1) + 1); wv = __ldg(ep + 3 * (b + 1) + 2); }
+      fma8_bf16<0>(acc, v[0], w.x); fma8_bf16<1>(acc, v[1], w.x);
+      fma8_bf16<0>(acc, v[2], w.y); fma8_bf16<1>(acc, v[3], w.y);
+      fma8_bf16<0>(acc, v[4], w.z); fma8_bf16<1>(acc, v[5], w.z);
+      fma8_bf16<0>(acc, v[6], w.w); fma8_bf16<1>(acc, v[7], w.w);
     }
     // [pixel][channel] registers -> transpose buffer
 #pragma unroll
@@ -379,6 +404,7 @@ int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& 
   int* start = (int*)(base + P.start_off);
   int* bsum = (int*)(base + P.bsum_off);
   CEntry* ent = (CEntry*)(base + P.ent_off);
+  uint4* blocks = (uint4*)(base + P.blk_off);
   CsrTable t{};
   t.g = g;
   int total = 0, m = 0;
@@ -403,11 +429,14 @@ int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& 
   csr_scan_final_kernel<<<P.scan_blocks, 256, 0, st>>>(cnt, bsum, start, nkeys);
   csr_fill_kernel<<<hgrid, 256, 0, st>>>(t, cnt, start, ent);
   csr_sort_kernel<<<cdiv(nkeys, 256), 256, 0, st>>>(start, ent, nkeys, g.taps());
-  SDB_LAUNCHED(7);
+  // start[nkeys] = total entries, a multiple of LIST_ALIGN; the pack covers the worst case (unused blocks are zeros)
+  const int nblocks = (int)(P.ent_cap / LIST_ALIGN);
+  csr_pack_kernel<<<cdiv(nblocks, 256), 256, 0, st>>>(ent, blocks, nblocks);
+  SDB_LAUNCHED(8);
   SDB_CHECK_CUDA(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     const long long kb = P.key_base[P.group_of[i]];
-    pb[i].start = start + kb; pb[i].ent = ent;
+    pb[i].start = start + kb; pb[i].ent = blocks;
   }
   return SDB_OK;
 }
@@ -423,7 +452,7 @@ int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accu
     const long long pin = (long long)pb[i].d.N * pb[i].d.H * pb[i].d.W;
     if (pin == 0) continue;
     DxProb& q = p.pr[m];
-    q.dcol = pb[i].dcol; q.start = pb[i].start; q.ent = (const CEntry*)pb[i].ent;
+    q.dcol = pb[i].dcol; q.start = pb[i].start; q.ent = (const uint32_t*)pb[i].ent;
     q.out = pb[i].gx; q.d = pb[i].d;
     p.map.start[m] = total;
     total += cdiv(pin, TILE_M) * nch;

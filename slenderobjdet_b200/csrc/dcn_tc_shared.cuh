@@ -49,7 +49,8 @@ struct TcPlan {
   int group_of[16], group_rep[16], ngroups;
   long long key_base[16], nkeys;
   int scan_blocks;
-  size_t cnt_off, ent_off, clear_bytes, start_off, bsum_off;
+  size_t cnt_off, ent_off, clear_bytes, start_off, bsum_off, blk_off;
+  long long ent_cap;             // entries the pool holds (multiple of LIST_ALIGN)
   int tiles_per_split[4], splits[4];           // weight-gradient split-K of the re-sampling kernel
   int tiles_per_split_col[4], splits_col[4];   // ... of the kernel over saved columns
   size_t total;
@@ -341,12 +342,14 @@ inline int okb_of(const Geo& g) { return 2 * ((g.O + 127) / 128); }     // 64-wi
 __host__ __device__ inline int nch_of(const Geo& g) { return g.C % 128 == 0 ? 128 : 64; }
 inline int nch_chunks(const Geo& g) { return g.C / nch_of(g); }
 
-// entry of the transposed sampling index (dcn_tc_dx.cu)
+// entry of the transposed sampling index while it is built (dcn_tc_dx.cu)
 struct __align__(8) CEntry {
-  uint32_t row16;   // ((pos >> 7) * taps * nch + tap * nch) * (tile bytes / 16) + (pos & 127) * (row bytes / 16), pos = band-order position of p
+  uint32_t row16;   // dcol row in 16-byte units into the problem's dcol tiles, channel chunk 0:
+                    // ((pos >> 7) * taps * nch + tap * nch) * (tile bytes / 16) + (pos & 127) * (row bytes / 16), pos = band-order position of p
   uint32_t tw;      // tap << 16 | weight (bf16 bits; zero only in padding)
 };
-constexpr int LIST_ALIGN = 8;   // entries
+constexpr int LIST_ALIGN = 8;            // every input pixel's list is padded to a multiple of eight entries
+constexpr int ENT_BLOCK_BYTES = 48;      // final form: blocks of eight entries = 8 x u32 row + 8 x bf16 weight (csr_pack_kernel)
 constexpr int SCAN_PER_BLOCK = 2048;   // keys per 256-thread block of the index scan
 
 // ------------------------------------------------------------------------------------------------
