@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]  # P3..P7 of an 800x1344 image
 C_IN = C_OUT = 256
 BATCH_PER_GPU = 2
+NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "8"))  # CTAs of the overlapped all-reduce = SMs the persistent kernels leave free
 HEAD_PARAMS = 5341556  # RepPoints head parameter count; all-reduced when N > 1
 FLOP_PER_PIXEL_PASS = 2 * C_IN * C_OUT * 9  # 1 179 648
 METRIC = "reppoints_head_dcn_fwd_bwd_images_per_s"
@@ -288,8 +289,10 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
                     with torch.cuda.graph(ga, stream=stream):
                         wl.phase_forward(stream)
                         wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+                    L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))   # grids are baked into the graph at capture
                     with torch.cuda.graph(gb, stream=stream):
                         wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+                    L.lib().sdb_set_sm_reserve(0)
                     graphs = [ga, gb]
             except Exception as e:  # keep running eagerly, say so in config
                 graphs = None
@@ -314,7 +317,9 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
         if graphs:
             graphs[1].replay()
         else:
+            L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))
             wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+            L.lib().sdb_set_sm_reserve(0)
         if work is not None:
             work.wait()
 
@@ -354,7 +359,15 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # the weight-gradient all-reduce runs BESIDE the persistent data-gradient kernels: cap NCCL at NCCL_CTAS CTAs and
+        # leave that many SMs free (sdb_set_sm_reserve) so neither waits for the other's SMs
+        if NCCL_CTAS > 0:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = NCCL_CTAS
+            opts.config.min_ctas = 1
+            dist.init_process_group("nccl", device_id=device, pg_options=opts)
+        else:   # developer knob: NCCL's own CTA count, nothing reserved
+            dist.init_process_group("nccl", device_id=device)
     lib = L.lib()
     peaks = load_peaks()
     batch = BATCH_PER_GPU
@@ -476,7 +489,7 @@ def run_ours(args):
                        "launch": mode, "launches_per_step": int(launches_per_step + torch_fills_per_step),
                        "tflops_per_s": round(flops_step * world / (step_ms * 1e-3) / 1e12, 2),
                        "allreduce_bytes": HEAD_PARAMS * 4 if world > 1 else 0,
-                       "allreduce": "overlapped with grad_input / grad_offset, 1/world folded into the kernel" if world > 1 else None},
+                       "allreduce": ("overlapped with grad_input / grad_offset on %d NCCL CTAs (that many SMs left free by the persistent kernels), 1/world folded into the kernel" % NCCL_CTAS) if world > 1 else None},
             "roofline": roofline,
             "parity": parity,
             "cpu_baseline": {"value": round(cb["value"], 5), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 3
+#define SDB_ABI_VERSION 4
 
 typedef enum {
   SDB_OK = 0,
@@ -44,7 +44,18 @@ typedef enum { SDB_F32 = 0, SDB_BF16 = 1 } sdb_dtype;
  * BF16: tcgen05 tensor-core kernels; sampled values and weights rounded to bf16, fp32
  * accumulate in TMEM.  Requires groups == 1, deformable_groups == 1, C_in % 64 == 0,
  * C_out % 16 == 0, C_out <= 256 (sdb_dcn_supported tells). */
-typedef enum { SDB_MATH_FP32 = 0, SDB_MATH_BF16 = 1 } sdb_math;
+typedef enum {
+  SDB_MATH_FP32 = 0,
+  SDB_MATH_BF16 = 1,
+  /* float32 tensors on tcgen05.mma.kind::tf32 (FORWARD; the backward entry points run the exact FP32 kernels, so
+   * gradients keep fp32 accuracy).  The bilinear sample is computed in fp32, then
+   *   TF32  : sample and weight rounded to tf32 (10 mantissa bits), one pass: rel ~4e-4;
+   *   TF32X3: error-compensated split hi + lo of both operands, three passes (lo*hi + hi*lo + hi*hi): fp32-accurate,
+   *           rel ~2e-5 against the fp32 oracle at K = 2304 (what is left is the accumulator's fp32 additions).
+   * Require groups == 1, deformable_groups == 1, C_in % 32 == 0, C_out % 16 == 0, C_out <= 256, kH*kW <= 16. */
+  SDB_MATH_TF32 = 2,
+  SDB_MATH_TF32X3 = 3
+} sdb_math;
 
 /* Geometry of one deformable convolution (same meaning as the integer arguments of
  * deform_conv_forward / modulated_deform_conv_forward, d2/layers/csrc/deformable/deform_conv.h:8-112).
@@ -346,6 +357,12 @@ int sdb_profile_reset(void);
 int sdb_profile_read(int slot, float* total_ms, int* launches);
 /* Number of kernels this library has launched (or captured into a CUDA graph) since it was loaded. */
 long long sdb_launch_count(void);
+/* SMs the persistent tensor-core kernels leave free (default 0; process-wide, applies to launches made -- or captured
+ * into a CUDA graph -- after the call).  Their CTAs walk a static tile schedule, so a CTA that must wait for an SM held
+ * by a co-running kernel delays the whole launch by that wait; a data-parallel caller that overlaps the weight-gradient
+ * all-reduce (d2/engine/defaults.py:280-283) with the data-gradient kernels reserves as many SMs as the collective
+ * uses CTAs (bench.py: NCCL max_ctas). */
+int sdb_set_sm_reserve(int n_sms);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDB_LIB_PATH") or os.path.join(_PKG, "libslender_b200.so")
 
 SDB_F32, SDB_BF16 = 0, 1
-SDB_MATH_FP32, SDB_MATH_BF16 = 0, 1
+SDB_MATH_FP32, SDB_MATH_BF16, SDB_MATH_TF32, SDB_MATH_TF32X3 = 0, 1, 2, 3
+SDB_TF32_MODES = (SDB_MATH_TF32, SDB_MATH_TF32X3)
 SDB_OP_FORWARD, SDB_OP_BACKWARD_DATA, SDB_OP_BACKWARD_WEIGHT = 0, 1, 2
 SDB_LOSS_IOU, SDB_LOSS_LINEAR_IOU, SDB_LOSS_GIOU, SDB_LOSS_SMOOTH_L1, SDB_LOSS_GIOU_FVCORE = range(5)
 SDB_BOX_LTRB, SDB_BOX_XYXY = 0, 1
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
     "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
-    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count",
+    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count", "sdb_set_sm_reserve",
 ]
 
 
@@ -119,6 +120,8 @@ def _declare(lib):
     lib.sdb_reppoints_dcn_offset_backward.argtypes = [_vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]
     lib.sdb_launch_count.restype = ctypes.c_longlong
     lib.sdb_launch_count.argtypes = []
+    lib.sdb_set_sm_reserve.restype = ctypes.c_int
+    lib.sdb_set_sm_reserve.argtypes = [_i32]
     lib.sdb_profile_enable.argtypes = [ctypes.c_int]
     lib.sdb_profile_read.argtypes = [ctypes.c_int, ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_int)]
     return lib

@@ -11,6 +11,7 @@ namespace sdb {
 
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+namespace tcshared { int g_sm_reserve = 0; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -66,11 +67,14 @@ int check_geom(const sdb_dcn_geom* g) {
 
 static int check_io(int io_dtype, int math) {
   SDB_REQUIRE(io_dtype == SDB_F32 || io_dtype == SDB_BF16, SDB_ERR_INVALID, "unknown io_dtype %d", io_dtype);
-  SDB_REQUIRE(math == SDB_MATH_FP32 || math == SDB_MATH_BF16, SDB_ERR_INVALID, "unknown math mode %d", math);
-  SDB_REQUIRE(!(math == SDB_MATH_FP32 && io_dtype != SDB_F32), SDB_ERR_UNSUPPORTED,
-              "SDB_MATH_FP32 needs float32 tensors (bf16 tensors use SDB_MATH_BF16)");
+  SDB_REQUIRE(math == SDB_MATH_FP32 || math == SDB_MATH_BF16 || math == SDB_MATH_TF32 || math == SDB_MATH_TF32X3,
+              SDB_ERR_INVALID, "unknown math mode %d", math);
+  SDB_REQUIRE(!(math != SDB_MATH_BF16 && io_dtype != SDB_F32), SDB_ERR_UNSUPPORTED,
+              "SDB_MATH_FP32 / TF32 / TF32X3 need float32 tensors (bf16 tensors use SDB_MATH_BF16)");
   return SDB_OK;
 }
+static inline bool is_tf32(int math) { return math == SDB_MATH_TF32 || math == SDB_MATH_TF32X3; }
+static inline int tf32_passes(int math) { return math == SDB_MATH_TF32X3 ? 3 : 1; }
 
 static int require_device() {
   int dev = -1;
@@ -125,6 +129,11 @@ const char* sdb_last_error(void) { return g_err; }
 int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 
 long long sdb_launch_count(void) { return g_launches; }
+int sdb_set_sm_reserve(int n) {
+  SDB_REQUIRE(n >= 0 && n < 128, SDB_ERR_INVALID, "SM reserve must be in [0, 128), got %d", n);
+  tcshared::g_sm_reserve = n;
+  return SDB_OK;
+}
 int sdb_profile_enable(int on) {
   g_prof.on = on != 0;
   return SDB_OK;
@@ -161,8 +170,8 @@ int sdb_dcn_supported(const sdb_dcn_geom* g, int io_dtype, int math) {
   if (check_geom(g) || check_io(io_dtype, math)) return 0;
   if (math == SDB_MATH_FP32) return 1;
   const char* why = "";
-  if (!tc_supported(make_geo(*g), &why)) {
-    set_error("SDB_MATH_BF16 unsupported for this geometry: %s", why);
+  if (is_tf32(math) ? !tf32_supported(make_geo(*g), &why) : !tc_supported(make_geo(*g), &why)) {
+    set_error("%s unsupported for this geometry: %s", is_tf32(math) ? "SDB_MATH_TF32" : "SDB_MATH_BF16", why);
     return 0;
   }
   return 1;
@@ -281,6 +290,42 @@ int multi_fp32(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, co
   return SDB_OK;
 }
 
+// kind::tf32 forward (dcn_tf32.cu): validate the table, translate it, run.  `ws` == nullptr: only the size is wanted.
+int tf32_call(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, int nw, const Geo& g, int passes, uint8_t* ws,
+              size_t ws_bytes, size_t* need, bool size_only, cudaStream_t st) {
+  SDB_REQUIRE(probs && n >= 1 && n <= tcshared::MAX_PROBS, SDB_ERR_INVALID, "need 1..%d problems, got %d", tcshared::MAX_PROBS, n);
+  SDB_REQUIRE(w && nw >= 1 && nw <= tcshared::MAX_WEIGHTS, SDB_ERR_INVALID, "need 1..%d weight tensors, got %d", tcshared::MAX_WEIGHTS, nw);
+  TcProblem pb[tcshared::MAX_PROBS];
+  bool have_prep[tcshared::MAX_WEIGHTS];
+  const void *wt[tcshared::MAX_WEIGHTS], *bs[tcshared::MAX_WEIGHTS], *prep[tcshared::MAX_WEIGHTS];
+  for (int k = 0; k < nw; ++k) {
+    have_prep[k] = w[k].prepared != nullptr;
+    wt[k] = w[k].weight; bs[k] = w[k].bias; prep[k] = w[k].prepared;
+    SDB_REQUIRE(size_only || wt[k] || prep[k], SDB_ERR_INVALID, "weight %d: neither weight nor prepared image given", k);
+  }
+  for (int i = 0; i < n; ++i) {
+    const sdb_dcn_problem& q = probs[i];
+    SDB_REQUIRE(q.N >= 0 && q.H > 0 && q.W > 0, SDB_ERR_INVALID, "problem %d: bad size N=%d H=%d W=%d", i, q.N, q.H, q.W);
+    SDB_REQUIRE(q.weight_id >= 0 && q.weight_id < nw, SDB_ERR_INVALID, "problem %d: weight_id %d out of range", i, q.weight_id);
+    Geo gi = g;
+    gi.N = q.N; gi.H = q.H; gi.W = q.W;
+    gi.Ho = (q.H + 2 * g.ph - (g.dh * (g.KH - 1) + 1)) / g.sh + 1;
+    gi.Wo = (q.W + 2 * g.pw - (g.dw * (g.KW - 1) + 1)) / g.sw + 1;
+    SDB_REQUIRE(gi.Ho > 0 && gi.Wo > 0, SDB_ERR_INVALID, "problem %d: output size (%d x %d) is too small", i, gi.Ho, gi.Wo);
+    const char* why = "";
+    SDB_REQUIRE(tf32_supported(gi, &why), SDB_ERR_UNSUPPORTED, "problem %d: tf32 tensor-core path unsupported: %s", i, why);
+    TcProblem& t = pb[i];
+    t = TcProblem{};
+    t.d = Dims{q.N, q.H, q.W, gi.Ho, gi.Wo};
+    t.weight_id = q.weight_id;
+    t.x = q.x; t.off = q.offset; t.mask = q.mask; t.out = q.out;
+  }
+  *need = tf32_forward_workspace_bytes(pb, n, nw, have_prep, g, passes);
+  if (size_only) return SDB_OK;
+  SDB_REQUIRE(*need == 0 || (ws && ws_bytes >= *need), SDB_ERR_WORKSPACE, "forward workspace too small: %zu < %zu", ws_bytes, *need);
+  return tf32_forward_all(pb, n, wt, bs, prep, nw, g, passes, ws, st);
+}
+
 // the single-problem entry points are one-row tables
 struct Single {
   sdb_dcn_problem p;
@@ -317,6 +362,7 @@ size_t sdb_dcn_prepared_weight_bytes(const sdb_dcn_geom* g, int io_dtype, int ma
   if (!g) return 0;
   const sdb_dcn_geom cg = common_geom(g);
   if (check_geom(&cg) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
+  if (is_tf32(math)) return tf32_prepared_weight_bytes(make_geo(cg), tf32_passes(math));
   return tc_prepared_weight_bytes(make_geo(cg));
 }
 
@@ -326,6 +372,10 @@ int sdb_dcn_prepare_weights(const void* weight, const void* bias, const sdb_dcn_
   if (math == SDB_MATH_FP32) return SDB_OK;
   SDB_REQUIRE(weight && prepared, SDB_ERR_INVALID, "weight and prepared must be non-NULL");
   const char* why = "";
+  if (is_tf32(math)) {
+    SDB_REQUIRE(tf32_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_TF32 unsupported: %s", why);
+    return tf32_prepare_weights((const float*)weight, (const float*)bias, d, tf32_passes(math), prepared, st);
+  }
   SDB_REQUIRE(tc_supported(d, &why), SDB_ERR_UNSUPPORTED, "SDB_MATH_BF16 unsupported: %s", why);
   return tc_prepare_weights(weight, bias, d, io_dtype, prepared, 3, st);
 }
@@ -335,6 +385,11 @@ size_t sdb_dcn_multi_workspace_bytes(const sdb_dcn_problem* problems, int32_t n,
   if (!g) return 0;
   const sdb_dcn_geom cg = common_geom(g);
   if (check_geom(&cg) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
+  if (is_tf32(math)) {   // the backward of the tf32 modes is the exact fp32 path: no workspace
+    size_t need = 0;
+    if (backward || tf32_call(problems, n, weights, nw, make_geo(cg), tf32_passes(math), nullptr, 0, &need, true, nullptr)) return 0;
+    return need;
+  }
   MultiCall mc;
   if (build_call(problems, n, weights, nw, make_geo(cg), backward != 0, mc)) return 0;
   return mc.plan.total;
@@ -349,6 +404,10 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].out), SDB_ERR_INVALID,
                 "problem %d: x, offset and out must be non-NULL", i);
   if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, false, 1.f, 0, st);
+  if (is_tf32(math)) {
+    size_t need = 0;
+    return tf32_call(problems, n, weights, nw, d, tf32_passes(math), (uint8_t*)workspace, workspace_bytes, &need, false, st);
+  }
   MultiCall mc;
   rc = build_call(problems, n, weights, nw, d, false, mc);
   if (rc) return rc;
@@ -395,7 +454,7 @@ int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb
   for (int i = 0; i < n; ++i)
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].grad_out), SDB_ERR_INVALID,
                 "problem %d: x, offset and grad_out must be non-NULL", i);
-  if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, true, scale, flags, st);
+  if (math == SDB_MATH_FP32 || is_tf32(math)) return multi_fp32(problems, n, weights, d, true, scale, flags, st);
   return backward_multi_impl(problems, n, weights, nw, d, io_dtype, scale, 0, flags, workspace, workspace_bytes, st);
 }
 
@@ -448,7 +507,7 @@ int sdb_dcn_backward_data(const void* x, const float* offset, const float* mask,
   SDB_PROLOGUE();
   SDB_REQUIRE(x && offset && weight && grad_out, SDB_ERR_INVALID,
               "x, offset, weight and grad_out must be non-NULL");
-  if (math == SDB_MATH_FP32)
+  if (math == SDB_MATH_FP32 || is_tf32(math))
     return simt_backward_data((const float*)x, offset, mask, (const float*)weight,
                               (const float*)grad_out, (float*)grad_x, grad_offset, grad_mask, d, st);
   Single s = single_of(g);
@@ -465,7 +524,7 @@ int sdb_dcn_backward_weight(const void* x, const float* offset, const float* mas
                             size_t workspace_bytes, const void* x_packed, void* stream) {
   SDB_PROLOGUE();
   SDB_REQUIRE(x && offset && grad_out, SDB_ERR_INVALID, "x, offset and grad_out must be non-NULL");
-  if (math == SDB_MATH_FP32)
+  if (math == SDB_MATH_FP32 || is_tf32(math))
     return simt_backward_weight((const float*)x, offset, mask, (const float*)grad_out, grad_weight,
                                 grad_bias, scale, d, st);
   Single s = single_of(g);

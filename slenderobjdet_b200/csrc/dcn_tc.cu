@@ -548,7 +548,7 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
   const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < grid_sms() ? total : grid_sms();
   const bool obf = io_dtype == SDB_BF16;
   if (lpp == 16) return obf ? launch_fwd<16, true>(p, smem, grid, st) : launch_fwd<16, false>(p, smem, grid, st);
   return obf ? launch_fwd<8, true>(p, smem, grid, st) : launch_fwd<8, false>(p, smem, grid, st);

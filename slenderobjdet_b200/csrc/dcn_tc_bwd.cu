@@ -1160,7 +1160,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
       SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
       p.nsb = (int)nsb;
       const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
-      const int grid = total < num_sms() ? total : num_sms();
+      const int grid = total < grid_sms() ? total : grid_sms();
       if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<128>, smem);
       else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
       {

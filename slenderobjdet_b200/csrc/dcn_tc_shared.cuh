@@ -69,6 +69,15 @@ int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dty
                        cudaStream_t st);   // which: 1 = forward image, 2 = dcol image (3 = both)
 int tc_lanes_per_pixel(const Geo& g);
 
+// tcgen05 kind::tf32 forward with float32 tensors (dcn_tf32.cu); passes = 1 (tf32) or 3 (error-compensated, fp32-accurate)
+bool tf32_supported(const Geo& g, const char** why);
+size_t tf32_prepared_weight_bytes(const Geo& g, int passes);
+int tf32_prepare_weights(const float* w, const float* bias, const Geo& g, int passes, void* prepared, cudaStream_t st);
+size_t tf32_forward_workspace_bytes(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g,
+                                    int passes);
+int tf32_forward_all(const TcProblem* pb, int n, const void* const* weights, const void* const* biases,
+                     const void* const* prepared, int nweights, const Geo& g, int passes, uint8_t* ws, cudaStream_t st);
+
 namespace tcshared {
 using namespace tc;
 
@@ -410,6 +419,14 @@ __device__ __forceinline__ BSample make_bsample(const Geo& g, const float* __res
 }
 
 
+// SMs the persistent kernels may occupy: all of them minus the caller's reserve (sdb_set_sm_reserve) -- a statically
+// scheduled persistent CTA that has to wait for an SM held by a co-running collective delays the whole kernel by that wait
+extern int g_sm_reserve;
+inline int num_sms();
+inline int grid_sms() {
+  const int n = num_sms() - g_sm_reserve;
+  return n > 1 ? n : 1;
+}
 inline int num_sms() {
   static int n = 0;
   if (!n) {

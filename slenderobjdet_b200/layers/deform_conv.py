@@ -16,6 +16,9 @@ Arithmetic (``set_dcn_math`` / ``SDB_DCN_MATH``).  The reference computes float3
 tensors run the exact fp32 kernels (rel <= 1e-4 against the oracle).  The tcgen05 tensor-core kernels (bf16
 operands, fp32 accumulation in TMEM, rel <= 1e-2) are used when the TENSORS are bfloat16, under
 ``torch.autocast(dtype=torch.bfloat16)``, or when ``set_dcn_math("bf16")`` asks for them explicitly.
+``set_dcn_math("tf32")`` / ``"tf32x3"`` run the FORWARD of float32 tensors on ``tcgen05.mma.kind::tf32`` (fp32
+bilinear sampling; one pass with tf32-rounded operands, rel ~3e-4, or three error-compensated passes, rel ~2e-5 at
+K = 2304); their backward stays on the exact fp32 kernels, so gradients keep fp32 accuracy.
 float16 tensors are computed in float32 (the reference dispatches half too); float64 is refused.
 """
 import contextlib
@@ -32,16 +35,20 @@ from torch.nn.modules.utils import _pair
 
 from .. import _lib
 
-_MATH = os.environ.get("SDB_DCN_MATH", "auto")  # "auto" | "bf16" | "fp32"
+_MATH = os.environ.get("SDB_DCN_MATH", "auto")  # "auto" | "bf16" | "fp32" | "tf32" | "tf32x3"
+_MODES = ("auto", "bf16", "fp32", "tf32", "tf32x3")
 
 
 def set_dcn_math(mode):
     """'auto': follow the tensors -- float32 tensors use the exact fp32 kernels, bfloat16 tensors (or float32 under
     bf16 autocast) the tcgen05 tensor-core kernels when the geometry allows, else fp32;
     'bf16': require the tensor-core path whatever the tensor dtype (tolerance rel <= 1e-2);
-    'fp32': always the exact fp32 path (rel <= 1e-4)."""
+    'fp32': always the exact fp32 path (rel <= 1e-4);
+    'tf32' / 'tf32x3': float32 tensors, forward on kind::tf32 tensor cores in one pass (rel ~3e-4) / three
+    error-compensated passes (rel ~2e-5, inside the 1e-4 bound of fp32 math), backward on the exact fp32 kernels; geometries the tensor-core kernel does not
+    cover raise."""
     global _MATH
-    assert mode in ("auto", "bf16", "fp32")
+    assert mode in _MODES
     _MATH = mode
 
 
@@ -118,6 +125,11 @@ def _pick_math(g, iod, autocast=False):
     lib = _lib.lib()
     if _MATH == "fp32":
         return _lib.SDB_MATH_FP32
+    if _MATH in ("tf32", "tf32x3"):
+        mth = _lib.SDB_MATH_TF32 if _MATH == "tf32" else _lib.SDB_MATH_TF32X3
+        if not lib.sdb_dcn_supported(ctypes.byref(g), _lib.SDB_F32, mth):
+            raise RuntimeError("slender_b200: " + lib.sdb_last_error().decode())
+        return mth
     if _MATH == "auto" and iod == _lib.SDB_F32 and not autocast:
         return _lib.SDB_MATH_FP32     # a float32 model keeps the reference's fp32 numerics unless told otherwise
     ok = bool(lib.sdb_dcn_supported(ctypes.byref(g), iod, _lib.SDB_MATH_BF16))
@@ -154,7 +166,7 @@ def _plan(input, weight, g):
     cdt = _compute_dtype(input)
     iod = _lib.SDB_F32 if cdt == torch.float32 else _lib.SDB_BF16
     mth = _pick_math(g, iod, autocast)
-    if mth == _lib.SDB_MATH_FP32 and iod != _lib.SDB_F32:
+    if mth != _lib.SDB_MATH_BF16 and iod != _lib.SDB_F32:
         cdt, iod = torch.float32, _lib.SDB_F32
     ho, wo = ctypes.c_int32(0), ctypes.c_int32(0)
     _lib.check(lib.sdb_dcn_output_size(ctypes.byref(g), ho, wo))
@@ -212,9 +224,9 @@ def invalidate_prepared_weights():
 
 def _prepared_weights(weight, bias, g, iod, mth):
     """-> uint8 tensor with the operand images of (weight, bias), cached on (tensor identity, version)."""
-    if mth != _lib.SDB_MATH_BF16:
+    if mth == _lib.SDB_MATH_FP32:
         return None
-    key = (id(weight), weight.device.index)
+    key = (id(weight), weight.device.index, mth)
     ver = (weight._version, weight.data_ptr(), None if bias is None else (id(bias), bias._version, bias.data_ptr()),
            iod, g.C_in, g.C_out, g.kH, g.kW)
     hit = _PREPARED.get(key)
@@ -259,6 +271,7 @@ def _multi_forward(xs, offs, masks, weights, biases, wids, groups, g, iod, mth, 
     lib = _lib.lib()
     n, dev = len(xs), xs[0].device
     tc = mth == _lib.SDB_MATH_BF16
+    tf = mth in _lib.SDB_TF32_MODES
     gp = ctypes.byref(g)
     outs, packed, cols = [], [], []
     for i, x in enumerate(xs):
@@ -275,7 +288,7 @@ def _multi_forward(xs, offs, masks, weights, biases, wids, groups, g, iod, mth, 
     prep = [_prepared_weights(w, b, g, iod, mth) for w, b in zip(weights, biases)]
     wts = (_lib.Weights * len(weights))(*[_lib.Weights(_lib.addr(w), _lib.addr(b), _lib.addr(p), None, None)
                                           for w, b, p in zip(weights, biases, prep)])
-    wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 0)) if tc else 0
+    wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 0)) if (tc or tf) else 0
     ws = _ws(wsb, dev)
     with _on_device(dev):
         _lib.check(lib.sdb_dcn_forward_multi(probs, n, wts, len(weights), gp, iod, mth, _lib.ptr(ws), wsb,
@@ -290,6 +303,8 @@ def _multi_backward(xs, offs, masks, weights, biases, wids, groups, gys, packed,
     -> (grad_x list, grad_offset list, grad_mask list, grad_weight list (fp32), grad_bias list (fp32))."""
     lib = _lib.lib()
     n, dev = len(xs), xs[0].device
+    if mth in _lib.SDB_TF32_MODES:   # the tf32 modes are forward modes: gradients come from the exact fp32 kernels
+        mth, packed = _lib.SDB_MATH_FP32, None
     tc = mth == _lib.SDB_MATH_BF16
     gp = ctypes.byref(g)
     # v1 computes grad_input and grad_offset together if either is needed (deform_conv.py:88); the kernels can skip either

@@ -22,7 +22,7 @@ def _header_functions():
 
 def test_library_is_built_and_loads():
     assert os.path.exists(_lib.LIB_PATH), "run python -m slenderobjdet_b200.csrc.build"
-    assert _lib.lib().sdb_abi_version() == 3
+    assert _lib.lib().sdb_abi_version() == 4
 
 
 def test_exports_every_declared_symbol():
