@@ -43,7 +43,9 @@ sys.path.insert(0, ROOT)
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]  # P3..P7 of an 800x1344 image
 C_IN = C_OUT = 256
 BATCH_PER_GPU = 2
-NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "8"))  # CTAs of the overlapped all-reduce = SMs the persistent kernels leave free
+NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "0"))  # developer knob: cap the overlapped all-reduce at this many CTAs and leave
+# that many SMs free in the persistent kernels (sdb_set_sm_reserve).  Measured on 2 GPUs: 0 (NCCL default) 0.877 ms, 16 -> 0.877, 8 -> 0.891,
+# 4 -> 0.952 (the all-reduce outlasts the data-gradient kernels): SM contention is not what the N > 1 step pays for; default off.
 HEAD_PARAMS = 5341556  # RepPoints head parameter count; all-reduced when N > 1
 FLOP_PER_PIXEL_PASS = 2 * C_IN * C_OUT * 9  # 1 179 648
 METRIC = "reppoints_head_dcn_fwd_bwd_images_per_s"
@@ -489,7 +491,7 @@ def run_ours(args):
                        "launch": mode, "launches_per_step": int(launches_per_step + torch_fills_per_step),
                        "tflops_per_s": round(flops_step * world / (step_ms * 1e-3) / 1e12, 2),
                        "allreduce_bytes": HEAD_PARAMS * 4 if world > 1 else 0,
-                       "allreduce": ("overlapped with grad_input / grad_offset on %d NCCL CTAs (that many SMs left free by the persistent kernels), 1/world folded into the kernel" % NCCL_CTAS) if world > 1 else None},
+                       "allreduce": "overlapped with grad_input / grad_offset, 1/world folded into the kernel" if world > 1 else None},
             "roofline": roofline,
             "parity": parity,
             "cpu_baseline": {"value": round(cb["value"], 5), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
