@@ -247,6 +247,42 @@ int sdb_centerness_targets(const float* reg_targets, int64_t R, float* out, void
  * c = min(l,r)/max(l,r) * min(t,b)/max(t,b), w = l + r, h = t + b -- the slender-object exponent. */
 int sdb_slender_centerness_targets(const float* reg_targets, int64_t R, float* out, void* stream);
 
+/* ---- GroupNorm + ReLU of the head towers ---------------------------------------
+ * The towers are stacks of Conv2d(3x3, bias=False) -> GroupNorm(32, C) -> ReLU(inplace)
+ * (sd/modeling/meta_arch/reppoints/reppointsv2.py:644-675, applied per FPN level :733-736; fcos/fcos.py:494-538).
+ * One call normalises every tensor of a table (FPN levels x towers): y = relu(group_norm(x, G, gamma, beta, eps)) with
+ * torch.nn.functional.group_norm semantics (biased variance over (C/G, H, W) per image, eps inside the square root).
+ * Tensors NCHW contiguous, io_dtype float32 or bfloat16; gamma / beta / their gradients float32 [C]; `stats`
+ * [N, G, 2] float32 = (mean, rstd), written by the forward and read by the backward.  Backward: grad_x is
+ * overwritten (may be NULL), grad_gamma / grad_beta are ACCUMULATED into (summed over images and over every tensor
+ * that names the parameter set, in a fixed order); the ReLU mask is recomputed from x.  `relu` == 0 gives plain
+ * GroupNorm.  Workspace: sdb_gn_relu_workspace_bytes (same size for both directions). */
+typedef struct {
+  const void* x;        /* [N, C, H, W] input of the normalisation (the convolution's output) */
+  void* y;              /* forward: output */
+  const void* grad_y;   /* backward: gradient w.r.t. y */
+  void* grad_x;         /* backward: gradient w.r.t. x, or NULL */
+  float* stats;         /* [N, G, 2] */
+  int32_t N, HW;        /* batch, H * W */
+  int32_t param_id;     /* which (gamma, beta) of the parameter table */
+  int32_t reserved;
+} sdb_gn_tensor;
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  float* grad_gamma;    /* backward, may be NULL */
+  float* grad_beta;
+} sdb_gn_params;
+#define SDB_GN_MAX_TENSORS 16
+#define SDB_GN_MAX_PARAMS 4
+size_t sdb_gn_relu_workspace_bytes(const sdb_gn_tensor* tensors, int32_t n, int32_t C, int32_t G);
+int sdb_gn_relu_forward(const sdb_gn_tensor* tensors, int32_t n, const sdb_gn_params* params, int32_t n_params, int32_t C,
+                        int32_t G, float eps, int32_t relu, int io_dtype, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int sdb_gn_relu_backward(const sdb_gn_tensor* tensors, int32_t n, const sdb_gn_params* params, int32_t n_params, int32_t C,
+                         int32_t G, float eps, int32_t relu, int io_dtype, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* ---- RepPoints DCN offset construction (first piece) -------------------------
  * dcn_offset = ((1 - gm) * pts.detach() + gm * pts) - dcn_base_offset   (reppointsv2.py:638-642, 742-744;
  * rpd.py:105-110, 624-635), fused into one pass.  pts, out: [N, 2*K, H, W] float32, K = ks*ks points;

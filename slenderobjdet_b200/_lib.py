@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
     "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
-    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count", "sdb_set_sm_reserve",
+    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count", "sdb_set_sm_reserve", "sdb_gn_relu_workspace_bytes", "sdb_gn_relu_forward", "sdb_gn_relu_backward",
 ]
 
 
@@ -50,6 +50,19 @@ class Weights(ctypes.Structure):
     """sdb_dcn_weights: one weight tensor of a whole-head call"""
     _fields_ = [("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("prepared", ctypes.c_void_p),
                 ("grad_weight", ctypes.c_void_p), ("grad_bias", ctypes.c_void_p)]
+
+
+class GnTensor(ctypes.Structure):
+    """sdb_gn_tensor"""
+    _fields_ = [("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("grad_y", ctypes.c_void_p), ("grad_x", ctypes.c_void_p),
+                ("stats", ctypes.c_void_p), ("N", ctypes.c_int32), ("HW", ctypes.c_int32), ("param_id", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+class GnParams(ctypes.Structure):
+    """sdb_gn_params"""
+    _fields_ = [("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("grad_gamma", ctypes.c_void_p),
+                ("grad_beta", ctypes.c_void_p)]
 
 
 class PPLevel(ctypes.Structure):
@@ -120,6 +133,11 @@ def _declare(lib):
     lib.sdb_reppoints_dcn_offset_backward.argtypes = [_vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp]
     lib.sdb_launch_count.restype = ctypes.c_longlong
     lib.sdb_launch_count.argtypes = []
+    lib.sdb_gn_relu_workspace_bytes.restype = _sz
+    lib.sdb_gn_relu_workspace_bytes.argtypes = [ctypes.POINTER(GnTensor), _i32, _i32, _i32]
+    for f in (lib.sdb_gn_relu_forward, lib.sdb_gn_relu_backward):
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.POINTER(GnTensor), _i32, ctypes.POINTER(GnParams), _i32, _i32, _i32, _f32, _i32, _i32, _vp, _sz, _vp]
     lib.sdb_set_sm_reserve.restype = ctypes.c_int
     lib.sdb_set_sm_reserve.argtypes = [_i32]
     lib.sdb_profile_enable.argtypes = [ctypes.c_int]

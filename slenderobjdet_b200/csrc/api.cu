@@ -210,6 +210,15 @@ int build_call(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, in
     SDB_REQUIRE(gi.Ho > 0 && gi.Wo > 0, SDB_ERR_INVALID, "problem %d: output size (%d x %d) is too small", i, gi.Ho, gi.Wo);
     const char* why = "";
     SDB_REQUIRE(tc_supported(gi, &why), SDB_ERR_UNSUPPORTED, "problem %d: tensor-core path unsupported: %s", i, why);
+    // plain-convolution mode: offset == NULL for EVERY problem of the call (the towers' Conv2d, reppointsv2.py:644-675)
+    SDB_REQUIRE((q.offset == nullptr) == (probs[0].offset == nullptr), SDB_ERR_INVALID,
+                "problem %d: either every problem has an offset tensor or none has (plain convolution)", i);
+    if (q.offset == nullptr) {
+      SDB_REQUIRE(q.mask == nullptr && q.grad_offset == nullptr && q.grad_mask == nullptr, SDB_ERR_INVALID,
+                  "problem %d: plain convolution takes no mask and yields no offset / mask gradient", i);
+      SDB_REQUIRE(tc_conv_supported(gi, backward && q.grad_x != nullptr, &why), SDB_ERR_UNSUPPORTED,
+                  "problem %d: plain convolution unsupported: %s", i, why);
+    }
     TcProblem& t = mc.pb[i];
     t = TcProblem{};
     t.d = Dims{q.N, q.H, q.W, gi.Ho, gi.Wo};
@@ -238,7 +247,7 @@ int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g
     if (!prep) {
       int which = 0;   // only the images this call reads
       if (!backward) which = 1;
-      else {
+      else if (!mc.plan.conv) {
         for (int i = 0; i < n; ++i)
           if (mc.pb[i].weight_id == k && (mc.pb[i].goff || mc.pb[i].gmask || mc.pb[i].gx)) which |= 2;
       }
@@ -401,8 +410,8 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_
   SDB_MULTI_PROLOGUE();
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)
-    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].out), SDB_ERR_INVALID,
-                "problem %d: x, offset and out must be non-NULL", i);
+    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].out && (problems[i].offset || math == SDB_MATH_BF16)),
+                SDB_ERR_INVALID, "problem %d: x, offset and out must be non-NULL (offset == NULL, plain convolution, needs SDB_MATH_BF16)", i);
   if (math == SDB_MATH_FP32) return multi_fp32(problems, n, weights, d, false, 1.f, 0, st);
   if (is_tf32(math)) {
     size_t need = 0;
@@ -441,6 +450,18 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     for (int k = 0; k < nw; ++k) mc.gw[k] = mc.gb[k] = nullptr;
   if (flags & SDB_BWD_WEIGHT_ONLY)
     for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
+  if (mc.plan.conv) {
+    SDB_REQUIRE(!accumulate_gx && !(flags & SDB_BWD_GRAD_PACKED), SDB_ERR_UNSUPPORTED,
+                "plain convolution: grad_x is overwritten, and SDB_BWD_GRAD_PACKED is not supported");
+    const void* wt[tcshared::MAX_WEIGHTS];
+    for (int k = 0; k < nw; ++k) {
+      wt[k] = weights[k].weight;
+      bool needs = false;
+      for (int i = 0; i < n; ++i) needs |= mc.pb[i].weight_id == k && mc.pb[i].gx != nullptr;
+      SDB_REQUIRE(!needs || wt[k], SDB_ERR_INVALID, "weight %d: the weight tensor is needed for grad_x", k);
+    }
+    return tc_conv_backward_all(mc.pb, n, wt, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, (uint8_t*)workspace, st);
+  }
   return tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
                          (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st);
 }
@@ -452,8 +473,8 @@ int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb
   SDB_REQUIRE((flags & ~7) == 0 && (flags & 3) != 3, SDB_ERR_INVALID, "bad backward flags %d", flags);
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)
-    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].offset && problems[i].grad_out), SDB_ERR_INVALID,
-                "problem %d: x, offset and grad_out must be non-NULL", i);
+    SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].grad_out && (problems[i].offset || math == SDB_MATH_BF16)),
+                SDB_ERR_INVALID, "problem %d: x, offset and grad_out must be non-NULL (offset == NULL, plain convolution, needs SDB_MATH_BF16)", i);
   if (math == SDB_MATH_FP32 || is_tf32(math)) return multi_fp32(problems, n, weights, d, true, scale, flags, st);
   return backward_multi_impl(problems, n, weights, nw, d, io_dtype, scale, 0, flags, workspace, workspace_bytes, st);
 }

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SO = os.path.join(PKG, "libslender_b200.so")
-SOURCES = ["api.cu", "dcn_simt.cu", "dcn_tc.cu", "dcn_tc_bwd.cu", "dcn_tc_dx.cu", "dcn_tf32.cu", "assign.cu", "losses.cu", "postproc.cu"]
+SOURCES = ["api.cu", "dcn_simt.cu", "dcn_tc.cu", "dcn_tc_bwd.cu", "dcn_tc_dx.cu", "dcn_tf32.cu", "gn.cu", "assign.cu", "losses.cu", "postproc.cu"]
 HEADERS = ["common.cuh", "tc_common.cuh", "dcn_tc_shared.cuh", os.path.join("..", "..", "include", "slender_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -38,11 +38,13 @@ constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
 // tcgen05.mma reads:
 //   image 0 (forward B operand)   per (channel chunk of `cps`, tap, 64-channel block): [O rows][64 c]
 //   image 1 (dcol = dY W^T)       per (tap, channel chunk of `nch`, 64-o block):       [nch rows (c)][64 o], o >= O zero
+//   image 2 (plain-convolution grad_input = conv(dY, W')): image 0 of W'[c][o][i][j] = W[o][c][KH-1-i][KW-1-j], i.e. the
+//           forward B operand of the convolution with input / output channels swapped and the taps reversed
 // blockIdx.y selects the image; bias -> fp32 behind them.
 struct PrepLayout {
-  size_t fwd_off, dgrad_off, bias_off, total;
-  int cps, nch, okb;
-  int which;   // images to write: 1 = forward, 2 = dcol (backward data)
+  size_t fwd_off, dgrad_off, bias_off, conv_off, total;
+  int cps, nch, okb, cps_t;
+  int which;   // images to write: 1 = forward, 2 = dcol (backward data), 4 = transposed convolution
 };
 template <typename T>
 __global__ void __launch_bounds__(256) prep_weights_kernel(const T* __restrict__ w, const T* __restrict__ bias,
@@ -72,6 +74,26 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const T* __restrict__
     if (blockIdx.x == 0)
       for (int o = threadIdx.x; o < O; o += blockDim.x)
         reinterpret_cast<float*>(img + L.bias_off)[o] = bias ? to_f32(bias[o]) : 0.f;
+    return;
+  }
+  if (which == 2) {
+    // W' : output channels C (rows), input channels O (K), taps reversed
+    const int kbps = L.cps_t / 64;
+    const long long total = (long long)C * taps * (O / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c8 = (int)(i % (O / 8));
+      const int tap = (int)((i / (O / 8)) % taps);
+      const int orow = (int)(i / ((long long)(O / 8) * taps));   // = input channel c of W
+      const int ck = c8 * 8;                                      // = output channel o of W
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = to_f32(w[((size_t)(ck + j) * C + orow) * taps + (taps - 1 - tap)]);
+      uint4 pk;
+      pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+      pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+      const size_t tile = ((size_t)(ck / L.cps_t) * taps + tap) * kbps + ((ck % L.cps_t) >> 6);
+      *reinterpret_cast<uint4*>(img + L.conv_off + tile * ((size_t)C * 128) + sw128_offset(orow, (ck & 63) >> 3)) = pk;
+    }
     return;
   }
   const int o8n = L.okb * 8;   // 8-wide o chunks incl. zero padding
@@ -110,7 +132,7 @@ __device__ __forceinline__ RawOff fetch_raw(const Geo& g, const float* __restric
                                             const float* __restrict__ mask, bool valid, int n, int ho, int wo,
                                             int tap) {
   RawOff r = {0.f, 0.f, 1.f};
-  if (!valid) return r;
+  if (!valid || !off) return r;   // off == nullptr: plain convolution (zero offsets)
   const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
   const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
   r.dy = __ldg(o);
@@ -166,7 +188,9 @@ struct FwdParams {
 
 
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
-template <int LPP, bool OUT_BF16>
+// CONV: plain convolution (no offsets, no mask): one source row per (pixel, tap) -- one 16-byte load per lane instead of
+// four, no interpolation arithmetic; the descriptor is (row offset, inside-the-image flag).
+template <int LPP, bool OUT_BF16, bool CONV>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   constexpr int CPS = LPP * 8;           // channels per A stage
   constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
@@ -347,9 +371,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
           const int tap = lane / PIX_PER_WARP + r * TPR;
-          raw[r] = fetch_raw(g, pr.off, pr.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
+          if (!CONV) raw[r] = fetch_raw(g, pr.off, pr.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
         }
-        {
+        if (!CONV) {
           const int nwork = work + gridDim.x;
           if (nwork < num_work) {
             const int npi = find_range(p.map, nwork);
@@ -372,7 +396,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
           const int tap = lane / PIX_PER_WARP + r * TPR;
-          if (tap < taps) {
+          if (CONV) {
+            if (tap < taps) {
+              const int i = tap / g.KW, j = tap - i * g.KW;
+              const int h = ho * g.sh - g.ph + i * g.dh, w = wo * g.sw - g.pw + j * g.dw;
+              const bool ok = valid && h >= 0 && h < g.H && w >= 0 && w < g.W;
+              uint4 o;
+              o.x = ok ? (uint32_t)((n * g.H + h) * g.W + w) * (uint32_t)(C / 8) : 0u;
+              o.y = ok ? 1u : 0u;
+              o.z = o.w = 0u;
+              *reinterpret_cast<uint4*>((sD + tap * TILE_M + r0 + px)->off) = o;
+            }
+          } else if (tap < taps) {
             const Sample sm_ = make_sample(g, raw[r], valid, n, ho, wo, tap);
             uint4 o, w;
             o.x = (uint32_t)sm_.idx[0] * (uint32_t)(C / 8); o.y = (uint32_t)sm_.idx[1] * (uint32_t)(C / 8);
@@ -392,12 +427,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
       {                                                                                          \
         const GDesc* d_ = sD + (tap_) * TILE_M + r0 + (it_) * PPI + grp;                         \
         const uint4 o_ = *reinterpret_cast<const uint4*>(d_->off);                               \
-        wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                     \
         const uint4* xb_ = xbase + (ch_) * (CPS / 8);                                            \
         v[slot_][0] = __ldg(xb_ + o_.x);                                                         \
-        v[slot_][1] = __ldg(xb_ + o_.y);                                                         \
-        v[slot_][2] = __ldg(xb_ + o_.z);                                                         \
-        v[slot_][3] = __ldg(xb_ + o_.w);                                                         \
+        if (CONV) {                                                                              \
+          wq[slot_].x = o_.y;                                                                    \
+        } else {                                                                                 \
+          wq[slot_] = *reinterpret_cast<const uint4*>(d_->w2);                                   \
+          v[slot_][1] = __ldg(xb_ + o_.y);                                                       \
+          v[slot_][2] = __ldg(xb_ + o_.z);                                                       \
+          v[slot_][3] = __ldg(xb_ + o_.w);                                                       \
+        }                                                                                        \
       }
 #define SDB_INTERP(a_, slot_)                                                                    \
         a_.x = bf2_fma(wq[slot_].w, v[slot_][3].x, bf2_fma(wq[slot_].z, v[slot_][2].x, bf2_fma(wq[slot_].y, v[slot_][1].x, bf2_mul(wq[slot_].x, v[slot_][0].x)))); \
@@ -417,7 +456,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         for (int it = 0; it < ITERS; ++it) {
           const int slot = it % RING;
           uint4 a;
-          SDB_INTERP(a, slot)
+          if (CONV) {
+            a = wq[slot].x ? v[slot][0] : make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            SDB_INTERP(a, slot)
+          }
           const uint32_t soff = sw128_offset(r0 + it * PPI + grp, lig & 7);
           *reinterpret_cast<uint4*>(dst + soff) = a;
           if (colp) __stcs(reinterpret_cast<uint4*>(colp + (size_t)st * A_BYTES + soff), a);   // streaming: keep x in L2
@@ -442,11 +485,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
-template <int LPP, bool OUT_BF16>
+template <int LPP, bool OUT_BF16, bool CONV>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16>), smem);
+  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV>), smem);
   ProfScope prof(SDB_OP_FORWARD, st);
-  dcn_fwd_tc_kernel<LPP, OUT_BF16><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -496,6 +539,8 @@ static PrepLayout prep_layout(const Geo& g) {
   L.fwd_off = o;   o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
   L.dgrad_off = o; o = align_up(o + (size_t)g.taps() * g.C * L.okb * 64 * 2, 1024);
   L.bias_off = o;  o = align_up(o + (size_t)g.O * 4, 1024);
+  L.cps_t = g.O % 128 == 0 ? 128 : 64;
+  L.conv_off = o;  o = align_up(o + (size_t)g.taps() * g.C * g.O * 2, 1024);
   L.total = o;
   return L;
 }
@@ -504,15 +549,15 @@ TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bia
   const PrepLayout L = prep_layout(g);
   const uint8_t* b = (const uint8_t*)prepared;
   TcWeightImages w;
-  w.fwd = b + L.fwd_off; w.dgrad = b + L.dgrad_off;
+  w.fwd = b + L.fwd_off; w.dgrad = b + L.dgrad_off; w.convt = b + L.conv_off;
   w.bias = has_bias ? (const float*)(b + L.bias_off) : nullptr;
   return w;
 }
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
                        cudaStream_t st) {
   PrepLayout L = prep_layout(g);
-  L.which = which & 3;
-  const int nimg = (which & 1) + ((which >> 1) & 1);
+  L.which = which & 7;
+  const int nimg = (which & 1) + ((which >> 1) & 1) + ((which >> 2) & 1);
   if (nimg == 0) return SDB_OK;
   const long long total = (long long)g.taps() * g.C * L.okb * 8;
   const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
@@ -550,8 +595,12 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   const int grid = total < grid_sms() ? total : grid_sms();
   const bool obf = io_dtype == SDB_BF16;
-  if (lpp == 16) return obf ? launch_fwd<16, true>(p, smem, grid, st) : launch_fwd<16, false>(p, smem, grid, st);
-  return obf ? launch_fwd<8, true>(p, smem, grid, st) : launch_fwd<8, false>(p, smem, grid, st);
+  if (pb[0].off == nullptr) {   // plain convolution: every problem of the call (api.cu checks that they agree)
+    if (lpp == 16) return obf ? launch_fwd<16, true, true>(p, smem, grid, st) : launch_fwd<16, false, true>(p, smem, grid, st);
+    return obf ? launch_fwd<8, true, true>(p, smem, grid, st) : launch_fwd<8, false, true>(p, smem, grid, st);
+  }
+  if (lpp == 16) return obf ? launch_fwd<16, true, false>(p, smem, grid, st) : launch_fwd<16, false, false>(p, smem, grid, st);
+  return obf ? launch_fwd<8, true, false>(p, smem, grid, st) : launch_fwd<8, false, false>(p, smem, grid, st);
 }
 
 }  // namespace sdb

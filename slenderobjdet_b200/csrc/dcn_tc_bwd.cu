@@ -994,6 +994,8 @@ Side* side_of_device() {
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward) {
   TcPlan P{};
   const int okb = okb_of(g);
+  const bool conv = n > 0 && pb[0].off == nullptr;   // plain convolution: no dcol tiles, no transposed index
+  P.conv = conv;
   size_t o = 0;
   for (int i = 0; i < n; ++i) {
     const Geo gi = with_dims(g, pb[i].d);
@@ -1002,12 +1004,17 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     if (backward) {
       const size_t tiles = (size_t)cdiv(gi.P(), TILE_M);
       P.gy_off[i] = o;  o = align_up(o + tiles * okb * (TILE_M * 128), 1024);
-      P.dcol_off[i] = o; o = align_up(o + tiles * g.taps() * nch_chunks(g) * stg_tile_bytes(nch_of(g)), 1024);
+      P.dcol_off[i] = o;
+      if (!conv) o = align_up(o + tiles * g.taps() * nch_chunks(g) * stg_tile_bytes(nch_of(g)), 1024);
+      P.gyp_off[i] = o;
+      if (conv) o = align_up(o + (size_t)gi.P() * g.O * 2, 1024);
     }
   }
   for (int w = 0; w < nweights; ++w) {
     P.prep_off[w] = o;
-    if (!have_prepared[w]) o = align_up(o + tc_prepared_weight_bytes(g), 1024);
+    if (!have_prepared[w] && !(conv && backward)) o = align_up(o + tc_prepared_weight_bytes(g), 1024);
+    P.convw_off[w] = o;
+    if (conv && backward) o = align_up(o + tc_prepared_weight_bytes(g), 1024);
   }
   if (backward) {
     // offset groups: canonical index = order of first appearance; problems with group < 0 are their own group
@@ -1022,7 +1029,7 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     }
     P.ngroups = ng;
     long long keys = 0, ents = 1;
-    for (int k = 0; k < ng; ++k) {
+    for (int k = 0; k < (conv ? 0 : ng); ++k) {
       const Geo gk = with_dims(g, pb[P.group_rep[k]].d);
       P.key_base[k] = keys;
       const long long pix_in = (long long)cdiv((long long)gk.N * gk.H * gk.W, TILE_M) * TILE_M;
@@ -1032,14 +1039,16 @@ TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepar
     }
     P.nkeys = keys;
     P.scan_blocks = cdiv(keys, SCAN_PER_BLOCK);
-    // cnt and the entry pool are cleared by ONE memset (pad entries must read as zero): keep them adjacent
-    P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
-    P.ent_cap = (long long)cdiv(ents, LIST_ALIGN) * LIST_ALIGN;
-    P.ent_off = o;   o = align_up(o + (size_t)P.ent_cap * sizeof(CEntry), 1024);
-    P.clear_bytes = o - P.cnt_off;
-    P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
-    P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
-    P.blk_off = o;   o = align_up(o + (size_t)(P.ent_cap / LIST_ALIGN) * ENT_BLOCK_BYTES, 1024);
+    if (!conv) {
+      // cnt and the entry pool are cleared by ONE memset (pad entries must read as zero): keep them adjacent
+      P.cnt_off = o;   o = align_up(o + (size_t)keys * 4, 1024);
+      P.ent_cap = (long long)cdiv(ents, LIST_ALIGN) * LIST_ALIGN;
+      P.ent_off = o;   o = align_up(o + (size_t)P.ent_cap * sizeof(CEntry), 1024);
+      P.clear_bytes = o - P.cnt_off;
+      P.start_off = o; o = align_up(o + (size_t)(keys + 1) * 4, 1024);
+      P.bsum_off = o;  o = align_up(o + (size_t)P.scan_blocks * 4, 1024);
+      P.blk_off = o;   o = align_up(o + (size_t)(P.ent_cap / LIST_ALIGN) * ENT_BLOCK_BYTES, 1024);
+    }
     // weight-gradient split-K: all weights share the machine
     int tiles_w[MAX_WEIGHTS] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) tiles_w[pb[i].weight_id] += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
@@ -1300,6 +1309,67 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     SDB_CHECK_CUDA(cudaGetLastError());
   }
   return SDB_OK;
+}
+
+
+// ---- plain convolution (the towers' Conv2d 3x3, reppointsv2.py:644-675): offset == nullptr ------------------------------
+// "same" convolutions only (stride 1, 2 * pad == dil * (k - 1)): grad_input is then the convolution of dY with the
+// transposed, tap-reversed weights at the same geometry, which the forward kernel computes from weight image 2.
+bool tc_conv_supported(const Geo& g, bool need_grad_input, const char** why) {
+  if (!tc_supported(g, why)) return false;
+  if (g.sh != 1 || g.sw != 1) { *why = "plain-convolution mode needs stride 1"; return false; }
+  if (2 * g.ph != g.dh * (g.KH - 1) || 2 * g.pw != g.dw * (g.KW - 1)) { *why = "plain-convolution mode needs 'same' padding"; return false; }
+  if (need_grad_input) {
+    Geo t = g;
+    t.C = g.O; t.O = g.C;
+    if (!tc_supported(t, why)) return false;
+  }
+  return true;
+}
+
+int tc_conv_backward_all(TcProblem* pb, int n, const void* const* weights, float* const* gw, float* const* gb, int nweights,
+                         const TcPlan& P, const Geo& g, int io_dtype, float scale, bool pack_x, uint8_t* base,
+                         cudaStream_t st) {
+  // (1) grad_weight / grad_bias: the generic path with the data gradients masked off (packs dY into tiles, then the GEMM
+  //     over the saved columns -- or the re-sampling kernel, whose null offsets read as zero)
+  void* gx[MAX_PROBS];
+  bool any_gx = false;
+  for (int i = 0; i < n; ++i) { gx[i] = pb[i].gx; any_gx |= gx[i] != nullptr; pb[i].gx = nullptr; pb[i].goff = nullptr; pb[i].gmask = nullptr; }
+  int rc = tc_backward_all(pb, n, gw, gb, nweights, P, g, io_dtype, scale, pack_x, 0, false, base, st);
+  for (int i = 0; i < n; ++i) pb[i].gx = gx[i];
+  if (rc || !any_gx) return rc;
+  // (2) grad_input = conv(dY, W'): dY -> NHWC bf16, weight image 2, forward kernel with C and O swapped
+  Geo gt = g;
+  gt.C = g.O; gt.O = g.C;
+  PackJob jobs[MAX_PROBS];
+  TcProblem q[MAX_PROBS];
+  bool used[MAX_WEIGHTS] = {false, false, false, false};
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!pb[i].gx || with_dims(g, pb[i].d).P() == 0) continue;
+    used[pb[i].weight_id] = true;
+    jobs[m] = PackJob{pb[i].gy, base + P.gyp_off[i], pb[i].d.N, pb[i].d.Ho * pb[i].d.Wo};
+    q[m] = TcProblem{};
+    q[m].d = Dims{pb[i].d.N, pb[i].d.Ho, pb[i].d.Wo, pb[i].d.H, pb[i].d.W};
+    q[m].weight_id = pb[i].weight_id;
+    q[m].xp = base + P.gyp_off[i];
+    q[m].out = pb[i].gx;
+    ++m;
+  }
+  if (m == 0) return SDB_OK;
+  for (int w = 0; w < nweights; ++w) {
+    if (!used[w]) continue;
+    rc = tc_prepare_weights(weights[w], nullptr, g, io_dtype, base + P.convw_off[w], 4, st);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < m; ++k) {
+    const TcWeightImages img = tc_weight_images(g, base + P.convw_off[q[k].weight_id], false);
+    q[k].w.fwd = img.convt;
+    q[k].w.bias = nullptr;
+  }
+  rc = pack_nhwc_multi(jobs, m, g.O, g.O, io_dtype == SDB_BF16, st);
+  if (rc) return rc;
+  return tc_forward_multi(q, m, gt, io_dtype, st);
 }
 
 }  // namespace sdb

@@ -12,6 +12,7 @@ namespace sdb {
 struct TcWeightImages {
   const uint8_t* fwd;     // forward B operand
   const uint8_t* dgrad;   // W^T tiles of the dcol GEMM (grad_offset / grad_mask / grad_input)
+  const uint8_t* convt;   // forward image of the transposed, tap-reversed weights (plain-convolution grad_input)
   const float* bias;      // fp32 [O] or nullptr
 };
 // host-side description of one problem of a multi-problem call, pointers resolved into the workspace
@@ -46,6 +47,9 @@ struct TcProblem {
 struct TcPlan {
   size_t xp_off[16], gy_off[16], dcol_off[16];
   size_t prep_off[4], part_off[4];
+  int conv;                      // plain-convolution call (every problem has offset == nullptr)
+  size_t gyp_off[16];            // conv backward: NHWC bf16 copy of grad_out (input of the transposed convolution)
+  size_t convw_off[4];           // conv backward: weight image 2 of every weight tensor
   int group_of[16], group_rep[16], ngroups;
   long long key_base[16], nkeys;
   int scan_blocks;
@@ -63,6 +67,11 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
                     int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
                     cudaStream_t st);
+// plain convolution (offset == nullptr): grad_weight over the saved columns, grad_input = conv(dY, W') by the forward kernel
+int tc_conv_backward_all(TcProblem* pb, int n, const void* const* weights, float* const* gw, float* const* gb, int nweights,
+                         const TcPlan& P, const Geo& g, int io_dtype, float scale, bool pack_x, uint8_t* base,
+                         cudaStream_t st);
+bool tc_conv_supported(const Geo& g, bool need_grad_input, const char** why);
 size_t tc_prepared_weight_bytes(const Geo& g);
 TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bias);
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
@@ -377,7 +386,7 @@ __device__ __forceinline__ RawB fetch_rawb(const Geo& g, const float* __restrict
                                            const float* __restrict__ mask, bool valid, int n, int ho, int wo,
                                            int tap) {
   RawB r = {0.f, 0.f, 1.f};
-  if (!valid) return r;
+  if (!valid || !off) return r;   // off == nullptr: plain convolution (zero offsets)
   const int hw = g.Ho * g.Wo, k2 = g.KH * g.KW;
   const float* o = off + ((size_t)n * 2 * k2 + 2 * tap) * hw + ho * g.Wo + wo;
   r.dy = __ldg(o);

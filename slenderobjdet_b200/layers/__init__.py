@@ -6,5 +6,7 @@ from .losses import (sigmoid_focal_loss, sigmoid_focal_loss_jit, sigmoid_focal_l
                      iou_loss, box_iou_loss, smooth_l1_loss, smooth_l1_loss_with_weight, giou_loss,
                      compute_centerness_targets, compute_slender_centerness_targets)
 from .reppoints_offset import reppoints_dcn_offset, dcn_base_offset
+from .group_norm import GroupNormReLU, group_norm_relu, group_norm_relu_multi
+from .conv_tower import TowerConv2d, conv2d_multi, build_tower, towers_forward
 
 __all__ = [k for k in globals().keys() if not k.startswith("_")]
