@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     //     is consumed, across stage boundaries, so 16 loads per warp stay in flight instead of every
     //     warp paying the full memory latency once per stage in lock-step.
     constexpr int ITERS = PIX_PER_WARP / PPI;   // warp iterations per stage
-    constexpr int RING = 4;
+    // plain convolution: one load per iteration instead of four, so the ring is twice as deep for the same bytes in flight
+    constexpr int RING = (CONV && ITERS % 8 == 0) ? 8 : 4;
     static_assert(ITERS % RING == 0, "ring must divide the per-stage iteration count");
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;

@@ -14,6 +14,7 @@
 // backward reads (x, dy) twice and writes dx once.  Tensors are NCHW, float32 or bfloat16; statistics in fp32 / fp64.
 // Semantics: torch.nn.functional.group_norm (biased variance, eps inside the square root) followed by relu.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "dcn_tc_shared.cuh"
 
 namespace sdb {
@@ -32,6 +33,8 @@ struct GnEntry {
   void* gx;
   float* stats;      // [N][G][2]: mean, rstd
   int N, HW, param, splits;
+  int vec_slice;     // (image, group) slices start 16-byte aligned and hold whole vectors (all pointers aligned)
+  int vec_plane;     // the same for (image, channel) planes
   long long part0;   // first partial of this tensor in the workspace
 };
 struct GnTable {
@@ -51,6 +54,35 @@ template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat
 template <typename T> __device__ __forceinline__ void st(T* p, long long i, float v);
 template <> __device__ __forceinline__ void st<float>(float* p, long long i, float v) { p[i] = v; }
 template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// 16-byte vectors: 8 bf16 / 4 fp32 per load (a warp instruction moves 512 contiguous bytes)
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+    v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = tc::pack_bf16x2(v[0], v[1]); t.y = tc::pack_bf16x2(v[2], v[3]);
+    t.z = tc::pack_bf16x2(v[4], v[5]); t.w = tc::pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
 
 // block-wide sums of two doubles (valid on every thread)
 __device__ __forceinline__ void block_sum2(double& a, double& b) {
@@ -92,8 +124,8 @@ __device__ __forceinline__ Slice slice_of(const GnTable& t) {
   const int cpg = t.C / t.G;
   s.m = cpg * e.HW;
   s.base = ((long long)s.n * t.C + (long long)s.g * cpg) * e.HW;
-  const int per = (s.m + e.splits - 1) / e.splits;
-  s.lo = s.split * per;
+  const int per = ((s.m + e.splits - 1) / e.splits + 7) & ~7;   // whole 16-byte vectors
+  s.lo = min(s.m, s.split * per);
   s.hi = min(s.m, s.lo + per);
   return s;
 }
@@ -106,11 +138,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   float fs = 0.f, fq = 0.f;
   double ds = 0, dq = 0;
   int k = 0;
-  for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
-    const float v = ld<T>(x, i);
-    fs += v;
-    fq = fmaf(v, v, fq);
-    if (++k == 16) { ds += fs; dq += fq; fs = fq = 0.f; k = 0; }   // short fp32 runs, fp64 across them
+  if (e.vec_slice) {
+    constexpr int VN = Vec<T>::N;
+    for (int i = s.lo + threadIdx.x * VN; i < s.hi; i += 256 * VN) {
+      float v[8];
+      Vec<T>::load(x + i, v);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { fs += v[j]; fq = fmaf(v[j], v[j], fq); }
+      if (++k == 4) { ds += fs; dq += fq; fs = fq = 0.f; k = 0; }   // short fp32 runs, fp64 across them
+    }
+  } else {
+    for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
+      const float v = ld<T>(x, i);
+      fs += v;
+      fq = fmaf(v, v, fq);
+      if (++k == 16) { ds += fs; dq += fq; fs = fq = 0.f; k = 0; }
+    }
   }
   ds += fs; dq += fq;
   block_sum2(ds, dq);
@@ -146,11 +189,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
   const float* beta = t.beta[e.param] + s.g * cpg;
   const T* x = (const T*)e.x + s.base;
   T* y = (T*)e.y + s.base;
-  for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
-    const int c = i / HW;
-    float v = (ld<T>(x, i) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-    if (t.relu) v = fmaxf(v, 0.f);
-    st<T>(y, i, v);
+  if (e.vec_slice) {
+    constexpr int VN = Vec<T>::N;
+    for (int i = s.lo + threadIdx.x * VN; i < s.hi; i += 256 * VN) {
+      float v[8];
+      Vec<T>::load(x + i, v);
+      int c = i / HW, left = HW - (i - c * HW);   // elements of channel c from i on
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        while (left == 0) { ++c; left = HW; }
+        float r = (v[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (t.relu) r = fmaxf(r, 0.f);
+        v[j] = r;
+        --left;
+      }
+      Vec<T>::store(y + i, v);
+    }
+  } else {
+    for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
+      const int c = i / HW;
+      float v = (ld<T>(x, i) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      if (t.relu) v = fmaxf(v, 0.f);
+      st<T>(y, i, v);
+    }
   }
 }
 
@@ -169,13 +230,31 @@ __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const __grid_constant_
   float fa = 0.f, fb = 0.f;
   double da = 0, db = 0;
   int k = 0;
-  for (int i = threadIdx.x; i < e.HW; i += 256) {
-    const float xh = (ld<T>(x, i) - mean) * rstd;
-    float d = ld<T>(gy, i);
-    if (t.relu && !(fmaf(xh, gm, bt) > 0.f)) d = 0.f;
-    fa += d;
-    fb = fmaf(d, xh, fb);
-    if (++k == 16) { da += fa; db += fb; fa = fb = 0.f; k = 0; }
+  if (e.vec_plane) {
+    constexpr int VN = Vec<T>::N;
+    for (int i = threadIdx.x * VN; i < e.HW; i += 256 * VN) {
+      float xv[8], dv[8];
+      Vec<T>::load(x + i, xv);
+      Vec<T>::load(gy + i, dv);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const float xh = (xv[j] - mean) * rstd;
+        float d = dv[j];
+        if (t.relu && !(fmaf(xh, gm, bt) > 0.f)) d = 0.f;
+        fa += d;
+        fb = fmaf(d, xh, fb);
+      }
+      if (++k == 4) { da += fa; db += fb; fa = fb = 0.f; k = 0; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < e.HW; i += 256) {
+      const float xh = (ld<T>(x, i) - mean) * rstd;
+      float d = ld<T>(gy, i);
+      if (t.relu && !(fmaf(xh, gm, bt) > 0.f)) d = 0.f;
+      fa += d;
+      fb = fmaf(d, xh, fb);
+      if (++k == 16) { da += fa; db += fb; fa = fb = 0.f; k = 0; }
+    }
   }
   da += fa; db += fb;
   block_sum2(da, db);
@@ -207,13 +286,34 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __grid_constant
   const T* x = (const T*)e.x + s.base;
   const T* gy = (const T*)e.gy + s.base;
   T* gx = (T*)e.gx + s.base;
-  for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
-    const int c = i / HW;
-    const float gm = __ldg(gamma + c);
-    const float xh = (ld<T>(x, i) - mean) * rstd;
-    float d = ld<T>(gy, i);
-    if (t.relu && !(fmaf(xh, gm, __ldg(beta + c)) > 0.f)) d = 0.f;
-    st<T>(gx, i, rstd * (gm * d - fmaf(xh, m2, m1)));
+  if (e.vec_slice) {
+    constexpr int VN = Vec<T>::N;
+    for (int i = s.lo + threadIdx.x * VN; i < s.hi; i += 256 * VN) {
+      float xv[8], dv[8];
+      Vec<T>::load(x + i, xv);
+      Vec<T>::load(gy + i, dv);
+      int c = i / HW, left = HW - (i - c * HW);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        while (left == 0) { ++c; left = HW; }
+        const float gm = __ldg(gamma + c);
+        const float xh = (xv[j] - mean) * rstd;
+        float d = dv[j];
+        if (t.relu && !(fmaf(xh, gm, __ldg(beta + c)) > 0.f)) d = 0.f;
+        dv[j] = rstd * (gm * d - fmaf(xh, m2, m1));
+        --left;
+      }
+      Vec<T>::store(gx + i, dv);
+    }
+  } else {
+    for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
+      const int c = i / HW;
+      const float gm = __ldg(gamma + c);
+      const float xh = (ld<T>(x, i) - mean) * rstd;
+      float d = ld<T>(gy, i);
+      if (t.relu && !(fmaf(xh, gm, __ldg(beta + c)) > 0.f)) d = 0.f;
+      st<T>(gx, i, rstd * (gm * d - fmaf(xh, m2, m1)));
+    }
   }
 }
 
@@ -243,7 +343,7 @@ int splits_of(int m) {
 
 // builds the table; `planes`: CTA = (image, channel) plane (backward sums) instead of (image, group, split) slices
 int build_table(const sdb_gn_tensor* ts, int n, const sdb_gn_params* ps, int np, int C, int G, float eps, int relu, bool planes,
-                GnTable& t, long long* nparts) {
+                int elem_bytes, GnTable& t, long long* nparts) {
   SDB_REQUIRE(ts && n >= 1 && n <= MAX_PROBS, SDB_ERR_INVALID, "need 1..%d tensors, got %d", MAX_PROBS, n);
   SDB_REQUIRE(np >= 1 && np <= MAX_PARAMS, SDB_ERR_INVALID, "need 1..%d parameter sets, got %d", MAX_PARAMS, np);
   SDB_REQUIRE(C > 0 && G > 0 && C % G == 0, SDB_ERR_INVALID, "num_channels %d must be divisible by num_groups %d", C, G);
@@ -263,6 +363,12 @@ int build_table(const sdb_gn_tensor* ts, int n, const sdb_gn_params* ps, int np,
     e.x = ts[i].x; e.y = ts[i].y; e.gy = ts[i].grad_y; e.gx = ts[i].grad_x; e.stats = ts[i].stats;
     e.N = ts[i].N; e.HW = ts[i].HW; e.param = ts[i].param_id;
     e.splits = splits_of(C / G * ts[i].HW);
+    {
+      const size_t ptrs = (size_t)e.x | (size_t)e.y | (size_t)e.gy | (size_t)e.gx;
+      const int vn = 16 / elem_bytes;
+      e.vec_slice = (ptrs & 15) == 0 && ((long long)(C / G) * e.HW) % vn == 0;
+      e.vec_plane = (ptrs & 15) == 0 && e.HW % vn == 0;
+    }
     // one partial numbering serves both passes of a direction: forward (image, group, split), backward (image, channel)
     e.part0 = parts;
     const long long fwd = (long long)e.N * G * e.splits, bwd = (long long)e.N * C;
@@ -300,7 +406,7 @@ size_t sdb_gn_relu_workspace_bytes(const sdb_gn_tensor* tensors, int32_t n, int3
   int np = 1;
   for (int i = 0; tensors && i < n && i < MAX_PROBS; ++i)
     if (tensors[i].param_id >= np && tensors[i].param_id < MAX_PARAMS) np = tensors[i].param_id + 1;
-  if (build_table(tensors, n, dummy, np, C, G, 1e-5f, 1, false, t, &parts)) return 0;
+  if (build_table(tensors, n, dummy, np, C, G, 1e-5f, 1, false, 2, t, &parts)) return 0;
   return (size_t)parts * 2 * sizeof(double) + 256;
 }
 
@@ -310,7 +416,7 @@ int sdb_gn_relu_forward(const sdb_gn_tensor* tensors, int32_t n, const sdb_gn_pa
   SDB_REQUIRE(params != nullptr, SDB_ERR_INVALID, "NULL parameter table");
   GnTable t;
   long long parts = 0;
-  int rc = build_table(tensors, n, params, np, C, G, eps, relu, false, t, &parts);
+  int rc = build_table(tensors, n, params, np, C, G, eps, relu, false, io_dtype == SDB_BF16 ? 2 : 4, t, &parts);
   if (rc) return rc;
   for (int k = 0; k < np; ++k) SDB_REQUIRE(params[k].gamma && params[k].beta, SDB_ERR_INVALID, "parameter set %d: gamma and beta must be non-NULL", k);
   for (int i = 0; i < t.map.n; ++i) SDB_REQUIRE(t.e[i].x && t.e[i].y, SDB_ERR_INVALID, "x and y must be non-NULL");
@@ -337,7 +443,7 @@ int sdb_gn_relu_backward(const sdb_gn_tensor* tensors, int32_t n, const sdb_gn_p
   SDB_REQUIRE(params != nullptr, SDB_ERR_INVALID, "NULL parameter table");
   GnTable t;
   long long parts = 0;
-  int rc = build_table(tensors, n, params, np, C, G, eps, relu, true, t, &parts);
+  int rc = build_table(tensors, n, params, np, C, G, eps, relu, true, io_dtype == SDB_BF16 ? 2 : 4, t, &parts);
   if (rc) return rc;
   for (int k = 0; k < np; ++k) SDB_REQUIRE(params[k].gamma && params[k].beta, SDB_ERR_INVALID, "parameter set %d: gamma and beta must be non-NULL", k);
   for (int i = 0; i < t.map.n; ++i)

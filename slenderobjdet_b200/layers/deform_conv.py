@@ -13,7 +13,9 @@ directly) and ``im2col_step`` is accepted and validated but not used.
 
 Arithmetic (``set_dcn_math`` / ``SDB_DCN_MATH``).  The reference computes float32 tensors in exact fp32
 (im2col + fp32 GEMM, deform_conv_cuda_kernel.cu:486), so the default ``"auto"`` does the same: float32
-tensors run the exact fp32 kernels (rel <= 1e-4 against the oracle).  The tcgen05 tensor-core kernels (bf16
+tensors run the exact fp32 kernels (rel <= 1e-4 against the oracle) -- except that their FORWARD uses the
+error-compensated ``tf32x3`` tensor-core kernel where the geometry allows (rel ~2e-5, still inside that bound;
+``SDB_DCN_AUTO_TF32X3=0`` turns this off).  The tcgen05 tensor-core kernels (bf16
 operands, fp32 accumulation in TMEM, rel <= 1e-2) are used when the TENSORS are bfloat16, under
 ``torch.autocast(dtype=torch.bfloat16)``, or when ``set_dcn_math("bf16")`` asks for them explicitly.
 ``set_dcn_math("tf32")`` / ``"tf32x3"`` run the FORWARD of float32 tensors on ``tcgen05.mma.kind::tf32`` (fp32
@@ -37,10 +39,12 @@ from .. import _lib
 
 _MATH = os.environ.get("SDB_DCN_MATH", "auto")  # "auto" | "bf16" | "fp32" | "tf32" | "tf32x3"
 _MODES = ("auto", "bf16", "fp32", "tf32", "tf32x3")
+_AUTO_TF32X3 = os.environ.get("SDB_DCN_AUTO_TF32X3", "1") != "0"   # 'auto' + float32 tensors: tf32x3 forward when supported
 
 
 def set_dcn_math(mode):
-    """'auto': follow the tensors -- float32 tensors use the exact fp32 kernels, bfloat16 tensors (or float32 under
+    """'auto': follow the tensors -- float32 tensors use fp32-accurate kernels (forward: tf32x3 tensor cores where the
+    geometry allows, else the exact fp32 kernel; backward: the exact fp32 kernels), bfloat16 tensors (or float32 under
     bf16 autocast) the tcgen05 tensor-core kernels when the geometry allows, else fp32;
     'bf16': require the tensor-core path whatever the tensor dtype (tolerance rel <= 1e-2);
     'fp32': always the exact fp32 path (rel <= 1e-4);
@@ -131,7 +135,12 @@ def _pick_math(g, iod, autocast=False):
             raise RuntimeError("slender_b200: " + lib.sdb_last_error().decode())
         return mth
     if _MATH == "auto" and iod == _lib.SDB_F32 and not autocast:
-        return _lib.SDB_MATH_FP32     # a float32 model keeps the reference's fp32 numerics unless told otherwise
+        # a float32 model keeps the reference's fp32 numerics unless told otherwise: the forward runs on tensor cores in
+        # the error-compensated tf32x3 mode where the geometry allows (rel ~2e-5, inside the 1e-4 bound of fp32 math;
+        # 14x the SIMT kernel), the backward always on the exact fp32 kernels
+        if _AUTO_TF32X3 and lib.sdb_dcn_supported(ctypes.byref(g), _lib.SDB_F32, _lib.SDB_MATH_TF32X3):
+            return _lib.SDB_MATH_TF32X3
+        return _lib.SDB_MATH_FP32
     ok = bool(lib.sdb_dcn_supported(ctypes.byref(g), iod, _lib.SDB_MATH_BF16))
     if ok:
         return _lib.SDB_MATH_BF16
