@@ -145,7 +145,11 @@ typedef struct {
   int32_t offset_group;     /* >= 0: shares offset / mask (same pointers, same N, H, W) with equal values; -1: own */
   int32_t reserved;
   const void* x;            /* [N, C_in, H, W]                                                                    */
-  const float* offset;      /* [N, 2*kH*kW, Ho, Wo]                                                               */
+  const float* offset;      /* [N, 2*kH*kW, Ho, Wo].  NULL in EVERY problem of a table (also in the size query) = plain
+                               convolution, the zero-offset specialisation used for the head towers (reppointsv2.py:
+                               644-675): SDB_MATH_BF16 only, no mask, stride 1 and 'same' padding (2*pad == dil*(k-1));
+                               one input row per tap is loaded instead of four, grad_x = the forward kernel on grad_out
+                               with the transposed tap-reversed weights (needs C_out % 64 == 0, C_in % 16 == 0)       */
   const float* mask;        /* [N, kH*kW, Ho, Wo] or NULL (v1)                                                    */
   void* out;                /* forward:  [N, C_out, Ho, Wo]                                                       */
   void* x_packed;           /* optional NHWC-bf16 copy of x (sdb_dcn_packed_input_bytes): forward fills it,

@@ -483,6 +483,7 @@ int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb
 size_t sdb_dcn_workspace_bytes(int op, const sdb_dcn_geom* g, int io_dtype, int math) {
   if (check_geom(g) || check_io(io_dtype, math) || math == SDB_MATH_FP32) return 0;
   Single s = single_of(g);
+  s.p.offset = reinterpret_cast<const float*>(sizeof(float));   // size query of a DEFORMABLE convolution (NULL = plain convolution); never read
   return sdb_dcn_multi_workspace_bytes(&s.p, 1, &s.w, 1, g, io_dtype, math, op != SDB_OP_FORWARD);
 }
 

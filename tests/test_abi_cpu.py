@@ -147,6 +147,19 @@ def test_multi_problem_table_host_logic_without_gpu():
     g1 = _lib.Geom(2, 256, 100, 168, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
     one = lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_DATA, ctypes.byref(g1), _lib.SDB_BF16, _lib.SDB_MATH_BF16)
     assert one > 0 and one == lib.sdb_dcn_workspace_bytes(_lib.SDB_OP_BACKWARD_WEIGHT, ctypes.byref(g1), _lib.SDB_BF16, _lib.SDB_MATH_BF16)
+    assert one > 2 * 100 * 168 * 9 * 256 * 2      # a DEFORMABLE convolution's plan: holds the dcol tiles (taps * C bf16 per pixel)
+    # offset == NULL in every problem = plain convolution (tower Conv2d): no dcol tiles, no transposed index; mixed tables
+    # are refused
+    conv, nc = _table(levels)
+    for i in range(nc):
+        conv[i].offset = None
+        conv[i].grad_offset = None
+        conv[i].offset_group = -1
+    bwd_conv = lib.sdb_dcn_multi_workspace_bytes(conv, nc, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1)
+    assert 0 < bwd_conv < bwd - px * 9 * 256 * 2 // 2
+    conv[2].offset = 0x2000
+    assert lib.sdb_dcn_multi_workspace_bytes(conv, nc, wts, 2, gp, _lib.SDB_BF16, _lib.SDB_MATH_BF16, 1) == 0
+    assert b"plain convolution" in lib.sdb_last_error()
 
 
 def test_deform_conv_multi_argument_checks():
