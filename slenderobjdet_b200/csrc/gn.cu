@@ -84,6 +84,17 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
+// y = fmaf(x, a, b) with a = rstd * gamma, b = beta - mean * a: the scale / shift form (one FMA per element).  The forward
+// output, the ReLU mask recomputed by both backward kernels and xhat all come from these helpers, so the mask the backward
+// sees is bit for bit the sign the forward saw.
+struct Affine { float a, b; };
+__device__ __forceinline__ Affine affine_of(float mean, float rstd, float gamma, float beta) {
+  Affine f;
+  f.a = rstd * gamma;
+  f.b = fmaf(-mean, f.a, beta);
+  return f;
+}
+
 // block-wide sums of two doubles (valid on every thread)
 __device__ __forceinline__ void block_sum2(double& a, double& b) {
   __shared__ double sa[32], sb[32];
@@ -195,22 +206,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
       float v[8];
       Vec<T>::load(x + i, v);
       int c = i / HW, left = HW - (i - c * HW);   // elements of channel c from i on
+      if (left >= VN) {                            // the whole vector lies in one channel (all but one vector per plane)
+        const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        while (left == 0) { ++c; left = HW; }
-        float r = (v[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (t.relu) r = fmaxf(r, 0.f);
-        v[j] = r;
-        --left;
+        for (int j = 0; j < VN; ++j) {
+          const float r = fmaf(v[j], f.a, f.b);
+          v[j] = t.relu ? fmaxf(r, 0.f) : r;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          while (left == 0) { ++c; left = HW; }
+          const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
+          const float r = fmaf(v[j], f.a, f.b);
+          v[j] = t.relu ? fmaxf(r, 0.f) : r;
+          --left;
+        }
       }
       Vec<T>::store(y + i, v);
     }
   } else {
     for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
       const int c = i / HW;
-      float v = (ld<T>(x, i) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      if (t.relu) v = fmaxf(v, 0.f);
-      st<T>(y, i, v);
+      const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
+      const float v = fmaf(ld<T>(x, i), f.a, f.b);
+      st<T>(y, i, t.relu ? fmaxf(v, 0.f) : v);
     }
   }
 }
@@ -224,7 +244,8 @@ __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const __grid_constant_
   const int c = local % t.C, n = local / t.C;
   const int cpg = t.C / t.G, g = c / cpg;
   const float mean = e.stats[2 * (n * t.G + g)], rstd = e.stats[2 * (n * t.G + g) + 1];
-  const float gm = __ldg(t.gamma[e.param] + c), bt = __ldg(t.beta[e.param] + c);
+  const Affine f = affine_of(mean, rstd, __ldg(t.gamma[e.param] + c), __ldg(t.beta[e.param] + c));
+  const float nmr = -mean * rstd;   // xhat = fmaf(x, rstd, nmr)
   const T* x = (const T*)e.x + (long long)local * e.HW;
   const T* gy = (const T*)e.gy + (long long)local * e.HW;
   float fa = 0.f, fb = 0.f;
@@ -238,21 +259,18 @@ __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const __grid_constant_
       Vec<T>::load(gy + i, dv);
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
-        const float xh = (xv[j] - mean) * rstd;
-        float d = dv[j];
-        if (t.relu && !(fmaf(xh, gm, bt) > 0.f)) d = 0.f;
+        const float d = (t.relu && !(fmaf(xv[j], f.a, f.b) > 0.f)) ? 0.f : dv[j];
         fa += d;
-        fb = fmaf(d, xh, fb);
+        fb = fmaf(d, fmaf(xv[j], rstd, nmr), fb);
       }
       if (++k == 4) { da += fa; db += fb; fa = fb = 0.f; k = 0; }
     }
   } else {
     for (int i = threadIdx.x; i < e.HW; i += 256) {
-      const float xh = (ld<T>(x, i) - mean) * rstd;
-      float d = ld<T>(gy, i);
-      if (t.relu && !(fmaf(xh, gm, bt) > 0.f)) d = 0.f;
+      const float xs = ld<T>(x, i);
+      const float d = (t.relu && !(fmaf(xs, f.a, f.b) > 0.f)) ? 0.f : ld<T>(gy, i);
       fa += d;
-      fb = fmaf(d, xh, fb);
+      fb = fmaf(d, fmaf(xs, rstd, nmr), fb);
       if (++k == 16) { da += fa; db += fb; fa = fb = 0.f; k = 0; }
     }
   }
@@ -283,6 +301,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __grid_constant
   __syncthreads();
   const float m1 = sh[0], m2 = sh[1];
   const float mean = e.stats[2 * (s.n * t.G + s.g)], rstd = e.stats[2 * (s.n * t.G + s.g) + 1];
+  const float k1 = rstd * m1, k2 = rstd * m2, nmr = -mean * rstd;   // dx = a * dy' - k2 * xhat - k1
   const T* x = (const T*)e.x + s.base;
   const T* gy = (const T*)e.gy + s.base;
   T* gx = (T*)e.gx + s.base;
@@ -293,26 +312,32 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __grid_constant
       Vec<T>::load(x + i, xv);
       Vec<T>::load(gy + i, dv);
       int c = i / HW, left = HW - (i - c * HW);
+      if (left >= VN) {
+        const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        while (left == 0) { ++c; left = HW; }
-        const float gm = __ldg(gamma + c);
-        const float xh = (xv[j] - mean) * rstd;
-        float d = dv[j];
-        if (t.relu && !(fmaf(xh, gm, __ldg(beta + c)) > 0.f)) d = 0.f;
-        dv[j] = rstd * (gm * d - fmaf(xh, m2, m1));
-        --left;
+        for (int j = 0; j < VN; ++j) {
+          const float d = (t.relu && !(fmaf(xv[j], f.a, f.b) > 0.f)) ? 0.f : dv[j];
+          dv[j] = fmaf(f.a, d, fmaf(-k2, fmaf(xv[j], rstd, nmr), -k1));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          while (left == 0) { ++c; left = HW; }
+          const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
+          const float d = (t.relu && !(fmaf(xv[j], f.a, f.b) > 0.f)) ? 0.f : dv[j];
+          dv[j] = fmaf(f.a, d, fmaf(-k2, fmaf(xv[j], rstd, nmr), -k1));
+          --left;
+        }
       }
       Vec<T>::store(gx + i, dv);
     }
   } else {
     for (int i = s.lo + threadIdx.x; i < s.hi; i += 256) {
       const int c = i / HW;
-      const float gm = __ldg(gamma + c);
-      const float xh = (ld<T>(x, i) - mean) * rstd;
-      float d = ld<T>(gy, i);
-      if (t.relu && !(fmaf(xh, gm, __ldg(beta + c)) > 0.f)) d = 0.f;
-      st<T>(gx, i, rstd * (gm * d - fmaf(xh, m2, m1)));
+      const Affine f = affine_of(mean, rstd, __ldg(gamma + c), __ldg(beta + c));
+      const float xs = ld<T>(x, i);
+      const float d = (t.relu && !(fmaf(xs, f.a, f.b) > 0.f)) ? 0.f : ld<T>(gy, i);
+      st<T>(gx, i, fmaf(f.a, d, fmaf(-k2, fmaf(xs, rstd, nmr), -k1)));
     }
   }
 }
