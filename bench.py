@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]  # P3..P7 of an 800x1344 image
 C_IN = C_OUT = 256
 BATCH_PER_GPU = 2
+ONE_GRAPH = os.environ.get("SDB_BENCH_ONE_GRAPH", "1") != "0"   # N > 1: capture the all-reduce into the step's CUDA graph
 NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "0"))  # developer knob: cap the overlapped all-reduce at this many CTAs and leave
 # that many SMs free in the persistent kernels (sdb_set_sm_reserve).  Measured on 2 GPUs: 0 (NCCL default) 0.877 ms, 16 -> 0.877, 8 -> 0.891,
 # 4 -> 0.952 (the all-reduce outlasts the data-gradient kernels): SM contention is not what the N > 1 step pays for; default off.
@@ -279,27 +280,51 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
     with torch.cuda.stream(stream):
         wl.step(stream)
         stream.synchronize()
+        def capture_single():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                wl.step(stream)
+            return [g]
+
+        def capture_with_allreduce():
+            # the whole step INCLUDING the all-reduce as one graph: the collective is captured on NCCL's stream between
+            # the weight-gradient kernels and the join, beside the data-gradient kernels -- no host launch gaps
+            for _ in range(2):   # NCCL warm-up outside the capture (communicator setup, buffer registration)
+                w0 = wl.bucket.all_reduce(average=True, async_op=True, prescaled=True)
+                if w0 is not None:
+                    w0.wait()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                wl.phase_forward(stream)
+                wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+                work = wl.bucket.all_reduce(average=True, async_op=True, prescaled=True)
+                wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+                if work is not None:
+                    work.wait()
+            return [g]
+
+        def capture_two_halves():
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, stream=stream):
+                wl.phase_forward(stream)
+                wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+            L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))   # grids are baked into the graph at capture
+            with torch.cuda.graph(gb, stream=stream):
+                wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+            L.lib().sdb_set_sm_reserve(0)
+            return [ga, gb]
+
         if graph_ok:
-            try:
-                if world == 1:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=stream):
-                        wl.step(stream)
-                    graphs = [g]
-                else:
-                    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(ga, stream=stream):
-                        wl.phase_forward(stream)
-                        wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
-                    L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))   # grids are baked into the graph at capture
-                    with torch.cuda.graph(gb, stream=stream):
-                        wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
-                    L.lib().sdb_set_sm_reserve(0)
-                    graphs = [ga, gb]
-            except Exception as e:  # keep running eagerly, say so in config
-                graphs = None
-                sys.stderr.write("bench.py: CUDA graph capture failed (%r); timing eager launches\n" % (e,))
-                torch.cuda.synchronize()
+            plans = [capture_single] if world == 1 else ([capture_with_allreduce] if ONE_GRAPH else []) + [capture_two_halves]
+            for plan in plans:
+                try:
+                    graphs = plan()
+                    break
+                except Exception as e:  # next plan, or eager launches: say so
+                    graphs = None
+                    sys.stderr.write("bench.py: CUDA graph capture (%s) failed (%r)\n" % (plan.__name__, e))
+                    torch.cuda.synchronize()
 
     def one_step():
         if world == 1:
@@ -307,6 +332,9 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
                 graphs[0].replay()
             else:
                 wl.step(stream)
+            return
+        if graphs and len(graphs) == 1:   # step and collective in one graph
+            graphs[0].replay()
             return
         if graphs:
             graphs[0].replay()
@@ -344,6 +372,8 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
         sync_all()
     ms = sum(a.elapsed_time(b) for a, b in ev) / steps
     mode = ("cuda_graph" if graphs else "eager") + ", one launch per kernel over all levels and both branches"
+    if world > 1 and graphs:
+        mode += ", all-reduce captured in the step's graph" if len(graphs) == 1 else ", two graphs around an eager all-reduce"
     return ms, mode
 
 
