@@ -377,6 +377,74 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
     return ms, mode
 
 
+def extra_paths(torch, sdb, device, l2_flush):
+    """The round's other tensor-core paths through the operator API, as CUDA-graph replays (median of 10, L2 flushed):
+    the forward of float32 tensors (SIMT fp32 vs kind::tf32, one DCN on the P3 map) and one tower layer
+    (conv 3x3 -> GroupNorm(32) -> ReLU, reppointsv2.py:644-675) over P3-P7 x 2 towers, forward + backward."""
+    import slenderobjdet_b200.layers as LL
+    bf = torch.bfloat16
+    g = torch.Generator().manual_seed(0)
+
+    def replay_us(fn, iters=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fn()
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            l2_flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return round(ts[len(ts) // 2], 1)
+
+    out = {}
+    H, W = LEVELS[0]
+    x = torch.randn(BATCH_PER_GPU, C_IN, H, W, generator=g).to(device)
+    w = (torch.randn(C_OUT, C_IN, 3, 3, generator=g) * 0.01).to(device)
+    off = (torch.randn(BATCH_PER_GPU, 18, H, W, generator=g) * 2).to(device)
+    f32 = {}
+    ref = None
+    for mode in ("fp32", "tf32x3", "tf32"):
+        def fwd():
+            with sdb.dcn_math(mode), torch.no_grad():
+                return sdb.deform_conv(x, off, w, 1, 1, 1, 1, 1)
+        f32[mode + "_us"] = replay_us(fwd)
+        y = fwd().double()
+        ref = y if ref is None else ref
+        f32[mode + "_rel_err_vs_fp32"] = float("%.2e" % float((y - ref).norm() / ref.norm()))
+    out["float32 tensors: forward of one DeformConv 256->256 on the P3 map, batch 2 (fp32 = SIMT kernel; tf32x3 is what 'auto' runs)"] = f32
+    xs = [torch.randn(BATCH_PER_GPU, C_IN, h, w_, generator=g).to(bf).to(device).requires_grad_() for _ in range(2) for (h, w_) in LEVELS]
+    gys = [torch.randn(BATCH_PER_GPU, C_IN, h, w_, generator=g).to(bf).to(device) for _ in range(2) for (h, w_) in LEVELS]
+    ids = [t for t in range(2) for _ in LEVELS]
+    ws = [(torch.randn(C_OUT, C_IN, 3, 3, generator=g) * 0.01).to(bf).to(device).requires_grad_() for _ in range(2)]
+    gam = [torch.ones(C_OUT, device=device).requires_grad_() for _ in range(2)]
+    bet = [torch.zeros(C_OUT, device=device).requires_grad_() for _ in range(2)]
+
+    def conv_fb():
+        torch.autograd.backward(LL.conv2d_multi(xs, ws, None, 1, 1, ids), gys)
+
+    def gn_fb():
+        torch.autograd.backward(LL.group_norm_relu_multi(xs, gam, bet, 32, 1e-5, ids), gys)
+    px = sum(h * w_ for (h, w_) in LEVELS) * BATCH_PER_GPU * 2
+    tc, tg = replay_us(conv_fb), replay_us(gn_fb)
+    out["tower layer (conv 3x3 -> GroupNorm(32) -> ReLU) over P3-P7 x 2 towers, batch 2, bf16, forward + backward"] = {
+        "conv_us": tc, "conv_tflops_per_s": round(3 * 2.0 * px * C_IN * C_OUT * 9 / tc / 1e6, 1),
+        "groupnorm_relu_us": tg, "groupnorm_relu_gb_per_s": round(8 * px * C_OUT * 2 / tg / 1e3, 1)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -496,6 +564,11 @@ def run_ours(args):
                 torch.cuda.empty_cache()
             except Exception as e:  # never lose the headline line to an extra
                 extra[tag] = {"error": repr(e)[:200]}
+
+        try:
+            extra.update(extra_paths(torch, sdb, device, l2_flush))
+        except Exception as e:
+            extra["float32 forward / tower layer"] = {"error": repr(e)[:200]}
 
     # ---- e2e: public Python API, host buffers, H2D + D2H inside the timed region -----------------
     e2e = measure_e2e(torch, sdb, device, stream, batch, args, world, dist if world > 1 else None, rank)
