@@ -403,6 +403,10 @@ long long sdb_launch_count(void);
  * all-reduce (d2/engine/defaults.py:280-283) with the data-gradient kernels reserves as many SMs as the collective
  * uses CTAs (bench.py: NCCL max_ctas). */
 int sdb_set_sm_reserve(int n_sms);
+/* The forward kernel (deformable and plain convolution) runs as clusters of two CTAs issuing tcgen05.mma.cta_group::2
+ * (M = 256: each CTA gathers its own 128 output pixels and streams half of every weight tile) when C_in % 128 == 0 and
+ * C_out % 32 == 0.  on == 0 selects the one-CTA kernel (M = 128) instead -- results are identical; process-wide. */
+int sdb_set_forward_pair(int on);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ namespace sdb {
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
 namespace tcshared { int g_sm_reserve = 0; }
+extern int g_fwd_pair;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -129,6 +130,10 @@ const char* sdb_last_error(void) { return g_err; }
 int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 
 long long sdb_launch_count(void) { return g_launches; }
+int sdb_set_forward_pair(int on) {
+  g_fwd_pair = on != 0;
+  return SDB_OK;
+}
 int sdb_set_sm_reserve(int n) {
   SDB_REQUIRE(n >= 0 && n < 128, SDB_ERR_INVALID, "SM reserve must be in [0, 128), got %d", n);
   tcshared::g_sm_reserve = n;

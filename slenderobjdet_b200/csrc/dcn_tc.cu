@@ -190,7 +190,11 @@ struct FwdParams {
 // LPP = lanes per pixel in the gather (8 channels per lane): channels per A stage CPS = 8*LPP.
 // CONV: plain convolution (no offsets, no mask): one source row per (pixel, tap) -- one 16-byte load per lane instead of
 // four, no interpolation arithmetic; the descriptor is (row offset, inside-the-image flag).
-template <int LPP, bool OUT_BF16, bool CONV>
+// PAIR: the kernel runs as clusters of two CTAs (cta_group::2).  A work item is a PAIR of 128-pixel tiles of one problem:
+// each CTA gathers its own tile's A rows and streams HALF of every weight tile (C_out/2 rows), the leader's MMA warp
+// issues M = 256 instructions for both, so every SM writes and fetches half the B bytes per FLOP.  The non-leader's MMA
+// warp relays its CTA's a_full / b_full completions to the leader; commits are multicast to both CTAs.
+template <int LPP, bool OUT_BF16, bool CONV, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_constant__ FwdParams p) {
   constexpr int CPS = LPP * 8;           // channels per A stage
   constexpr int KBPS = CPS / 64;         // 64-channel k-blocks per A stage
@@ -203,11 +207,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
   __shared__ __align__(8) uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t peer_b[MAX_B_STAGES];   // PAIR, leader: the peer's weight stage is full
   __shared__ uint32_t tmem_base_s;
 
   const int O = p.g.O, C = p.g.C, taps = p.g.KH * p.g.KW, nchunks = C / CPS;
   const int num_work = p.map.start[p.map.n];
-  const uint32_t B_BYTES = (uint32_t)O * 128u;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;           // 0 = leader
+  const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t B_TILE = (uint32_t)O * 128u;                   // one [O x 64] weight tile of the image
+  const uint32_t B_BYTES = PAIR ? B_TILE / 2 : B_TILE;          // slot size = what this CTA loads of it (PAIR: C_out/2 rows)
+  const uint32_t B_LOAD = B_BYTES;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sA = sm;
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nsa; ++s) {
-      mbar_init(&a_full[s], NPW);   // one arrival per gather warp
+      mbar_init(&a_full[s], PAIR ? 2 * NPW : NPW);   // one arrival per gather warp (PAIR: of both CTAs, on the leader's barrier)
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < p.nsb; ++s) {
@@ -230,13 +240,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], PAIR ? 8 : 4);   // one arrival per epilogue warp (of both CTAs)
     }
+    if (PAIR)
+      for (int s = 0; s < p.nsb; ++s) mbar_init(&peer_b[s], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc2(&tmem_base_s, ncols);
+    else tmem_alloc(&tmem_base_s, ncols);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
@@ -245,49 +261,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     if (lane == 0) {
       uint32_t bs = 0, bp = 0;
       const int nkb_total = taps * (C / 64);
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const uint8_t* wsrc = p.pr[find_range(p.map, work)].wimg;
+      for (int work = work0; work < num_work; work += wstep) {
+        const uint8_t* wsrc = p.pr[find_range(p.map, work)].wimg + (size_t)rank * B_LOAD;   // PAIR: rows [rank * O/2, ...)
         for (int kb = 0; kb < nkb_total; ++kb) {
           mbar_wait(&b_empty[bs], bp ^ 1);
-          mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-          bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)kb * B_BYTES, B_BYTES, &b_full[bs]);
+          mbar_arrive_expect_tx(&b_full[bs], B_LOAD);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)kb * B_TILE, B_LOAD, &b_full[bs]);
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_bf16(TILE_M, O, 0, 0);
+    // ===== MMA issuer (PAIR: leader only; the peer's warp relays its CTA's full barriers) =====
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, O, 0, 0);
     uint32_t as = 0, ap = 0, bs = 0, bp = 0, acc = 0, accp = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      mbar_wait(&acc_empty[acc], accp ^ 1);
+    if (PAIR && rank != 0) {
+      for (int work = work0; work < num_work; work += wstep)
+        for (int kb = 0; kb < taps * nchunks * KBPS; ++kb) {   // the weight tiles land on local barriers (complete_tx): relay them
+          mbar_wait(&b_full[bs], bp);
+          if (lane == 0) mbar_arrive_remote(&peer_b[bs], 0);
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+    } else
+    for (int work = work0; work < num_work; work += wstep) {
+      if (PAIR) mbar_wait_cluster(&acc_empty[acc], accp ^ 1);
+      else mbar_wait(&acc_empty[acc], accp ^ 1);
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + acc * acc_stride;
       uint32_t accumulate = 0;
       for (int it = 0; it < taps * nchunks; ++it) {
-        mbar_wait(&a_full[as], ap);
+        if (PAIR) mbar_wait_cluster(&a_full[as], ap);
+        else mbar_wait(&a_full[as], ap);
         for (int kb = 0; kb < KBPS; ++kb) {
           mbar_wait(&b_full[bs], bp);
+          if (PAIR) mbar_wait_cluster(&peer_b[bs], bp);
           tc_fence_after_sync();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + as * A_BYTES + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + p.nsa * A_BYTES + bs * B_BYTES;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
-                        make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
+              if (PAIR)
+                umma_bf16_pair(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                               make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
+              else
+                umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                          make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(&b_empty[bs]);
+            if (PAIR) umma_commit_pair(&b_empty[bs]);
+            else umma_commit(&b_empty[bs]);
           }
           __syncwarp();
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
-        if (elect_one()) umma_commit(&a_empty[as]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&a_empty[as]);
+          else umma_commit(&a_empty[as]);
+        }
         __syncwarp();
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
       }
-      if (elect_one()) umma_commit(&acc_full[acc]);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(&acc_full[acc]);
+        else umma_commit(&acc_full[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
@@ -295,10 +333,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     // ===== epilogue: TMEM -> registers -> NCHW global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t acc = 0, accp = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += wstep) {
       const int pi = find_range(p.map, work);
       const FwdProb& pr = p.pr[pi];
-      const int tile = work - p.map.start[pi];
+      const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
       const int hw = pr.d.Ho * pr.d.Wo;
       mbar_wait(&acc_full[acc], accp);
       tc_fence_after_sync();
@@ -328,7 +366,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
         }
       }
       tc_fence_before_sync();
-      mbar_arrive_warp(&acc_empty[acc]);
+      if (PAIR && rank != 0) {      // the accumulator pair is released on the LEADER's barrier
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+      } else {
+        mbar_arrive_warp(&acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
   } else {
@@ -348,14 +391,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     GDesc* sD = reinterpret_cast<GDesc*>(sB + (size_t)p.nsb * B_BYTES);   // [taps][TILE_M]
     const int nstages = taps * nchunks;
     uint32_t as = 0, ap = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += wstep) {
       const int pi = find_range(p.map, work);
       const FwdProb& pr = p.pr[pi];
-      const int tile = work - p.map.start[pi];
+      const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
       const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
       // saved columns (sdb_dcn_problem.columns): every sampled row also goes to HBM, in the operand layout of the stage
       // it is stored to, so the weight-gradient GEMM of the backward pass streams it back instead of sampling again
       uint8_t* colp = pr.col ? pr.col + (size_t)tile * nstages * A_BYTES + (lig >> 3) * (TILE_M * 128) : nullptr;
+      if (PAIR && (long long)tile * TILE_M >= pr.mP) colp = nullptr;   // the all-invalid second tile of an odd problem
       {
         const Geo g = with_dims(p.g, pr.d);
         const int px = lane % PIX_PER_WARP;
@@ -375,11 +419,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
           if (!CONV) raw[r] = fetch_raw(g, pr.off, pr.mask, valid && tap < taps, n, ho, wo, tap < taps ? tap : 0);
         }
         if (!CONV) {
-          const int nwork = work + gridDim.x;
+          const int nwork = work + wstep;
           if (nwork < num_work) {
             const int npi = find_range(p.map, nwork);
             const FwdProb& npr = p.pr[npi];
-            const long long npix = (long long)(nwork - p.map.start[npi]) * TILE_M + r0 + px;
+            const int ntile = PAIR ? 2 * (nwork - p.map.start[npi]) + rank : nwork - p.map.start[npi];
+            const long long npix = (long long)ntile * TILE_M + r0 + px;
             if (npix < npr.mP) {
               const Geo ng = with_dims(p.g, npr.d);
               int nn, nho, nwo;
@@ -471,8 +516,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
             SDB_ISSUE(ntap, nch, it + RING - ITERS, slot)
           }
         }
+        // (fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC; moving it to the MMA warp, so that the gather
+        // warps do not wait for the next stage's loads they have just issued, was measured: no difference)
         fence_proxy_async_smem();
-        mbar_arrive_warp(&a_full[as]);
+        if (PAIR && rank != 0) {      // the pair's A stage is complete when both CTAs' warps have arrived on the LEADER's barrier
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&a_full[as], 0);
+        } else {
+          mbar_arrive_warp(&a_full[as]);
+        }
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
         tap = ntap;
         ch = nch;
@@ -482,15 +534,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tc_kernel(const __grid_co
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (PAIR) cluster_sync_all();   // both CTAs are done with the pair's tensor memory
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc2(tmem_base, ncols);
+    else tmem_dealloc(tmem_base, ncols);
+  }
 }
 
-template <int LPP, bool OUT_BF16, bool CONV>
+template <int LPP, bool OUT_BF16, bool CONV, bool PAIR>
 int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV>), smem);
+  SDB_ENSURE_SMEM((dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV, PAIR>), smem);
   ProfScope prof(SDB_OP_FORWARD, st);
-  dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV, PAIR>, p));
+    SDB_LAUNCHED(1);
+  } else {
+    dcn_fwd_tc_kernel<LPP, OUT_BF16, CONV, PAIR><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  }
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -498,6 +565,11 @@ int launch_fwd(const FwdParams& p, size_t smem, int grid, cudaStream_t st) {
 // Stage counts from the shared-memory budget; returns the dynamic smem size (0 = does not fit).  200 KB of the 228 KB
 // array go to shared memory: giving the L1 more (budgets of 140 / 170 KB, 64- instead of 128-channel stages) was
 // measured to change the forward by -1 .. +7 % (profiles/r2_tuning.md) -- the gather is not bound by L1 capacity.
+}  // namespace
+// CTA-pair forward (sdb_set_forward_pair): on by default.  Measured on the benchmarked head: forward 215 -> 209 us, the
+// plain-convolution forward 147 -> 137 us (shared-memory "bank conflict" arbitration -60 %, LSU wavefronts -11 %).
+int g_fwd_pair = 1;
+namespace {
 size_t plan_smem(FwdParams& p, size_t a_bytes, size_t b_bytes, size_t d_bytes) {
   const size_t budget = 200 * 1024;
   p.nsa = 2;
@@ -594,14 +666,36 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
   const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
-  const int grid = total < grid_sms() ? total : grid_sms();
   const bool obf = io_dtype == SDB_BF16;
-  if (pb[0].off == nullptr) {   // plain convolution: every problem of the call (api.cu checks that they agree)
-    if (lpp == 16) return obf ? launch_fwd<16, true, true>(p, smem, grid, st) : launch_fwd<16, false, true>(p, smem, grid, st);
-    return obf ? launch_fwd<8, true, true>(p, smem, grid, st) : launch_fwd<8, false, true>(p, smem, grid, st);
+  const bool conv = pb[0].off == nullptr;   // plain convolution: every problem of the call (api.cu checks that they agree)
+  // CTA pairs: work items are PAIRS of tiles of one problem (an odd tile count leaves the second CTA of the last pair an
+  // all-invalid tile), C_out split in two halves of a multiple of 16 rows
+  const bool pair = g_fwd_pair && g.O % 32 == 0 && lpp == 16;
+  if (pair) {
+    // half-size weight slots free shared memory for a third A stage (the two CTAs advance in lock-step: slack helps)
+    p.nsa = 3;
+    long long nsb = ((long long)(200 * 1024) - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)(b_bytes / 2);
+    if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+    SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
+    p.nsb = (int)nsb;
+    const size_t smem2 = p.nsa * a_bytes + p.nsb * (b_bytes / 2) + d_bytes + 1024;
+    total = 0;
+    for (int i = 0; i < n; ++i) {
+      p.map.start[i] = total;
+      total += cdiv(cdiv(with_dims(g, pb[i].d).P(), TILE_M), 2);
+    }
+    p.map.start[n] = total;
+    const int clusters = total < grid_sms() / 2 ? total : grid_sms() / 2;
+    if (conv) return obf ? launch_fwd<16, true, true, true>(p, smem2, 2 * clusters, st) : launch_fwd<16, false, true, true>(p, smem2, 2 * clusters, st);
+    return obf ? launch_fwd<16, true, false, true>(p, smem2, 2 * clusters, st) : launch_fwd<16, false, false, true>(p, smem2, 2 * clusters, st);
   }
-  if (lpp == 16) return obf ? launch_fwd<16, true, false>(p, smem, grid, st) : launch_fwd<16, false, false>(p, smem, grid, st);
-  return obf ? launch_fwd<8, true, false>(p, smem, grid, st) : launch_fwd<8, false, false>(p, smem, grid, st);
+  const int grid = total < grid_sms() ? total : grid_sms();
+  if (conv) {
+    if (lpp == 16) return obf ? launch_fwd<16, true, true, false>(p, smem, grid, st) : launch_fwd<16, false, true, false>(p, smem, grid, st);
+    return obf ? launch_fwd<8, true, true, false>(p, smem, grid, st) : launch_fwd<8, false, true, false>(p, smem, grid, st);
+  }
+  if (lpp == 16) return obf ? launch_fwd<16, true, false, false>(p, smem, grid, st) : launch_fwd<16, false, false, false>(p, smem, grid, st);
+  return obf ? launch_fwd<8, true, false, false>(p, smem, grid, st) : launch_fwd<8, false, false, false>(p, smem, grid, st);
 }
 
 }  // namespace sdb

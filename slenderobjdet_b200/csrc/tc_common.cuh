@@ -178,16 +178,19 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of every 
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+  // default semantics (as cutlass::arch::ClusterBarrier::arrive): the .release.cluster form compiles to MEMBAR.ALL +
+  // ERRBAR, which makes a gather warp wait for every load it has in flight; what crosses CTAs here is shared memory
+  // written for the async proxy (fence.proxy.async by the writers), not generic-proxy data
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
-// wait (cluster-scope acquire) on a local mbarrier whose arrivals come from the peer CTA; bounded like mbar_wait
+// wait on a local mbarrier whose arrivals come (also) from the peer CTA; bounded like mbar_wait
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");

@@ -20,6 +20,9 @@ ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--iters", type=int, default=20)
 a = ap.parse_args()
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+if os.environ.get("PAIR"):   # developer switch: CTA-pair forward kernel
+    from slenderobjdet_b200 import _lib as _L
+    _L.lib().sdb_set_forward_pair(int(os.environ["PAIR"]))
 bf = torch.bfloat16
 g = torch.Generator().manual_seed(0)
 C = 256
