@@ -407,6 +407,8 @@ int sdb_set_sm_reserve(int n_sms);
  * (M = 256: each CTA gathers its own 128 output pixels and streams half of every weight tile) when C_in % 128 == 0 and
  * C_out % 32 == 0.  on == 0 selects the one-CTA kernel (M = 128) instead -- results are identical; process-wide. */
 int sdb_set_forward_pair(int on);
+/* The same for the grad_offset / dcol kernel of the backward (C_in % 128 == 0). */
+int sdb_set_backward_pair(int on);
 
 #ifdef __cplusplus
 }

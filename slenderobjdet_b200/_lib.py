@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sdb_dcn_backward_data", "sdb_dcn_backward_weight", "sdb_dcn_prepared_weight_bytes", "sdb_dcn_prepare_weights",
     "sdb_dcn_multi_workspace_bytes", "sdb_dcn_forward_multi", "sdb_dcn_backward_multi", "sdb_assign_workspace_bytes",
     "sdb_iou_assign", "sdb_match_quality_assign", "sdb_pairwise_iou", "sdb_sigmoid_focal_loss",
-    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count", "sdb_set_sm_reserve", "sdb_set_forward_pair", "sdb_gn_relu_workspace_bytes", "sdb_gn_relu_forward", "sdb_gn_relu_backward",
+    "sdb_box_reg_loss", "sdb_centerness_targets", "sdb_slender_centerness_targets", "sdb_fcos_location_targets_batched", "sdb_points_postprocess_workspace_bytes", "sdb_points_postprocess", "sdb_point_targets_workspace_bytes", "sdb_point_targets", "sdb_fcos_location_targets", "sdb_fcos_topk_workspace_bytes", "sdb_fcos_topk_location_targets", "sdb_reppoints_dcn_offset", "sdb_reppoints_dcn_offset_backward", "sdb_profile_enable", "sdb_profile_reset", "sdb_profile_read", "sdb_launch_count", "sdb_set_sm_reserve", "sdb_set_forward_pair", "sdb_set_backward_pair", "sdb_gn_relu_workspace_bytes", "sdb_gn_relu_forward", "sdb_gn_relu_backward",
 ]
 
 
@@ -138,6 +138,8 @@ def _declare(lib):
     for f in (lib.sdb_gn_relu_forward, lib.sdb_gn_relu_backward):
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.POINTER(GnTensor), _i32, ctypes.POINTER(GnParams), _i32, _i32, _i32, _f32, _i32, _i32, _vp, _sz, _vp]
+    lib.sdb_set_backward_pair.restype = ctypes.c_int
+    lib.sdb_set_backward_pair.argtypes = [_i32]
     lib.sdb_set_forward_pair.restype = ctypes.c_int
     lib.sdb_set_forward_pair.argtypes = [_i32]
     lib.sdb_set_sm_reserve.restype = ctypes.c_int

@@ -12,7 +12,7 @@ namespace sdb {
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
 namespace tcshared { int g_sm_reserve = 0; }
-extern int g_fwd_pair;
+extern int g_fwd_pair, g_bwd_pair;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -132,6 +132,10 @@ int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 long long sdb_launch_count(void) { return g_launches; }
 int sdb_set_forward_pair(int on) {
   g_fwd_pair = on != 0;
+  return SDB_OK;
+}
+int sdb_set_backward_pair(int on) {
+  g_bwd_pair = on != 0;
   return SDB_OK;
 }
 int sdb_set_sm_reserve(int n) {

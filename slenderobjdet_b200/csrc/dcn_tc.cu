@@ -673,7 +673,7 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   const bool pair = g_fwd_pair && g.O % 32 == 0 && lpp == 16;
   if (pair) {
     // half-size weight slots free shared memory for a third A stage (the two CTAs advance in lock-step: slack helps)
-    p.nsa = 3;
+    p.nsa = 3;   // measured: 2 or 4 A stages (with 6 / 2 weight slots) are 1-2 % slower
     long long nsb = ((long long)(200 * 1024) - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)(b_bytes / 2);
     if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
     SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");

@@ -213,19 +213,27 @@ __device__ __forceinline__ void fma_pair_hi(float& acc, uint32_t s2, uint32_t c2
       "fma.rn.f32.bf16 %0, sl, ch, %0;\n fma.rn.f32.bf16 %0, sh, ch, %0;\n }" : "+f"(acc) : "r"(s2), "r"(c2));
 }
 
-template <int NCH>
+// PAIR: clusters of two CTAs (cta_group::2, M = 256): a work item is a pair of tiles of one problem; each CTA loads its own
+// dY tile and HALF of every W^T tile (NCH/2 rows), the leader's MMA warp issues for both, the peer's MMA warp relays its
+// CTA's a_full / b_full completions; everything downstream of TMEM (drain, reduce, export) stays per CTA.
+template <int NCH, bool PAIR>
 __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __grid_constant__ DgradParams p) {
   constexpr int LPB = NCH / 8, PPI = 32 / LPB;
-  constexpr uint32_t B_BYTES = NCH * 128;            // one [NCH c][64 o] weight tile
+  constexpr uint32_t B_TILE = NCH * 128;             // one [NCH c][64 o] weight tile of the image
+  constexpr uint32_t B_BYTES = PAIR ? B_TILE / 2 : B_TILE;   // what this CTA loads of it = slot size
   constexpr uint32_t STG_BYTES = stg_tile_bytes(NCH);   // bf16 staging tile (padded rows)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full, a_empty;
   __shared__ __align__(8) uint64_t b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], stg_full[2], stg_empty[2];
+  __shared__ __align__(8) uint64_t peer_a, peer_b[MAX_B_STAGES];   // PAIR, leader: the peer's dY tile / weight slot is full
   __shared__ uint32_t tmem_base_s;
 
   const int C = p.g.C, taps = p.g.KH * p.g.KW, nch = C / NCH, units = taps * nch, okb = p.okb;
-  const int num_tiles = p.map.start[p.map.n];
+  const int num_tiles = p.map.start[p.map.n];   // PAIR: number of tile PAIRS
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t A_BYTES = (uint32_t)okb * (TILE_M * 128);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -246,15 +254,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);        // one arrival per drain warp
+      mbar_init(&acc_empty[s], PAIR ? 8 : 4);   // one arrival per drain warp (of both CTAs)
       mbar_init(&stg_full[s], 4);
       mbar_init(&stg_empty[s], NSW + 1);  // one arrival per reduce warp + the exporter
     }
+    if (PAIR) {
+      mbar_init(&peer_a, 1);
+      for (int s = 0; s < p.nsb; ++s) mbar_init(&peer_b[s], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, NCOLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc2(&tmem_base_s, NCOLS);
+    else tmem_alloc(&tmem_base_s, NCOLS);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
@@ -265,63 +281,96 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     // ===== bulk producer: dY tile once per tile, W^T tiles per (tap, chunk, o-block) =====
     if (lane == 0) {
       uint32_t bs = 0, bp = 0, ap = 0;
-      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      for (int work = work0; work < num_tiles; work += wstep) {
         const int pi = find_range(p.map, work);
         const DgradProb& pr = p.pr[pi];
-        const int tile = work - p.map.start[pi];
+        int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
+        // PAIR: the all-invalid second tile of an odd problem re-reads the first one (its results are never stored)
+        if (PAIR && (long long)tile * TILE_M >= (long long)pr.d.N * pr.d.Ho * pr.d.Wo) --tile;
         mbar_wait(&a_empty, ap ^ 1);
         mbar_arrive_expect_tx(&a_full, A_BYTES);
         bulk_g2s(sA, pr.gy_img + (size_t)tile * A_BYTES, A_BYTES, &a_full);
         ap ^= 1;
+        const uint8_t* wsrc = pr.wt_img + (size_t)rank * B_BYTES;   // PAIR: rows [rank * NCH/2, ...) of every tile
         for (int i = 0; i < units * okb; ++i) {
           mbar_wait(&b_empty[bs], bp ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-          bulk_g2s(sB + (size_t)bs * B_BYTES, pr.wt_img + (size_t)i * B_BYTES, B_BYTES, &b_full[bs]);
+          bulk_g2s(sB + (size_t)bs * B_BYTES, wsrc + (size_t)i * B_TILE, B_BYTES, &b_full[bs]);
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: dcol[128 x NCH] = dY_tile[128 x O] * W^T =====
-    const uint32_t idesc = make_idesc_bf16(TILE_M, NCH, 0, 0);
+    // ===== MMA issuer: dcol[128 x NCH] = dY_tile[128 x O] * W^T (PAIR: the leader, for both CTAs' tiles) =====
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, NCH, 0, 0);
     uint32_t bs = 0, bp = 0, acc = 0, accp = 0, ap = 0;
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+    if (PAIR && rank != 0) {
+      // the peer's bulk copies complete on its own barriers: relay them to the leader
+      for (int work = work0; work < num_tiles; work += wstep) {
+        mbar_wait(&a_full, ap);
+        ap ^= 1;
+        if (lane == 0) mbar_arrive_remote(&peer_a, 0);
+        for (int i = 0; i < units * okb; ++i) {
+          mbar_wait(&b_full[bs], bp);
+          if (lane == 0) mbar_arrive_remote(&peer_b[bs], 0);
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+      }
+    } else
+    for (int work = work0; work < num_tiles; work += wstep) {
       mbar_wait(&a_full, ap);
+      if (PAIR) mbar_wait_cluster(&peer_a, ap);
       ap ^= 1;
       for (int u = 0; u < units; ++u) {
-        mbar_wait(&acc_empty[acc], accp ^ 1);
+        if (PAIR) mbar_wait_cluster(&acc_empty[acc], accp ^ 1);
+        else mbar_wait(&acc_empty[acc], accp ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * NCH;
         for (int kb = 0; kb < okb; ++kb) {
           mbar_wait(&b_full[bs], bp);
+          if (PAIR) mbar_wait_cluster(&peer_b[bs], bp);
           tc_fence_after_sync();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + kb * (TILE_M * 128);
             const uint32_t b_addr = smem_base + A_BYTES + bs * B_BYTES;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
-                        make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, (kb | k4) != 0);
-            umma_commit(&b_empty[bs]);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (PAIR)
+                umma_bf16_pair(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                               make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, (kb | k4) != 0);
+              else
+                umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32, 16, 1024),
+                          make_smem_desc_sw128(b_addr + k4 * 32, 16, 1024), idesc, (kb | k4) != 0);
+            }
+            if (PAIR) umma_commit_pair(&b_empty[bs]);
+            else umma_commit(&b_empty[bs]);
           }
           __syncwarp();
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
         }
-        if (elect_one()) umma_commit(&acc_full[acc]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&acc_full[acc]);
+          else umma_commit(&acc_full[acc]);
+        }
         __syncwarp();
         if (++acc == 2) { acc = 0; accp ^= 1; }
       }
-      if (elect_one()) umma_commit(&a_empty);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(&a_empty);
+        else umma_commit(&a_empty);
+      }
       __syncwarp();
     }
   } else if (warp == 2) {
     // ===== dcol exporter: every finished staging tile goes to HBM as one bulk copy (the grad_input gather reads it) =====
     if (lane == 0) {
       uint32_t sb = 0, sp = 0;
-      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+      for (int work = work0; work < num_tiles; work += wstep) {
         const int pi = find_range(p.map, work);
         uint8_t* dst = p.pr[pi].dcol;
-        if (dst) dst += (size_t)(work - p.map.start[pi]) * units * STG_BYTES;
+        const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
+        if (PAIR && (long long)tile * TILE_M >= (long long)p.pr[pi].d.N * p.pr[pi].d.Ho * p.pr[pi].d.Wo) dst = nullptr;
+        if (dst) dst += (size_t)tile * units * STG_BYTES;
         for (int u = 0; u < units; ++u) {
           mbar_wait(&stg_full[sb], sp);
           if (dst) {
@@ -343,7 +392,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     const int q = warp & 3;
     const uint32_t row = q * 32 + lane;
     uint32_t acc = 0, accp = 0;
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+    for (int work = work0; work < num_tiles; work += wstep) {
       for (int u = 0; u < units; ++u) {
         mbar_wait(&acc_full[acc], accp);
         tc_fence_after_sync();
@@ -366,7 +415,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
         }
         tc_fence_before_sync();
         fence_proxy_async_smem();            // the exporter's bulk copy reads the tile through the async proxy
-        mbar_arrive_warp(&acc_empty[acc]);   // TMEM buffer may be overwritten
+        if (PAIR && rank != 0) {             // TMEM buffer may be overwritten: the pair's buffer is released on the leader
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+        } else {
+          mbar_arrive_warp(&acc_empty[acc]);
+        }
         mbar_arrive_warp(&stg_full[acc]);    // staging tile is ready (release)
         if (++acc == 2) { acc = 0; accp ^= 1; }
       }
@@ -390,10 +444,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     const int sw = warp - G_SW0, r0 = sw * PIX_PER_WARP;
     const int grp = lane / LPB, lig = lane % LPB;
     uint32_t sb = 0, sp = 0;
-    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+    for (int work = work0; work < num_tiles; work += wstep) {
       const int pi = find_range(p.map, work);
       const DgradProb& pr = p.pr[pi];
-      const int tile = work - p.map.start[pi];
+      const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
       if (!pr.goff && !pr.gmask) {   // problem that only wants dcol (grad_input without grad_offset): release the tiles
         for (int u = 0; u < units; ++u) {
           mbar_wait(&stg_full[sb], sp);
@@ -532,8 +586,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) dcn_bwd_data_tc_kernel(const __g
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, NCOLS);
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc2(tmem_base, NCOLS);
+    else tmem_dealloc(tmem_base, NCOLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1087,6 +1145,9 @@ int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_
   return tc_forward_multi(pb, n, g, io_dtype, st);
 }
 
+// CTA-pair grad_offset kernel (sdb_set_backward_pair)
+int g_bwd_pair = 1;
+
 // ---- backward: grad_offset / grad_mask, grad_input, grad_weight / grad_bias of all problems ------------------------
 // dY is packed once per problem (tile image + NHWC rows) and serves the three kernels; the transposed index is built
 // once per offset group; one launch per kernel over all problems.
@@ -1163,19 +1224,44 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     }
     p.map.n = m; p.map.start[m] = total;
     if (total > 0) {
-      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = NCH * 128, stg = 2 * (size_t)stg_tile_bytes(NCH);
+      // CTA pairs (sdb_set_backward_pair): work items are PAIRS of tiles of one problem, half-size weight slots
+      const bool pair = g_bwd_pair && NCH == 128;
+      if (pair) {
+        total = 0;
+        for (int k = 0; k < m; ++k) {
+          p.map.start[k] = total;
+          total += cdiv(cdiv((long long)p.pr[k].d.N * p.pr[k].d.Ho * p.pr[k].d.Wo, TILE_M), 2);
+        }
+        p.map.start[m] = total;
+      }
+      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = (size_t)NCH * 128 / (pair ? 2 : 1), stg = 2 * (size_t)stg_tile_bytes(NCH);
       long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
       if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
       SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
       p.nsb = (int)nsb;
       const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
-      const int grid = total < grid_sms() ? total : grid_sms();
-      if (NCH == 128) SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<128>, smem);
-      else SDB_ENSURE_SMEM(dcn_bwd_data_tc_kernel<64>, smem);
       {
         ProfScope prof(SDB_OP_BACKWARD_DATA, st);
-        if (NCH == 128) dcn_bwd_data_tc_kernel<128><<<grid, G_THREADS, smem, st>>>(p);
-        else dcn_bwd_data_tc_kernel<64><<<grid, G_THREADS, smem, st>>>(p);
+        if (pair) {
+          const int clusters = total < grid_sms() / 2 ? total : grid_sms() / 2;
+          SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, true>), smem);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(G_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          SDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dcn_bwd_data_tc_kernel<128, true>, p));
+        } else {
+          const int grid = total < grid_sms() ? total : grid_sms();
+          if (NCH == 128) {
+            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, false>), smem);
+            dcn_bwd_data_tc_kernel<128, false><<<grid, G_THREADS, smem, st>>>(p);
+          } else {
+            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<64, false>), smem);
+            dcn_bwd_data_tc_kernel<64, false><<<grid, G_THREADS, smem, st>>>(p);
+          }
+        }
         SDB_LAUNCHED(1);
       }
       SDB_CHECK_CUDA(cudaGetLastError());
