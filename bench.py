@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]  # P3..P7 of an 800x1344 image
 C_IN = C_OUT = 256
 BATCH_PER_GPU = 2
+GATHER_OVERLAP = os.environ.get("SDB_BENCH_GATHER_OVERLAP", "0") != "0"   # measured on 2 GPUs: 0.896 ms vs 0.860 ms for the default order
 ONE_GRAPH = os.environ.get("SDB_BENCH_ONE_GRAPH", "1") != "0"   # N > 1: capture the all-reduce into the step's CUDA graph
 NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "0"))  # developer knob: cap the overlapped all-reduce at this many CTAs and leave
 # that many SMs free in the persistent kernels (sdb_set_sm_reserve).  Measured on 2 GPUs: 0 (NCCL default) 0.877 ms, 16 -> 0.877, 8 -> 0.891,
@@ -277,6 +278,16 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
     with the data-gradient kernels."""
     L = wl._lib
     graphs = None
+    # N > 1, default order: weight gradients first, then the all-reduce beside grad_offset + grad_input.
+    # SDB_BENCH_GATHER_OVERLAP=1 (experiment, slower): grad_offset / grad_mask first, then the weight gradients, then the
+    # all-reduce beside the grad_input gather only (an ordinary grid) -- the collective then starts later than it can
+    # finish behind a 150 us HBM-latency-bound kernel
+    if GATHER_OVERLAP:
+        FIRST_HALF = L.SDB_BWD_DATA_ONLY | L.SDB_BWD_NO_GATHER
+        SECOND_HALF = L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GATHER_ONLY | L.SDB_BWD_GRAD_PACKED
+    else:
+        FIRST_HALF = L.SDB_BWD_WEIGHT_ONLY
+        SECOND_HALF = L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED
     with torch.cuda.stream(stream):
         wl.step(stream)
         stream.synchronize()
@@ -297,9 +308,11 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 wl.phase_forward(stream)
-                wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+                wl.phase_backward(stream, FIRST_HALF)
+                if GATHER_OVERLAP:
+                    wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_GRAD_PACKED)
                 work = wl.bucket.all_reduce(average=True, async_op=True, prescaled=True)
-                wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+                wl.phase_backward(stream, SECOND_HALF)
                 if work is not None:
                     work.wait()
             return [g]
@@ -308,10 +321,12 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga, stream=stream):
                 wl.phase_forward(stream)
-                wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+                wl.phase_backward(stream, FIRST_HALF)
+                if GATHER_OVERLAP:
+                    wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_GRAD_PACKED)
             L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))   # grids are baked into the graph at capture
             with torch.cuda.graph(gb, stream=stream):
-                wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+                wl.phase_backward(stream, SECOND_HALF)
             L.lib().sdb_set_sm_reserve(0)
             return [ga, gb]
 
@@ -340,7 +355,9 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
             graphs[0].replay()
         else:
             wl.phase_forward(stream)
-            wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY)
+            wl.phase_backward(stream, FIRST_HALF)
+            if GATHER_OVERLAP:
+                wl.phase_backward(stream, L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_GRAD_PACKED)
         # the weight gradients (already scaled by 1/world in the kernel) are complete: reduce them on NCCL's stream
         # while grad_input / grad_offset run
         work = wl.bucket.all_reduce(average=True, async_op=True, prescaled=True)
@@ -348,7 +365,7 @@ def time_workload(torch, wl, stream, steps, warmup, l2_flush, world=1, dist=None
             graphs[1].replay()
         else:
             L.lib().sdb_set_sm_reserve(max(NCCL_CTAS, 0))
-            wl.phase_backward(stream, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED)
+            wl.phase_backward(stream, SECOND_HALF)
             L.lib().sdb_set_sm_reserve(0)
         if work is not None:
             work.wait()
@@ -594,7 +611,7 @@ def run_ours(args):
                        "launch": mode, "launches_per_step": int(launches_per_step + torch_fills_per_step),
                        "tflops_per_s": round(flops_step * world / (step_ms * 1e-3) / 1e12, 2),
                        "allreduce_bytes": HEAD_PARAMS * 4 if world > 1 else 0,
-                       "allreduce": "overlapped with grad_input / grad_offset, 1/world folded into the kernel" if world > 1 else None},
+                       "allreduce": ("overlapped with the grad_input gather (after grad_offset and the weight gradients), 1/world folded into the kernel" if GATHER_OVERLAP else "overlapped with grad_offset + grad_input, 1/world folded into the kernel") if world > 1 else None},
             "roofline": roofline,
             "parity": parity,
             "cpu_baseline": {"value": round(cb["value"], 5), "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],

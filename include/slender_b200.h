@@ -188,8 +188,13 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n_problems, c
  *   SDB_BWD_WEIGHT_ONLY  only grad_weight / grad_bias (first call: packs grad_out into the workspace);
  *   SDB_BWD_DATA_ONLY    only grad_x / grad_offset / grad_mask;
  *   SDB_BWD_GRAD_PACKED  the workspace still holds the packed grad_out of a previous call on the SAME table
- *                        (second call: SDB_BWD_DATA_ONLY | SDB_BWD_GRAD_PACKED while NCCL reduces the weight grads). */
-enum { SDB_BWD_WEIGHT_ONLY = 1, SDB_BWD_DATA_ONLY = 2, SDB_BWD_GRAD_PACKED = 4 };
+ *                        (second call: SDB_BWD_DATA_ONLY | SDB_BWD_GRAD_PACKED while NCCL reduces the weight grads);
+ *   SDB_BWD_NO_GATHER    grad_offset / grad_mask (and, unless DATA_ONLY, the weight gradients) now, the grad_x gather later:
+ *                        the dcol tiles and the transposed index stay in the workspace;
+ *   SDB_BWD_GATHER_ONLY  only the grad_x gather, from the workspace a SDB_BWD_NO_GATHER call on the SAME table left.
+ *                        (Lets a caller place the gather -- an ordinary, non-persistent grid -- wherever its schedule wants it;
+ *                        running the all-reduce beside the gather alone was measured slower than beside grad_offset + gather.) */
+enum { SDB_BWD_WEIGHT_ONLY = 1, SDB_BWD_DATA_ONLY = 2, SDB_BWD_GRAD_PACKED = 4, SDB_BWD_NO_GATHER = 8, SDB_BWD_GATHER_ONLY = 16 };
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
                            int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags,
                            void* workspace, size_t workspace_bytes, void* stream);

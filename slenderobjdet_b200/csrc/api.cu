@@ -460,8 +460,8 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
   if (flags & SDB_BWD_WEIGHT_ONLY)
     for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
   if (mc.plan.conv) {
-    SDB_REQUIRE(!accumulate_gx && !(flags & SDB_BWD_GRAD_PACKED), SDB_ERR_UNSUPPORTED,
-                "plain convolution: grad_x is overwritten, and SDB_BWD_GRAD_PACKED is not supported");
+    SDB_REQUIRE(!accumulate_gx && !(flags & (SDB_BWD_GRAD_PACKED | SDB_BWD_NO_GATHER | SDB_BWD_GATHER_ONLY)), SDB_ERR_UNSUPPORTED,
+                "plain convolution: grad_x is overwritten, and the phased-backward flags are not supported");
     const void* wt[tcshared::MAX_WEIGHTS];
     for (int k = 0; k < nw; ++k) {
       wt[k] = weights[k].weight;
@@ -471,15 +471,18 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     }
     return tc_conv_backward_all(mc.pb, n, wt, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, (uint8_t*)workspace, st);
   }
+  const int phase = (flags & SDB_BWD_NO_GATHER) ? 1 : (flags & SDB_BWD_GATHER_ONLY) ? 2 : 0;
   return tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
-                         (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st);
+                         (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st, phase);
 }
 
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
                            const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags, void* workspace,
                            size_t workspace_bytes, void* stream) {
   SDB_MULTI_PROLOGUE();
-  SDB_REQUIRE((flags & ~7) == 0 && (flags & 3) != 3, SDB_ERR_INVALID, "bad backward flags %d", flags);
+  SDB_REQUIRE((flags & ~31) == 0 && (flags & 3) != 3 && (flags & 24) != 24 && !((flags & 24) && (flags & SDB_BWD_WEIGHT_ONLY)),
+              SDB_ERR_INVALID, "bad backward flags %d", flags);
+  SDB_REQUIRE(!(flags & 24) || math == SDB_MATH_BF16, SDB_ERR_UNSUPPORTED, "SDB_BWD_NO_GATHER / GATHER_ONLY need SDB_MATH_BF16");
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].grad_out && (problems[i].offset || math == SDB_MATH_BF16)),

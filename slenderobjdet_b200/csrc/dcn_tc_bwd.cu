@@ -1153,13 +1153,19 @@ int g_bwd_pair = 1;
 // once per offset group; one launch per kernel over all problems.
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
                     int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
-                    cudaStream_t st) {
+                    cudaStream_t st, int gather_phase) {
   const int NCH = nch_of(g), okb = okb_of(g);
   const bool bf = io_dtype == SDB_BF16;
   int rc;
   bool any_goff = false, any_gx = false, any_gw = false, any_gb = false;
   for (int i = 0; i < n; ++i) { any_goff |= pb[i].goff || pb[i].gmask; any_gx |= pb[i].gx != nullptr; }
   for (int w = 0; w < nweights; ++w) { any_gw |= gw[w] != nullptr; any_gb |= gb[w] != nullptr; }
+  if (gather_phase == 2) {   // only the gather: dcol tiles and index were left in the workspace by a phase-1 call
+    if (!any_gx) return SDB_OK;
+    rc = tc_build_transposed_index(pb, n, P, g, base, st, true);
+    if (rc) return rc;
+    return tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
+  }
 
   // (0) layouts: x -> NHWC (unless the forward exported it), dY -> tile image and NHWC rows
   if (pack_x && !grad_packed && (any_goff || any_gw)) {   // grad_input alone does not read x
@@ -1271,8 +1277,10 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   // (2b) grad_input: gather of the dcol tiles over the transposed index
   if (any_gx) {
     if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
-    if (rc) return rc;
+    if (gather_phase != 1) {
+      rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
+      if (rc) return rc;
+    }
   }
 
   // (3) grad_weight (+ grad_bias): one CTA per (weight, tap, channel chunk, pixel split) over that weight's tiles

@@ -399,12 +399,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1024 / THREADS) 
 }  // namespace
 
 // the transposed sampling index (one per offset group) of a call, on stream `st`
-int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st) {
+int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st,
+                              bool pointers_only) {
   int* cnt = (int*)(base + P.cnt_off);
   int* start = (int*)(base + P.start_off);
   int* bsum = (int*)(base + P.bsum_off);
   CEntry* ent = (CEntry*)(base + P.ent_off);
   uint4* blocks = (uint4*)(base + P.blk_off);
+  if (pointers_only) {   // the index of a previous call on the same table is still in the workspace (SDB_BWD_GATHER_ONLY)
+    for (int i = 0; i < n; ++i) {
+      pb[i].start = start + P.key_base[P.group_of[i]];
+      pb[i].ent = blocks;
+    }
+    return SDB_OK;
+  }
   CsrTable t{};
   t.g = g;
   int total = 0, m = 0;

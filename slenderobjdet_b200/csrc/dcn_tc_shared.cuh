@@ -62,11 +62,14 @@ struct TcPlan {
 TcPlan tc_plan(const TcProblem* pb, int n, int nweights, const bool* have_prepared, const Geo& g, bool backward);
 int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
 int tc_dx_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, int accumulate, cudaStream_t st);
-int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st);
+int tc_build_transposed_index(TcProblem* pb, int n, const TcPlan& P, const Geo& g, uint8_t* base, cudaStream_t st,
+                              bool pointers_only = false);
 int tc_forward_all(TcProblem* pb, int n, const Geo& g, int io_dtype, cudaStream_t st);
+// gather_phase: 0 = everything; 1 = everything but the grad_input gather (dcol tiles and the transposed index stay in the
+// workspace); 2 = only the gather, from the workspace a phase-1 call on the same table left behind
 int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, int nweights, const TcPlan& P, const Geo& g,
                     int io_dtype, float scale, bool pack_x, int accumulate_gx, bool grad_packed, uint8_t* base,
-                    cudaStream_t st);
+                    cudaStream_t st, int gather_phase = 0);
 // plain convolution (offset == nullptr): grad_weight over the saved columns, grad_input = conv(dY, W') by the forward kernel
 int tc_conv_backward_all(TcProblem* pb, int n, const void* const* weights, float* const* gw, float* const* gb, int nweights,
                          const TcPlan& P, const Geo& g, int io_dtype, float scale, bool pack_x, uint8_t* base,

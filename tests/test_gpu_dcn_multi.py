@@ -191,3 +191,41 @@ def test_prepared_weights_follow_weight_updates():
         y2 = conv(x, off)
     assert rel_err(y1.cpu().numpy(), (2 * y0).cpu().numpy()) < 1e-3
     assert rel_err(y2.cpu().numpy(), y0.cpu().numpy()) < 1e-3
+
+
+def test_phased_backward_through_the_c_abi_equals_one_call():
+    """sdb_dcn_backward_multi in phases -- the order bench.py uses to run the all-reduce beside the grad_input gather:
+    DATA_ONLY|NO_GATHER, then WEIGHT_ONLY|GRAD_PACKED, then DATA_ONLY|GATHER_ONLY -- gives the bits of the one-call
+    backward (same kernels, same workspace)."""
+    import bench
+    from slenderobjdet_b200 import _lib as L
+    dev = torch.device("cuda", 0)
+    wl = bench.Workload(torch, L, dev, seed=3, batch=2, levels=[(25, 42), (13, 21), (7, 11)])
+    st = torch.cuda.current_stream(dev)
+
+    brs = [br for lv in wl.lv for br in lv["br"]]
+
+    def grads():
+        return [b["gx"].clone() for b in brs] + [b["goff"].clone() for b in brs] + [g.clone() for g in wl.gw]
+
+    def clear():
+        for b in brs:
+            b["gx"].zero_()
+            b["goff"].zero_()
+        for g in wl.gw:
+            g.zero_()
+
+    wl.phase_forward(st)
+    clear()
+    wl.phase_backward(st, 0)
+    torch.cuda.synchronize()
+    one = grads()
+    clear()
+    wl.phase_backward(st, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_NO_GATHER)
+    torch.cuda.synchronize()
+    assert all(float(b["gx"].float().abs().max()) == 0.0 for b in brs)     # the gather has not run yet
+    wl.phase_backward(st, L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_GRAD_PACKED)
+    wl.phase_backward(st, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GATHER_ONLY | L.SDB_BWD_GRAD_PACKED)
+    torch.cuda.synchronize()
+    for a, b in zip(one, grads()):
+        assert torch.equal(a, b)
