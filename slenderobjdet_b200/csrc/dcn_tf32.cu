@@ -24,6 +24,7 @@
 #include "dcn_tc_shared.cuh"
 
 namespace sdb {
+extern int g_fwd_pair;   // dcn_tc.cu: CTA-pair forward switch (sdb_set_forward_pair)
 namespace {
 using namespace tc;
 using namespace tcshared;
@@ -47,6 +48,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4)                      // D format: f32
          | (2u << 7) | (2u << 10)       // A, B format: tf32, both K-major
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -176,9 +185,12 @@ __device__ __forceinline__ void make_fdesc(const Geo& g, float dy, float dx, flo
   if (b && r) { d.off[3] = (uint32_t)((base + h_high) * g.W + w_high) * row_units; d.w[3] = lh * lw * m; }
 }
 
-template <int PASSES>
+// PAIR: CTA pairs (cta_group::2, M = 256) exactly as in dcn_tc.cu: a work item is a pair of tiles of one problem, each CTA
+// streams half the rows of every weight tile, the leader issues, commits are multicast, the peer relays its weight barriers.
+template <int PASSES, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_constant__ F32Params p) {
   constexpr int PARTS = PASSES == 3 ? 2 : 1;
+  constexpr int SLOT = PAIR ? B_SLOT / 2 : B_SLOT;   // weight slot: this CTA's rows of a tile
   constexpr int A_BYTES = PARTS * PART_BYTES;
   constexpr int PPI = 32 / LPP;                // pixels per warp instruction (4)
   constexpr int PIX_PER_WARP = TILE_M / NPW;   // 16
@@ -188,12 +200,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
   __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A];
   __shared__ __align__(8) uint64_t b_full[MAX_B], b_empty[MAX_B];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t peer_b[MAX_B];   // PAIR, leader: the peer's weight slot is full
   __shared__ uint32_t tmem_base_s;
 
   const int O = p.g.O, C = p.g.C, taps = p.g.KH * p.g.KW, nchunks = C / CPS;
   const int nstages = taps * nchunks;
   const int nhalves = (O + 127) >> 7;
-  const int num_work = p.map.start[p.map.n];
+  const int num_work = p.map.start[p.map.n];   // PAIR: tile pairs
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sA = sm;
@@ -205,14 +221,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
   const uint32_t ncols = 2 * acc_stride;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nsa; ++s) { mbar_init(&a_full[s], NPW); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.nsa; ++s) { mbar_init(&a_full[s], PAIR ? 2 * NPW : NPW); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.nsb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR ? 8 : 4); }
+    if (PAIR)
+      for (int s = 0; s < p.nsb; ++s) mbar_init(&peer_b[s], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc2(&tmem_base_s, ncols);
+    else tmem_alloc(&tmem_base_s, ncols);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
@@ -220,70 +242,95 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
     // ===== weight producer: one bulk copy per (stage, half, part) tile, in image order =====
     if (lane == 0) {
       uint32_t bs = 0, bp = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (int work = work0; work < num_work; work += wstep) {
         const uint8_t* src = p.pr[find_range(p.map, work)].wimg;
         for (int st = 0; st < nstages; ++st)
           for (int h = 0; h < nhalves; ++h) {
-            const uint32_t bytes = (uint32_t)min(128, O - h * 128) * 128u;
+            const uint32_t tile_bytes = (uint32_t)min(128, O - h * 128) * 128u;
+            const uint32_t bytes = PAIR ? tile_bytes / 2 : tile_bytes;   // PAIR: rows [rank * N_h/2, ...) of the tile
 #pragma unroll
             for (int part = 0; part < PARTS; ++part) {
               mbar_wait(&b_empty[bs], bp ^ 1);
               mbar_arrive_expect_tx(&b_full[bs], bytes);
-              bulk_g2s(sB + (size_t)bs * B_SLOT, src, bytes, &b_full[bs]);
-              src += bytes;
+              bulk_g2s(sB + (size_t)bs * SLOT, src + (size_t)rank * bytes, bytes, &b_full[bs]);
+              src += tile_bytes;
               if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
             }
           }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (PAIR: leader only; the peer's warp relays its weight barriers) =====
     uint32_t as = 0, ap = 0, bs = 0, bp = 0, acc = 0, accp = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      mbar_wait(&acc_empty[acc], accp ^ 1);
+    if (PAIR && rank != 0) {
+      for (int work = work0; work < num_work; work += wstep)
+        for (int i = 0; i < nstages * nhalves * PARTS; ++i) {
+          mbar_wait(&b_full[bs], bp);
+          if (lane == 0) mbar_arrive_remote(&peer_b[bs], 0);
+          if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
+        }
+    } else
+    for (int work = work0; work < num_work; work += wstep) {
+      if (PAIR) mbar_wait_cluster(&acc_empty[acc], accp ^ 1);
+      else mbar_wait(&acc_empty[acc], accp ^ 1);
       tc_fence_after_sync();
       for (int st = 0; st < nstages; ++st) {
-        mbar_wait(&a_full[as], ap);
+        if (PAIR) mbar_wait_cluster(&a_full[as], ap);
+        else mbar_wait(&a_full[as], ap);
         const uint32_t a_hi = smem_base + as * A_BYTES, a_lo = a_hi + PART_BYTES;
         for (int h = 0; h < nhalves; ++h) {
-          const uint32_t idesc = make_idesc_tf32(TILE_M, min(128, O - h * 128));
+          const uint32_t idesc = make_idesc_tf32(PAIR ? 2 * TILE_M : TILE_M, min(128, O - h * 128));
           const uint32_t s_hi = bs;
           mbar_wait(&b_full[bs], bp);
+          if (PAIR) mbar_wait_cluster(&peer_b[bs], bp);
           if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
           uint32_t s_lo = s_hi;
           if (PARTS == 2) {
             s_lo = bs;
             mbar_wait(&b_full[bs], bp);
+            if (PAIR) mbar_wait_cluster(&peer_b[bs], bp);
             if (++bs == (uint32_t)p.nsb) { bs = 0; bp ^= 1; }
           }
           tc_fence_after_sync();
           if (elect_one()) {
-            const uint32_t b_hi = sB_u32 + s_hi * B_SLOT, b_lo = sB_u32 + s_lo * B_SLOT;
+            const uint32_t b_hi = sB_u32 + s_hi * SLOT, b_lo = sB_u32 + s_lo * SLOT;
             const uint32_t tmem_d = tmem_base + acc * acc_stride + (uint32_t)h * 128u;
             uint32_t accumulate = st > 0 ? 1u : 0u;
+            auto mma = [&](uint32_t a, uint32_t b, uint32_t accu) {
+              if (PAIR) umma_tf32_pair(tmem_d, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc, accu);
+              else umma_tf32(tmem_d, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc, accu);
+            };
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               if (PASSES == 3) {
-                umma_tf32(tmem_d, make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024), make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024),
-                          idesc, accumulate);
-                umma_tf32(tmem_d, make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024), make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024),
-                          idesc, 1u);
+                mma(a_lo + k4 * 32, b_hi + k4 * 32, accumulate);
+                mma(a_hi + k4 * 32, b_lo + k4 * 32, 1u);
                 accumulate = 1u;
               }
-              umma_tf32(tmem_d, make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024), make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024),
-                        idesc, accumulate);
+              mma(a_hi + k4 * 32, b_hi + k4 * 32, accumulate);
               accumulate = 1u;
             }
-            umma_commit(&b_empty[s_hi]);
-            if (PARTS == 2) umma_commit(&b_empty[s_lo]);
+            if (PAIR) {
+              umma_commit_pair(&b_empty[s_hi]);
+              if (PARTS == 2) umma_commit_pair(&b_empty[s_lo]);
+            } else {
+              umma_commit(&b_empty[s_hi]);
+              if (PARTS == 2) umma_commit(&b_empty[s_lo]);
+            }
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit(&a_empty[as]);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&a_empty[as]);
+          else umma_commit(&a_empty[as]);
+        }
         __syncwarp();
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
       }
-      if (elect_one()) umma_commit(&acc_full[acc]);
+      if (elect_one()) {
+        if (PAIR) umma_commit_pair(&acc_full[acc]);
+        else umma_commit(&acc_full[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
@@ -291,10 +338,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
     // ===== epilogue: TMEM -> registers -> NCHW global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t acc = 0, accp = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += wstep) {
       const int pi = find_range(p.map, work);
       const F32Prob& pr = p.pr[pi];
-      const int tile = work - p.map.start[pi];
+      const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
       const int hw = pr.d.Ho * pr.d.Wo;
       mbar_wait(&acc_full[acc], accp);
       tc_fence_after_sync();
@@ -322,7 +369,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
         }
       }
       tc_fence_before_sync();
-      mbar_arrive_warp(&acc_empty[acc]);
+      if (PAIR && rank != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+      } else {
+        mbar_arrive_warp(&acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; accp ^= 1; }
     }
   } else {
@@ -331,13 +383,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
     static_assert(ITERS == RING, "one ring revolution per stage");
     const int pw = warp - FIRST_PW, r0 = pw * PIX_PER_WARP;
     const int grp = lane / LPP, lig = lane % LPP;
-    FDesc* sD = reinterpret_cast<FDesc*>(sB + (size_t)p.nsb * B_SLOT);   // [taps][TILE_M]
+    FDesc* sD = reinterpret_cast<FDesc*>(sB + (size_t)p.nsb * SLOT);   // [taps][TILE_M]
     const uint32_t row_units = (uint32_t)(C / 4);
     uint32_t as = 0, ap = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += wstep) {
       const int pi = find_range(p.map, work);
       const F32Prob& pr = p.pr[pi];
-      const int tile = work - p.map.start[pi];
+      const int tile = PAIR ? 2 * (work - p.map.start[pi]) + rank : work - p.map.start[pi];
       const uint4* xbase = reinterpret_cast<const uint4*>(pr.xp) + lig;
       {
         const Geo g = with_dims(p.g, pr.d);
@@ -418,7 +470,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
           if (has_next) SDB_ISSUE(ntap, nch, it, it)
         }
         fence_proxy_async_smem();
-        mbar_arrive_warp(&a_full[as]);
+        if (PAIR && rank != 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&a_full[as], 0);
+        } else {
+          mbar_arrive_warp(&a_full[as]);
+        }
         if (++as == (uint32_t)p.nsa) { as = 0; ap ^= 1; }
         tap = ntap;
         ch = nch;
@@ -428,15 +485,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dcn_fwd_tf32_kernel(const __grid_
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc2(tmem_base, ncols);
+    else tmem_dealloc(tmem_base, ncols);
+  }
 }
 
-template <int PASSES>
+template <int PASSES, bool PAIR>
 int launch_tf32(const F32Params& p, size_t smem, int grid, cudaStream_t st) {
-  SDB_ENSURE_SMEM((dcn_fwd_tf32_kernel<PASSES>), smem);
+  SDB_ENSURE_SMEM((dcn_fwd_tf32_kernel<PASSES, PAIR>), smem);
   ProfScope prof(SDB_OP_FORWARD, st);
-  dcn_fwd_tf32_kernel<PASSES><<<grid, NTHREADS, smem, st>>>(p); SDB_LAUNCHED(1);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dcn_fwd_tf32_kernel<PASSES, PAIR>, p));
+  } else {
+    dcn_fwd_tf32_kernel<PASSES, PAIR><<<grid, NTHREADS, smem, st>>>(p);
+  }
+  SDB_LAUNCHED(1);
   SDB_CHECK_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -527,16 +599,29 @@ int tf32_forward_all(const TcProblem* pb, int n, const void* const* weights, con
   }
   p.map.start[n] = total;
   if (total == 0) return SDB_OK;
+  const bool pair = g_fwd_pair && g.O % 32 == 0;
+  if (pair) {   // work items = pairs of tiles of one problem
+    total = 0;
+    for (int i = 0; i < n; ++i) {
+      p.map.start[i] = total;
+      total += cdiv(cdiv(with_dims(g, pb[i].d).P(), TILE_M), 2);
+    }
+    p.map.start[n] = total;
+  }
   const size_t budget = 200 * 1024, d_bytes = (size_t)g.taps() * TILE_M * sizeof(FDesc);
-  const size_t a_bytes = (size_t)(passes == 3 ? 2 : 1) * PART_BYTES;
+  const size_t a_bytes = (size_t)(passes == 3 ? 2 : 1) * PART_BYTES, slot = pair ? B_SLOT / 2 : B_SLOT;
   p.nsa = passes == 3 ? 2 : 3;
-  long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / B_SLOT;
+  long long nsb = ((long long)budget - 1024 - (long long)d_bytes - (long long)(p.nsa * a_bytes)) / (long long)slot;
   if (nsb > MAX_B) nsb = MAX_B;
   SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
   p.nsb = (int)nsb;
-  const size_t smem = p.nsa * a_bytes + p.nsb * (size_t)B_SLOT + d_bytes + 1024;
+  const size_t smem = p.nsa * a_bytes + p.nsb * slot + d_bytes + 1024;
+  if (pair) {
+    const int clusters = total < grid_sms() / 2 ? total : grid_sms() / 2;
+    return passes == 3 ? launch_tf32<3, true>(p, smem, 2 * clusters, st) : launch_tf32<1, true>(p, smem, 2 * clusters, st);
+  }
   const int grid = total < grid_sms() ? total : grid_sms();
-  return passes == 3 ? launch_tf32<3>(p, smem, grid, st) : launch_tf32<1>(p, smem, grid, st);
+  return passes == 3 ? launch_tf32<3, false>(p, smem, grid, st) : launch_tf32<1, false>(p, smem, grid, st);
 }
 
 }  // namespace sdb
