@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]  # P3..P7 of an 800x1344 image
 C_IN = C_OUT = 256
 BATCH_PER_GPU = 2
+EXPLICIT_PREPARE = os.environ.get("SDB_BENCH_PREPARED", "0") != "0"
 GATHER_OVERLAP = os.environ.get("SDB_BENCH_GATHER_OVERLAP", "0") != "0"   # measured on 2 GPUs: 0.896 ms vs 0.860 ms for the default order
 ONE_GRAPH = os.environ.get("SDB_BENCH_ONE_GRAPH", "1") != "0"   # N > 1: capture the all-reduce into the step's CUDA graph
 NCCL_CTAS = int(os.environ.get("SDB_BENCH_NCCL_CTAS", "0"))  # developer knob: cap the overlapped all-reduce at this many CTAs and leave
@@ -214,7 +215,8 @@ class Workload:
             self.lv.append(lv)
         self.n = len(rows)
         self.probs = (L.Problem * self.n)(*rows)
-        self.wts = (L.Weights * 2)(*[L.Weights(L.addr(self.weights[k]), L.addr(self.biases[k]), L.addr(self.prepared[k]),
+        self.wts = (L.Weights * 2)(*[L.Weights(L.addr(self.weights[k]), L.addr(self.biases[k]),
+                                               L.addr(self.prepared[k]) if EXPLICIT_PREPARE else None,
                                                L.addr(self.gw[k]), L.addr(self.gb[k])) for k in range(2)])
         wsf = lib.sdb_dcn_multi_workspace_bytes(self.probs, self.n, self.wts, 2, gp, self.io, self.mth, 0)
         wsb = lib.sdb_dcn_multi_workspace_bytes(self.probs, self.n, self.wts, 2, gp, self.io, self.mth, 1)
@@ -230,7 +232,10 @@ class Workload:
                 self.gw[k].zero_()
                 if self.gb[k] is not None:
                     self.gb[k].zero_()
-        for k in range(2):   # the weights changed (optimiser step): rebuild their operand images, once for all levels
+        # the weights changed (optimiser step): their operand images are rebuilt once per step for all levels -- by the
+        # forward / backward calls themselves (prepared == NULL: on the library's side stream, beside the layout packs);
+        # SDB_BENCH_PREPARED=1: by explicit sdb_dcn_prepare_weights calls on the step's stream, as before
+        for k in range(2 if EXPLICIT_PREPARE else 0):
             L.check(lib.sdb_dcn_prepare_weights(P(self.weights[k]), P(self.biases[k]), gp, self.io, self.mth,
                                                 P(self.prepared[k]), sp))
         L.check(lib.sdb_dcn_forward_multi(self.probs, self.n, self.wts, 2, gp, self.io, self.mth, P(self.ws),

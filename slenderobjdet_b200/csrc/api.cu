@@ -251,6 +251,8 @@ int build_call(const sdb_dcn_problem* probs, int n, const sdb_dcn_weights* w, in
 int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g, int io_dtype, bool backward, uint8_t* base,
             bool* packed_from_caller, cudaStream_t st) {
   TcWeightImages img[tcshared::MAX_WEIGHTS];
+  cudaStream_t pst = st;   // images the call has to build itself: on the side stream, beside the layout packs
+  bool forked = false;
   for (int k = 0; k < nw; ++k) {
     const void* prep = w[k].prepared;
     if (!prep) {
@@ -260,12 +262,14 @@ int resolve(MultiCall& mc, int n, const sdb_dcn_weights* w, int nw, const Geo& g
         for (int i = 0; i < n; ++i)
           if (mc.pb[i].weight_id == k && (mc.pb[i].goff || mc.pb[i].gmask || mc.pb[i].gx)) which |= 2;
       }
-      int rc = tc_prepare_weights(w[k].weight, w[k].bias, g, io_dtype, base + mc.plan.prep_off[k], which, st);
+      if (which && !forked) { pst = tc_prep_begin(st); forked = true; }
+      int rc = tc_prepare_weights(w[k].weight, w[k].bias, g, io_dtype, base + mc.plan.prep_off[k], which, pst);
       if (rc) return rc;
       prep = base + mc.plan.prep_off[k];
     }
     img[k] = tc_weight_images(g, prep, w[k].bias != nullptr);
   }
+  if (forked) tc_prep_end(st, pst);
   *packed_from_caller = true;
   for (int i = 0; i < n; ++i) {
     TcProblem& t = mc.pb[i];
@@ -434,7 +438,9 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_
   bool from_caller;
   rc = resolve(mc, n, weights, nw, d, io_dtype, false, (uint8_t*)workspace, &from_caller, st);
   if (rc) return rc;
-  return tc_forward_all(mc.pb, n, d, io_dtype, st);
+  rc = tc_forward_all(mc.pb, n, d, io_dtype, st);
+  const int rcw = tc_prep_wait(st);   // no-op unless no kernel consumed the in-call weight preparation
+  return rc ? rc : rcw;
 }
 
 static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
@@ -445,9 +451,17 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
   if (rc) return rc;
   SDB_REQUIRE(workspace && workspace_bytes >= mc.plan.total, SDB_ERR_WORKSPACE, "backward workspace too small: %zu < %zu",
               workspace_bytes, mc.plan.total);
+  if (flags & SDB_BWD_DATA_ONLY)
+    for (int k = 0; k < nw; ++k) mc.gw[k] = mc.gb[k] = nullptr;
+  if (flags & SDB_BWD_WEIGHT_ONLY)
+    for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
   bool from_caller;
-  rc = resolve(mc, n, weights, nw, d, io_dtype, true, (uint8_t*)workspace, &from_caller, st);
-  if (rc) return rc;
+  if (!(flags & SDB_BWD_GATHER_ONLY)) {   // the gather reads no weight image
+    rc = resolve(mc, n, weights, nw, d, io_dtype, true, (uint8_t*)workspace, &from_caller, st);
+    if (rc) return rc;
+  } else {
+    for (int i = 0; i < n; ++i) mc.pb[i].dcol = (uint8_t*)workspace + mc.plan.dcol_off[i];
+  }
   // x_packed given for SOME problems only: the pack launch covers the ones that live in the workspace
   bool pack_any = false;
   for (int i = 0; i < n; ++i) {
@@ -455,10 +469,6 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     pack_any |= own;
     if (!own) mc.pb[i].x = nullptr;   // pack_nhwc_multi skips NULL sources
   }
-  if (flags & SDB_BWD_DATA_ONLY)
-    for (int k = 0; k < nw; ++k) mc.gw[k] = mc.gb[k] = nullptr;
-  if (flags & SDB_BWD_WEIGHT_ONLY)
-    for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
   if (mc.plan.conv) {
     SDB_REQUIRE(!accumulate_gx && !(flags & (SDB_BWD_GRAD_PACKED | SDB_BWD_NO_GATHER | SDB_BWD_GATHER_ONLY)), SDB_ERR_UNSUPPORTED,
                 "plain convolution: grad_x is overwritten, and the phased-backward flags are not supported");
@@ -469,11 +479,15 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
       for (int i = 0; i < n; ++i) needs |= mc.pb[i].weight_id == k && mc.pb[i].gx != nullptr;
       SDB_REQUIRE(!needs || wt[k], SDB_ERR_INVALID, "weight %d: the weight tensor is needed for grad_x", k);
     }
-    return tc_conv_backward_all(mc.pb, n, wt, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, (uint8_t*)workspace, st);
+    rc = tc_conv_backward_all(mc.pb, n, wt, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, (uint8_t*)workspace, st);
+    const int rcw = tc_prep_wait(st);
+    return rc ? rc : rcw;
   }
   const int phase = (flags & SDB_BWD_NO_GATHER) ? 1 : (flags & SDB_BWD_GATHER_ONLY) ? 2 : 0;
-  return tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
-                         (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st, phase);
+  rc = tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
+                       (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st, phase);
+  const int rcw = tc_prep_wait(st);   // no-op unless no kernel consumed the in-call weight preparation
+  return rc ? rc : rcw;
 }
 
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,

@@ -666,6 +666,10 @@ int tc_forward_multi(const TcProblem* pb, int n, const Geo& g, int io_dtype, cud
   const size_t d_bytes = (size_t)g.taps() * TILE_M * sizeof(GDesc);   // per-tile sampling descriptors
   const size_t smem = plan_smem(p, a_bytes, b_bytes, d_bytes);
   SDB_REQUIRE(smem > 0, SDB_ERR_UNSUPPORTED, "shared memory budget too small for this geometry");
+  {
+    const int rcw = tc_prep_wait(st);   // weight images prepared in this call, on the side stream
+    if (rcw) return rcw;
+  }
   const bool obf = io_dtype == SDB_BF16;
   const bool conv = pb[0].off == nullptr;   // plain convolution: every problem of the call (api.cu checks that they agree)
   // CTA pairs: work items are PAIRS of tiles of one problem (an odd tile count leaves the second CTA of the last pair an

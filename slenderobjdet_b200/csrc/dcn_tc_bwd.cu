@@ -1021,7 +1021,10 @@ __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const __grid_constant
 namespace {
 struct Side {
   cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;     // index build
+  cudaEvent_t fork2 = nullptr, join2 = nullptr;   // weight-gradient split reduce
+  cudaEvent_t fork3 = nullptr, join3 = nullptr;   // in-call weight-image preparation
+  bool prep_pending = false;
 };
 Side* side_of_device() {
   static Side tab[64];
@@ -1031,7 +1034,11 @@ Side* side_of_device() {
   if (!d.s) {
     if (cudaStreamCreateWithFlags(&d.s, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.join2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.fork3, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.join3, cudaEventDisableTiming) != cudaSuccess) {
       d.s = nullptr;
       cudaGetLastError();
       return nullptr;
@@ -1040,6 +1047,30 @@ Side* side_of_device() {
   return &d;
 }
 }  // namespace
+
+// In-call weight preparation (a call whose weights came without prepared images) runs on the side stream, beside the
+// call's layout packs; the first kernel that reads the images waits for it (tc_prep_wait).
+cudaStream_t tc_prep_begin(cudaStream_t st) {
+  Side* side = side_of_device();
+  if (!side) return st;
+  if (cudaEventRecord(side->fork3, st) != cudaSuccess || cudaStreamWaitEvent(side->s, side->fork3, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return st;
+  }
+  return side->s;
+}
+void tc_prep_end(cudaStream_t st, cudaStream_t used) {
+  Side* side = side_of_device();
+  if (!side || used == st) return;
+  if (cudaEventRecord(side->join3, side->s) == cudaSuccess) side->prep_pending = true;
+}
+int tc_prep_wait(cudaStream_t st) {
+  Side* side = side_of_device();
+  if (!side || !side->prep_pending) return SDB_OK;
+  side->prep_pending = false;
+  SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join3, 0));
+  return SDB_OK;
+}
 
 // ---- workspace plan of a multi-problem call ------------------------------------------------------------------------
 // Everything a call needs beyond its tensors lives in ONE caller-provided workspace, laid out as a pure function of
@@ -1199,9 +1230,10 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   }
 
   // (2a) transposed sampling index for grad_input, on the side stream, beside the grad_offset kernel
-  Side* side = any_gx ? side_of_device() : nullptr;
+  Side* side = (any_gx || any_gw) ? side_of_device() : nullptr;
+  bool reduce_pending = false;
   cudaStream_t ist = st;   // stream of the index build
-  if (side) {
+  if (side && any_gx) {
     SDB_CHECK_CUDA(cudaEventRecord(side->fork, st));
     SDB_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
     ist = side->s;
@@ -1212,78 +1244,8 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     if (side) SDB_CHECK_CUDA(cudaEventRecord(side->join, side->s));
   }
 
-  // (1) grad_offset / grad_mask: dcol GEMM + channel reduction; the dcol tiles of the problems that want grad_input
-  //     are exported for the gather (2b)
-  if (any_goff || any_gx) {
-    DgradParams p{};
-    p.g = g; p.okb = okb;
-    int m = 0, total = 0;
-    for (int i = 0; i < n; ++i) {
-      if (!pb[i].goff && !pb[i].gmask && !pb[i].gx) continue;
-      DgradProb& q = p.pr[m];
-      q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.gy_img = pb[i].gy_img;
-      q.wt_img = pb[i].w.dgrad; q.goff = pb[i].goff; q.gmask = pb[i].mask ? pb[i].gmask : nullptr; q.d = pb[i].d;
-      q.dcol = pb[i].gx ? pb[i].dcol : nullptr;
-      p.map.start[m] = total;
-      total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
-      ++m;
-    }
-    p.map.n = m; p.map.start[m] = total;
-    if (total > 0) {
-      // CTA pairs (sdb_set_backward_pair): work items are PAIRS of tiles of one problem, half-size weight slots
-      const bool pair = g_bwd_pair && NCH == 128;
-      if (pair) {
-        total = 0;
-        for (int k = 0; k < m; ++k) {
-          p.map.start[k] = total;
-          total += cdiv(cdiv((long long)p.pr[k].d.N * p.pr[k].d.Ho * p.pr[k].d.Wo, TILE_M), 2);
-        }
-        p.map.start[m] = total;
-      }
-      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = (size_t)NCH * 128 / (pair ? 2 : 1), stg = 2 * (size_t)stg_tile_bytes(NCH);
-      long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
-      if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
-      SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
-      p.nsb = (int)nsb;
-      const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
-      {
-        ProfScope prof(SDB_OP_BACKWARD_DATA, st);
-        if (pair) {
-          const int clusters = total < grid_sms() / 2 ? total : grid_sms() / 2;
-          SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, true>), smem);
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(G_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeClusterDimension;
-          attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-          cfg.attrs = attr; cfg.numAttrs = 1;
-          SDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dcn_bwd_data_tc_kernel<128, true>, p));
-        } else {
-          const int grid = total < grid_sms() ? total : grid_sms();
-          if (NCH == 128) {
-            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, false>), smem);
-            dcn_bwd_data_tc_kernel<128, false><<<grid, G_THREADS, smem, st>>>(p);
-          } else {
-            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<64, false>), smem);
-            dcn_bwd_data_tc_kernel<64, false><<<grid, G_THREADS, smem, st>>>(p);
-          }
-        }
-        SDB_LAUNCHED(1);
-      }
-      SDB_CHECK_CUDA(cudaGetLastError());
-    }
-  }
-
-  // (2b) grad_input: gather of the dcol tiles over the transposed index
-  if (any_gx) {
-    if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    if (gather_phase != 1) {
-      rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
-      if (rc) return rc;
-    }
-  }
-
-  // (3) grad_weight (+ grad_bias): one CTA per (weight, tap, channel chunk, pixel split) over that weight's tiles
+  // (3) grad_weight (+ grad_bias) FIRST -- it needs only dY and the saved columns, its split reduce then runs beside the
+  // data-gradient kernels, and the gather still follows grad_offset directly (it reads the L2-resident tail of dcol first) --: one CTA per (weight, tap, channel chunk, pixel split) over that weight's tiles
   bool all_col = any_gw;   // every problem that contributes to a wanted weight gradient brings its saved columns
   for (int i = 0; i < n; ++i)
     if (gw[pb[i].weight_id] && with_dims(g, pb[i].d).P() > 0 && !pb[i].col) all_col = false;
@@ -1331,7 +1293,15 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
         SDB_LAUNCHED(1);
       }
       SDB_CHECK_CUDA(cudaGetLastError());
-      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      // the split reduce runs on the side stream (behind the index build), beside grad_offset / grad_input
+      cudaStream_t rst = st;
+      if (side) {
+        SDB_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+        SDB_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));
+        rst = side->s;
+      }
+      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, rst>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      if (side) { SDB_CHECK_CUDA(cudaEventRecord(side->join2, side->s)); reduce_pending = true; }
       SDB_CHECK_CUDA(cudaGetLastError());
     }
   } else if (any_gw) {
@@ -1383,10 +1353,91 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
       }
       SDB_CHECK_CUDA(cudaGetLastError());
       // weights with no tile contribute nothing: the reduce of a weight with splits == 0 returns at once
-      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, st>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      // the split reduce runs on the side stream (behind the index build), beside grad_offset / grad_input
+      cudaStream_t rst = st;
+      if (side) {
+        SDB_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+        SDB_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));
+        rst = side->s;
+      }
+      wgrad_reduce_kernel<<<dim3(g.O * ((g.C + 127) / 128), nweights), 128, 0, rst>>>(rt, scale, g.taps(), g.O, g.C); SDB_LAUNCHED(1);
+      if (side) { SDB_CHECK_CUDA(cudaEventRecord(side->join2, side->s)); reduce_pending = true; }
       SDB_CHECK_CUDA(cudaGetLastError());
     }
   }
+  // (1) grad_offset / grad_mask: dcol GEMM + channel reduction; the dcol tiles of the problems that want grad_input
+  //     are exported for the gather (2b)
+  if (any_goff || any_gx) {
+    DgradParams p{};
+    p.g = g; p.okb = okb;
+    int m = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!pb[i].goff && !pb[i].gmask && !pb[i].gx) continue;
+      DgradProb& q = p.pr[m];
+      q.xp = (const __nv_bfloat16*)pb[i].xp; q.off = pb[i].off; q.mask = pb[i].mask; q.gy_img = pb[i].gy_img;
+      q.wt_img = pb[i].w.dgrad; q.goff = pb[i].goff; q.gmask = pb[i].mask ? pb[i].gmask : nullptr; q.d = pb[i].d;
+      q.dcol = pb[i].gx ? pb[i].dcol : nullptr;
+      p.map.start[m] = total;
+      total += cdiv(with_dims(g, pb[i].d).P(), TILE_M);
+      ++m;
+    }
+    p.map.n = m; p.map.start[m] = total;
+    if (total > 0) {
+      // CTA pairs (sdb_set_backward_pair): work items are PAIRS of tiles of one problem, half-size weight slots
+      const bool pair = g_bwd_pair && NCH == 128;
+      if (pair) {
+        total = 0;
+        for (int k = 0; k < m; ++k) {
+          p.map.start[k] = total;
+          total += cdiv(cdiv((long long)p.pr[k].d.N * p.pr[k].d.Ho * p.pr[k].d.Wo, TILE_M), 2);
+        }
+        p.map.start[m] = total;
+      }
+      const size_t a_bytes = (size_t)okb * TILE_M * 128, b_bytes = (size_t)NCH * 128 / (pair ? 2 : 1), stg = 2 * (size_t)stg_tile_bytes(NCH);
+      long long nsb = ((long long)(208 * 1024) - 1024 - (long long)a_bytes - (long long)stg) / (long long)b_bytes;
+      if (nsb > MAX_B_STAGES) nsb = MAX_B_STAGES;
+      SDB_REQUIRE(nsb >= 2, SDB_ERR_UNSUPPORTED, "shared memory budget too small for backward_data");
+      p.nsb = (int)nsb;
+      const size_t smem = a_bytes + p.nsb * b_bytes + stg + 1024;
+      rc = tc_prep_wait(st);   // weight images prepared in this call, on the side stream
+      if (rc) return rc;
+      {
+        ProfScope prof(SDB_OP_BACKWARD_DATA, st);
+        if (pair) {
+          const int clusters = total < grid_sms() / 2 ? total : grid_sms() / 2;
+          SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, true>), smem);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(G_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          SDB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dcn_bwd_data_tc_kernel<128, true>, p));
+        } else {
+          const int grid = total < grid_sms() ? total : grid_sms();
+          if (NCH == 128) {
+            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<128, false>), smem);
+            dcn_bwd_data_tc_kernel<128, false><<<grid, G_THREADS, smem, st>>>(p);
+          } else {
+            SDB_ENSURE_SMEM((dcn_bwd_data_tc_kernel<64, false>), smem);
+            dcn_bwd_data_tc_kernel<64, false><<<grid, G_THREADS, smem, st>>>(p);
+          }
+        }
+        SDB_LAUNCHED(1);
+      }
+      SDB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+
+  // (2b) grad_input: gather of the dcol tiles over the transposed index
+  if (any_gx) {
+    if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    if (gather_phase != 1) {
+      rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
+      if (rc) return rc;
+    }
+  }
+
   if (any_gb) {
     BiasGradTable t{};
     int m = 0;
@@ -1402,9 +1453,9 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     SDB_LAUNCHED(1);
     SDB_CHECK_CUDA(cudaGetLastError());
   }
+  if (reduce_pending) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join2, 0));   // the split reduce ran on the side stream
   return SDB_OK;
 }
-
 
 // ---- plain convolution (the towers' Conv2d 3x3, reppointsv2.py:644-675): offset == nullptr ------------------------------
 // "same" convolutions only (stride 1, 2 * pad == dil * (k - 1)): grad_input is then the convolution of dY with the

@@ -80,6 +80,10 @@ TcWeightImages tc_weight_images(const Geo& g, const void* prepared, bool has_bia
 int tc_prepare_weights(const void* w, const void* bias, const Geo& g, int io_dtype, void* prepared, int which,
                        cudaStream_t st);   // which: 1 = forward image, 2 = dcol image (3 = both)
 int tc_lanes_per_pixel(const Geo& g);
+// in-call weight preparation on the side stream (dcn_tc_bwd.cu)
+cudaStream_t tc_prep_begin(cudaStream_t st);
+void tc_prep_end(cudaStream_t st, cudaStream_t used);
+int tc_prep_wait(cudaStream_t st);
 
 // tcgen05 kind::tf32 forward with float32 tensors (dcn_tf32.cu); passes = 1 (tf32) or 3 (error-compensated, fp32-accurate)
 bool tf32_supported(const Geo& g, const char** why);

@@ -235,6 +235,10 @@ def _prepared_weights(weight, bias, g, iod, mth):
     """-> uint8 tensor with the operand images of (weight, bias), cached on (tensor identity, version)."""
     if mth == _lib.SDB_MATH_FP32:
         return None
+    if mth == _lib.SDB_MATH_BF16 and weight.requires_grad:
+        # training: the values change every step, so a cached image would be rebuilt every step anyway -- let the calls
+        # build what they need themselves (on the library's side stream, beside their layout packs)
+        return None
     key = (id(weight), weight.device.index, mth)
     ver = (weight._version, weight.data_ptr(), None if bias is None else (id(bias), bias._version, bias.data_ptr()),
            iod, g.C_in, g.C_out, g.kH, g.kW)
