@@ -193,8 +193,15 @@ int sdb_dcn_forward_multi(const sdb_dcn_problem* problems, int32_t n_problems, c
  *                        the dcol tiles and the transposed index stay in the workspace;
  *   SDB_BWD_GATHER_ONLY  only the grad_x gather, from the workspace a SDB_BWD_NO_GATHER call on the SAME table left.
  *                        (Lets a caller place the gather -- an ordinary, non-persistent grid -- wherever its schedule wants it;
- *                        running the all-reduce beside the gather alone was measured slower than beside grad_offset + gather.) */
-enum { SDB_BWD_WEIGHT_ONLY = 1, SDB_BWD_DATA_ONLY = 2, SDB_BWD_GRAD_PACKED = 4, SDB_BWD_NO_GATHER = 8, SDB_BWD_GATHER_ONLY = 16 };
+ *                        running the all-reduce beside the gather alone was measured slower than beside grad_offset + gather.);
+ *   SDB_BWD_BUILD_INDEX  with SDB_BWD_WEIGHT_ONLY: also build the transposed sampling index of the problems that name a grad_x
+ *                        (beside the weight-gradient GEMM, where it costs nothing; beside the statically scheduled
+ *                        grad_offset kernel it costs ~35 us) and leave it in the workspace;
+ *   SDB_BWD_INDEX_READY  with SDB_BWD_DATA_ONLY: use that index instead of building one.
+ *                        (For callers whose schedule has room before the collective; in bench.py's two-half step it delays
+ *                        the start of the all-reduce and is off by default.) */
+enum { SDB_BWD_WEIGHT_ONLY = 1, SDB_BWD_DATA_ONLY = 2, SDB_BWD_GRAD_PACKED = 4, SDB_BWD_NO_GATHER = 8, SDB_BWD_GATHER_ONLY = 16,
+       SDB_BWD_BUILD_INDEX = 32, SDB_BWD_INDEX_READY = 64 };
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n_problems, const sdb_dcn_weights* weights,
                            int32_t n_weights, const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags,
                            void* workspace, size_t workspace_bytes, void* stream);

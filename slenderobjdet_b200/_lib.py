@@ -73,6 +73,7 @@ class PPLevel(ctypes.Structure):
 
 SDB_MAX_PROBLEMS, SDB_MAX_WEIGHTS = 16, 4
 SDB_BWD_WEIGHT_ONLY, SDB_BWD_DATA_ONLY, SDB_BWD_GRAD_PACKED, SDB_BWD_NO_GATHER, SDB_BWD_GATHER_ONLY = 1, 2, 4, 8, 16
+SDB_BWD_BUILD_INDEX, SDB_BWD_INDEX_READY = 32, 64
 
 _lib = None
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t

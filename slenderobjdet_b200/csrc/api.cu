@@ -453,8 +453,11 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
               workspace_bytes, mc.plan.total);
   if (flags & SDB_BWD_DATA_ONLY)
     for (int k = 0; k < nw; ++k) mc.gw[k] = mc.gb[k] = nullptr;
-  if (flags & SDB_BWD_WEIGHT_ONLY)
-    for (int i = 0; i < n; ++i) mc.pb[i].gx = nullptr, mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
+  if (flags & SDB_BWD_WEIGHT_ONLY)   // BUILD_INDEX keeps grad_x: it tells which offset groups need a transposed index
+    for (int i = 0; i < n; ++i) {
+      if (!(flags & SDB_BWD_BUILD_INDEX)) mc.pb[i].gx = nullptr;
+      mc.pb[i].goff = nullptr, mc.pb[i].gmask = nullptr;
+    }
   bool from_caller;
   if (!(flags & SDB_BWD_GATHER_ONLY)) {   // the gather reads no weight image
     rc = resolve(mc, n, weights, nw, d, io_dtype, true, (uint8_t*)workspace, &from_caller, st);
@@ -470,7 +473,7 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     if (!own) mc.pb[i].x = nullptr;   // pack_nhwc_multi skips NULL sources
   }
   if (mc.plan.conv) {
-    SDB_REQUIRE(!accumulate_gx && !(flags & (SDB_BWD_GRAD_PACKED | SDB_BWD_NO_GATHER | SDB_BWD_GATHER_ONLY)), SDB_ERR_UNSUPPORTED,
+    SDB_REQUIRE(!accumulate_gx && !(flags & (SDB_BWD_GRAD_PACKED | SDB_BWD_NO_GATHER | SDB_BWD_GATHER_ONLY | SDB_BWD_BUILD_INDEX | SDB_BWD_INDEX_READY)), SDB_ERR_UNSUPPORTED,
                 "plain convolution: grad_x is overwritten, and the phased-backward flags are not supported");
     const void* wt[tcshared::MAX_WEIGHTS];
     for (int k = 0; k < nw; ++k) {
@@ -483,7 +486,8 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
     const int rcw = tc_prep_wait(st);
     return rc ? rc : rcw;
   }
-  const int phase = (flags & SDB_BWD_NO_GATHER) ? 1 : (flags & SDB_BWD_GATHER_ONLY) ? 2 : 0;
+  const int phase = (flags & SDB_BWD_NO_GATHER) ? 1 : (flags & SDB_BWD_GATHER_ONLY) ? 2 : (flags & SDB_BWD_BUILD_INDEX) ? 3
+                    : (flags & SDB_BWD_INDEX_READY) ? 4 : 0;
   rc = tc_backward_all(mc.pb, n, mc.gw, mc.gb, nw, mc.plan, d, io_dtype, scale, pack_any, accumulate_gx,
                        (flags & SDB_BWD_GRAD_PACKED) != 0, (uint8_t*)workspace, st, phase);
   const int rcw = tc_prep_wait(st);   // no-op unless no kernel consumed the in-call weight preparation
@@ -494,9 +498,12 @@ int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb
                            const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags, void* workspace,
                            size_t workspace_bytes, void* stream) {
   SDB_MULTI_PROLOGUE();
-  SDB_REQUIRE((flags & ~31) == 0 && (flags & 3) != 3 && (flags & 24) != 24 && !((flags & 24) && (flags & SDB_BWD_WEIGHT_ONLY)),
+  SDB_REQUIRE((flags & ~127) == 0 && (flags & 3) != 3 && (flags & 24) != 24 && !((flags & 24) && (flags & SDB_BWD_WEIGHT_ONLY)) &&
+                  !((flags & SDB_BWD_BUILD_INDEX) && (flags & ~(SDB_BWD_BUILD_INDEX | SDB_BWD_WEIGHT_ONLY))) &&
+                  !((flags & SDB_BWD_BUILD_INDEX) && !(flags & SDB_BWD_WEIGHT_ONLY)) &&
+                  !((flags & SDB_BWD_INDEX_READY) && (flags & (24 | SDB_BWD_WEIGHT_ONLY))),
               SDB_ERR_INVALID, "bad backward flags %d", flags);
-  SDB_REQUIRE(!(flags & 24) || math == SDB_MATH_BF16, SDB_ERR_UNSUPPORTED, "SDB_BWD_NO_GATHER / GATHER_ONLY need SDB_MATH_BF16");
+  SDB_REQUIRE(!(flags & 120) || math == SDB_MATH_BF16, SDB_ERR_UNSUPPORTED, "the phased-backward flags need SDB_MATH_BF16");
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)
     SDB_REQUIRE(problems[i].N == 0 || (problems[i].x && problems[i].grad_out && (problems[i].offset || math == SDB_MATH_BF16)),

@@ -1191,6 +1191,10 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   bool any_goff = false, any_gx = false, any_gw = false, any_gb = false;
   for (int i = 0; i < n; ++i) { any_goff |= pb[i].goff || pb[i].gmask; any_gx |= pb[i].gx != nullptr; }
   for (int w = 0; w < nweights; ++w) { any_gw |= gw[w] != nullptr; any_gb |= gb[w] != nullptr; }
+  // gather_phase 3: weight gradients + the transposed index only (the index is built beside the weight-gradient GEMM; no
+  // grad_offset kernel, no gather); 4: grad_offset + gather over the index a phase-3 call on the same table left behind
+  const bool index_only = gather_phase == 3, index_ready = gather_phase == 4;
+  if (index_only) any_goff = false;
   if (gather_phase == 2) {   // only the gather: dcol tiles and index were left in the workspace by a phase-1 call
     if (!any_gx) return SDB_OK;
     rc = tc_build_transposed_index(pb, n, P, g, base, st, true);
@@ -1242,7 +1246,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
     ist = side->s;
   }
   if (any_gx) {
-    rc = tc_build_transposed_index(pb, n, P, g, base, ist);
+    rc = tc_build_transposed_index(pb, n, P, g, base, ist, index_ready);
     if (rc) return rc;
     if (side) SDB_CHECK_CUDA(cudaEventRecord(side->join, side->s));
   }
@@ -1370,7 +1374,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   }
   // (1) grad_offset / grad_mask: dcol GEMM + channel reduction; the dcol tiles of the problems that want grad_input
   //     are exported for the gather (2b)
-  if (any_goff || any_gx) {
+  if ((any_goff || any_gx) && !index_only) {
     DgradParams p{};
     p.g = g; p.okb = okb;
     int m = 0, total = 0;
@@ -1435,7 +1439,7 @@ int tc_backward_all(TcProblem* pb, int n, float* const* gw, float* const* gb, in
   // (2b) grad_input: gather of the dcol tiles over the transposed index
   if (any_gx) {
     if (side) SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    if (gather_phase != 1) {
+    if (gather_phase != 1 && !index_only) {
       rc = tc_dx_multi(pb, n, g, io_dtype, accumulate_gx, st);
       if (rc) return rc;
     }

@@ -229,3 +229,12 @@ def test_phased_backward_through_the_c_abi_equals_one_call():
     torch.cuda.synchronize()
     for a, b in zip(one, grads()):
         assert torch.equal(a, b)
+    # the two-half order of bench.py at N > 1: the transposed index is built in the weight-gradient half
+    clear()
+    wl.phase_backward(st, L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_BUILD_INDEX)
+    torch.cuda.synchronize()
+    assert all(float(b["gx"].float().abs().max()) == 0.0 and float(b["goff"].abs().max()) == 0.0 for b in brs)
+    wl.phase_backward(st, L.SDB_BWD_DATA_ONLY | L.SDB_BWD_GRAD_PACKED | L.SDB_BWD_INDEX_READY)
+    torch.cuda.synchronize()
+    for a, b in zip(one, grads()):
+        assert torch.equal(a, b)
