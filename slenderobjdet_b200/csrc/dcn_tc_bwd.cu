@@ -1024,8 +1024,11 @@ struct Side {
   cudaEvent_t fork = nullptr, join = nullptr;     // index build
   cudaEvent_t fork2 = nullptr, join2 = nullptr;   // weight-gradient split reduce
   cudaEvent_t fork3 = nullptr, join3 = nullptr;   // in-call weight-image preparation
-  bool prep_pending = false;
 };
+// "this host thread has forked a weight preparation that no kernel has waited for yet": per thread, so that a call running on
+// another thread (autograd's engine thread) cannot consume it; the events themselves may be shared -- they are all recorded
+// on the one side stream, so waiting for a later record only waits for more
+thread_local bool t_prep_pending = false;
 Side* side_of_device() {
   static Side tab[64];
   int dev = 0;
@@ -1062,12 +1065,12 @@ cudaStream_t tc_prep_begin(cudaStream_t st) {
 void tc_prep_end(cudaStream_t st, cudaStream_t used) {
   Side* side = side_of_device();
   if (!side || used == st) return;
-  if (cudaEventRecord(side->join3, side->s) == cudaSuccess) side->prep_pending = true;
+  if (cudaEventRecord(side->join3, side->s) == cudaSuccess) t_prep_pending = true;
 }
 int tc_prep_wait(cudaStream_t st) {
   Side* side = side_of_device();
-  if (!side || !side->prep_pending) return SDB_OK;
-  side->prep_pending = false;
+  if (!side || !t_prep_pending) return SDB_OK;
+  t_prep_pending = false;
   SDB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join3, 0));
   return SDB_OK;
 }

@@ -72,7 +72,7 @@ class _ConvMulti(Function):
         save = [bool(ctx.needs_input_grad[1 + n + wids[i]]) for i in range(n)]
         outs, packed = _dc._multi_forward(cx, [None] * n, [None] * n, cw, cb, wids, [-1] * n, g, iod, mth, cdt, save)
         ctx.save_for_backward(*tensors)
-        ctx.meta_, ctx.packed_, ctx.g_ = meta, packed, g
+        ctx.meta_, ctx.packed_, ctx.g_, ctx.plan_ = meta, packed, g, (cdt, iod, mth)   # the backward uses the forward's arithmetic
         return tuple(o if o.dtype == xs[i].dtype else o.to(xs[i].dtype) for i, o in enumerate(outs))
 
     @staticmethod
@@ -83,7 +83,7 @@ class _ConvMulti(Function):
         xs, ws = list(tensors[:n]), list(tensors[n:n + k])
         bs = list(tensors[n + k:n + 2 * k]) if has_bias else [None] * k
         g = ctx.g_
-        _, cdt, iod, mth = _conv_plan(xs[0], ws[0], padding, dilation)
+        cdt, iod, mth = ctx.plan_
         need = ctx.needs_input_grad[1:]
         need_x = [bool(need[i]) for i in range(n)]
         need_w = [bool(need[n + j]) for j in range(k)]

@@ -231,13 +231,11 @@ def invalidate_prepared_weights():
     _PREPARED.clear()
 
 
-def _prepared_weights(weight, bias, g, iod, mth):
-    """-> uint8 tensor with the operand images of (weight, bias), cached on (tensor identity, version)."""
-    if mth == _lib.SDB_MATH_FP32:
-        return None
-    if mth == _lib.SDB_MATH_BF16 and weight.requires_grad:
-        # training: the values change every step, so a cached image would be rebuilt every step anyway -- let the calls
-        # build what they need themselves (on the library's side stream, beside their layout packs)
+def _prepared_weights(weight, bias, g, iod, mth, training=False):
+    """-> uint8 tensor with the operand images of (weight, bias), cached on (tensor identity, version); None (= the
+    native call builds what it needs itself, on the library's side stream beside its layout packs) for fp32 math and for
+    training-mode bf16 calls, whose weights change every step so that a cached image would be rebuilt every step anyway."""
+    if mth == _lib.SDB_MATH_FP32 or (training and mth == _lib.SDB_MATH_BF16):
         return None
     key = (id(weight), weight.device.index, mth)
     ver = (weight._version, weight.data_ptr(), None if bias is None else (id(bias), bias._version, bias.data_ptr()),
@@ -298,7 +296,8 @@ def _multi_forward(xs, offs, masks, weights, biases, wids, groups, g, iod, mth, 
         cols.append(_ws(lib.sdb_dcn_columns_bytes(ctypes.byref(gi), mth), dev) if want else None)
     probs = (_lib.Problem * n)(*[_problem(xs[i], offs[i], masks[i], wids[i], groups[i], outs[i], packed[i], cols=cols[i])
                                  for i in range(n)])
-    prep = [_prepared_weights(w, b, g, iod, mth) for w, b in zip(weights, biases)]
+    training = save_cols is not None and any(save_cols)   # a weight gradient will be wanted: training step
+    prep = [_prepared_weights(w, b, g, iod, mth, training) for w, b in zip(weights, biases)]
     wts = (_lib.Weights * len(weights))(*[_lib.Weights(_lib.addr(w), _lib.addr(b), _lib.addr(p), None, None)
                                           for w, b, p in zip(weights, biases, prep)])
     wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 0)) if (tc or tf) else 0
@@ -333,7 +332,7 @@ def _multi_backward(xs, offs, masks, weights, biases, wids, groups, gys, packed,
                                  for i in range(n)])
     # the weight VALUES are read only by grad_input / grad_offset / grad_mask; a grad_weight-only call needs no image
     reads = [any(wids[i] == k and (need_x[i] or need_off[i] or need_mask[i]) for i in range(n)) for k in range(len(weights))]
-    prep = [_prepared_weights(w, b, g, iod, mth) if r else None for w, b, r in zip(weights, biases, reads)]
+    prep = [_prepared_weights(w, b, g, iod, mth, any(need_w)) if r else None for w, b, r in zip(weights, biases, reads)]
     wts = (_lib.Weights * len(weights))(*[_lib.Weights(_lib.addr(w), _lib.addr(b), _lib.addr(p), _lib.addr(gw), _lib.addr(gb))
                                           for w, b, p, gw, gb in zip(weights, biases, prep, gws, gbs)])
     wsb = int(lib.sdb_dcn_multi_workspace_bytes(probs, n, wts, len(weights), gp, iod, mth, 1)) if tc else 0
