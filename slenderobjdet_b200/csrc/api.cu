@@ -497,12 +497,13 @@ static int backward_multi_impl(const sdb_dcn_problem* problems, int32_t n, const
 int sdb_dcn_backward_multi(const sdb_dcn_problem* problems, int32_t n, const sdb_dcn_weights* weights, int32_t nw,
                            const sdb_dcn_geom* g, int io_dtype, int math, float scale, int flags, void* workspace,
                            size_t workspace_bytes, void* stream) {
-  SDB_MULTI_PROLOGUE();
+  // argument checks that need no device come first
   SDB_REQUIRE((flags & ~127) == 0 && (flags & 3) != 3 && (flags & 24) != 24 && !((flags & 24) && (flags & SDB_BWD_WEIGHT_ONLY)) &&
                   !((flags & SDB_BWD_BUILD_INDEX) && (flags & ~(SDB_BWD_BUILD_INDEX | SDB_BWD_WEIGHT_ONLY))) &&
                   !((flags & SDB_BWD_BUILD_INDEX) && !(flags & SDB_BWD_WEIGHT_ONLY)) &&
                   !((flags & SDB_BWD_INDEX_READY) && (flags & (24 | SDB_BWD_WEIGHT_ONLY))),
               SDB_ERR_INVALID, "bad backward flags %d", flags);
+  SDB_MULTI_PROLOGUE();
   SDB_REQUIRE(!(flags & 120) || math == SDB_MATH_BF16, SDB_ERR_UNSUPPORTED, "the phased-backward flags need SDB_MATH_BF16");
   SDB_REQUIRE(problems && weights, SDB_ERR_INVALID, "NULL table");
   for (int i = 0; i < n; ++i)

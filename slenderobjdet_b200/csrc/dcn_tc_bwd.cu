@@ -21,6 +21,11 @@
 //   Two variants: over the columns the forward pass saved (dcn_wgrad_col_tc_kernel: both operands stream in
 //   by bulk copy, O x 256 accumulators) or, when they were not saved, re-sampling them with the forward's
 //   gather producer (dcn_bwd_weight_tc_kernel).  Replaces K1' + G3 of the reference (deform_conv_cuda.cu:738-778).
+//
+// Order of a backward call (tc_backward_all): layout packs -> fork: transposed-index build on the side stream || weight-
+// gradient GEMM -> its split reduce on the side stream || grad_offset kernel -> grad_input gather -> join.  The grad_offset
+// kernel (and the forward) are persistent with a static tile schedule and run ALONE: any co-running kernel that holds SMs
+// delays the whole launch.  grad_offset and the forward run as CTA pairs (cta_group::2, M = 256) by default.
 #include "dcn_tc_shared.cuh"
 
 namespace sdb {

@@ -171,3 +171,21 @@ def test_deform_conv_multi_argument_checks():
     with pytest.raises(NotImplementedError):   # CPU tensors, like the reference (deform_conv.py:48-49)
         sdb.deform_conv_multi([torch.zeros(1, 4, 5, 5)], [torch.zeros(1, 18, 5, 5)], w, 1, 1, 1)
     assert sdb.deform_conv_multi([], [], w) == []
+
+
+def test_backward_flag_validation_without_gpu():
+    """sdb_dcn_backward_multi refuses contradictory phase flags before touching the device (flags are validated first)."""
+    lib = _lib.lib()
+    g = _lib.Geom(1, 256, 8, 8, 256, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1)
+    probs, n = _table([(25, 42)])
+    wts = (_lib.Weights * 2)(_lib.Weights(0x7000, None, None, 0x8000, None), _lib.Weights(0x7100, None, None, 0x8100, None))
+    L = _lib
+    bad = [L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_DATA_ONLY, L.SDB_BWD_NO_GATHER | L.SDB_BWD_GATHER_ONLY,
+           L.SDB_BWD_WEIGHT_ONLY | L.SDB_BWD_GATHER_ONLY, L.SDB_BWD_BUILD_INDEX, L.SDB_BWD_BUILD_INDEX | L.SDB_BWD_DATA_ONLY,
+           L.SDB_BWD_INDEX_READY | L.SDB_BWD_WEIGHT_ONLY, L.SDB_BWD_INDEX_READY | L.SDB_BWD_NO_GATHER, 128]
+    for f in bad:
+        rc = lib.sdb_dcn_backward_multi(probs, n, wts, 2, ctypes.byref(g), L.SDB_BF16, L.SDB_MATH_BF16, ctypes.c_float(1.0), f,
+                                        None, 0, None)
+        assert rc != 0, f
+        msg = lib.sdb_last_error()
+        assert b"bad backward flags" in msg, (f, msg)
