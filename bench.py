@@ -496,6 +496,8 @@ def run_ours(args):
         else:   # developer knob: NCCL's own CTA count, nothing reserved
             dist.init_process_group("nccl", device_id=device)
     lib = L.lib()
+    if os.environ.get("SDB_BENCH_PAIR_BWD") is not None:   # developer knob: CTA-pair grad_offset kernel on / off
+        lib.sdb_set_backward_pair(int(os.environ["SDB_BENCH_PAIR_BWD"]))
     peaks = load_peaks()
     batch = BATCH_PER_GPU
     stream = torch.cuda.Stream(device)
