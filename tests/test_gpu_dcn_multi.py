@@ -238,3 +238,31 @@ def test_phased_backward_through_the_c_abi_equals_one_call():
     torch.cuda.synchronize()
     for a, b in zip(one, grads()):
         assert torch.equal(a, b)
+
+
+def test_cta_pair_kernels_give_the_bits_of_the_single_cta_kernels():
+    """sdb_set_forward_pair / sdb_set_backward_pair only change how tiles are mapped to CTAs (cta_group::2, M = 256, two
+    tiles per cluster, an all-invalid second tile when a problem's tile count is odd): every output and gradient is
+    bit-identical to the one-CTA-per-tile kernels (include/slender_b200.h says so)."""
+    import bench
+    from slenderobjdet_b200 import _lib as L
+    lib = L.lib()
+    dev = torch.device("cuda", 0)
+    wl = bench.Workload(torch, L, dev, seed=5, batch=1, levels=[(50, 84), (25, 42), (13, 21), (7, 11)])   # 33, 9, 3, 1 tiles
+    st = torch.cuda.current_stream(dev)
+    brs = [br for lv in wl.lv for br in lv["br"]]
+    res = {}
+    try:
+        for pair in (0, 1):
+            lib.sdb_set_forward_pair(pair)
+            lib.sdb_set_backward_pair(pair)
+            for b in brs:
+                b["out"].zero_(); b["gx"].zero_(); b["goff"].zero_()
+            wl.step(st)
+            torch.cuda.synchronize()
+            res[pair] = [b[k].clone() for b in brs for k in ("out", "gx", "goff")] + [g.clone() for g in wl.gw]
+    finally:
+        lib.sdb_set_forward_pair(1)
+        lib.sdb_set_backward_pair(1)
+    assert all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
+    assert float(res[1][0].float().abs().max()) > 0
